@@ -1,0 +1,170 @@
+/*
+ * diskann_b200.h — C ABI of the B200-native StreamingDiskANN index-scan engine.
+ *
+ * This is the drop-in boundary for pgvectorscale's `diskann` index *scan* path: the
+ * Rust/pgrx access-method callbacks stay host code and call these entry points where
+ * they used to run `TSVScanState::initialize` and `TSVResponseIterator::next_with_resort`.
+ * Reference citations are relative to /root/reference/pgvectorscale/src/access_method/.
+ *
+ *   reference interface                              replaced by
+ *   ------------------------------------------------ -----------------------------------
+ *   ambeginscan            scan.rs:309-333           dann_scan_begin
+ *   amrescan               scan.rs:336-367           dann_scan_rescan
+ *     TSVScanState::initialize      scan.rs:57-88
+ *     LabeledVector::from_scan_key_data labels/mod.rs:209-238
+ *     Graph::greedy_search_streaming_init graph/mod.rs:331-354
+ *   amgettuple             scan.rs:370-436           dann_scan_gettuple
+ *     TSVResponseIterator::next_with_resort scan.rs:244-305
+ *     Graph::greedy_search_iterate  graph/mod.rs:357-385
+ *     SbqSpeedupStorage::visit_lsn  sbq/storage.rs:125-190
+ *     get_full_distance_for_resort  sbq/storage.rs:304-328
+ *   amendscan              scan.rs:439-476           dann_scan_end (+ dann_scan_stats)
+ *   MetaPage::fetch / SbqMeans::load (index -> RAM)  dann_index_load (index -> HBM)
+ *   distance_xor_optimized distance/mod.rs:265-323   dann_sbq_distance (micro-kernel)
+ *   distance_l2 / _cosine / _inner_product :88-209   dann_full_distance (micro-kernel)
+ *   SbqQuantizer::quantize sbq/quantize.rs:52-102    dann_prepare_queries
+ *
+ * Conventions: every function returns DANN_OK (0) or a negative dann_status; nothing
+ * throws, longjmps or aborts (the Rust shim turns a non-zero code into pgrx::error!).
+ * dann_last_error() gives a thread-local message.  Host pointers are borrowed for the
+ * duration of the call only.  A dann_index is immutable after load and may be shared
+ * by host threads (calls on one index are serialised internally); a dann_scan is
+ * single-threaded, like a Postgres backend.
+ */
+#ifndef DISKANN_B200_H
+#define DISKANN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DANN_INVALID_NODE 0xFFFFFFFFu          /* InvalidBlockNumber, sbq/node.rs:261-273 */
+#define DANN_INVALID_TID 0xFFFFFFFFFFFFFFFFull /* "no row" in batch outputs */
+
+typedef enum {
+    DANN_OK = 0,
+    DANN_ERR_INVALID_ARG = -1,
+    DANN_ERR_CUDA = -2,      /* sticky: the handle is poisoned */
+    DANN_ERR_NO_DEVICE = -3, /* no CUDA device / driver: there is NO CPU fallback */
+    DANN_ERR_OOM = -4,
+    DANN_ERR_CAPACITY = -5,  /* per-query state outgrew the largest workspace we may allocate */
+    DANN_ERR_STATE = -6
+} dann_status;
+
+typedef enum { DANN_COSINE = 0, DANN_L2 = 1, DANN_IP = 2 } dann_distance; /* distance/mod.rs:11-15 */
+
+/* Flat snapshot of one diskann index (host memory, row-major). See
+ * pgvectorscale_b200/snapshot.py for the field-by-field provenance. */
+typedef struct {
+    uint32_t n;             /* nodes */
+    uint32_t dim;           /* heap vector dimensions */
+    uint32_t dim_index;     /* num_dimensions_to_index, pg_vector.rs:143-148 */
+    uint32_t bits;          /* SBQ bits per dimension, meta_page.rs:312-323 */
+    uint32_t words;         /* u64 per code = ceil(dim_index*bits/64), quantize.rs:38-46 */
+    uint32_t R;             /* num_neighbors, meta_page.rs:284-294 */
+    int32_t distance_type;  /* dann_distance */
+    int32_t has_labels;
+    uint64_t count;         /* SbqMeans.count */
+    const float *mean;      /* [dim_index] */
+    const float *m2;        /* [dim_index], may be NULL when bits == 1 */
+    const uint64_t *codes;  /* [n*words] */
+    const uint32_t *nbrs;   /* [n*R], list ends at first DANN_INVALID_NODE */
+    const uint64_t *heap_tid; /* [n] (block<<16)|offset, offset 0 = deleted */
+    const float *vectors;   /* [n*dim] raw heap vectors */
+    uint32_t start_default; /* DANN_INVALID_NODE = empty graph */
+    uint32_t n_start_labels;
+    const int16_t *start_labels;       /* ascending */
+    const uint32_t *start_label_nodes;
+    const uint32_t *label_off;         /* [n+1] if has_labels */
+    const int16_t *labels;             /* sorted, dedup per node */
+} dann_snapshot_desc;
+
+/* Per-query counters: the ones the reference logs at amendscan (scan.rs:461-472). */
+typedef struct {
+    uint32_t visits;      /* visits=      */
+    uint32_t d_quantized; /* d_quantized= */
+    uint32_t candidates;  /* candidate=   */
+    uint32_t d_full;      /* d_full=      */
+    uint32_t stream_len;  /* non-deleted items consumed from the ListSearchResult */
+    uint32_t status;      /* 0 ok; internal overflow bits are retried and never surface */
+} dann_query_stats;
+
+typedef struct dann_index dann_index;
+typedef struct dann_scan dann_scan;
+
+const char *dann_last_error(void);
+int dann_device_count(void);
+
+/* ---- index lifetime ----------------------------------------------------------- */
+/* Copies the snapshot into HBM of `device` (vectors cosine-normalised once, with the
+ * reference's preprocess_cosine arithmetic, distance/mod.rs:225-253). */
+int dann_index_load(const dann_snapshot_desc *snap, int device, dann_index **out);
+void dann_index_free(dann_index *ix);
+/* Bytes of HBM held by the index arrays (codes, nbrs, tids, vectors, labels, means). */
+uint64_t dann_index_hbm_bytes(const dann_index *ix);
+
+/* ---- scan operator: one row at a time, amgettuple order ------------------------ */
+int dann_scan_begin(dann_index *ix, dann_scan **out);
+/* query: [dim] raw floats, NULL = SQL NULL order-by argument (zero vector, no labels,
+ * labels/mod.rs:214-216). nlabels < 0 = no scan key; >= 0 = `labels && ARRAY[...]`
+ * (sorted+dedup is done here, labels/mod.rs:30-37). search_list_size / rescore are the
+ * GUCs diskann.query_search_list_size / diskann.query_rescore (guc.rs:3-4). */
+int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
+                     int search_list_size, int rescore);
+/* Returns 1 and fills the outputs for the next row, 0 at end of scan, <0 on error.
+ * dist is the exact rerank distance (NaN when rescore == 0). Any output may be NULL. */
+int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id,
+                       float *dist);
+int dann_scan_stats(dann_scan *sc, dann_query_stats *out);
+void dann_scan_end(dann_scan *sc);
+
+/* ---- batch: B independent scans, first k rows of each ---------------------------- */
+/* Host buffers; H2D/D2H copies are part of the call (this is the end-to-end path).
+ * labels/label_off: CSR of each query's scan-key labels, label_off == NULL = no key.
+ * out_tid [B*k] (block<<16|offset, DANN_INVALID_TID past out_count[b]), out_dist [B*k],
+ * out_count [B] rows produced, out_stats [B] (each may be NULL except out_tid). */
+int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
+                      const int32_t *label_off, int B, int k, int search_list_size,
+                      int rescore, uint64_t *out_tid, float *out_dist, uint32_t *out_count,
+                      dann_query_stats *out_stats);
+/* Same with every buffer already resident in HBM of the index's device; work is
+ * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns
+ * after the stream has drained (it must read back a 4-byte overflow flag). Query labels
+ * must already be sorted+dedup per query. */
+int dann_search_batch_device(dann_index *ix, const float *d_queries, const int16_t *d_labels,
+                             const int32_t *d_label_off, int B, int k, int search_list_size,
+                             int rescore, uint64_t *d_out_tid, float *d_out_dist,
+                             uint32_t *d_out_count, dann_query_stats *d_out_stats,
+                             void *stream);
+
+/* ---- stand-alone kernels (roofline metric + per-kernel parity tests), device buffers -- */
+/* amrescan's vector preparation: cosine-normalise + SBQ-quantize B queries.
+ * d_q_full [B*dim] (may be NULL), d_q_codes [B*dann_code_stride(ix)]. */
+int dann_prepare_queries(dann_index *ix, const float *d_queries, int B, float *d_q_full,
+                         uint64_t *d_q_codes, void *stream);
+uint32_t dann_code_stride(const dann_index *ix); /* u64 per code row in HBM (words rounded up to even) */
+/* SBQ distance: out[i] = popcount(code[pair_node[i]] ^ qcode[pair_q[i]]). */
+int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const uint32_t *d_pair_q,
+                      const uint32_t *d_pair_node, size_t npairs, uint32_t *d_out, void *stream);
+/* Exact rerank distance: out[b*m+i] = distance_fn(vectors[nodes[b*m+i]], q_full[b]);
+ * nodes == DANN_INVALID_NODE are skipped (out = NaN). */
+int dann_full_distance(dann_index *ix, const float *d_q_full, const uint32_t *d_nodes, int B,
+                       int m, float *d_out, void *stream);
+
+/* Number of this library's kernel launches since load (bench.py "gpu_launches"). */
+uint64_t dann_kernel_launches(const dann_index *ix);
+
+/* ---- device-timed leg of the last batch call (CUDA events on the launch stream) ---- */
+typedef struct {
+    float prepare_ms, search_ms, rerank_ms, resort_ms, total_ms;
+    uint32_t retries; /* workspace-growth retries of the search kernel */
+} dann_batch_timing;
+int dann_last_batch_timing(dann_index *ix, dann_batch_timing *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

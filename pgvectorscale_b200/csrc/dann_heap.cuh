@@ -1,0 +1,98 @@
+// dann_heap.cuh — device clone of Rust's std::collections::BinaryHeap sift rules.
+//
+// The reference keeps its candidates in `BinaryHeap<Reverse<ListSearchNeighbor>>`
+// (graph/mod.rs:75,144-147,166) and its rerank window in `BinaryHeap<ResortData>` with a
+// reversed Ord (scan.rs:91-117,279-304).  SBQ Hamming distances are small integers, so ties
+// are everywhere and the ORDER IN WHICH TIES POP is whatever std's heap does; returned row
+// ids are only bit-exact if the device runs the same algorithm
+// (alloc::collections::binary_heap, Rust 1.7x-1.8x):
+//
+//   push  = Vec::push + sift_up(0, old_len)
+//   pop   = Vec::pop, swap with data[0], sift_down_to_bottom(0)
+//   sift_up(start,pos): move the hole up while !(elem <= parent)
+//   sift_down_to_bottom(pos): walk the hole to the bottom taking
+//         child += (data[child] <= data[child+1])      (right child on ties)
+//       then sift_up(start, hole)
+//
+// Both reference heaps are "min on key": for Reverse<T> and for ResortData,
+// `a <= b` <=> key(b) <= key(a).  An entry packs the key in its high bits (KSHIFT) and a
+// payload below; only the key takes part in comparisons (ties compare Equal:
+// neighbor_with_distance.rs:31-43,74-83 for candidates, scan.rs:111-117 for the window).
+#pragma once
+#include <stdint.h>
+
+template <typename E, int KSHIFT>
+struct RustHeap {
+    static __device__ __forceinline__ uint32_t key(E e) { return (uint32_t)(e >> KSHIFT); }
+
+    template <typename Store>
+    static __device__ __forceinline__ uint32_t sift_up(Store &s, uint32_t start, uint32_t pos,
+                                                       E elem) {
+        const uint32_t k = key(elem);
+        while (pos > start) {
+            uint32_t parent = (pos - 1) >> 1;
+            E pe = s.get(parent);
+            if (key(pe) <= k) break; /* hole.element() <= hole.get(parent) */
+            s.set(pos, pe);
+            pos = parent;
+        }
+        s.set(pos, elem);
+        return pos;
+    }
+
+    template <typename Store>
+    static __device__ __forceinline__ void push(Store &s, uint32_t &len, E elem) {
+        sift_up(s, 0, len, elem);
+        len++;
+    }
+
+    /* len must be > 0 */
+    template <typename Store>
+    static __device__ __forceinline__ E pop(Store &s, uint32_t &len) {
+        E item = s.get(len - 1);
+        len--;
+        if (len == 0) return item;
+        E root = s.get(0);
+        /* swap(item, data[0]); sift_down_to_bottom(0) with the hole holding `item` */
+        const uint32_t end = len;
+        const uint32_t lim = end >= 2 ? end - 2 : 0; /* end.saturating_sub(2) */
+        uint32_t pos = 0, child = 1;
+        while (child <= lim) {
+            E cl = s.get(child), cr = s.get(child + 1);
+            if (key(cr) <= key(cl)) { /* data[child] <= data[child+1] */
+                child++;
+                cl = cr;
+            }
+            s.set(pos, cl);
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            s.set(pos, s.get(child));
+            pos = child;
+        }
+        sift_up(s, 0, pos, item);
+        return root;
+    }
+};
+
+/* plain array store (shared or global) */
+template <typename E>
+struct ArrayStore {
+    E *p;
+    __device__ __forceinline__ E get(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ void set(uint32_t i, E v) { p[i] = v; }
+};
+
+/* first `hs` entries in shared memory, the rest in the warp's HBM workspace */
+template <typename E>
+struct SplitStore {
+    E *sm;
+    E *gl;
+    uint32_t hs;
+    __device__ __forceinline__ E get(uint32_t i) const { return i < hs ? sm[i] : gl[i]; }
+    __device__ __forceinline__ void set(uint32_t i, E v) {
+        if (i < hs) sm[i] = v;
+        else gl[i] = v;
+    }
+};

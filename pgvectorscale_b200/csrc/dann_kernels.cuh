@@ -1,0 +1,438 @@
+// dann_kernels.cuh — the non-graph kernels of the scan path (sm_100a):
+//   prepare_queries  : amrescan's vector preparation (cosine normalise + SBQ quantize)
+//   sbq_distance     : stand-alone batched SBQ XOR+popcount gather (the roofline kernel)
+//   full_distance    : exact f32 L2 / cosine / inner product, AVX2 summation order
+//   rerank_resort    : get_full_distance_for_resort + the sliding rerank window
+//   normalize_rows / pad_rows : index load helpers
+// Reference paths are relative to /root/reference/pgvectorscale/src/access_method/.
+// Every f32 operation that decides a result is spelled with an explicit-rounding
+// intrinsic (__fadd_rn, __fmul_rn, __fmaf_rn, __fdiv_rn, __fsqrt_rn): nvcc never
+// contracts or reorders those, so the arithmetic is the reference's op for op.
+#pragma once
+#include <math_constants.h>
+
+#include "dann_device.cuh"
+#include "dann_heap.cuh"
+
+/* ------------------------------------------------------------------------------------ */
+/* preprocess_cosine (distance/mod.rs:225-253): norm = sequential f32 sum of v*v;        */
+/* returns the divisor (sqrt(norm)) or 0 when the vector is left untouched.              */
+__device__ __forceinline__ float cosine_divisor_from_norm(float norm, uint32_t len) {
+    const float eps = 1.1920929e-07f; /* f32::EPSILON */
+    float adj = __fmul_rn(eps, (float)len);
+    if (norm < eps) return 0.0f;
+    if (norm >= __fsub_rn(1.0f, adj) && norm <= __fadd_rn(1.0f, adj)) return 0.0f;
+    return __fsqrt_rn(norm);
+}
+
+/* SbqQuantizer::quantize, one dimension (sbq/quantize.rs:52-102): number of leading ones */
+__device__ __forceinline__ uint32_t sbq_count_ones(float v, float mean, float m2, float count_f,
+                                                   uint32_t bits) {
+    if (bits == 1) return v > mean ? 1u : 0u;
+    float variance = __fdiv_rn(m2, count_f);
+    float std_dev = __fsqrt_rn(variance);
+    float z = __fdiv_rn(__fsub_rn(v, mean), std_dev);
+    float ranges = (float)(bits + 1);
+    float index = __fdiv_rn(__fadd_rn(z, 2.0f), __fdiv_rn(4.0f, ranges));
+    if (index < 1.0f) return 0u;
+    float fl = floorf(index); /* `index.floor() as usize`: saturating, NaN -> 0 */
+    uint32_t as_u;
+    if (!(fl == fl)) as_u = 0u;
+    else if (fl >= 4294967040.0f) as_u = 0xFFFFFFFFu;
+    else if (fl <= 0.0f) as_u = 0u;
+    else as_u = (uint32_t)fl;
+    return as_u < bits ? as_u : bits;
+}
+
+/* One CTA per query.  q_full_out [B][dim] (optional), q_codes_out [B][cw].
+ * labels/mod.rs:209-238 (from_scan_key_data) -> pg_vector.rs:125-157 (create_inner: the
+ * index copy is truncated to dim_index, each copy normalised on its own) ->
+ * sbq/mod.rs:145-148 (quantize the index copy). */
+__global__ void __launch_bounds__(128) dann_prepare_kernel(IndexView ix, const float *queries, int B,
+                                                           float *q_full_out, uint64_t *q_codes_out) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    float *qi = reinterpret_cast<float *>(dann_smem); /* [dim_index] normalised index copy */
+    __shared__ float s_div[2];
+    const int q = blockIdx.x;
+    const float *src = queries + (size_t)q * ix.dim;
+    const bool cosine = ix.distance_type == DANN_COSINE;
+    if (cosine) {
+        /* Iterator::sum over v*v in index order: a sequential dependent chain; two warps
+         * run the two chains (full copy / truncated copy) side by side. */
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const uint32_t len = threadIdx.x == 0 ? ix.dim : ix.dim_index;
+            float norm = 0.0f;
+            for (uint32_t i = 0; i < len; i++) {
+                float v = src[i];
+                norm = __fadd_rn(norm, __fmul_rn(v, v));
+            }
+            s_div[threadIdx.x >> 5] = cosine_divisor_from_norm(norm, len);
+        }
+    } else if (threadIdx.x == 0) {
+        s_div[0] = 0.0f;
+        s_div[1] = 0.0f;
+    }
+    __syncthreads();
+    const float dfull = s_div[0], dindex = s_div[1];
+    for (uint32_t i = threadIdx.x; i < ix.dim; i += blockDim.x) {
+        float v = src[i];
+        if (q_full_out) q_full_out[(size_t)q * ix.dim + i] = dfull != 0.0f ? __fdiv_rn(v, dfull) : v;
+        if (i < ix.dim_index) qi[i] = dindex != 0.0f ? __fdiv_rn(v, dindex) : v;
+    }
+    __syncthreads();
+    const float count_f = __ull2float_rn(ix.count); /* `self.count as f32` */
+    for (uint32_t w = threadIdx.x; w < ix.cw; w += blockDim.x) {
+        uint64_t word = 0;
+        if (w < ix.words) {
+            for (uint32_t b = 0; b < 64; b++) {
+                uint32_t p = w * 64 + b;
+                uint32_t i = p / ix.bits, j = p - i * ix.bits;
+                if (i >= ix.dim_index) break;
+                uint32_t ones = sbq_count_ones(qi[i], ix.mean[i], ix.bits > 1 ? ix.m2[i] : 0.0f,
+                                               count_f, ix.bits);
+                if (j < ones) word |= 1ull << b;
+            }
+        }
+        q_codes_out[(size_t)q * ix.cw + w] = word;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Stand-alone SBQ distance: out[i] = popcount(code[pair_node[i]] ^ qcode[pair_q[i]])     */
+/* (distance_xor_optimized, distance/mod.rs:265-323).  G lanes share one code row with    */
+/* 128-bit no-allocate loads; UNR pairs are in flight per lane group.                     */
+template <int NCH, int UNR>
+__global__ void __launch_bounds__(256) dann_sbq_distance_kernel(const uint64_t *__restrict__ codes,
+                                                                uint32_t cw,
+                                                                const uint64_t *__restrict__ qcodes,
+                                                                const uint32_t *__restrict__ pair_q,
+                                                                const uint32_t *__restrict__ pair_node,
+                                                                size_t npairs, uint32_t *__restrict__ out,
+                                                                uint32_t G, uint32_t Gshift) {
+    const uint32_t lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const uint32_t nchunks = cw >> 1;
+    const size_t groups_per_block = blockDim.x >> Gshift;
+    const size_t gid = (size_t)blockIdx.x * groups_per_block + (threadIdx.x >> Gshift);
+    const size_t ngroups = (size_t)gridDim.x * groups_per_block;
+    for (size_t p0 = gid * UNR; p0 < npairs; p0 += ngroups * UNR) {
+        uint32_t nq[UNR], nn[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            size_t p = p0 + u;
+            bool ok = p < npairs;
+            nq[u] = ok ? ldg_stream_u32(pair_q + p) : 0u;
+            nn[u] = ok ? ldg_stream_u32(pair_node + p) : 0u;
+        }
+        ulonglong2 v[UNR][NCH];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(codes + (size_t)nn[u] * cw);
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                uint32_t c = gl + i * G;
+                v[u][i] = (c < nchunks && p0 + u < npairs) ? ldg_stream_u128(row + c) : make_ulonglong2(0, 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const ulonglong2 *qrow = reinterpret_cast<const ulonglong2 *>(qcodes + (size_t)nq[u] * cw);
+            uint32_t s = 0;
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                uint32_t c = gl + i * G;
+                if (c < nchunks) {
+                    ulonglong2 qv = __ldg(qrow + c);
+                    s += __popcll(v[u][i].x ^ qv.x) + __popcll(v[u][i].y ^ qv.y);
+                }
+            }
+            for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+            if (gl == 0 && p0 + u < npairs) out[p0 + u] = s;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Exact distance with the reference's AVX2 summation order.                             */
+/* distance_l2_simd_body! / inner_product_simd_body! (distance/mod.rs:325-434) with       */
+/* S = Avx2: element e = 32*i + 8*k + j goes to accumulator k, lane j, steps i in order.  */
+/* Here 8 GPU lanes share one row: lane m (0..7) owns the four accumulator slots          */
+/* 4m..4m+3 (k = m/2, j = 4*(m%2)+t), i.e. one float4 per 32-element stride, so the 8      */
+/* lanes read 128 contiguous bytes per step.  `y` is the query (shared memory).           */
+/* Returns the finished distance on every lane of the 8-lane group.                      */
+template <bool VEC4>
+__device__ __forceinline__ float full_distance_group8(int type, const float *__restrict__ x,
+                                                      const float *__restrict__ y, uint32_t n,
+                                                      uint32_t m, unsigned gmask_base_lane) {
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    const uint32_t nfull = n >> 5;
+    const bool l2 = type == DANN_L2;
+    constexpr int UN = 8;
+    for (uint32_t i0 = 0; i0 < nfull; i0 += UN) {
+        float4 xv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+            uint32_t i = i0 + u;
+            if (i < nfull) {
+                const float *px = x + 32 * i + 4 * m;
+                if (VEC4) xv[u] = ldg_stream_f4(px);
+                else xv[u] = make_float4(ldg_stream_f1(px), ldg_stream_f1(px + 1), ldg_stream_f1(px + 2),
+                                         ldg_stream_f1(px + 3));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+            uint32_t i = i0 + u;
+            if (i < nfull) {
+                const float *py = y + 32 * i + 4 * m;
+                float4 yv = VEC4 ? *reinterpret_cast<const float4 *>(py) : make_float4(py[0], py[1], py[2], py[3]);
+                if (l2) { /* accum = accum + ((x - y) * (x - y)) : separate sub, mul, add */
+                    float d0 = __fsub_rn(xv[u].x, yv.x), d1 = __fsub_rn(xv[u].y, yv.y);
+                    float d2 = __fsub_rn(xv[u].z, yv.z), d3 = __fsub_rn(xv[u].w, yv.w);
+                    a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
+                    a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
+                    a2 = __fadd_rn(a2, __fmul_rn(d2, d2));
+                    a3 = __fadd_rn(a3, __fmul_rn(d3, d3));
+                } else { /* accum = fmadd(x, y, accum) */
+                    a0 = __fmaf_rn(xv[u].x, yv.x, a0);
+                    a1 = __fmaf_rn(xv[u].y, yv.y, a1);
+                    a2 = __fmaf_rn(xv[u].z, yv.z, a2);
+                    a3 = __fmaf_rn(xv[u].w, yv.w, a3);
+                }
+            }
+        }
+    }
+    /* simdeez Avx2::horizontal_add_ps: ((a0+a4)+(a1+a5)) + ((a2+a6)+(a3+a7)); the pair of
+     * lanes (2k, 2k+1) holds accumulator k: lane 2k has j=0..3, lane 2k+1 has j=4..7. */
+    float v0 = __fadd_rn(a0, __shfl_xor_sync(DANN_FULL, a0, 1));
+    float v1 = __fadd_rn(a1, __shfl_xor_sync(DANN_FULL, a1, 1));
+    float v2 = __fadd_rn(a2, __shfl_xor_sync(DANN_FULL, a2, 1));
+    float v3 = __fadd_rn(a3, __shfl_xor_sync(DANN_FULL, a3, 1));
+    float h = __fadd_rn(__fadd_rn(v0, v1), __fadd_rn(v2, v3));
+    float h0 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 0);
+    float h1 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 2);
+    float h2 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 4);
+    float h3 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 6);
+    float dist = __fadd_rn(__fadd_rn(__fadd_rn(h0, h1), h2), h3);
+    /* scalar tail, in order (every lane of the group computes the same chain) */
+    for (uint32_t i = nfull << 5; i < n; i++) {
+        float xi = ldg_stream_f1(x + i), yi = y[i];
+        if (l2) {
+            float diff = __fsub_rn(xi, yi);
+            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
+        } else {
+            dist = __fadd_rn(dist, __fmul_rn(xi, yi));
+        }
+    }
+    if (type == DANN_L2) return dist;                 /* distance/mod.rs:88-104 (no sqrt) */
+    if (type == DANN_IP) return -dist;                /* :175-190 */
+    float r = __fsub_rn(1.0f, dist);                  /* distance_x86.rs:34-36 (1.0 - ip).max(0.0) */
+    return r > 0.0f ? r : 0.0f;
+}
+
+/* ---- 1-D TMA bulk copy (cp.async.bulk) of one query row into shared memory ---------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+/* Stage query row `src` [n floats] into shared `dst`: TMA bulk copy when the row is a
+ * multiple of 16 B and 16-B aligned, plain loads otherwise.  Block-wide. */
+__device__ __forceinline__ void stage_query_row(float *dst, const float *src, uint32_t n, uint64_t *bar) {
+    const bool tma_ok = (n & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    if (tma_ok) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(dst, src, n * 4u, bar);
+        mbar_wait(bar, 0);
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+}
+
+/* out[b*m+i] = distance_fn(vectors[nodes[b*m+i]], q_full[b]) ; one CTA per query */
+__global__ void __launch_bounds__(128) dann_full_distance_kernel(IndexView ix, const float *q_full,
+                                                                 const uint32_t *nodes, int m, float *out) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    float *qs = reinterpret_cast<float *>(dann_smem);
+    __shared__ uint64_t bar;
+    const int q = blockIdx.x;
+    stage_query_row(qs, q_full + (size_t)q * ix.dim, ix.dim, &bar);
+    const uint32_t lane = threadIdx.x & 31, mm = lane & 7, gbase = lane & 24;
+    const uint32_t group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+    const bool vec4 = (ix.dim & 3u) == 0;
+    const uint32_t rounds = ((uint32_t)m + ngroups - 1) / ngroups;
+    for (uint32_t r = 0; r < rounds; r++) {
+        uint32_t it = r * ngroups + group;
+        uint32_t node = it < (uint32_t)m ? nodes[(size_t)q * m + it] : DANN_INVALID_NODE;
+        const float *x = ix.vectors + (size_t)(node == DANN_INVALID_NODE ? 0 : node) * ix.dim;
+        float d = vec4 ? full_distance_group8<true>(ix.distance_type, x, qs, ix.dim, mm, gbase)
+                       : full_distance_group8<false>(ix.distance_type, x, qs, ix.dim, mm, gbase);
+        if (mm == 0 && it < (uint32_t)m) out[(size_t)q * m + it] = node == DANN_INVALID_NODE ? CUDART_NAN_F : d;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* next_with_resort (scan.rs:244-305) for the first k rows of one query per CTA:          */
+/*   phase 1  get_full_distance_for_resort (sbq/storage.rs:304-328) of every streamed     */
+/*            node — 8 lanes per 3-KB row, 128-bit loads, query row staged by TMA;        */
+/*   phase 2  the sliding window: a BinaryHeap<ResortData> (min on total_cmp distance,    */
+/*            scan.rs:111-117) filled to `rescore`, pop one, refill one, ...              */
+/* rescore == 0 bypasses phase 1 and returns the stream order (scan.rs:251-253).          */
+struct RerankArgs {
+    IndexView ix;
+    const float *q_full;        /* [B][dim] */
+    const uint32_t *stream;     /* [B][c_target] */
+    const uint32_t *stream_len; /* [B] */
+    uint32_t c_target, k, rescore;
+    uint64_t *out_tid;          /* [B][k] */
+    float *out_dist;            /* [B][k] or NULL */
+    uint32_t *out_node;         /* [B][k] or NULL */
+    uint32_t *out_count;        /* [B] or NULL */
+    dann_query_stats *stats;    /* [B] or NULL : d_full is filled here */
+};
+
+__global__ void __launch_bounds__(128) dann_rerank_kernel(const RerankArgs a) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    const IndexView &ix = a.ix;
+    float *qs = reinterpret_cast<float *>(dann_smem);                    /* [dim rounded to 4] */
+    const uint32_t dim4 = (ix.dim + 3u) & ~3u;
+    float *ds = qs + dim4;                                              /* [c_target] */
+    uint64_t *hp = reinterpret_cast<uint64_t *>(ds + ((a.c_target + 1u) & ~1u)); /* [rescore] */
+    __shared__ uint64_t bar;
+    const int q = blockIdx.x;
+    const uint32_t sl = a.stream_len[q];
+    const uint32_t *st = a.stream + (size_t)q * a.c_target;
+    uint64_t *otid = a.out_tid + (size_t)q * a.k;
+
+    if (a.rescore == 0) {
+        for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
+            bool ok = i < sl;
+            uint32_t node = ok ? st[i] : DANN_INVALID_NODE;
+            otid[i] = ok ? ix.tids[node] : DANN_INVALID_TID;
+            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = CUDART_NAN_F;
+            if (a.out_node) a.out_node[(size_t)q * a.k + i] = node;
+        }
+        if (threadIdx.x == 0 && a.out_count) a.out_count[q] = sl < a.k ? sl : a.k;
+        return;
+    }
+
+    stage_query_row(qs, a.q_full + (size_t)q * ix.dim, ix.dim, &bar);
+    {
+        const uint32_t lane = threadIdx.x & 31, mm = lane & 7, gbase = lane & 24;
+        const uint32_t group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+        const bool vec4 = (ix.dim & 3u) == 0;
+        const uint32_t rounds = (sl + ngroups - 1) / ngroups;
+        for (uint32_t r = 0; r < rounds; r++) {
+            uint32_t it = r * ngroups + group;
+            uint32_t node = it < sl ? st[it] : 0u;
+            const float *x = ix.vectors + (size_t)node * ix.dim;
+            float d = vec4 ? full_distance_group8<true>(ix.distance_type, x, qs, ix.dim, mm, gbase)
+                           : full_distance_group8<false>(ix.distance_type, x, qs, ix.dim, mm, gbase);
+            if (mm == 0 && it < sl) ds[it] = d;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        using H = RustHeap<uint64_t, 32>;
+        ArrayStore<uint64_t> store{hp};
+        uint32_t len = 0, si = 0, rows = 0;
+        for (; rows < a.k; rows++) {
+            while (len < a.rescore && si < sl) { /* refill: resort_buffer.push(ResortData{..}) */
+                H::push(store, len, ((uint64_t)total_ukey(ds[si]) << 32) | si);
+                si++;
+            }
+            if (len == 0) break;
+            uint64_t e = H::pop(store, len);
+            uint32_t idx = (uint32_t)e, node = st[idx];
+            otid[rows] = ix.tids[node];
+            if (a.out_dist) a.out_dist[(size_t)q * a.k + rows] = ds[idx];
+            if (a.out_node) a.out_node[(size_t)q * a.k + rows] = node;
+        }
+        if (a.out_count) a.out_count[q] = rows;
+        if (a.stats) a.stats[q].d_full = si; /* full_distance_comparisons, scan.rs:258 */
+        for (uint32_t i = rows; i < a.k; i++) {
+            otid[i] = DANN_INVALID_TID;
+            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = CUDART_NAN_F;
+            if (a.out_node) a.out_node[(size_t)q * a.k + i] = DANN_INVALID_NODE;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Index load: cosine rows are normalised ONCE with preprocess_cosine's arithmetic        */
+/* (sequential sum per row).  Each warp takes 32 rows: coalesced 128-B row segments go     */
+/* through a padded shared tile so that every lane runs the sequential chain of one row.  */
+__global__ void __launch_bounds__(256) dann_normalize_rows_kernel(float *vectors, uint32_t n, uint32_t dim) {
+    __shared__ float tile[8][32][33];
+    __shared__ float divs[8][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblocks32 = (n + 31) / 32;
+    for (uint32_t blk = blockIdx.x * 8 + warp; blk < nblocks32; blk += gridDim.x * 8) {
+        const uint32_t row0 = blk * 32;
+        float norm = 0.0f;
+        for (uint32_t c0 = 0; c0 < dim; c0 += 32) {
+            for (uint32_t r = 0; r < 32; r++) {
+                uint32_t row = row0 + r, col = c0 + lane;
+                tile[warp][r][lane] = (row < n && col < dim) ? vectors[(size_t)row * dim + col] : 0.0f;
+            }
+            __syncwarp();
+            uint32_t lim = dim - c0 < 32 ? dim - c0 : 32;
+            for (uint32_t j = 0; j < lim; j++) {
+                float v = tile[warp][lane][j];
+                norm = __fadd_rn(norm, __fmul_rn(v, v));
+            }
+            __syncwarp();
+        }
+        divs[warp][lane] = cosine_divisor_from_norm(norm, dim);
+        __syncwarp();
+        for (uint32_t r = 0; r < 32; r++) {
+            uint32_t row = row0 + r;
+            float dv = divs[warp][r];
+            if (row < n && dv != 0.0f)
+                for (uint32_t col = lane; col < dim; col += 32) {
+                    size_t o = (size_t)row * dim + col;
+                    vectors[o] = __fdiv_rn(vectors[o], dv);
+                }
+        }
+        __syncwarp();
+    }
+}
+
+/* dst[n][dst_w] <- src[n][src_w] padded with `fill` (u32 rows: neighbour lists; u64: codes) */
+template <typename Tp>
+__global__ void dann_pad_rows_kernel(Tp *dst, const Tp *src, size_t n, uint32_t src_w, uint32_t dst_w,
+                                     Tp fill) {
+    size_t total = n * dst_w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i / dst_w;
+        uint32_t c = (uint32_t)(i - r * dst_w);
+        dst[i] = c < src_w ? src[r * src_w + c] : fill;
+    }
+}

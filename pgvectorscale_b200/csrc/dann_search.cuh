@@ -1,0 +1,392 @@
+// dann_search.cuh — persistent warp-per-query StreamingDiskANN beam search (sm_100a).
+//
+// Replaces, for one query per warp (reference paths relative to
+// /root/reference/pgvectorscale/src/access_method/):
+//   Graph::greedy_search_streaming_init      graph/mod.rs:331-354
+//   ListSearchResult::{new,prepare_insert,insert_neighbor,visit_closest,consume}
+//                                            graph/mod.rs:97-185
+//   Graph::greedy_search_iterate             graph/mod.rs:357-385
+//   SbqSpeedupStorage::visit_lsn_internal    sbq/storage.rs:125-190 (Disk arm)
+//   create_lsn_for_start_node / return_lsn   sbq/storage.rs:365-414
+//   distance_xor_optimized                   distance/mod.rs:265-323
+//   TSVResponseIterator::next                scan.rs:210-242 (deleted-tuple skip)
+//
+// Work split inside a warp
+//   * all lanes: neighbour-list fetch, dedupe (match_any + a CAS hash set in HBM),
+//     label overlap, SBQ code gathers (G lanes per code row, 128-bit no-allocate loads),
+//     XOR+popcount with shfl reduction, visited-list shifting.
+//   * lane 0: the candidate heap — an exact clone of Rust's BinaryHeap (dann_heap.cuh),
+//     because Hamming ties pop in heap order and that order decides returned row ids.
+//
+// State placement
+//   shared : visited list (sorted, (dist<<32)|node), first `hs` heap entries, 64-entry
+//            staging list for one neighbour list.
+//   HBM    : per-warp workspace — hash set, seq->node table, heap tail beyond `hs`.
+//   The heap entry packs (dist, seq): u32 = dist16|seq16 when both fit, else u64.
+#pragma once
+#include "dann_device.cuh"
+#include "dann_heap.cuh"
+
+struct SearchArgs {
+    IndexView ix;
+    const uint64_t *q_codes;    /* [B][cw] */
+    const int16_t *q_labels;    /* CSR values, sorted+dedup per query */
+    const int32_t *q_label_off; /* [B+1]; NULL => no scan key (labels None) */
+    const uint32_t *qlist;      /* optional [nq] query ids (retry pass) */
+    uint32_t nq;
+    uint32_t L, c_target;
+    uint32_t *stream;           /* [B][c_target] node ids in consume order */
+    uint32_t *stream_len;       /* [B] */
+    dann_query_stats *stats;    /* [B] */
+    uint32_t *overflow;         /* OR of status bits over all queries of this launch */
+    uint32_t *counter;          /* work-queue head */
+    uint32_t *hash;             /* [slots][hash_cap] */
+    uint32_t hash_cap;          /* power of two */
+    uint32_t *cand_node;        /* [slots][cand_cap] */
+    uint32_t cand_cap;
+    void *heap_tail;            /* [slots][cand_cap] entries E (indices >= hs used) */
+    uint32_t hs, vcap;
+    uint32_t G, Gshift;         /* lanes per code row (power of two) */
+    uint32_t per_warp_smem;
+};
+
+#define DANN_LIST_CAP 64u
+
+template <typename E>
+struct EntryTraits;
+template <>
+struct EntryTraits<uint32_t> {
+    static constexpr int KSHIFT = 16;
+    static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 16) | seq; }
+    static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0xFFFFu; }
+};
+template <>
+struct EntryTraits<uint64_t> {
+    static constexpr int KSHIFT = 32;
+    static __device__ __forceinline__ uint64_t make(uint32_t d, uint32_t seq) {
+        return ((uint64_t)d << 32) | seq;
+    }
+    static __device__ __forceinline__ uint32_t seq(uint64_t e) { return (uint32_t)e; }
+};
+
+template <typename E, int NCH>
+struct SearchWarp {
+    using T = EntryTraits<E>;
+    using H = RustHeap<E, T::KSHIFT>;
+    /* code rows gathered per lane group before reducing (16-B loads in flight = RPI*NCH) */
+    static constexpr int RPI = NCH <= 3 ? 4 : (NCH == 4 ? 2 : 1);
+
+    const SearchArgs &a;
+    const int lane;
+    /* per-warp storage */
+    uint64_t *vis;
+    uint32_t *list, *dl;
+    uint32_t *hash, *cnode;
+    SplitStore<E> heap;
+    /* query */
+    ulonglong2 qc[NCH];
+    const int16_t *ql;
+    uint32_t nql;
+    bool filter;
+    /* warp-uniform state */
+    uint32_t heap_len, vis_head, vis_len, ncand, nins, listn;
+    uint32_t visits, dq, status;
+
+    __device__ __forceinline__ SearchWarp(const SearchArgs &a_, int lane_) : a(a_), lane(lane_) {}
+
+    /* ---- stage: dedupe + label filter of up to 32 neighbour ids (one per lane), appended
+     * to the staging list in lane order.  sbq/storage.rs:149-172 */
+    __device__ __forceinline__ void stage(uint32_t n, bool valid, bool apply_filter) {
+        if (__ballot_sync(DANN_FULL, valid) == 0) return;
+        /* a node listed twice in one chunk: only its first occurrence may insert */
+        unsigned mm = __match_any_sync(DANN_FULL, n);
+        bool first = valid && ((__ffs(mm) - 1) == lane);
+        bool isnew = false;
+        if (first) { /* prepare_insert: HashSet::insert (graph/mod.rs:126-128) */
+            const uint32_t mask = a.hash_cap - 1;
+            uint32_t h = (n * 2654435761u) >> (32 - __popc(mask));
+            for (uint32_t probe = 0; probe <= mask; probe++) {
+                uint32_t old = atomicCAS(hash + h, DANN_INVALID_NODE, n);
+                if (old == DANN_INVALID_NODE) {
+                    isnew = true;
+                    break;
+                }
+                if (old == n) break;
+                h = (h + 1) & mask;
+            }
+        }
+        unsigned nm = __ballot_sync(DANN_FULL, isnew);
+        nins += __popc(nm);
+        if (nins * 2 > a.hash_cap) {
+            status |= DANN_ST_HASH;
+            return;
+        }
+        bool pass = isnew;
+        if (apply_filter && isnew) { /* labels.overlaps(node_neighbor.get_labels()) */
+            pass = false;
+            if (a.ix.has_labels) {
+                uint32_t o0 = __ldg(a.ix.label_off + n), o1 = __ldg(a.ix.label_off + n + 1);
+                pass = labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
+            }
+        }
+        unsigned pm = __ballot_sync(DANN_FULL, pass);
+        uint32_t t = __popc(pm);
+        if (t == 0) return;
+        if (ncand + listn + t > a.cand_cap) {
+            status |= DANN_ST_HEAP;
+            return;
+        }
+        if (pass) {
+            uint32_t pos = listn + __popc(pm & ((1u << lane) - 1u));
+            list[pos] = n;
+            cnode[ncand + pos] = n;
+        }
+        listn += t;
+        __syncwarp();
+    }
+
+    /* ---- flush: SBQ distance of every staged node (distance/mod.rs:265-323) and the
+     * ordered heap pushes (insert_neighbor, graph/mod.rs:144-147) */
+    __device__ __forceinline__ void flush() {
+        const uint32_t tn = listn;
+        if (tn == 0 || status) {
+            listn = 0;
+            return;
+        }
+        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
+        const uint32_t nchunks = a.ix.cw >> 1;
+        for (uint32_t b = 0; b < tn; b += RP * RPI) {
+            ulonglong2 v[RPI][NCH];
+#pragma unroll
+            for (int u = 0; u < RPI; u++) {
+                uint32_t r = b + u * RP + grp;
+                uint32_t node = r < tn ? list[r] : 0u;
+                const ulonglong2 *row =
+                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)node * a.ix.cw);
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    uint32_t c = gl + i * G;
+                    v[u][i] = (r < tn && c < nchunks) ? ldg_stream_u128(row + c) : qc[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RPI; u++) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int i = 0; i < NCH; i++)
+                    s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
+                for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+                uint32_t r = b + u * RP + grp;
+                if (gl == 0 && r < tn) dl[r] = s;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t hl = heap_len;
+            for (uint32_t r = 0; r < tn; r++) H::push(heap, hl, T::make(dl[r], ncand + r));
+        }
+        heap_len += tn;
+        ncand += tn;
+        dq += tn;
+        listn = 0;
+        __syncwarp();
+    }
+
+    /* ---- expand one visited node: sbq/storage.rs:135-190 */
+    __device__ __forceinline__ void expand(uint32_t v) {
+        const uint32_t *row = a.ix.nbrs + (size_t)v * a.ix.Rp;
+        const uint32_t R = a.ix.R;
+        uint32_t nxt = lane < R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+        for (uint32_t base = 0; base < R && !status; base += 32) {
+            uint32_t n = nxt;
+            uint32_t j2 = base + 32 + lane;
+            nxt = j2 < R ? ldg_stream_u32(row + j2) : DANN_INVALID_NODE;
+            /* iter_neighbors stops at the first InvalidBlockNumber slot (sbq/node.rs:261-285) */
+            unsigned inv = __ballot_sync(DANN_FULL, n == DANN_INVALID_NODE);
+            uint32_t cut = inv ? (uint32_t)(__ffs(inv) - 1) : 32u;
+            stage(n, (uint32_t)lane < cut, filter);
+            if (listn + 32 > DANN_LIST_CAP) flush();
+            if (inv) break;
+        }
+        flush();
+    }
+
+    /* ---- visited.insert(partition_point(x < c), c) : graph/mod.rs:166-168 */
+    __device__ __forceinline__ void visited_insert(uint32_t d, uint32_t node) {
+        if (vis_head + vis_len + 1 > a.vcap) { /* slide the window back to offset 0 */
+            if (vis_len + 1 > a.vcap) {
+                status |= DANN_ST_VIS;
+                return;
+            }
+            for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
+                uint32_t i = i0 + lane;
+                uint64_t e = 0;
+                if (i < vis_len) e = vis[vis_head + i];
+                __syncwarp();
+                if (i < vis_len) vis[i] = e;
+                __syncwarp();
+            }
+            vis_head = 0;
+        }
+        uint64_t *w = vis + vis_head;
+        uint32_t idx = 0;
+        for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
+            uint32_t i = i0 + lane;
+            bool lt = i < vis_len && (uint32_t)(w[i] >> 32) < d;
+            idx += __popc(__ballot_sync(DANN_FULL, lt));
+        }
+        for (int hi = (int)vis_len; hi > (int)idx; hi -= 32) {
+            int i = hi - 1 - lane;
+            uint64_t e = 0;
+            bool act = i >= (int)idx;
+            if (act) e = w[i];
+            __syncwarp();
+            if (act) w[i + 1] = e;
+            __syncwarp();
+        }
+        if (lane == 0) w[idx] = ((uint64_t)d << 32) | node;
+        vis_len++;
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void run(uint32_t q) {
+        const IndexView &ix = a.ix;
+        heap_len = vis_head = vis_len = ncand = nins = listn = 0;
+        visits = dq = status = 0;
+        uint32_t scount = 0;
+        /* query code chunks this lane compares against (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) */
+        {
+            const uint32_t gl = lane & (a.G - 1), nchunks = ix.cw >> 1;
+            const ulonglong2 *qrow = reinterpret_cast<const ulonglong2 *>(a.q_codes + (size_t)q * ix.cw);
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                uint32_t c = gl + i * a.G;
+                qc[i] = c < nchunks ? qrow[c] : make_ulonglong2(0, 0);
+            }
+        }
+        /* inserted = HashSet::new() */
+        {
+            uint4 ff = make_uint4(DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE);
+            uint4 *h4 = reinterpret_cast<uint4 *>(hash);
+            for (uint32_t i = lane; i < a.hash_cap / 4; i += 32) h4[i] = ff;
+            __threadfence_block();
+            __syncwarp();
+        }
+        ql = nullptr;
+        nql = 0;
+        filter = false;
+        /* greedy_search_streaming_init + ListSearchResult::new (graph/mod.rs:97-124,331-354) */
+        if (ix.start_default != DANN_INVALID_NODE) {
+            if (a.q_label_off) { /* StartNodes::get_for_node(Some(labels)), start_nodes.rs:39-48 */
+                int32_t o0 = a.q_label_off[q], o1 = a.q_label_off[q + 1];
+                ql = a.q_labels + o0;
+                nql = (uint32_t)(o1 - o0);
+                filter = nql > 0; /* has_label_filter, scan.rs:189 */
+                for (uint32_t b = 0; b < nql && !status; b += 32) {
+                    uint32_t i = b + lane, n = DANN_INVALID_NODE;
+                    bool valid = false;
+                    if (i < nql) {
+                        int16_t lab = __ldg(ql + i);
+                        uint32_t lo = 0, hi = ix.n_start_labels;
+                        while (lo < hi) {
+                            uint32_t mid = (lo + hi) >> 1;
+                            if (__ldg(ix.start_labels + mid) < lab) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < ix.n_start_labels && __ldg(ix.start_labels + lo) == lab) {
+                            n = __ldg(ix.start_label_nodes + lo);
+                            valid = true;
+                        }
+                    }
+                    stage(n, valid, false); /* start nodes are not label-checked (storage.rs:365-391) */
+                    flush();
+                }
+            } else {
+                stage(lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, false);
+                flush();
+            }
+        }
+
+        bool done = false;
+        while (!done && !status) { /* TSVResponseIterator::next, scan.rs:210-242 */
+            /* greedy_search_iterate: while let Some(idx) = visit_closest(L) */
+            while (true) {
+                E head = 0;
+                int go = 0;
+                if (lane == 0 && heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
+                    go = 1;
+                    if (vis_len > a.L) {
+                        E h = heap.get(0);
+                        uint64_t at = vis[vis_head + a.L - 1];
+                        if (H::key(h) >= (uint32_t)(at >> 32)) go = 0;
+                    }
+                    if (go) {
+                        uint32_t hl = heap_len;
+                        head = H::pop(heap, hl);
+                    }
+                }
+                go = __shfl_sync(DANN_FULL, go, 0);
+                if (!go) break;
+                head = __shfl_sync(DANN_FULL, head, 0);
+                heap_len--;
+                const uint32_t d = H::key(head);
+                const uint32_t node = __ldcg(cnode + T::seq(head));
+                visited_insert(d, node);
+                if (status) break;
+                visits++;
+                expand(node);
+                if (status) break;
+            }
+            if (status) break;
+            if (vis_len == 0) break; /* consume() -> None */
+            uint64_t e = vis[vis_head]; /* visited.remove(0), graph/mod.rs:174-184 */
+            __syncwarp();
+            vis_head++;
+            vis_len--;
+            uint32_t node = (uint32_t)e;
+            uint64_t tid = __ldg(ix.tids + node); /* return_lsn, sbq/storage.rs:404-414 */
+            if ((tid & 0xFFFFull) == 0) continue; /* InvalidOffsetNumber: deleted tuple, scan.rs:231-234 */
+            if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = node;
+            scount++;
+            if (scount == a.c_target) done = true;
+        }
+        if (lane == 0) {
+            a.stream_len[q] = scount;
+            dann_query_stats st;
+            st.visits = visits;
+            st.d_quantized = dq;
+            st.candidates = dq;
+            st.d_full = 0;
+            st.stream_len = scount;
+            st.status = status;
+            a.stats[q] = st;
+            if (status) atomicOr(a.overflow, status);
+        }
+        __syncwarp();
+    }
+};
+
+template <typename E, int NCH>
+__global__ void __launch_bounds__(512, 1) dann_search_kernel(const SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t slot = blockIdx.x * W + warp;
+    unsigned char *base = dann_smem + (size_t)warp * a.per_warp_smem;
+    SearchWarp<E, NCH> w(a, lane);
+    w.vis = reinterpret_cast<uint64_t *>(base);
+    E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
+    w.list = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));
+    w.dl = w.list + DANN_LIST_CAP;
+    w.hash = a.hash + (size_t)slot * a.hash_cap;
+    w.cnode = a.cand_node + (size_t)slot * a.cand_cap;
+    w.heap.sm = hsm;
+    w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;
+    w.heap.hs = a.hs;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(a.counter, 1u);
+        qi = __shfl_sync(DANN_FULL, qi, 0);
+        if (qi >= a.nq) break;
+        w.run(a.qlist ? a.qlist[qi] : qi);
+    }
+}

@@ -1,0 +1,739 @@
+// diskann_b200.cu — C ABI (include/diskann_b200.h) over the sm_100a kernels.
+//
+// There is NO CPU fallback anywhere in this file: without a CUDA device every entry
+// point that computes returns DANN_ERR_NO_DEVICE.  The CPU oracle under oracle/ is
+// test infrastructure and is never linked or called from here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dann_device.cuh"
+#include "dann_kernels.cuh"
+#include "dann_search.cuh"
+
+/* ------------------------------------------------------------------------------------ */
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+extern "C" const char *dann_last_error(void) { return g_err.c_str(); }
+
+extern "C" int dann_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            if (ix) ix->poisoned = (e_ != cudaErrorMemoryAllocation);                          \
+            cudaGetLastError();                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? DANN_ERR_OOM : DANN_ERR_CUDA,        \
+                        "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+        }                                                                                      \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct dann_index {
+    int device = 0;
+    IndexView v{};
+    std::vector<void *> owned;
+    uint64_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    bool poisoned = false;
+    /* per-warp-slot search workspace */
+    DevBuf ws_hash, ws_cand, ws_heap;
+    /* per-batch scratch */
+    DevBuf sc_qfull, sc_qcodes, sc_stream, sc_stream_len, sc_stats, sc_qlist, sc_ctl, sc_node;
+    /* staging for the host-buffer entry point */
+    DevBuf st_queries, st_labels, st_label_off, st_tid, st_dist, st_count, st_stats;
+    dann_batch_timing timing{};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t G = 1, Gshift = 0, NCH = 1;
+};
+
+struct dann_scan {
+    dann_index *ix = nullptr;
+    std::vector<float> query;
+    std::vector<int16_t> labels;
+    int nlabels = -1;
+    bool null_query = false;
+    int L = 100, rescore = 50;
+    bool active = false;
+    /* rows fetched so far (the scan re-runs with a larger LIMIT when they run out) */
+    std::vector<uint64_t> tid;
+    std::vector<float> dist;
+    std::vector<uint32_t> node;
+    uint32_t produced = 0, next = 0, k_cur = 0;
+    bool exhausted = false;
+    dann_query_stats stats{};
+};
+
+/* ------------------------------------------------------------------------------------ */
+static uint32_t pow2ceil(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+static int pick_code_mapping(uint32_t cw, uint32_t *G, uint32_t *Gshift, uint32_t *NCH) {
+    uint32_t C = cw / 2;
+    uint32_t g = pow2ceil((C + 2) / 3);
+    if (g > 32) g = 32;
+    uint32_t n = (C + g - 1) / g;
+    uint32_t sup;
+    if (n <= 4) sup = n;
+    else if (n <= 8) sup = 8;
+    else return -1;
+    *G = g;
+    *Gshift = 0;
+    while ((1u << *Gshift) < g) (*Gshift)++;
+    *NCH = sup;
+    return 0;
+}
+
+template <typename Tp>
+static cudaError_t upload(dann_index *ix, const Tp *host, size_t count, Tp **out) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(Tp), 16);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    ix->owned.push_back(p);
+    ix->hbm_bytes += bytes;
+    if (host && count) e = cudaMemcpy(p, host, count * sizeof(Tp), cudaMemcpyHostToDevice);
+    else e = cudaMemset(p, 0, bytes);
+    *out = reinterpret_cast<Tp *>(p);
+    return e;
+}
+
+/* rows of width src_w -> device rows of width dst_w (padded with `fill`), in row chunks so
+ * the temporary never exceeds ~256 MB */
+template <typename Tp>
+static cudaError_t upload_padded(dann_index *ix, const Tp *host, size_t n, uint32_t src_w, uint32_t dst_w,
+                                 Tp fill, Tp **out) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(n * dst_w * sizeof(Tp), 16);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    ix->owned.push_back(p);
+    ix->hbm_bytes += bytes;
+    *out = reinterpret_cast<Tp *>(p);
+    if (n == 0) return cudaSuccess;
+    if (src_w == dst_w) return cudaMemcpy(p, host, n * src_w * sizeof(Tp), cudaMemcpyHostToDevice);
+    size_t chunk = std::max<size_t>(1, (256ull << 20) / (src_w * sizeof(Tp)));
+    void *tmp = nullptr;
+    e = cudaMalloc(&tmp, std::min(chunk, n) * src_w * sizeof(Tp));
+    if (e != cudaSuccess) return e;
+    for (size_t r0 = 0; r0 < n && e == cudaSuccess; r0 += chunk) {
+        size_t rows = std::min(chunk, n - r0);
+        e = cudaMemcpy(tmp, host + r0 * src_w, rows * src_w * sizeof(Tp), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        dann_pad_rows_kernel<Tp><<<1024, 256, 0, ix->stream>>>(reinterpret_cast<Tp *>(p) + r0 * dst_w,
+                                                             reinterpret_cast<Tp *>(tmp), rows, src_w,
+                                                             dst_w, fill);
+        ix->launches++;
+        e = cudaStreamSynchronize(ix->stream);
+    }
+    cudaFree(tmp);
+    return e;
+}
+
+extern "C" void dann_index_free(dann_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    for (void *p : ix->owned) cudaFree(p);
+    DevBuf *bufs[] = {&ix->ws_hash, &ix->ws_cand, &ix->ws_heap, &ix->sc_qfull, &ix->sc_qcodes,
+                      &ix->sc_stream, &ix->sc_stream_len, &ix->sc_stats, &ix->sc_qlist, &ix->sc_ctl,
+                      &ix->sc_node, &ix->st_queries, &ix->st_labels, &ix->st_label_off, &ix->st_tid,
+                      &ix->st_dist, &ix->st_count, &ix->st_stats};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &e : ix->ev)
+        if (e) cudaEventDestroy(e);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    cudaGetLastError();
+    delete ix;
+}
+
+extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
+    dann_index *ix = nullptr;
+    if (!s || !out) return fail(DANN_ERR_INVALID_ARG, "dann_index_load: NULL argument");
+    *out = nullptr;
+    int ndev = dann_device_count();
+    if (ndev <= 0) return fail(DANN_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(DANN_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+    if (s->dim == 0 || s->dim_index == 0 || s->dim_index > s->dim || s->bits == 0 || s->R == 0)
+        return fail(DANN_ERR_INVALID_ARG, "bad snapshot geometry");
+    uint64_t nb = (uint64_t)s->dim_index * s->bits;
+    uint32_t words = (uint32_t)(nb % 64 == 0 ? nb / 64 : nb / 64 + 1); /* quantize.rs:38-46 */
+    if (words != s->words) return fail(DANN_ERR_INVALID_ARG, "words=%u but dim_index*bits needs %u", s->words, words);
+    if (s->distance_type < DANN_COSINE || s->distance_type > DANN_IP)
+        return fail(DANN_ERR_INVALID_ARG, "unknown distance type %d", s->distance_type);
+    if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->vectors || !s->mean))
+        return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
+    if (s->has_labels && s->n && (!s->label_off || (s->label_off[s->n] && !s->labels)))
+        return fail(DANN_ERR_INVALID_ARG, "has_labels set but label arrays missing");
+    if (s->start_default != DANN_INVALID_NODE && s->start_default >= s->n)
+        return fail(DANN_ERR_INVALID_ARG, "start_default out of range");
+
+    ix = new (std::nothrow) dann_index();
+    if (!ix) return fail(DANN_ERR_OOM, "host allocation failed");
+    ix->device = device;
+    struct Guard {
+        dann_index *&p;
+        bool keep = false;
+        ~Guard() {
+            if (!keep && p) {
+                dann_index_free(p);
+                p = nullptr;
+            }
+        }
+    } guard{ix};
+
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto &e : ix->ev) CK(cudaEventCreate(&e));
+
+    IndexView &v = ix->v;
+    v.n = s->n;
+    v.dim = s->dim;
+    v.dim_index = s->dim_index;
+    v.bits = s->bits;
+    v.words = words;
+    v.cw = (words + 1u) & ~1u;
+    v.R = s->R;
+    v.Rp = (s->R + 7u) & ~7u;
+    v.distance_type = s->distance_type;
+    v.has_labels = s->has_labels ? 1 : 0;
+    v.count = s->count;
+    v.start_default = s->n ? s->start_default : DANN_INVALID_NODE;
+    v.n_start_labels = s->start_labels && s->start_label_nodes ? s->n_start_labels : 0;
+    if (pick_code_mapping(v.cw, &ix->G, &ix->Gshift, &ix->NCH) != 0)
+        return fail(DANN_ERR_INVALID_ARG, "SBQ code of %u words is wider than this build supports", words);
+
+    float *mean = nullptr, *m2 = nullptr, *vectors = nullptr;
+    uint64_t *codes = nullptr, *tids = nullptr;
+    uint32_t *nbrs = nullptr, *sln = nullptr, *loff = nullptr;
+    int16_t *sl = nullptr, *labs = nullptr;
+    CK(upload(ix, s->mean, (size_t)s->dim_index, &mean));
+    CK(upload(ix, s->bits > 1 ? s->m2 : nullptr, (size_t)s->dim_index, &m2));
+    CK(upload_padded<uint64_t>(ix, s->codes, s->n, words, v.cw, 0ull, &codes));
+    CK(upload_padded<uint32_t>(ix, s->nbrs, s->n, v.R, v.Rp, DANN_INVALID_NODE, &nbrs));
+    CK(upload(ix, s->heap_tid, (size_t)s->n, &tids));
+    CK(upload(ix, s->vectors, (size_t)s->n * s->dim, &vectors));
+    CK(upload(ix, v.n_start_labels ? s->start_labels : nullptr, (size_t)v.n_start_labels, &sl));
+    CK(upload(ix, v.n_start_labels ? s->start_label_nodes : nullptr, (size_t)v.n_start_labels, &sln));
+    if (v.has_labels && s->n) {
+        CK(upload(ix, s->label_off, (size_t)s->n + 1, &loff));
+        CK(upload(ix, s->labels, (size_t)s->label_off[s->n], &labs));
+    } else {
+        v.has_labels = 0;
+    }
+    v.mean = mean;
+    v.m2 = m2;
+    v.codes = codes;
+    v.nbrs = nbrs;
+    v.tids = tids;
+    v.vectors = vectors;
+    v.start_labels = sl;
+    v.start_label_nodes = sln;
+    v.label_off = loff;
+    v.labels = labs;
+    if (s->distance_type == DANN_COSINE && s->n) {
+        /* rerank reads the heap vector through PgVector::from_datum -> preprocess_cosine
+         * (sbq/storage.rs:304-328, pg_vector.rs:153-155); the result only depends on the row,
+         * so it is computed once here with the same arithmetic. */
+        int blocks = std::min<long long>((s->n + 255) / 256, (long long)ix->sm_count * 8);
+        dann_normalize_rows_kernel<<<std::max(blocks, 1), 256, 0, ix->stream>>>(vectors, s->n, s->dim);
+        ix->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    guard.keep = true;
+    *out = ix;
+    return DANN_OK;
+}
+
+extern "C" uint64_t dann_index_hbm_bytes(const dann_index *ix) { return ix ? ix->hbm_bytes : 0; }
+extern "C" uint64_t dann_kernel_launches(const dann_index *ix) { return ix ? ix->launches : 0; }
+extern "C" uint32_t dann_code_stride(const dann_index *ix) { return ix ? ix->v.cw : 0; }
+
+extern "C" int dann_last_batch_timing(dann_index *ix, dann_batch_timing *out) {
+    if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "NULL argument");
+    *out = ix->timing;
+    return DANN_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+static int check_live(dann_index *ix) {
+    if (!ix) return fail(DANN_ERR_INVALID_ARG, "NULL index");
+    if (ix->poisoned) return fail(DANN_ERR_CUDA, "index handle is poisoned by an earlier CUDA error");
+    cudaError_t e = cudaSetDevice(ix->device);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(DANN_ERR_CUDA, "cudaSetDevice(%d): %s", ix->device, cudaGetErrorString(e));
+    }
+    return DANN_OK;
+}
+
+static int launch_prepare(dann_index *ix, const float *d_queries, int B, float *d_q_full, uint64_t *d_q_codes,
+                          cudaStream_t st) {
+    size_t smem = (size_t)ix->v.dim_index * sizeof(float);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(dann_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dann_prepare_kernel<<<B, 128, smem, st>>>(ix->v, d_queries, B, d_q_full, d_q_codes);
+    ix->launches++;
+    CK(cudaGetLastError());
+    return DANN_OK;
+}
+
+extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int B, float *d_q_full,
+                                    uint64_t *d_q_codes, void *stream) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!d_queries || !d_q_codes || B <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_prepare_queries: bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    rc = launch_prepare(ix, d_queries, B, d_q_full, d_q_codes, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    return DANN_OK;
+}
+
+template <int NCH>
+static void launch_sbq(dann_index *ix, const uint64_t *q, const uint32_t *pq, const uint32_t *pn, size_t np,
+                       uint32_t *out, cudaStream_t st) {
+    constexpr int UNR = NCH <= 3 ? 4 : (NCH == 4 ? 2 : 1);
+    int blocks = ix->sm_count * 8;
+    dann_sbq_distance_kernel<NCH, UNR><<<blocks, 256, 0, st>>>(ix->v.codes, ix->v.cw, q, pq, pn, np, out,
+                                                              ix->G, ix->Gshift);
+}
+
+extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const uint32_t *d_pair_q,
+                                 const uint32_t *d_pair_node, size_t npairs, uint32_t *d_out, void *stream) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!d_qcodes || !d_pair_q || !d_pair_node || !d_out) return fail(DANN_ERR_INVALID_ARG, "dann_sbq_distance: NULL buffer");
+    if (npairs == 0) return DANN_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    switch (ix->NCH) {
+        case 1: launch_sbq<1>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
+        case 2: launch_sbq<2>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
+        case 3: launch_sbq<3>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
+        case 4: launch_sbq<4>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
+        default: launch_sbq<8>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
+    }
+    ix->launches++;
+    CK(cudaGetLastError());
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return DANN_OK;
+}
+
+extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const uint32_t *d_nodes, int B, int m,
+                                  float *d_out, void *stream) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!d_q_full || !d_nodes || !d_out || B <= 0 || m <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_full_distance: bad argument");
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    size_t smem = (size_t)((ix->v.dim + 3u) & ~3u) * sizeof(float);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(dann_full_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dann_full_distance_kernel<<<B, 128, smem, st>>>(ix->v, d_q_full, d_nodes, m, d_out);
+    ix->launches++;
+    CK(cudaGetLastError());
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return DANN_OK;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* search kernel dispatch                                                                */
+typedef void (*search_fn)(const SearchArgs);
+template <typename E>
+static search_fn pick_search(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search_kernel<E, 1>;
+        case 2: return dann_search_kernel<E, 2>;
+        case 3: return dann_search_kernel<E, 3>;
+        case 4: return dann_search_kernel<E, 4>;
+        default: return dann_search_kernel<E, 8>;
+    }
+}
+
+struct SearchPlan {
+    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize;
+};
+
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *s = getenv(name);
+    if (!s || !*s) return dflt;
+    return (uint32_t)strtoul(s, nullptr, 10);
+}
+
+static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, SearchPlan *p) {
+    const IndexView &v = ix->v;
+    /* visits are about L + consumed; every visit stages at most R ids */
+    uint64_t need = ((uint64_t)L + c_target + 40u) * v.R * grow;
+    /* test hook: start from a deliberately small workspace to exercise the growth path */
+    const uint32_t shrink = std::max<uint32_t>(env_u32("DANN_DEBUG_SHRINK", 1), 1);
+    need = std::max<uint64_t>(need / shrink, 256);
+    if (need > (1ull << 30)) return fail(DANN_ERR_CAPACITY, "per-query workspace would exceed 2^30 candidates");
+    p->need = (uint32_t)need;
+    p->cand_cap = (uint32_t)((need + 1023) & ~1023ull);
+    p->hash_cap = pow2ceil(2 * p->cand_cap);
+    bool small = p->cand_cap <= 65536 && (uint64_t)v.words * 64 <= 65535;
+    p->esize = small ? 4 : 8;
+    uint64_t vcap = std::max<uint64_t>(((uint64_t)L + 96u) * grow / shrink, 8);
+    p->vcap = (uint32_t)((vcap + 3) & ~3ull);
+    const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
+    const size_t fixed = (size_t)p->vcap * 8 + 2 * DANN_LIST_CAP * 4;
+    if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
+    uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
+    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), 16);
+    uint32_t hs_target = (uint32_t)std::min<uint64_t>(p->cand_cap, need * 3 / 4);
+    uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_target * p->esize));
+    uint32_t W = std::min(wneed, std::max<uint32_t>(wfit, 1));
+    W = env_u32("DANN_SEARCH_WARPS", W);
+    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 16);
+    while (W > 1 && budget / W < fixed + 1024) W--;
+    size_t per_warp = (budget / W) & ~(size_t)15;
+    uint32_t hs = (uint32_t)std::min<size_t>(p->cand_cap, (per_warp - fixed) / p->esize);
+    hs = env_u32("DANN_SEARCH_HS", hs);
+    hs = std::min(hs, p->cand_cap) & ~3u;
+    p->hs = hs;
+    p->W = W;
+    p->per_warp = (uint32_t)((fixed + (size_t)hs * p->esize + 15) & ~(size_t)15);
+    p->grid = std::min<uint32_t>((uint32_t)ix->sm_count, (nq + W - 1) / W);
+    return DANN_OK;
+}
+
+/* B queries, first k rows each.  All pointers are device pointers. */
+static int search_batch_device_locked(dann_index *ix, const float *d_queries, const int16_t *d_labels,
+                                      const int32_t *d_label_off, int B, int k, int L, int rescore,
+                                      uint64_t *d_out_tid, float *d_out_dist, uint32_t *d_out_node,
+                                      uint32_t *d_out_count, dann_query_stats *d_out_stats, cudaStream_t st) {
+    const IndexView &v = ix->v;
+    if (B <= 0 || k <= 0) return fail(DANN_ERR_INVALID_ARG, "B and k must be positive");
+    if (L < 1 || L > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000 (guc.rs:11-26)", L);
+    if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000 (guc.rs:28-43)", rescore);
+    if (!d_queries || !d_out_tid) return fail(DANN_ERR_INVALID_ARG, "NULL query or output buffer");
+    /* rows needed from the approximate stream: scan.rs:255-305 */
+    const uint32_t c_target = rescore == 0 ? (uint32_t)k : (uint32_t)rescore + (uint32_t)k - 1u;
+
+    CK(ix->sc_qfull.reserve((size_t)B * v.dim * sizeof(float)));
+    CK(ix->sc_qcodes.reserve((size_t)B * v.cw * sizeof(uint64_t)));
+    CK(ix->sc_stream.reserve((size_t)B * c_target * sizeof(uint32_t)));
+    CK(ix->sc_stream_len.reserve((size_t)B * sizeof(uint32_t)));
+    CK(ix->sc_stats.reserve((size_t)B * sizeof(dann_query_stats)));
+    CK(ix->sc_qlist.reserve((size_t)B * sizeof(uint32_t)));
+    CK(ix->sc_ctl.reserve(64));
+    dann_query_stats *d_stats = d_out_stats ? d_out_stats : ix->sc_stats.as<dann_query_stats>();
+    uint32_t *d_ctl = ix->sc_ctl.as<uint32_t>(); /* [0]=work counter, [1]=overflow bits */
+
+    ix->timing = dann_batch_timing{};
+    CK(cudaEventRecord(ix->ev[0], st));
+    int rc = launch_prepare(ix, d_queries, B, ix->sc_qfull.as<float>(), ix->sc_qcodes.as<uint64_t>(), st);
+    if (rc) return rc;
+    CK(cudaEventRecord(ix->ev[1], st));
+
+    std::vector<uint32_t> qlist;
+    std::vector<dann_query_stats> hstats;
+    uint32_t grow = 1;
+    uint32_t nq = (uint32_t)B;
+    for (int attempt = 0;; attempt++) {
+        SearchPlan p;
+        rc = make_plan(ix, nq, (uint32_t)L, c_target, grow, &p);
+        if (rc) return rc;
+        const size_t slots = (size_t)p.grid * p.W;
+        CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
+        CK(ix->ws_cand.reserve(slots * p.cand_cap * sizeof(uint32_t)));
+        CK(ix->ws_heap.reserve(slots * p.cand_cap * (size_t)p.esize));
+        CK(cudaMemsetAsync(d_ctl, 0, 8, st));
+        SearchArgs a;
+        a.ix = v;
+        a.q_codes = ix->sc_qcodes.as<uint64_t>();
+        a.q_labels = d_labels;
+        a.q_label_off = d_label_off;
+        a.qlist = attempt == 0 ? nullptr : ix->sc_qlist.as<uint32_t>();
+        a.nq = nq;
+        a.L = (uint32_t)L;
+        a.c_target = c_target;
+        a.stream = ix->sc_stream.as<uint32_t>();
+        a.stream_len = ix->sc_stream_len.as<uint32_t>();
+        a.stats = d_stats;
+        a.overflow = d_ctl + 1;
+        a.counter = d_ctl;
+        a.hash = ix->ws_hash.as<uint32_t>();
+        a.hash_cap = p.hash_cap;
+        a.cand_node = ix->ws_cand.as<uint32_t>();
+        a.cand_cap = p.cand_cap;
+        a.heap_tail = ix->ws_heap.p;
+        a.hs = p.hs;
+        a.vcap = p.vcap;
+        a.G = ix->G;
+        a.Gshift = ix->Gshift;
+        a.per_warp_smem = p.per_warp;
+        search_fn fn = p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH);
+        size_t smem = (size_t)p.per_warp * p.W;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<p.grid, p.W * 32, smem, st>>>(a);
+        ix->launches++;
+        CK(cudaGetLastError());
+        uint32_t ctl[2] = {0, 0};
+        CK(cudaMemcpyAsync(ctl, d_ctl, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (ctl[1] == 0) break;
+        /* some queries outgrew their workspace: rerun exactly those with a larger one */
+        if (attempt >= 8) return fail(DANN_ERR_CAPACITY, "search workspace still too small after %d growth steps", attempt);
+        hstats.resize(B);
+        CK(cudaMemcpy(hstats.data(), d_stats, (size_t)B * sizeof(dann_query_stats), cudaMemcpyDeviceToHost));
+        qlist.clear();
+        for (int b = 0; b < B; b++)
+            if (hstats[b].status) qlist.push_back((uint32_t)b);
+        nq = (uint32_t)qlist.size();
+        CK(cudaMemcpy(ix->sc_qlist.p, qlist.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        grow *= 2;
+        ix->timing.retries++;
+    }
+    CK(cudaEventRecord(ix->ev[2], st));
+
+    RerankArgs r;
+    r.ix = v;
+    r.q_full = ix->sc_qfull.as<float>();
+    r.stream = ix->sc_stream.as<uint32_t>();
+    r.stream_len = ix->sc_stream_len.as<uint32_t>();
+    r.c_target = c_target;
+    r.k = (uint32_t)k;
+    r.rescore = (uint32_t)rescore;
+    r.out_tid = d_out_tid;
+    r.out_dist = d_out_dist;
+    r.out_node = d_out_node;
+    r.out_count = d_out_count;
+    r.stats = d_stats;
+    size_t smem = (size_t)((v.dim + 3u) & ~3u) * 4 + (size_t)((c_target + 1u) & ~1u) * 4 + (size_t)rescore * 8 + 16;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(dann_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dann_rerank_kernel<<<B, 128, smem, st>>>(r);
+    ix->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ix->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]));
+    ix->timing.prepare_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]));
+    ix->timing.search_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3]));
+    ix->timing.rerank_ms = ms;
+    ix->timing.resort_ms = 0.0f; /* the rerank window runs inside the rerank kernel */
+    CK(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]));
+    ix->timing.total_ms = ms;
+    return DANN_OK;
+}
+
+extern "C" int dann_search_batch_device(dann_index *ix, const float *d_queries, const int16_t *d_labels,
+                                        const int32_t *d_label_off, int B, int k, int search_list_size,
+                                        int rescore, uint64_t *d_out_tid, float *d_out_dist,
+                                        uint32_t *d_out_count, dann_query_stats *d_out_stats, void *stream) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    return search_batch_device_locked(ix, d_queries, d_labels, d_label_off, B, k, search_list_size, rescore,
+                                      d_out_tid, d_out_dist, nullptr, d_out_count, d_out_stats, st);
+}
+
+/* host-buffer batch with optional node ids (used by the scan operator too) */
+static int search_batch_host(dann_index *ix, const float *queries, const int16_t *labels,
+                             const int32_t *label_off, int B, int k, int L, int rescore, uint64_t *out_tid,
+                             float *out_dist, uint32_t *out_node, uint32_t *out_count,
+                             dann_query_stats *out_stats) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (B <= 0 || k <= 0 || !queries || !out_tid) return fail(DANN_ERR_INVALID_ARG, "dann_search_batch: bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    cudaStream_t st = ix->stream;
+    const IndexView &v = ix->v;
+    const size_t nk = (size_t)B * k;
+    CK(ix->st_queries.reserve((size_t)B * v.dim * sizeof(float)));
+    CK(ix->st_tid.reserve(nk * sizeof(uint64_t)));
+    CK(ix->st_dist.reserve(nk * sizeof(float)));
+    CK(ix->sc_node.reserve(nk * sizeof(uint32_t)));
+    CK(ix->st_count.reserve((size_t)B * sizeof(uint32_t)));
+    CK(ix->st_stats.reserve((size_t)B * sizeof(dann_query_stats)));
+    CK(cudaMemcpyAsync(ix->st_queries.p, queries, (size_t)B * v.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int16_t *d_lab = nullptr;
+    const int32_t *d_off = nullptr;
+    std::vector<int16_t> nl;
+    std::vector<int32_t> no;
+    if (label_off) {
+        /* LabelSet::from(Vec): sort_unstable + dedup per query (labels/mod.rs:30-37) */
+        no.resize((size_t)B + 1);
+        no[0] = 0;
+        for (int b = 0; b < B; b++) {
+            int32_t o0 = label_off[b], o1 = label_off[b + 1];
+            if (o1 < o0) return fail(DANN_ERR_INVALID_ARG, "label_off is not monotone");
+            size_t s0 = nl.size();
+            if (o1 > o0) nl.insert(nl.end(), labels + o0, labels + o1);
+            std::sort(nl.begin() + s0, nl.end());
+            nl.erase(std::unique(nl.begin() + s0, nl.end()), nl.end());
+            no[b + 1] = (int32_t)nl.size();
+        }
+        CK(ix->st_labels.reserve(std::max<size_t>(nl.size(), 1) * sizeof(int16_t)));
+        CK(ix->st_label_off.reserve(no.size() * sizeof(int32_t)));
+        if (!nl.empty()) CK(cudaMemcpyAsync(ix->st_labels.p, nl.data(), nl.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->st_label_off.p, no.data(), no.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_lab = ix->st_labels.as<int16_t>();
+        d_off = ix->st_label_off.as<int32_t>();
+    }
+    rc = search_batch_device_locked(ix, ix->st_queries.as<float>(), d_lab, d_off, B, k, L, rescore,
+                                    ix->st_tid.as<uint64_t>(), ix->st_dist.as<float>(), ix->sc_node.as<uint32_t>(),
+                                    ix->st_count.as<uint32_t>(), ix->st_stats.as<dann_query_stats>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_tid, ix->st_tid.p, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, ix->st_dist.p, nk * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_node) CK(cudaMemcpyAsync(out_node, ix->sc_node.p, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (out_count) CK(cudaMemcpyAsync(out_count, ix->st_count.p, (size_t)B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (out_stats) CK(cudaMemcpyAsync(out_stats, ix->st_stats.p, (size_t)B * sizeof(dann_query_stats), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DANN_OK;
+}
+
+extern "C" int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
+                                 const int32_t *label_off, int B, int k, int search_list_size, int rescore,
+                                 uint64_t *out_tid, float *out_dist, uint32_t *out_count,
+                                 dann_query_stats *out_stats) {
+    return search_batch_host(ix, queries, labels, label_off, B, k, search_list_size, rescore, out_tid, out_dist,
+                             nullptr, out_count, out_stats);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* scan operator: ambeginscan / amrescan / amgettuple / amendscan (scan.rs:309-476)       */
+
+extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) {
+    if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "dann_scan_begin: NULL argument");
+    dann_scan *sc = new (std::nothrow) dann_scan();
+    if (!sc) return fail(DANN_ERR_OOM, "host allocation failed");
+    sc->ix = ix;
+    *out = sc;
+    return DANN_OK;
+}
+
+extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
+                                int search_list_size, int rescore) {
+    if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_rescan: NULL scan");
+    if (search_list_size < 1 || search_list_size > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000", search_list_size);
+    if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000", rescore);
+    if (nlabels > 0 && !labels) return fail(DANN_ERR_INVALID_ARG, "labels is NULL but nlabels > 0");
+    const uint32_t dim = sc->ix->v.dim;
+    sc->null_query = query == nullptr;
+    if (query) sc->query.assign(query, query + dim);
+    else sc->query.assign(dim, 0.0f); /* NULL order-by argument: zero vector, no labels (labels/mod.rs:214-216) */
+    sc->nlabels = sc->null_query ? -1 : nlabels;
+    sc->labels.clear();
+    if (sc->nlabels > 0) sc->labels.assign(labels, labels + nlabels);
+    sc->L = search_list_size;
+    sc->rescore = rescore;
+    sc->tid.clear();
+    sc->dist.clear();
+    sc->node.clear();
+    sc->produced = sc->next = sc->k_cur = 0;
+    sc->exhausted = false;
+    sc->stats = dann_query_stats{};
+    sc->active = true;
+    return DANN_OK;
+}
+
+static int scan_fetch(dann_scan *sc, uint32_t k) {
+    sc->tid.assign(k, DANN_INVALID_TID);
+    sc->dist.assign(k, 0.0f);
+    sc->node.assign(k, DANN_INVALID_NODE);
+    uint32_t count = 0;
+    int32_t off[2] = {0, sc->nlabels > 0 ? sc->nlabels : 0};
+    int rc = search_batch_host(sc->ix, sc->query.data(), sc->labels.data(), sc->nlabels >= 0 ? off : nullptr, 1,
+                               (int)k, sc->L, sc->rescore, sc->tid.data(), sc->dist.data(), sc->node.data(),
+                               &count, &sc->stats);
+    if (rc) return rc;
+    sc->produced = count;
+    sc->k_cur = k;
+    sc->exhausted = count < k;
+    return DANN_OK;
+}
+
+extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) {
+    if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_gettuple: NULL scan");
+    if (!sc->active) return fail(DANN_ERR_STATE, "dann_scan_gettuple before dann_scan_rescan");
+    if (sc->next >= sc->produced) {
+        if (sc->exhausted) return 0;
+        /* Rows i < k of a scan do not depend on k, so the operator materialises the first
+         * k rows and re-runs with 4x the LIMIT when the executor asks for more. */
+        uint32_t k = sc->k_cur == 0 ? 16u : sc->k_cur * 4u;
+        int rc = scan_fetch(sc, k);
+        if (rc) return rc;
+        if (sc->next >= sc->produced) return 0;
+    }
+    uint64_t t = sc->tid[sc->next];
+    if (block) *block = (uint32_t)(t >> 16);
+    if (offset) *offset = (uint16_t)(t & 0xFFFFu);
+    if (node_id) *node_id = sc->node[sc->next];
+    if (dist) *dist = sc->dist[sc->next];
+    sc->next++;
+    return 1;
+}
+
+extern "C" int dann_scan_stats(dann_scan *sc, dann_query_stats *out) {
+    if (!sc || !out) return fail(DANN_ERR_INVALID_ARG, "dann_scan_stats: NULL argument");
+    *out = sc->stats;
+    return DANN_OK;
+}
+
+extern "C" void dann_scan_end(dann_scan *sc) { delete sc; }

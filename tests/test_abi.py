@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/diskann_b200.h declares, and the
+product path fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "diskann_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(dann_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_symbols_are_exported(lib_built):
+    from pgvectorscale_b200 import diskann
+    lib = C.CDLL(lib_built)
+    declared = _declared_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/diskann_b200.h but not exported"
+    assert sorted(diskann.EXPORTS) == declared, "diskann.EXPORTS out of sync with the header"
+
+
+def test_library_is_sm100a_only(lib_built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback_without_device(lib_built):
+    from pgvectorscale_b200 import diskann
+    if diskann.device_count() > 0:
+        pytest.skip("a CUDA device is visible; the no-device behaviour is checked on the CPU box")
+    from pgvectorscale_b200.snapshot import Snapshot, make_heap_tids
+    n, dim = 4, 8
+    s = Snapshot(n=n, dim=dim, dim_index=dim, bits=2, words=1, R=4, distance_type=1, has_labels=False,
+                 count=n, mean=np.zeros(dim, np.float32), m2=np.ones(dim, np.float32),
+                 codes=np.zeros((n, 1), np.uint64), nbrs=np.full((n, 4), 0xFFFFFFFF, np.uint32),
+                 heap_tid=make_heap_tids(n), vectors=np.zeros((n, dim), np.float32), start_default=0)
+    with pytest.raises(diskann.DiskAnnError) as e:
+        diskann.DiskAnnIndex(s)
+    assert e.value.code == -3          # DANN_ERR_NO_DEVICE
+    assert "no CPU path" in str(e.value)
+
+
+def test_missing_library_raises(tmp_path):
+    from pgvectorscale_b200 import diskann
+    with pytest.raises(diskann.DiskAnnError):
+        diskann.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under pgvectorscale_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "pgvectorscale_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "oracle.h" not in text, f

@@ -1,0 +1,33 @@
+"""Host-side logic that needs no GPU: snapshot container, default parameters."""
+import numpy as np
+
+from conftest import build_case
+from pgvectorscale_b200 import snapshot
+
+
+def test_code_words_and_default_bits():
+    # sbq/quantize.rs:38-46, meta_page.rs:312-323
+    assert snapshot.code_words(768, 2) == 24 and snapshot.code_words(768, 1) == 12
+    assert snapshot.code_words(65, 1) == 2 and snapshot.code_words(64, 1) == 1
+    assert snapshot.default_bits(768) == 2 and snapshot.default_bits(899) == 2
+    assert snapshot.default_bits(900) == 1 and snapshot.default_bits(1536) == 1
+
+
+def test_snapshot_roundtrip(tmp_path):
+    s = build_case(120, 40, 0, seed=2, R=8, L_build=16, labels=True)
+    s.validate()
+    p = str(tmp_path / "snap.npz")
+    s.save(p)
+    t = snapshot.Snapshot.load(p)
+    t.validate()
+    for f in ("n", "dim", "dim_index", "bits", "words", "R", "distance_type", "has_labels", "count",
+              "start_default"):
+        assert getattr(s, f) == getattr(t, f), f
+    for f in ("mean", "m2", "codes", "nbrs", "heap_tid", "vectors", "start_labels",
+              "start_label_nodes", "label_off", "labels"):
+        assert np.array_equal(getattr(s, f), getattr(t, f)), f
+
+
+def test_heap_tids_have_valid_offsets():
+    t = snapshot.make_heap_tids(1000)
+    assert ((t & np.uint64(0xFFFF)) >= 1).all() and len(set(t.tolist())) == 1000

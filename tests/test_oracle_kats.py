@@ -1,0 +1,274 @@
+"""CPU tests that pin the oracle (oracle/oracle.cpp) before it is trusted as the checker.
+
+Sources of truth, in order:
+  * the reference's own portable known-answer tests, restated as data:
+      labels/mod.rs:249-425 (overlap / intersection truth tables),
+      distance_x86.rs:40-63 (SIMD order vs scalar within 1e-6),
+      build.rs:1419-1556 (rescore semantics, L2 / IP 3-vector sanity checks),
+      build.rs:2016-2044 (NULL query returns every row),
+      build.rs:1311-1396 and labels/filtering_tests.rs:880-1024 (recall properties);
+  * a second, independent Python restatement (tests/pyref.py) of the scan written from the
+    reference sources;
+  * committed golden outputs (tests/golden/, regenerate with tests/golden/make_golden.py).
+The two third-party pieces the reference does not vendor (Rust std BinaryHeap sift order,
+simdeez horizontal_add_ps order) cannot be executed here: for them parity is "unpinned" and
+these tests only prove that both restatements implement the same published algorithm.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pyref
+from conftest import build_case
+from oracle import fixtures, oracle
+
+COSINE, L2, IP = 0, 1, 2
+
+
+# ---- labels/mod.rs:253-425 -------------------------------------------------------------
+OVERLAP_KATS = [
+    ([], [1, 2, 3], False), ([1, 2], [2, 3], True), ([1, 2], [3, 4], False),
+    ([1, 2, 3, 4, 5], [1, 2, 3, 4], True), ([1, 2, 3, 4, 5], [6, 7, 8, 9, 10], False),
+    ([1, 2, 3, 4, 5], [2, 3, 4, 5, 6], True), ([1, 3, 5, 10, 11], [2, 4, 6, 8, 11], True),
+]
+INTERSECTION_KATS = [  # (a, b, c, c.contains_intersection(a, b))
+    ([1, 3, 5, 10, 11], [2, 4, 6, 8, 11], list(range(1, 12)), True),
+    ([], [1, 2, 3], [1, 2, 3], True),
+    ([1, 2, 3], [4, 5, 6], [1, 2, 3, 4, 5, 6], True),
+    ([1, 2, 3], [2, 3, 4], [1, 3, 4], False),
+    ([1, 2, 3, 4], [2, 3, 4, 5], [1, 2, 4, 5], False),
+    ([1, 2, 3], [2, 3, 4], [], False),
+    ([1, 2, 3], [2, 3, 4], [2, 4], False),
+    ([1], [1], [1], True),
+    ([], [], [], True),
+    (list(range(1, 101)), list(range(50, 151)), list(range(1, 201)), True),
+    ([1, 1, 2, 2, 3, 3], [2, 2, 3, 3, 4, 4], [1, 2, 3, 4], True),
+    ([-3, -2, -1, 0], [-2, -1, 0, 1], [-3, -2, -1, 0, 1], True),
+]
+
+
+@pytest.mark.parametrize("a,b,want", OVERLAP_KATS)
+def test_label_overlap_truth_table(a, b, want):
+    assert oracle.labels_overlap(a, b) is want
+    assert oracle.labels_overlap(b, a) is want
+    assert pyref.overlaps(a, b) is want
+
+
+@pytest.mark.parametrize("a,b,c,want", INTERSECTION_KATS)
+def test_label_contains_intersection_truth_table(a, b, c, want):
+    a, b, c = (oracle.labels_normalize(x) for x in (a, b, c))      # LabelSet::from: sort + dedup
+    assert oracle.labels_contains_intersection(c, a, b) is want
+    assert oracle.labels_contains_intersection(c, b, a) is want
+
+
+def test_label_normalize_sorts_and_dedups():
+    assert list(oracle.labels_normalize([5, -1, 5, 3, 3, 0])) == [-1, 0, 3, 5]
+
+
+# ---- Rust BinaryHeap clone ---------------------------------------------------------------
+def test_binary_heap_hand_traced_tie_order():
+    # push 5 equal keys then pop all: sift_up never moves an equal element, pop swaps the last
+    # element to the root and walks it to the bottom preferring the RIGHT child on ties.
+    #   data=[0,1,2,3,4]
+    #   pop -> 0: last=4 takes the root, hole walks to child 2 (right on tie)   -> [2,1,4,3]
+    #   pop -> 2: last=3 takes the root, children (1,4) tie -> right child (4)  -> [4,1,3]
+    #   pop -> 4: last=3 takes the root, only child 1 moves up (child==end-1)   -> [1,3]
+    #   pop -> 1: last=3 takes the root                                          -> [3]
+    #   pop -> 3
+    ops = [7, 7, 7, 7, 7, -1, -1, -1, -1, -1]
+    assert list(oracle.binary_heap_script(ops)) == [0, 2, 4, 1, 3]
+    # distinct keys: plain max-heap order
+    ops = [3, 9, 1, 7, -1, -1, -1, -1]
+    assert list(oracle.binary_heap_script(ops)) == [1, 3, 0, 2]
+
+
+def test_binary_heap_matches_independent_python_clone():
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(1, 400))
+        ops = []
+        live = 0
+        for i in range(n):
+            if live and rng.random() < 0.4:
+                ops.append(-1)
+                live -= 1
+            else:
+                ops.append(int(rng.integers(0, 6)))     # few distinct keys => many ties
+                live += 1
+        ops += [-1] * live
+        h = pyref.RustBinaryHeap(lambda a, b: a[0] <= b[0])
+        want = []
+        for i, o in enumerate(ops):
+            if o >= 0:
+                h.push((o, i))
+            else:
+                want.append(h.pop()[1])
+        assert list(oracle.binary_heap_script(ops)) == want
+
+
+# ---- distances ---------------------------------------------------------------------------
+def test_simd_order_vs_scalar_reference_tolerance():
+    """distance_x86.rs:40-63: 2000-d normalised ramps, |simd - scalar| < 1e-6."""
+    r = np.arange(2000, dtype=np.float32) + 1.0
+    l = np.arange(2000, dtype=np.float32) + 2.0
+    r = r / np.float32(np.sqrt(np.float32(np.sum(r * r, dtype=np.float32))))
+    l = l / np.float32(np.sqrt(np.float32(np.sum(l * l, dtype=np.float32))))
+    for kind in (COSINE, L2):
+        for impl in ("emu", "avx2"):
+            assert abs(oracle.distance(kind, r, l, impl) - oracle.distance(kind, r, l, "unoptimized")) < 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 7, 31, 32, 33, 64, 100, 768, 1536, 2000])
+def test_scalar_emulation_equals_real_avx2_bits(n):
+    rng = np.random.default_rng(n)
+    for _ in range(20):
+        x = rng.standard_normal(n).astype(np.float32)
+        y = rng.standard_normal(n).astype(np.float32)
+        for kind in (COSINE, L2, IP):
+            a = np.float32(oracle.distance(kind, x, y, "emu"))
+            b = np.float32(oracle.distance(kind, x, y, "avx2"))
+            assert a.view(np.uint32) == b.view(np.uint32)
+    x = rng.standard_normal(n).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    for kind in (COSINE, L2, IP):
+        assert np.float32(pyref.distance(kind, x, y)).view(np.uint32) == \
+            np.float32(oracle.distance(kind, x, y, "emu")).view(np.uint32)
+
+
+def test_preprocess_cosine_edge_cases():
+    z = np.zeros(16, np.float32)
+    assert np.array_equal(oracle.preprocess_cosine(z), z)               # zero vector untouched
+    u = np.zeros(16, np.float32)
+    u[3] = 1.0
+    assert np.array_equal(oracle.preprocess_cosine(u), u)               # already unit: untouched
+    v = np.arange(1, 17, dtype=np.float32)
+    w = oracle.preprocess_cosine(v)
+    assert np.array_equal(w, pyref.preprocess_cosine(v))
+    assert np.array_equal(oracle.preprocess_cosine(w), w)               # idempotent (debug_assert in the reference)
+
+
+# ---- quantizer -----------------------------------------------------------------------------
+def test_quantizer_layout_and_buckets():
+    assert oracle.code_words(768, 2) == 24 and oracle.code_words(768, 1) == 12
+    assert oracle.code_words(100, 1) == 2 and oracle.code_words(3, 2) == 1
+    mean = np.zeros(4, np.float32)
+    m2 = np.full(4, 4.0, np.float32)                   # count 4 => variance 1, std 1
+    # z = -3 -> idx<1 -> 00 ; z = -0.5 -> idx 1.125 -> 1 one ; z = 1 -> idx 2.25 -> 2 ones ; z=5 -> min(5,2)
+    v = np.array([-3.0, -0.5, 1.0, 5.0], np.float32)
+    code = oracle.quantize(v, 2, mean, m2, 4)
+    assert int(code[0]) == (0b00) | (0b01 << 2) | (0b11 << 4) | (0b11 << 6)
+    # 1 bit: strictly greater than the mean
+    code = oracle.quantize(np.array([0.0, 1e-9, -1.0, 2.0], np.float32), 1, mean, m2, 4)
+    assert int(code[0]) == 0b1010
+    # index built on an empty table: count = 0 => std = NaN => every bucket is 0 (build.rs:1419-1433)
+    code = oracle.quantize(v, 2, mean, np.zeros(4, np.float32), 0)
+    assert int(code[0]) == 0
+
+
+def test_quantizer_matches_python_restatement():
+    rng = np.random.default_rng(2)
+    data = rng.standard_normal((50, 70)).astype(np.float32)
+    for bits in (1, 2, 3):
+        mean, m2, count = oracle.train(data, bits)
+        for i in range(5):
+            a = oracle.quantize(data[i], bits, mean, m2, count)
+            b = pyref.quantize(data[i], bits, mean, m2, count, len(a))
+            assert [int(x) for x in a] == b
+
+
+# ---- reference SQL KATs restated (index created BEFORE the inserts => zero means) -----------
+def _three_vector_index(dist):
+    v = np.array([[1, 1, 1], [2, 2, 2], [3, 3, 3]], np.float32)
+    return fixtures.make_index(v, dist, R=10, L_build=10, train_on_data=False), v
+
+
+def _top1(s, v, q, rescore=50):
+    r = oracle.scan(s, np.asarray(q, np.float32), None, 100, rescore, 1)
+    return v[r["node"][0]].tolist()
+
+
+def test_l2_sanity_check_kat():        # build.rs:1475-1516
+    s, v = _three_vector_index(L2)
+    for q in ([1, 1, 1], [2, 2, 2], [3, 3, 3]):
+        assert _top1(s, v, q) == q
+
+
+def test_ip_sanity_check_kat():        # build.rs:1518-1556
+    s, v = _three_vector_index(IP)
+    for q in ([1, 1, 1], [2, 2, 2], [3, 3, 3]):
+        assert _top1(s, v, q) == [3, 3, 3]
+
+
+def test_no_rescore_kat():             # build.rs:1419-1473
+    v = np.array([[1, 1, 1], [2, 2, 2]], np.float32)
+    s = fixtures.make_index(v, L2, train_on_data=False)
+    assert not s.codes.any()           # SBQ cannot tell the two rows apart
+    wrong_a = _top1(s, v, [1, 1, 1], rescore=0) != [1, 1, 1]
+    wrong_b = _top1(s, v, [2, 2, 2], rescore=0) != [2, 2, 2]
+    assert wrong_a or wrong_b
+    assert _top1(s, v, [1, 1, 1], rescore=2) == [1, 1, 1]
+    assert _top1(s, v, [2, 2, 2], rescore=2) == [2, 2, 2]
+
+
+def test_null_query_returns_all_rows():    # build.rs:2016-2044
+    s = build_case(300, 48, COSINE, seed=3, kind="uniform", R=20, L_build=40)
+    r = oracle.scan(s, None, None, 100, 50, 1000)
+    assert len(r["tid"]) == 300 and len(set(r["tid"].tolist())) == 300
+
+
+def test_recall_scaffold_property():       # build.rs:1311-1396: > 9 of 10 at L=25 on 300 vectors
+    s = build_case(300, 1536, L2, seed=4, kind="uniform")
+    q = np.ones(1536, np.float32)
+    r = oracle.scan(s, q, None, 25, 50, 10)
+    truth = np.argsort(((s.vectors - q) ** 2).sum(1), kind="stable")[:10]
+    assert len(set(r["node"].tolist()) & set(truth.tolist())) > 9 - 1   # reference asserts > 9 with pg's RNG; >= 9 here
+
+
+def test_labeled_recall_property():        # labels/filtering_tests.rs:880-1024: recall >= 0.9
+    s = build_case(1000, 128, L2, seed=6, kind="uniform", labels=True)
+    rng = np.random.default_rng(0)
+    hits = tot = 0
+    for t in range(20):
+        q = rng.random(128, dtype=np.float32)
+        lab = [int(rng.integers(1, 17))]
+        r = oracle.scan(s, q, lab, 100, 50, 10)
+        ok = np.array([oracle.labels_overlap(lab, s.labels[s.label_off[i]:s.label_off[i + 1]]) for i in range(s.n)])
+        d = ((s.vectors - q) ** 2).sum(1)
+        d[~ok] = np.inf
+        truth = np.argsort(d, kind="stable")[:10]
+        hits += len(set(r["node"].tolist()) & set(truth.tolist()))
+        tot += 10
+        assert all(ok[n] for n in r["node"])       # every returned row satisfies `labels && ARRAY[l]`
+    assert hits / tot >= 0.9
+
+
+# ---- the two restatements agree on whole scans ---------------------------------------------
+@pytest.mark.parametrize("dist,bits,labels,dim_index", [(COSINE, 2, False, None), (L2, 1, False, None),
+                                                        (IP, 2, True, None), (COSINE, 2, True, 40)])
+def test_cpp_oracle_equals_python_restatement(dist, bits, labels, dim_index):
+    s = build_case(400, 72, dist, bits=bits, seed=9 + dist, kind="normal", R=12, L_build=24,
+                   labels=labels, dim_index=dim_index, deleted_every=7)
+    q = fixtures.gen_vectors(6, 72, 33, "normal")
+    for i in range(6):
+        lab = None if not labels or i % 3 == 0 else [1 + i, 3]
+        for (L, rescore, rows) in ((20, 10, 15), (5, 0, 30), (40, 60, 12)):
+            a = oracle.scan(s, q[i], lab, L, rescore, rows)
+            b_rows, b_stats = pyref.scan(s, q[i], lab, L, rescore, rows)
+            assert a["tid"].tolist() == [r[0] for r in b_rows]
+            assert a["node"].tolist() == [r[1] for r in b_rows]
+            if rescore:
+                assert a["dist"].view(np.uint32).tolist() == \
+                    np.array([r[2] for r in b_rows], np.float32).view(np.uint32).tolist()
+            assert a["stats"] == b_stats
+
+
+# ---- committed golden vectors -----------------------------------------------------------------
+def test_golden_vectors():
+    path = os.path.join(os.path.dirname(__file__), "golden", "scan_golden.npz")
+    z = np.load(path)
+    from golden.make_golden import CASES, run_case
+    for name in CASES:
+        got = run_case(name)
+        for key, val in got.items():
+            assert np.array_equal(z[f"{name}/{key}"], val), (name, key)
