@@ -14,6 +14,9 @@
 #include "dann_device.cuh"
 #include "dann_heap.cuh"
 
+/* f32::NAN (0x7fc00000): the "no distance" value of padded / unrescored rows */
+#define DANN_NAN_F __int_as_float(0x7fc00000)
+
 /* ------------------------------------------------------------------------------------ */
 /* preprocess_cosine (distance/mod.rs:225-253): norm = sequential f32 sum of v*v;        */
 /* returns the divisor (sqrt(norm)) or 0 when the vector is left untouched.              */
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(128) dann_full_distance_kernel(IndexView ix, c
         const float *x = ix.vectors + (size_t)(node == DANN_INVALID_NODE ? 0 : node) * ix.dim;
         float d = vec4 ? full_distance_group8<true>(ix.distance_type, x, qs, ix.dim, mm, gbase)
                        : full_distance_group8<false>(ix.distance_type, x, qs, ix.dim, mm, gbase);
-        if (mm == 0 && it < (uint32_t)m) out[(size_t)q * m + it] = node == DANN_INVALID_NODE ? CUDART_NAN_F : d;
+        if (mm == 0 && it < (uint32_t)m) out[(size_t)q * m + it] = node == DANN_INVALID_NODE ? DANN_NAN_F : d;
     }
 }
 
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(128) dann_rerank_kernel(const RerankArgs a) {
             bool ok = i < sl;
             uint32_t node = ok ? st[i] : DANN_INVALID_NODE;
             otid[i] = ok ? ix.tids[node] : DANN_INVALID_TID;
-            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = CUDART_NAN_F;
+            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = DANN_NAN_F;
             if (a.out_node) a.out_node[(size_t)q * a.k + i] = node;
         }
         if (threadIdx.x == 0 && a.out_count) a.out_count[q] = sl < a.k ? sl : a.k;
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(128) dann_rerank_kernel(const RerankArgs a) {
         if (a.stats) a.stats[q].d_full = si; /* full_distance_comparisons, scan.rs:258 */
         for (uint32_t i = rows; i < a.k; i++) {
             otid[i] = DANN_INVALID_TID;
-            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = CUDART_NAN_F;
+            if (a.out_dist) a.out_dist[(size_t)q * a.k + i] = DANN_NAN_F;
             if (a.out_node) a.out_node[(size_t)q * a.k + i] = DANN_INVALID_NODE;
         }
     }

@@ -1,0 +1,66 @@
+"""Query-batch data parallelism over replicated indexes.
+
+Queries are independent units: every rank holds a full replica of the index in its own HBM,
+takes a contiguous slice of the batch, searches it locally, and the only exchange is one
+gather of `B/N x k` (tid u64, dist f32) rows at the end.  One process per GPU;
+`torch.distributed` is the plumbing (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of `total` queries for `rank` (first ranks take the remainder)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class QueryShardGroup:
+    """Splits a global query batch across the ranks of a process group and gathers the top-k rows.
+
+    search_fn(queries_slice) -> (tid [b,k] int64, dist [b,k] float32) tensors on `device`
+    (for the product it wraps DiskAnnIndex.search_batch_device on this rank's replica)."""
+
+    def __init__(self, search_fn: Callable, k: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.search_fn = search_fn
+        self.k = k
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def gather_rows(self, tid: torch.Tensor, dst_dist: torch.Tensor, per_rank: int):
+        """all_gather of equally sized [per_rank,k] blocks (ranks pad their slice to per_rank rows)."""
+        if self.world == 1:
+            return tid, dst_dist
+        tids = torch.empty((self.world * per_rank, self.k), dtype=tid.dtype, device=self.device)
+        dists = torch.empty((self.world * per_rank, self.k), dtype=dst_dist.dtype, device=self.device)
+        dist.all_gather_into_tensor(tids, tid.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(dists, dst_dist.contiguous(), group=self.group)
+        return tids, dists
+
+    def search(self, queries: torch.Tensor):
+        """queries: the GLOBAL batch [B, dim] (same tensor on every rank). Returns the global
+        (tid [B,k], dist [B,k]) on every rank, rows in query order."""
+        B = queries.shape[0]
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        per_rank = (B + self.world - 1) // self.world
+        tid = torch.full((per_rank, self.k), -1, dtype=torch.int64, device=self.device)
+        dst = torch.full((per_rank, self.k), float("nan"), dtype=torch.float32, device=self.device)
+        if hi > lo:
+            t, d = self.search_fn(queries[lo:hi])
+            tid[: hi - lo] = t
+            dst[: hi - lo] = d
+        tids, dists = self.gather_rows(tid, dst, per_rank)
+        if self.world == 1:
+            return tids[:B], dists[:B]
+        rows = []
+        for r in range(self.world):
+            a, b = shard_bounds(B, self.world, r)
+            rows.append(torch.arange(r * per_rank, r * per_rank + (b - a), device=self.device))
+        sel = torch.cat(rows)
+        return tids[sel], dists[sel]
