@@ -46,6 +46,61 @@ struct RustHeap {
         len++;
     }
 
+    /* ---- warp-cooperative forms (all 32 lanes call them with identical arguments) --------
+     * sift_up(0, pos) walks ONE root-ward path: lane j fetches the ancestor at height j+1
+     * (1-based index (pos+1) >> (j+1)), a ballot finds the first ancestor with key <= elem
+     * (where std's loop breaks), every ancestor below it moves one level down and the
+     * element lands in the freed slot.  Same final array as the sequential loop, at the cost
+     * of one load + one ballot + one store whatever the rise height. */
+    template <typename Store>
+    static __device__ __forceinline__ void sift_up_warp(Store &s, uint32_t pos, E elem, int lane) {
+        const uint32_t k = key(elem);
+        const uint32_t p1 = pos + 1;
+        const uint32_t a1 = lane < 31 ? (p1 >> (lane + 1)) : 0u; /* 1-based ancestor, 0 = none */
+        E av = 0;
+        if (a1) av = s.get(a1 - 1);
+        const unsigned above = __ballot_sync(0xFFFFFFFFu, a1 != 0 && key(av) > k);
+        const int rise = __ffs(~above) - 1; /* consecutive ancestors (from the parent up) the element passes */
+        if (lane < rise) s.set((p1 >> lane) - 1, av);
+        if (lane == 0) s.set((p1 >> rise) - 1, elem);
+        __syncwarp();
+    }
+
+    /* pop(): lane 0 walks the hole to the bottom (data-dependent path), then the displaced
+     * last element is sifted up cooperatively.  len must be > 0; returns nothing because the
+     * caller already knows the root (it peeked it). */
+    template <typename Store>
+    static __device__ __forceinline__ void pop_warp(Store &s, uint32_t &len, int lane) {
+        len--;
+        if (len == 0) return;
+        uint32_t pos = 0;
+        E item = 0;
+        if (lane == 0) {
+            item = s.get(len);
+            const uint32_t end = len;
+            const uint32_t lim = end >= 2 ? end - 2 : 0;
+            uint32_t child = 1;
+            while (child <= lim) {
+                E cl = s.get(child), cr = s.get(child + 1);
+                if (key(cr) <= key(cl)) { /* data[child] <= data[child+1]: right child on ties */
+                    child++;
+                    cl = cr;
+                }
+                s.set(pos, cl);
+                pos = child;
+                child = 2 * pos + 1;
+            }
+            if (child == end - 1) {
+                s.set(pos, s.get(child));
+                pos = child;
+            }
+        }
+        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        __syncwarp();
+        sift_up_warp(s, pos, item, lane);
+    }
+
     /* len must be > 0 */
     template <typename Store>
     static __device__ __forceinline__ E pop(Store &s, uint32_t &len) {

@@ -439,3 +439,32 @@ __global__ void dann_pad_rows_kernel(Tp *dst, const Tp *src, size_t n, uint32_t 
         dst[i] = c < src_w ? src[r * src_w + c] : fill;
     }
 }
+
+/* Index load: does any neighbour list repeat an id?  (The reference's builder never produces
+ * one — add_neighbors dedupes through a HashSet, graph/mod.rs:212-266 — but the scan must not
+ * depend on that: when a list does, the search kernel stages the list 32 ids at a time so the
+ * FIRST occurrence is the one that inserts.)  One warp per row, lists up to 64 ids. */
+__global__ void dann_check_unique_kernel(const uint32_t *nbrs, uint32_t n, uint32_t R, uint32_t Rp,
+                                         uint32_t *flag) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        const uint32_t *r = nbrs + (size_t)row * Rp;
+        uint32_t n0 = lane < R ? r[lane] : DANN_INVALID_NODE;
+        uint32_t n1 = lane + 32 < R ? r[lane + 32] : DANN_INVALID_NODE;
+        unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
+        unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
+        uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
+        uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
+        bool v0 = lane < cut0, v1 = lane < cut1;
+        if (!v0) n0 = DANN_INVALID_NODE;
+        if (!v1) n1 = DANN_INVALID_NODE;
+        const unsigned mm0 = __match_any_sync(DANN_FULL, n0), mm1 = __match_any_sync(DANN_FULL, n1);
+        bool dup = (v0 && __popc(mm0) > 1) || (v1 && __popc(mm1) > 1);
+        for (int k = 0; k < 32; k++) {
+            uint32_t x = __shfl_sync(DANN_FULL, n1, k);
+            dup |= v0 && x != DANN_INVALID_NODE && x == n0;
+        }
+        if (__any_sync(DANN_FULL, dup) && lane == 0) atomicOr(flag, 1u);
+    }
+}

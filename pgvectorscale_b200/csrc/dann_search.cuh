@@ -21,8 +21,19 @@
 // State placement
 //   shared : visited list (sorted, (dist<<32)|node), first `hs` heap entries, 64-entry
 //            staging list for one neighbour list.
-//   HBM    : per-warp workspace — hash set, seq->node table, heap tail beyond `hs`.
+//   HBM    : per-warp workspace — inserted-set, seq->node table, heap tail beyond `hs`.
+//            The inserted-set is a bitmap over node ids (one atomicOr per neighbour, cleared
+//            by replaying the list of inserted ids) when the index is small enough for
+//            one bitmap per resident warp, else an open-addressing CAS hash set.
 //   The heap entry packs (dist, seq): u32 = dist16|seq16 when both fit, else u64.
+//
+// Per visit the dependent memory round trips are: seq->node (L2) -> neighbour list (HBM,
+// overlapped with the pop's sift-down and the visited-list insert) -> inserted-set atomics
+// (L2, both 32-id chunks in flight together) -> SBQ code gather (HBM, every staged row in
+// flight at once).  Heap pushes: lanes test in parallel which new elements stay at their
+// leaf ("inert": parent <= elem, which later pushes cannot undo because a slot's value only
+// decreases during pushes) and write those directly; the rest are sifted one at a time, in
+// order, by the warp-cooperative sift-up of dann_heap.cuh (one lane per tree level).
 #pragma once
 #include "dann_device.cuh"
 #include "dann_heap.cuh"
@@ -40,13 +51,18 @@ struct SearchArgs {
     dann_query_stats *stats;    /* [B] */
     uint32_t *overflow;         /* OR of status bits over all queries of this launch */
     uint32_t *counter;          /* work-queue head */
-    uint32_t *hash;             /* [slots][hash_cap] */
+    uint32_t *hash;             /* [slots][hash_cap] (bitmap_words == 0) */
     uint32_t hash_cap;          /* power of two */
+    uint32_t *bitmap;           /* [slots][bitmap_words], all zero between queries */
+    uint32_t bitmap_words;      /* 0 => use the hash set */
+    uint32_t *ins_list;         /* [slots][ins_cap] inserted ids (bitmap mode: replayed to clear) */
+    uint32_t ins_cap;
     uint32_t *cand_node;        /* [slots][cand_cap] */
     uint32_t cand_cap;
     void *heap_tail;            /* [slots][cand_cap] entries E (indices >= hs used) */
     uint32_t hs, vcap;
     uint32_t G, Gshift;         /* lanes per code row (power of two) */
+    uint32_t lists_unique;      /* no neighbour list repeats an id (checked at index load) */
     uint32_t per_warp_smem;
 };
 
@@ -73,15 +89,16 @@ template <typename E, int NCH>
 struct SearchWarp {
     using T = EntryTraits<E>;
     using H = RustHeap<E, T::KSHIFT>;
-    /* code rows gathered per lane group before reducing (16-B loads in flight = RPI*NCH) */
-    static constexpr int RPI = NCH <= 3 ? 4 : (NCH == 4 ? 2 : 1);
+    /* code rows gathered per lane group before reducing (16-B loads in flight = RPI*NCH):
+     * with G=4 lanes per 192-B row, 8 x 8 rows = all 64 staged rows in one round */
+    static constexpr int RPI = NCH <= 3 ? 8 : (NCH == 4 ? 4 : 2);
 
     const SearchArgs &a;
     const int lane;
     /* per-warp storage */
     uint64_t *vis;
     uint32_t *list, *dl;
-    uint32_t *hash, *cnode;
+    uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
     /* query */
     ulonglong2 qc[NCH];
@@ -94,54 +111,95 @@ struct SearchWarp {
 
     __device__ __forceinline__ SearchWarp(const SearchArgs &a_, int lane_) : a(a_), lane(lane_) {}
 
-    /* ---- stage: dedupe + label filter of up to 32 neighbour ids (one per lane), appended
-     * to the staging list in lane order.  sbq/storage.rs:149-172 */
-    __device__ __forceinline__ void stage(uint32_t n, bool valid, bool apply_filter) {
-        if (__ballot_sync(DANN_FULL, valid) == 0) return;
-        /* a node listed twice in one chunk: only its first occurrence may insert */
-        unsigned mm = __match_any_sync(DANN_FULL, n);
-        bool first = valid && ((__ffs(mm) - 1) == lane);
-        bool isnew = false;
-        if (first) { /* prepare_insert: HashSet::insert (graph/mod.rs:126-128) */
-            const uint32_t mask = a.hash_cap - 1;
-            uint32_t h = (n * 2654435761u) >> (32 - __popc(mask));
-            for (uint32_t probe = 0; probe <= mask; probe++) {
-                uint32_t old = atomicCAS(hash + h, DANN_INVALID_NODE, n);
-                if (old == DANN_INVALID_NODE) {
-                    isnew = true;
-                    break;
-                }
-                if (old == n) break;
-                h = (h + 1) & mask;
+    /* prepare_insert: HashSet::insert (graph/mod.rs:126-128), hash-set flavour */
+    __device__ __forceinline__ bool hash_insert(uint32_t n) {
+        const uint32_t mask = a.hash_cap - 1;
+        uint32_t h = (n * 2654435761u) >> (32 - __popc(mask));
+        for (uint32_t probe = 0; probe <= mask; probe++) {
+            uint32_t old = atomicCAS(hash + h, DANN_INVALID_NODE, n);
+            if (old == DANN_INVALID_NODE) return true;
+            if (old == n) return false;
+            h = (h + 1) & mask;
+        }
+        return false;
+    }
+
+    __device__ __forceinline__ bool node_passes_filter(uint32_t n) {
+        /* labels.overlaps(node_neighbor.get_labels()), sbq/storage.rs:165-172 */
+        if (!a.ix.has_labels) return false;
+        uint32_t o0 = __ldg(a.ix.label_off + n), o1 = __ldg(a.ix.label_off + n + 1);
+        return labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
+    }
+
+    /* ---- stage: dedupe + label filter of up to 64 neighbour ids (two per lane: list slots
+     * `lane` and `lane+32`), appended to the staging list in list order.
+     * sbq/storage.rs:149-172. */
+    __device__ __forceinline__ void stage(uint32_t n0, bool v0, uint32_t n1, bool v1, bool apply_filter) {
+        if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
+        /* a node listed twice within a chunk: only its first occurrence may insert.  (A node
+         * repeated ACROSS the two chunks is handled by the caller: it stages the chunks one
+         * at a time unless the index was checked to have duplicate-free lists.) */
+        unsigned m0 = __match_any_sync(DANN_FULL, n0);
+        unsigned m1 = __match_any_sync(DANN_FULL, n1);
+        const bool f0 = v0 && ((__ffs(m0) - 1) == lane);
+        const bool f1 = v1 && ((__ffs(m1) - 1) == lane);
+        bool new0 = false, new1 = false;
+        if (a.bitmap_words) {
+            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+            const uint32_t b0 = 1u << (n0 & 31), b1 = 1u << (n1 & 31);
+            if (f0) o0 = atomicOr(bitmap + (n0 >> 5), b0);
+            if (f1) o1 = atomicOr(bitmap + (n1 >> 5), b1);
+            new0 = f0 && !(o0 & b0);
+            new1 = f1 && !(o1 & b1);
+        } else {
+            if (f0) new0 = hash_insert(n0);
+            __syncwarp();
+            if (f1) new1 = hash_insert(n1);
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned nm0 = __ballot_sync(DANN_FULL, new0), nm1 = __ballot_sync(DANN_FULL, new1);
+        const uint32_t c0 = __popc(nm0), c1 = __popc(nm1);
+        if (a.bitmap_words) {
+            if (nins + c0 + c1 > a.ins_cap) {
+                /* undo this round's bits so that the replay below leaves the bitmap all zero */
+                if (new0) atomicAnd(bitmap + (n0 >> 5), ~(1u << (n0 & 31)));
+                if (new1) atomicAnd(bitmap + (n1 >> 5), ~(1u << (n1 & 31)));
+                status |= DANN_ST_HASH;
+                return;
+            }
+            if (new0) ins[nins + __popc(nm0 & lt)] = n0;
+            if (new1) ins[nins + c0 + __popc(nm1 & lt)] = n1;
+            nins += c0 + c1;
+        } else {
+            nins += c0 + c1;
+            if (nins * 2 > a.hash_cap) {
+                status |= DANN_ST_HASH;
+                return;
             }
         }
-        unsigned nm = __ballot_sync(DANN_FULL, isnew);
-        nins += __popc(nm);
-        if (nins * 2 > a.hash_cap) {
-            status |= DANN_ST_HASH;
-            return;
+        bool p0 = new0, p1 = new1;
+        if (apply_filter) {
+            if (new0) p0 = node_passes_filter(n0);
+            if (new1) p1 = node_passes_filter(n1);
         }
-        bool pass = isnew;
-        if (apply_filter && isnew) { /* labels.overlaps(node_neighbor.get_labels()) */
-            pass = false;
-            if (a.ix.has_labels) {
-                uint32_t o0 = __ldg(a.ix.label_off + n), o1 = __ldg(a.ix.label_off + n + 1);
-                pass = labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
-            }
-        }
-        unsigned pm = __ballot_sync(DANN_FULL, pass);
-        uint32_t t = __popc(pm);
-        if (t == 0) return;
-        if (ncand + listn + t > a.cand_cap) {
+        const unsigned pm0 = __ballot_sync(DANN_FULL, p0), pm1 = __ballot_sync(DANN_FULL, p1);
+        const uint32_t t0 = __popc(pm0), t1 = __popc(pm1);
+        if (t0 + t1 == 0) return;
+        if (ncand + listn + t0 + t1 > a.cand_cap) {
             status |= DANN_ST_HEAP;
             return;
         }
-        if (pass) {
-            uint32_t pos = listn + __popc(pm & ((1u << lane) - 1u));
-            list[pos] = n;
-            cnode[ncand + pos] = n;
+        if (p0) {
+            uint32_t pos = listn + __popc(pm0 & lt);
+            list[pos] = n0;
+            cnode[ncand + pos] = n0;
         }
-        listn += t;
+        if (p1) {
+            uint32_t pos = listn + t0 + __popc(pm1 & lt);
+            list[pos] = n1;
+            cnode[ncand + pos] = n1;
+        }
+        listn += t0 + t1;
         __syncwarp();
     }
 
@@ -181,34 +239,65 @@ struct SearchWarp {
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            uint32_t hl = heap_len;
-            for (uint32_t r = 0; r < tn; r++) H::push(heap, hl, T::make(dl[r], ncand + r));
+        /* BinaryHeap::push x tn, in list order.  A new element whose parent already holds a key
+         * <= its own stays at its leaf whatever the earlier pushes of this batch do (a slot's key
+         * never increases during pushes, and sift_up only reads ancestors), so those "inert"
+         * elements are written in parallel; lane 0 replays only the others, in order. */
+        for (uint32_t base = 0; base < tn; base += 32) {
+            const uint32_t r = base + lane;
+            const bool have = r < tn;
+            const uint32_t dmine = have ? dl[r] : 0u;
+            bool inert = false;
+            if (have) {
+                const uint32_t pos = heap_len + r;
+                if (pos > 0) {
+                    const uint32_t parent = (pos - 1) >> 1;
+                    if (parent < heap_len + base) { /* parent is settled (old, or from an earlier round) */
+                        inert = H::key(heap.get(parent)) <= dmine;
+                        if (inert) heap.set(pos, T::make(dmine, ncand + r));
+                    }
+                }
+            }
+            unsigned act = __ballot_sync(DANN_FULL, have && !inert);
+            __syncwarp();
+            while (act) { /* warp-uniform loop: one cooperative sift-up per remaining element */
+                const int b = __ffs(act) - 1;
+                act &= act - 1;
+                const uint32_t d = __shfl_sync(DANN_FULL, dmine, b);
+                H::sift_up_warp(heap, heap_len + base + (uint32_t)b, T::make(d, ncand + base + (uint32_t)b), lane);
+            }
         }
         heap_len += tn;
         ncand += tn;
         dq += tn;
         listn = 0;
-        __syncwarp();
     }
 
-    /* ---- expand one visited node: sbq/storage.rs:135-190 */
-    __device__ __forceinline__ void expand(uint32_t v) {
+    /* ---- expand one visited node: sbq/storage.rs:135-190.  n0/n1 = list slots lane, lane+32
+     * (already loaded by the caller so that the HBM latency overlaps the heap pop). */
+    __device__ __forceinline__ void expand(uint32_t v, uint32_t n0, uint32_t n1) {
         const uint32_t *row = a.ix.nbrs + (size_t)v * a.ix.Rp;
         const uint32_t R = a.ix.R;
-        uint32_t nxt = lane < R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
-        for (uint32_t base = 0; base < R && !status; base += 32) {
-            uint32_t n = nxt;
-            uint32_t j2 = base + 32 + lane;
-            nxt = j2 < R ? ldg_stream_u32(row + j2) : DANN_INVALID_NODE;
+        for (uint32_t base = 0; base < R && !status; base += 64) {
+            if (base) {
+                n0 = base + lane < R ? ldg_stream_u32(row + base + lane) : DANN_INVALID_NODE;
+                n1 = base + 32 + lane < R ? ldg_stream_u32(row + base + 32 + lane) : DANN_INVALID_NODE;
+            }
             /* iter_neighbors stops at the first InvalidBlockNumber slot (sbq/node.rs:261-285) */
-            unsigned inv = __ballot_sync(DANN_FULL, n == DANN_INVALID_NODE);
-            uint32_t cut = inv ? (uint32_t)(__ffs(inv) - 1) : 32u;
-            stage(n, (uint32_t)lane < cut, filter);
-            if (listn + 32 > DANN_LIST_CAP) flush();
-            if (inv) break;
+            const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
+            const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
+            const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
+            const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
+            const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
+            if (a.lists_unique) {
+                stage(n0, v0, n1, v1, filter);
+            } else { /* a list may repeat an id: keep strict list order across the two chunks */
+                stage(n0, v0, DANN_INVALID_NODE, false, filter);
+                if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter);
+            }
+            flush();
+            if (i0 || i1) break;
         }
-        flush();
     }
 
     /* ---- visited.insert(partition_point(x < c), c) : graph/mod.rs:166-168 */
@@ -264,8 +353,8 @@ struct SearchWarp {
                 qc[i] = c < nchunks ? qrow[c] : make_ulonglong2(0, 0);
             }
         }
-        /* inserted = HashSet::new() */
-        {
+        /* inserted = HashSet::new() (the bitmap flavour is already all zero) */
+        if (!a.bitmap_words) {
             uint4 ff = make_uint4(DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE);
             uint4 *h4 = reinterpret_cast<uint4 *>(hash);
             for (uint32_t i = lane; i < a.hash_cap / 4; i += 32) h4[i] = ff;
@@ -298,11 +387,12 @@ struct SearchWarp {
                             valid = true;
                         }
                     }
-                    stage(n, valid, false); /* start nodes are not label-checked (storage.rs:365-391) */
+                    /* start nodes are not label-checked (storage.rs:365-391) */
+                    stage(n, valid, DANN_INVALID_NODE, false, false);
                     flush();
                 }
             } else {
-                stage(lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, false);
+                stage(lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, DANN_INVALID_NODE, false, false);
                 flush();
             }
         }
@@ -314,27 +404,28 @@ struct SearchWarp {
                 E head = 0;
                 int go = 0;
                 if (lane == 0 && heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
+                    head = heap.get(0);
                     go = 1;
                     if (vis_len > a.L) {
-                        E h = heap.get(0);
                         uint64_t at = vis[vis_head + a.L - 1];
-                        if (H::key(h) >= (uint32_t)(at >> 32)) go = 0;
-                    }
-                    if (go) {
-                        uint32_t hl = heap_len;
-                        head = H::pop(heap, hl);
+                        if (H::key(head) >= (uint32_t)(at >> 32)) go = 0;
                     }
                 }
                 go = __shfl_sync(DANN_FULL, go, 0);
                 if (!go) break;
                 head = __shfl_sync(DANN_FULL, head, 0);
-                heap_len--;
+                /* the popped element IS the current root: fetch its node id and neighbour list
+                 * first, then let the sift-down and the visited insert run under that latency */
                 const uint32_t d = H::key(head);
                 const uint32_t node = __ldcg(cnode + T::seq(head));
+                const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
+                const uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+                const uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
+                H::pop_warp(heap, heap_len, lane);
                 visited_insert(d, node);
                 if (status) break;
                 visits++;
-                expand(node);
+                expand(node, n0, n1);
                 if (status) break;
             }
             if (status) break;
@@ -349,6 +440,12 @@ struct SearchWarp {
             if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = node;
             scount++;
             if (scount == a.c_target) done = true;
+        }
+        /* bitmap flavour: clear exactly the bits this query set */
+        if (a.bitmap_words) {
+            __syncwarp();
+            for (uint32_t i = lane; i < nins; i += 32) bitmap[ins[i] >> 5] = 0u;
+            __threadfence_block();
         }
         if (lane == 0) {
             a.stream_len[q] = scount;
@@ -367,7 +464,7 @@ struct SearchWarp {
 };
 
 template <typename E, int NCH>
-__global__ void __launch_bounds__(512, 1) dann_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(384, 1) dann_search_kernel(const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char dann_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const uint32_t slot = blockIdx.x * W + warp;
@@ -378,6 +475,8 @@ __global__ void __launch_bounds__(512, 1) dann_search_kernel(const SearchArgs a)
     w.list = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));
     w.dl = w.list + DANN_LIST_CAP;
     w.hash = a.hash + (size_t)slot * a.hash_cap;
+    w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
+    w.ins = a.ins_list + (size_t)slot * a.ins_cap;
     w.cnode = a.cand_node + (size_t)slot * a.cand_cap;
     w.heap.sm = hsm;
     w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;

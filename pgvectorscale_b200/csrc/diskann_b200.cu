@@ -58,8 +58,11 @@ extern "C" int dann_device_count(void) {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool fresh = false; /* set when reserve() had to allocate new (uninitialised) memory */
     cudaError_t reserve(size_t bytes) {
+        fresh = false;
         if (bytes <= cap) return cudaSuccess;
+        fresh = true;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -89,7 +92,7 @@ struct dann_index {
     uint64_t launches = 0;
     bool poisoned = false;
     /* per-warp-slot search workspace */
-    DevBuf ws_hash, ws_cand, ws_heap;
+    DevBuf ws_hash, ws_cand, ws_heap, ws_bitmap, ws_ins;
     /* per-batch scratch */
     DevBuf sc_qfull, sc_qcodes, sc_stream, sc_stream_len, sc_stats, sc_qlist, sc_ctl, sc_node;
     /* staging for the host-buffer entry point */
@@ -97,6 +100,7 @@ struct dann_index {
     dann_batch_timing timing{};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t G = 1, Gshift = 0, NCH = 1;
+    uint32_t lists_unique = 0;
 };
 
 struct dann_scan {
@@ -189,7 +193,7 @@ extern "C" void dann_index_free(dann_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     for (void *p : ix->owned) cudaFree(p);
-    DevBuf *bufs[] = {&ix->ws_hash, &ix->ws_cand, &ix->ws_heap, &ix->sc_qfull, &ix->sc_qcodes,
+    DevBuf *bufs[] = {&ix->ws_hash, &ix->ws_cand, &ix->ws_heap, &ix->ws_bitmap, &ix->ws_ins, &ix->sc_qfull, &ix->sc_qcodes,
                       &ix->sc_stream, &ix->sc_stream_len, &ix->sc_stats, &ix->sc_qlist, &ix->sc_ctl,
                       &ix->sc_node, &ix->st_queries, &ix->st_labels, &ix->st_label_off, &ix->st_tid,
                       &ix->st_dist, &ix->st_count, &ix->st_stats};
@@ -289,6 +293,18 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
     v.start_label_nodes = sln;
     v.label_off = loff;
     v.labels = labs;
+    if (s->n && s->R <= 64) {
+        uint32_t *flag = nullptr;
+        CK(cudaMalloc(&flag, 4));
+        ix->owned.push_back(flag);
+        CK(cudaMemsetAsync(flag, 0, 4, ix->stream));
+        dann_check_unique_kernel<<<ix->sm_count * 8, 256, 0, ix->stream>>>(nbrs, s->n, v.R, v.Rp, flag);
+        ix->launches++;
+        uint32_t h = 1;
+        CK(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        ix->lists_unique = h == 0;
+    }
     if (s->distance_type == DANN_COSINE && s->n) {
         /* rerank reads the heap vector through PgVector::from_datum -> preprocess_cosine
          * (sbq/storage.rs:304-328, pg_vector.rs:153-155); the result only depends on the row,
@@ -410,7 +426,7 @@ static search_fn pick_search(uint32_t nch) {
 }
 
 struct SearchPlan {
-    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize;
+    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
 };
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
@@ -430,6 +446,11 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     p->need = (uint32_t)need;
     p->cand_cap = (uint32_t)((need + 1023) & ~1023ull);
     p->hash_cap = pow2ceil(2 * p->cand_cap);
+    /* inserted-set: one bitmap over node ids per resident warp while that stays small
+     * (<= 2 MB per warp, i.e. up to 16M nodes), else the CAS hash set */
+    const bool use_bitmap = env_u32("DANN_SEARCH_BITMAP", v.n <= (16u << 20) ? 1 : 0) != 0;
+    p->bitmap_words = use_bitmap ? ((v.n + 127u) / 128u) * 4u : 0u;
+    p->ins_cap = p->cand_cap;
     bool small = p->cand_cap <= 65536 && (uint64_t)v.words * 64 <= 65535;
     p->esize = small ? 4 : 8;
     uint64_t vcap = std::max<uint64_t>(((uint64_t)L + 96u) * grow / shrink, 8);
@@ -438,12 +459,12 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     const size_t fixed = (size_t)p->vcap * 8 + 2 * DANN_LIST_CAP * 4;
     if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
     uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
-    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), 16);
+    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), 12);
     uint32_t hs_target = (uint32_t)std::min<uint64_t>(p->cand_cap, need * 3 / 4);
     uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_target * p->esize));
     uint32_t W = std::min(wneed, std::max<uint32_t>(wfit, 1));
     W = env_u32("DANN_SEARCH_WARPS", W);
-    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 16);
+    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 12); /* __launch_bounds__(384) */
     while (W > 1 && budget / W < fixed + 1024) W--;
     size_t per_warp = (budget / W) & ~(size_t)15;
     uint32_t hs = (uint32_t)std::min<size_t>(p->cand_cap, (per_warp - fixed) / p->esize);
@@ -494,9 +515,14 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         rc = make_plan(ix, nq, (uint32_t)L, c_target, grow, &p);
         if (rc) return rc;
         const size_t slots = (size_t)p.grid * p.W;
-        CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
+        if (!p.bitmap_words) CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
         CK(ix->ws_cand.reserve(slots * p.cand_cap * sizeof(uint32_t)));
         CK(ix->ws_heap.reserve(slots * p.cand_cap * (size_t)p.esize));
+        if (p.bitmap_words) {
+            CK(ix->ws_bitmap.reserve(slots * (size_t)p.bitmap_words * 4));
+            if (ix->ws_bitmap.fresh) CK(cudaMemsetAsync(ix->ws_bitmap.p, 0, ix->ws_bitmap.cap, st));
+            CK(ix->ws_ins.reserve(slots * (size_t)p.ins_cap * 4));
+        }
         CK(cudaMemsetAsync(d_ctl, 0, 8, st));
         SearchArgs a;
         a.ix = v;
@@ -514,6 +540,11 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         a.counter = d_ctl;
         a.hash = ix->ws_hash.as<uint32_t>();
         a.hash_cap = p.hash_cap;
+        a.bitmap = ix->ws_bitmap.as<uint32_t>();
+        a.bitmap_words = p.bitmap_words;
+        a.ins_list = ix->ws_ins.as<uint32_t>();
+        a.ins_cap = p.ins_cap;
+        a.lists_unique = ix->lists_unique;
         a.cand_node = ix->ws_cand.as<uint32_t>();
         a.cand_cap = p.cand_cap;
         a.heap_tail = ix->ws_heap.p;
