@@ -61,8 +61,8 @@ struct RustHeap {
         if (a1) av = s.get(a1 - 1);
         const unsigned above = __ballot_sync(0xFFFFFFFFu, a1 != 0 && key(av) > k);
         const int rise = __ffs(~above) - 1; /* consecutive ancestors (from the parent up) the element passes */
-        if (lane < rise) s.set((p1 >> lane) - 1, av);
-        if (lane == 0) s.set((p1 >> rise) - 1, elem);
+        /* lanes below `rise` move their ancestor one level down, lane `rise` drops the element */
+        if (lane <= rise) s.set((p1 >> lane) - 1, lane < rise ? av : elem);
         __syncwarp();
     }
 

@@ -203,6 +203,40 @@ struct SearchWarp {
         __syncwarp();
     }
 
+    /* BinaryHeap::push x tn, in list order.  A new element whose parent already holds a key
+     * <= its own stays at its leaf whatever the earlier pushes of this batch do (a slot's key
+     * never increases during pushes, and sift_up only reads ancestors), so those "inert"
+     * elements are written in parallel; the others go through the warp-cooperative sift-up one
+     * at a time, in order. */
+    template <typename Store>
+    __device__ __forceinline__ void push_batch(Store &st, const uint32_t tn) {
+        for (uint32_t base = 0; base < tn; base += 32) {
+            const uint32_t r = base + lane;
+            const bool have = r < tn;
+            const uint32_t dmine = have ? dl[r] : 0u;
+            bool inert = false;
+            if (have) {
+                const uint32_t pos = heap_len + r;
+                if (pos > 0) {
+                    const uint32_t parent = (pos - 1) >> 1;
+                    if (parent < heap_len + base) { /* parent is settled (old, or from an earlier round) */
+                        inert = H::key(st.get(parent)) <= dmine;
+                        if (inert) st.set(pos, T::make(dmine, ncand + r));
+                    }
+                }
+            }
+            unsigned act = __ballot_sync(DANN_FULL, have && !inert);
+            __syncwarp();
+            const uint32_t pos0 = heap_len + base, seq0 = ncand + base;
+            while (act) { /* warp-uniform loop: one cooperative sift-up per remaining element */
+                const int b = __ffs(act) - 1;
+                act &= act - 1;
+                const uint32_t d = __shfl_sync(DANN_FULL, dmine, b);
+                H::sift_up_warp(st, pos0 + (uint32_t)b, T::make(d, seq0 + (uint32_t)b), lane);
+            }
+        }
+    }
+
     /* ---- flush: SBQ distance of every staged node (distance/mod.rs:265-323) and the
      * ordered heap pushes (insert_neighbor, graph/mod.rs:144-147) */
     __device__ __forceinline__ void flush() {
@@ -239,33 +273,12 @@ struct SearchWarp {
             }
         }
         __syncwarp();
-        /* BinaryHeap::push x tn, in list order.  A new element whose parent already holds a key
-         * <= its own stays at its leaf whatever the earlier pushes of this batch do (a slot's key
-         * never increases during pushes, and sift_up only reads ancestors), so those "inert"
-         * elements are written in parallel; lane 0 replays only the others, in order. */
-        for (uint32_t base = 0; base < tn; base += 32) {
-            const uint32_t r = base + lane;
-            const bool have = r < tn;
-            const uint32_t dmine = have ? dl[r] : 0u;
-            bool inert = false;
-            if (have) {
-                const uint32_t pos = heap_len + r;
-                if (pos > 0) {
-                    const uint32_t parent = (pos - 1) >> 1;
-                    if (parent < heap_len + base) { /* parent is settled (old, or from an earlier round) */
-                        inert = H::key(heap.get(parent)) <= dmine;
-                        if (inert) heap.set(pos, T::make(dmine, ncand + r));
-                    }
-                }
-            }
-            unsigned act = __ballot_sync(DANN_FULL, have && !inert);
-            __syncwarp();
-            while (act) { /* warp-uniform loop: one cooperative sift-up per remaining element */
-                const int b = __ffs(act) - 1;
-                act &= act - 1;
-                const uint32_t d = __shfl_sync(DANN_FULL, dmine, b);
-                H::sift_up_warp(heap, heap_len + base + (uint32_t)b, T::make(d, ncand + base + (uint32_t)b), lane);
-            }
+        /* BinaryHeap::push x tn, in list order (fast path: everything in shared memory) */
+        if (heap_len + tn <= heap.hs) {
+            ArrayStore<E> sm{heap.sm};
+            push_batch(sm, tn);
+        } else {
+            push_batch(heap, tn);
         }
         heap_len += tn;
         ncand += tn;
@@ -421,7 +434,12 @@ struct SearchWarp {
                 const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
                 const uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
                 const uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
-                H::pop_warp(heap, heap_len, lane);
+                if (heap_len <= heap.hs) {
+                    ArrayStore<E> sm{heap.sm};
+                    H::pop_warp(sm, heap_len, lane);
+                } else {
+                    H::pop_warp(heap, heap_len, lane);
+                }
                 visited_insert(d, node);
                 if (status) break;
                 visits++;

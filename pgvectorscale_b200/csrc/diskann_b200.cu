@@ -19,6 +19,7 @@
 #include "dann_device.cuh"
 #include "dann_kernels.cuh"
 #include "dann_search.cuh"
+#include "dann_search2.cuh"
 
 /* ------------------------------------------------------------------------------------ */
 static thread_local std::string g_err;
@@ -425,8 +426,20 @@ static search_fn pick_search(uint32_t nch) {
     }
 }
 
+template <typename E>
+static search_fn pick_search2(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search2_kernel<E, 1>;
+        case 2: return dann_search2_kernel<E, 2>;
+        case 3: return dann_search2_kernel<E, 3>;
+        case 4: return dann_search2_kernel<E, 4>;
+        default: return dann_search2_kernel<E, 8>;
+    }
+}
+
 struct SearchPlan {
     uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
+    bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
 };
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
@@ -456,15 +469,18 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     uint64_t vcap = std::max<uint64_t>(((uint64_t)L + 96u) * grow / shrink, 8);
     p->vcap = (uint32_t)((vcap + 3) & ~3ull);
     const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
-    const size_t fixed = (size_t)p->vcap * 8 + 2 * DANN_LIST_CAP * 4;
+    /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
+    p->pairs = v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
+    const uint32_t wmax = p->pairs ? 8u : 12u; /* __launch_bounds__ of the two kernels */
+    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) : 2 * DANN_LIST_CAP * 4);
     if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
     uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
-    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), 12);
+    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), wmax);
     uint32_t hs_target = (uint32_t)std::min<uint64_t>(p->cand_cap, need * 3 / 4);
     uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_target * p->esize));
     uint32_t W = std::min(wneed, std::max<uint32_t>(wfit, 1));
     W = env_u32("DANN_SEARCH_WARPS", W);
-    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 12); /* __launch_bounds__(384) */
+    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), wmax);
     while (W > 1 && budget / W < fixed + 1024) W--;
     size_t per_warp = (budget / W) & ~(size_t)15;
     uint32_t hs = (uint32_t)std::min<size_t>(p->cand_cap, (per_warp - fixed) / p->esize);
@@ -553,10 +569,11 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         a.G = ix->G;
         a.Gshift = ix->Gshift;
         a.per_warp_smem = p.per_warp;
-        search_fn fn = p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH);
+        search_fn fn = p.pairs ? (p.esize == 4 ? pick_search2<uint32_t>(ix->NCH) : pick_search2<uint64_t>(ix->NCH))
+                               : (p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH));
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<p.grid, p.W * 32, smem, st>>>(a);
+        fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);
         ix->launches++;
         CK(cudaGetLastError());
         uint32_t ctl[2] = {0, 0};

@@ -162,6 +162,43 @@ def test_workspace_growth_retry_is_invisible(lib, monkeypatch):
         monkeypatch.delenv("DANN_DEBUG_SHRINK")
 
 
+def test_single_warp_kernel_and_wide_lists(lib, monkeypatch):
+    """Both search kernels give the oracle's answer: the two-warp kernel is the default for
+    R <= 64; DANN_SEARCH_KERNEL=1 forces the single-warp kernel, which R > 64 always uses."""
+    s = build_case(2500, 128, COSINE, seed=21, labels=True, R=32, L_build=64)
+    q = _queries(s, 24, 5)
+    with lib.DiskAnnIndex(s) as idx:
+        monkeypatch.setenv("DANN_SEARCH_KERNEL", "1")
+        _compare_batch(s, idx, q, 10, 100, 50)
+        _compare_batch(s, idx, q, 10, 40, 20, labels=[[1 + (i % 16), 5] for i in range(24)])
+        monkeypatch.setenv("DANN_SEARCH_BITMAP", "0")         # CAS hash-set flavour of the inserted-set
+        _compare_batch(s, idx, q, 10, 100, 50)
+        monkeypatch.delenv("DANN_SEARCH_KERNEL")
+        _compare_batch(s, idx, q, 10, 100, 50)
+        _compare_batch(s, idx, q, 10, 40, 20, labels=[[1 + (i % 16), 5] for i in range(24)])
+        monkeypatch.delenv("DANN_SEARCH_BITMAP")
+    s = build_case(1200, 64, L2, seed=23, kind="uniform", R=70, L_build=80)
+    with lib.DiskAnnIndex(s) as idx:
+        _compare_batch(s, idx, _queries(s, 16, 6, "uniform"), 10, 60, 30)
+
+
+def test_duplicate_ids_inside_a_neighbour_list(lib):
+    """The reference's builder never repeats an id in a list, but the scan must not rely on it:
+    the first occurrence (in list order) is the one that inserts."""
+    s = build_case(1500, 96, COSINE, seed=29, R=40, L_build=60)
+    rng = np.random.default_rng(4)
+    nb = s.nbrs.copy()
+    for i in range(0, s.n, 3):            # duplicate an early id late in the list (crosses the 32-lane chunks)
+        deg = int((nb[i] != 0xFFFFFFFF).sum())
+        if deg >= 36:
+            nb[i, deg - 1] = nb[i, int(rng.integers(0, 8))]
+            nb[i, 33] = nb[i, 34]
+    s.nbrs = nb
+    q = _queries(s, 24, 7)
+    with lib.DiskAnnIndex(s) as idx:
+        _compare_batch(s, idx, q, 10, 100, 50)
+
+
 def test_sbq_distance_kernel(lib):
     import torch
     s = build_case(3000, 768, COSINE, bits=2, seed=13)
