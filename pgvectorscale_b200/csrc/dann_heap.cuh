@@ -101,6 +101,56 @@ struct RustHeap {
         sift_up_warp(s, pos, item, lane);
     }
 
+    /* ---- 1-based storage forms (slot p holds Rust's data[p-1]; parent p>>1, children 2p, 2p+1).
+     * Child pairs are then 8-byte aligned, so the pop's descent reads both children with one
+     * 64-bit load, and the ancestor index of lane j is simply p >> j. ------------------------ */
+    template <typename Store>
+    static __device__ __forceinline__ void sift_up_warp1(Store &s, uint32_t p, E elem, int lane) {
+        const uint32_t k = key(elem);
+        const uint32_t ast = p >> lane; /* slot at height `lane` on the path (0 = above the root) */
+        const uint32_t ald = ast >> 1;  /* its parent */
+        E av = 0;
+        if (ald) av = s.get(ald);
+        const unsigned above = __ballot_sync(0xFFFFFFFFu, ald != 0 && key(av) > k);
+        const unsigned tm = above & ~(above + 1u); /* trailing ones: the ancestors the element passes */
+        const unsigned wm = tm | (tm + 1u);        /* lanes 0..rise write */
+        if ((wm >> lane) & 1u) s.set(ast, ((tm >> lane) & 1u) ? av : elem);
+        __syncwarp();
+    }
+
+    /* len = number of elements (slots 1..len), must be > 0 */
+    template <typename Store>
+    static __device__ __forceinline__ void pop_warp1(Store &s, uint32_t &len, int lane) {
+        len--;
+        if (len == 0) return;
+        uint32_t p = 1;
+        E item = 0;
+        if (lane == 0) {
+            item = s.get(len + 1);
+            const uint32_t end = len;
+            uint32_t c = 2;
+            while (c + 1 <= end) { /* Rust: child <= end.saturating_sub(2) */
+                E cl, cr;
+                s.get2(c, cl, cr);
+                if (key(cr) <= key(cl)) { /* data[child] <= data[child+1]: right child on ties */
+                    c++;
+                    cl = cr;
+                }
+                s.set(p, cl);
+                p = c;
+                c = 2 * p;
+            }
+            if (c == end) { /* child == end - 1 */
+                s.set(p, s.get(c));
+                p = c;
+            }
+        }
+        p = __shfl_sync(0xFFFFFFFFu, p, 0);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        __syncwarp();
+        sift_up_warp1(s, p, item, lane);
+    }
+
     /* len must be > 0 */
     template <typename Store>
     static __device__ __forceinline__ E pop(Store &s, uint32_t &len) {
@@ -137,6 +187,18 @@ struct ArrayStore {
     E *p;
     __device__ __forceinline__ E get(uint32_t i) const { return p[i]; }
     __device__ __forceinline__ void set(uint32_t i, E v) { p[i] = v; }
+    /* entries i and i+1, i even: one aligned load of both */
+    __device__ __forceinline__ void get2(uint32_t i, E &a, E &b) const {
+        if constexpr (sizeof(E) == 4) {
+            uint2 v = *reinterpret_cast<const uint2 *>(p + i);
+            a = v.x;
+            b = v.y;
+        } else {
+            ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p + i);
+            a = v.x;
+            b = v.y;
+        }
+    }
 };
 
 /* first `hs` entries in shared memory, the rest in the warp's HBM workspace */
@@ -146,6 +208,11 @@ struct SplitStore {
     E *gl;
     uint32_t hs;
     __device__ __forceinline__ E get(uint32_t i) const { return i < hs ? sm[i] : gl[i]; }
+    __device__ __forceinline__ void get2(uint32_t i, E &a, E &b) const { /* hs is even: a pair never straddles */
+        const E *q = i < hs ? sm + i : gl + i;
+        a = q[0];
+        b = q[1];
+    }
     __device__ __forceinline__ void set(uint32_t i, E v) {
         if (i < hs) sm[i] = v;
         else gl[i] = v;

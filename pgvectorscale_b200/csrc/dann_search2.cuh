@@ -54,6 +54,8 @@ struct PairSearch {
     uint64_t *vis;
     uint32_t *listp, *dlp; /* [2][64] */
     PairCtl *ctl;
+    E *cqe;         /* [32] compacted active pushes: entry */
+    uint32_t *cqp;  /* [32]                          : 1-based slot */
     uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
 
@@ -133,7 +135,7 @@ struct PairSearch {
         const unsigned pm0 = __ballot_sync(DANN_FULL, p0), pm1 = __ballot_sync(DANN_FULL, p1);
         const uint32_t t0 = __popc(pm0), t1 = __popc(pm1);
         if (t0 + t1 == 0) return;
-        if (ncand + listn + t0 + t1 > a.cand_cap) {
+        if (ncand + listn + t0 + t1 + 1 > a.cand_cap) { /* 1-based heap slots: the last one is cand_cap-1 */
             status |= DANN_ST_HEAP;
             return;
         }
@@ -311,31 +313,45 @@ struct PairSearch {
     /* ================================= heap warp ======================================= */
     uint32_t heap_len, vis_head, vis_len, visits, dq, hstatus, hk;
 
+    /* BinaryHeap::push x tn in list order (insert_neighbor, graph/mod.rs:144-147); 1-based slots.
+     * Inert elements (parent key <= own key: they stay at their leaf whatever earlier pushes of
+     * the batch do) are written in parallel; the others are compacted into a small queue and
+     * replayed in order through the cooperative sift-up, the next one prefetched meanwhile. */
     template <typename Store>
     __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
+        const unsigned lt = (1u << lane) - 1u;
         for (uint32_t base = 0; base < tn; base += 32) {
             const uint32_t r = base + lane;
             const bool have = r < tn;
             const uint32_t dmine = have ? dl[r] : 0u;
+            const uint32_t slot = heap_len + r + 1;
+            const E mine = T::make(dmine, seq0 + r);
             bool inert = false;
-            if (have) {
-                const uint32_t pos = heap_len + r;
-                if (pos > 0) {
-                    const uint32_t parent = (pos - 1) >> 1;
-                    if (parent < heap_len + base) {
-                        inert = H::key(st.get(parent)) <= dmine;
-                        if (inert) st.set(pos, T::make(dmine, seq0 + r));
-                    }
+            if (have && slot > 1) {
+                const uint32_t parent = slot >> 1;
+                if (parent <= heap_len + base) { /* parent is settled (old, or from an earlier round) */
+                    inert = H::key(st.get(parent)) <= dmine;
+                    if (inert) st.set(slot, mine);
                 }
             }
-            unsigned act = __ballot_sync(DANN_FULL, have && !inert);
+            const unsigned act = __ballot_sync(DANN_FULL, have && !inert);
+            const uint32_t nact = __popc(act);
+            if (have && !inert) {
+                const uint32_t k = __popc(act & lt);
+                cqe[k] = mine;
+                cqp[k] = slot;
+            }
             __syncwarp();
-            const uint32_t pos0 = heap_len + base, s0 = seq0 + base;
-            while (act) {
-                const int b = __ffs(act) - 1;
-                act &= act - 1;
-                const uint32_t d = __shfl_sync(DANN_FULL, dmine, b);
-                H::sift_up_warp(st, pos0 + (uint32_t)b, T::make(d, s0 + (uint32_t)b), lane);
+            if (nact == 0) continue;
+            E e = cqe[0];
+            uint32_t sp = cqp[0];
+            for (uint32_t i = 0; i < nact; i++) {
+                const uint32_t nx = i + 1 < nact ? i + 1 : i;
+                const E en = cqe[nx];
+                const uint32_t sn = cqp[nx];
+                H::sift_up_warp1(st, sp, e, lane);
+                e = en;
+                sp = sn;
             }
         }
     }
@@ -344,7 +360,7 @@ struct PairSearch {
         const uint32_t tn = ctl->tn[p], seq0 = ctl->seq0[p];
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
         if (tn == 0) return;
-        if (heap_len + tn <= heap.hs) {
+        if (heap_len + tn < heap.hs) {
             ArrayStore<E> sm{heap.sm};
             push_batch(sm, dl, tn, seq0);
         } else {
@@ -415,7 +431,7 @@ struct PairSearch {
         }
         for (uint32_t k = 0; k < nstart_pages; k++) {
             E root = 0;
-            if (heap_len) root = heap.get(0);
+            if (heap_len) root = heap.get(1);
             handoff(1u, heap_len != 0, root);
             hstatus |= ctl->status_a;
             push_page((hk - 1) & 1);
@@ -426,20 +442,20 @@ struct PairSearch {
                 E head = 0, after = 0;
                 int go = 0, av = 0;
                 if (lane == 0 && heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
-                    head = heap.get(0);
+                    head = heap.get(1);
                     go = 1;
                     if (vis_len > a.L) {
                         uint64_t at = vis[vis_head + a.L - 1];
                         if (H::key(head) >= (uint32_t)(at >> 32)) go = 0;
                     }
                     if (go && heap_len > 1) { /* root of the heap once this pop is done */
-                        const uint32_t m = heap_len - 1;
-                        const E last = heap.get(m);
+                        const uint32_t m = heap_len - 1; /* elements left */
+                        const E last = heap.get(heap_len);
                         E c = last;
                         if (m >= 2) {
-                            c = heap.get(1);
+                            c = heap.get(2);
                             if (m >= 3) {
-                                E cr = heap.get(2);
+                                E cr = heap.get(3);
                                 if (H::key(cr) <= H::key(c)) c = cr;
                             }
                         }
@@ -459,11 +475,11 @@ struct PairSearch {
                 const uint32_t node = __ldcg(cnode + T::seq(head));
                 if (ctl->expect[p] != node) hstatus |= DANN_ST_INTERNAL;
                 if (hstatus) break;
-                if (heap_len <= heap.hs) {
+                if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
-                    H::pop_warp(sm, heap_len, lane);
+                    H::pop_warp1(sm, heap_len, lane);
                 } else {
-                    H::pop_warp(heap, heap_len, lane);
+                    H::pop_warp1(heap, heap_len, lane);
                 }
                 visited_insert(d, node);
                 if (hstatus) break;
@@ -514,6 +530,8 @@ __global__ void __launch_bounds__(512, 1) dann_search2_kernel(const SearchArgs a
     w.listp = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));
     w.dlp = w.listp + 2 * DANN_LIST_CAP;
     w.ctl = reinterpret_cast<PairCtl *>(w.dlp + 2 * DANN_LIST_CAP);
+    w.cqp = reinterpret_cast<uint32_t *>(w.ctl + 1);
+    w.cqe = reinterpret_cast<E *>(w.cqp + 32);
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.ins = a.ins_list + (size_t)slot * a.ins_cap;

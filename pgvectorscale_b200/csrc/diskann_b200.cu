@@ -472,12 +472,17 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
     p->pairs = v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
     const uint32_t wmax = p->pairs ? 8u : 12u; /* __launch_bounds__ of the two kernels */
-    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) : 2 * DANN_LIST_CAP * 4);
+    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
     if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
     uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
     wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), wmax);
-    uint32_t hs_target = (uint32_t)std::min<uint64_t>(p->cand_cap, need * 3 / 4);
-    uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_target * p->esize));
+    /* Concurrency first: a batch should run in one wave (queries are latency-bound, one or two
+     * warps each), so take as many query slots per SM as the batch needs and give each slot
+     * whatever shared memory is left for the top of its heap; deeper heap levels spill to the
+     * slot's HBM tail.  Only when that would leave fewer than 2048 in-smem entries (the top 11
+     * levels) do we trade slots for shared memory. */
+    const uint32_t hs_min = (uint32_t)std::min<uint64_t>(p->cand_cap, 2048);
+    uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_min * p->esize));
     uint32_t W = std::min(wneed, std::max<uint32_t>(wfit, 1));
     W = env_u32("DANN_SEARCH_WARPS", W);
     W = std::min<uint32_t>(std::max<uint32_t>(W, 1), wmax);
