@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
@@ -57,12 +57,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-SWEEP = [(25, 50), (50, 50), (100, 50), (100, 100), (200, 100), (200, 200), (400, 200), (400, 400),
-         (800, 400), (800, 800), (1600, 1000)]
+# (search_list_size, rescore) in increasing cost (visits ~ L + rescore); recall is driven mostly by rescore
+SWEEP = [(25, 50), (50, 50), (100, 50), (50, 100), (100, 100), (64, 150), (100, 150), (64, 200), (100, 200),
+         (150, 200), (200, 200), (150, 300), (200, 300), (400, 400), (800, 400), (800, 800), (1600, 1000)]
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (every ~5 ms through NVML;
+    falls back to polling nvidia-smi when pynvml is unavailable)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -70,23 +72,67 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.samples = []
+        self.sm = []
+        self.sm_max = None
+        self.reasons = set()
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            self.sm.append(float(f[0]))
+            self.sm_max = float(f[1])
+            for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if f[3 + i].lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005)
 
     def __enter__(self):
+        self._stop.clear()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
@@ -96,14 +142,12 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def measured_peak():
@@ -141,9 +185,17 @@ def recall_at_k(tid, truth_nodes, snap, k):
     return hits / (tid.shape[0] * k)
 
 
+def workload_name(args, bits):
+    return (f"configs[1]: {args.n}x{args.dim}-d {args.data} ('Cohere-shape' synthetic) SBQ {bits}-bit "
+            f"diskann index in HBM, batch={args.batch} queries/GPU/step, k={args.k}")
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Rust extension cannot be
-    built in this image) on this box's host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU algorithm for this path on the box's host cores.
+    The Rust/pgrx extension cannot be built in this image (no rustc/cargo/Postgres), so this is the
+    oracle port (oracle/oracle.cpp, the reference's AVX2+FMA flag family), one host thread per
+    core, on the same snapshot, queries, k and operating point as our arm.  The GPU is used only to
+    build the synthetic index fixture and the brute-force recall ground truth (untimed setup)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -154,17 +206,34 @@ def run_reference(args):
     torch.cuda.set_device(device)
     from tools import synth_index as si
     x, snap = build_fixture(args, device)
-    L, rescore = (args.L or 100), (args.rescore or 50)
+    B, k = args.batch, args.k
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(64, min(args.batch, 16 * cores))
-    q = si.gen_dataset((args.warmup + args.steps) * sample, args.dim, 0x5EED0011, args.data, device=device).cpu().numpy()
+    sample = args.cpu_sample or (B if cores >= 32 else max(64, 16 * cores))
+    sample = min(sample, B)
+    nb = args.warmup + args.steps
+    q_first = si.gen_dataset(B, args.dim, 0x5EED0011, args.data, device=device)      # our arm's first rank-0 batch
+    truth = si.ground_truth(x, q_first, k).cpu().numpy()
+    q_first = q_first.cpu().numpy()
     del x
     torch.cuda.empty_cache()
+    # same operating-point rule as our arm: first sweep point with recall@10 >= target
+    points = [(args.L, args.rescore or 50)] if args.L else SWEEP
+    chosen = None
+    for (L, rescore) in points:
+        tid, _, _, _ = oracle.scan_batch(snap, q_first, None, None, L, rescore, k, threads=0)
+        rec = recall_at_k(tid, truth, snap, k)
+        log(f"[bench/reference] sweep L={L} rescore={rescore}: recall@{k}={rec:.4f}")
+        chosen = (L, rescore, rec)
+        if rec >= args.target_recall:
+            break
+    L, rescore, recall = chosen
+    rng = np.random.default_rng(0x5EED0012)
+    qs = si.gen_dataset(nb * sample, args.dim, 0x5EED0013, args.data, device=device).cpu().numpy()
     for w in range(args.warmup):
-        oracle.scan_batch(snap, q[w * sample:(w + 1) * sample], None, None, L, rescore, args.k, threads=0)
+        oracle.scan_batch(snap, qs[w * sample:(w + 1) * sample], None, None, L, rescore, k, threads=0)
     t0 = time.perf_counter()
-    for s in range(args.warmup, args.warmup + args.steps):
-        oracle.scan_batch(snap, q[s * sample:(s + 1) * sample], None, None, L, rescore, args.k, threads=0)
+    for s in range(args.warmup, nb):
+        oracle.scan_batch(snap, qs[s * sample:(s + 1) * sample], None, None, L, rescore, k, threads=0)
     dt = time.perf_counter() - t0
     qps = args.steps * sample / dt
     line = {
@@ -172,10 +241,12 @@ def run_reference(args):
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 popcount + f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {args.n}x{args.dim}-d {args.data} SBQ {snap.bits}-bit index, "
-                               f"sample of {sample} queries/step, k={args.k}, L={L}, rescore={rescore}"},
+        "config": {"workload": workload_name(args, snap.bits), "search_list_size": L, "rescore": rescore,
+                   "recall_at_10": round(recall, 4),
+                   "note": f"CPU arm: each step scans a bounded sample of {sample} queries of the workload"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} queries, one host thread per core"},
+                         "sample": f"{args.steps} steps x {sample} queries, one host thread per core "
+                                   "(oracle/oracle.cpp, -O2 -mavx2 -mfma -mpopcnt)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -209,7 +280,10 @@ def main():
 
     # ---- queries: per-rank distinct batches, (warmup+steps) of them so no step repeats a batch
     nb = args.warmup + args.steps
-    q_all = si.gen_dataset(nb * B, dim, 0x5EED0011 + 7919 * rank, args.data, device=device)
+    # the first batch (recall / operating point / parity) is generated on its own so that the
+    # reference arm can reproduce exactly the same queries
+    q_all = torch.cat([si.gen_dataset(B, dim, 0x5EED0011 + 7919 * rank, args.data, device=device),
+                       si.gen_dataset((nb - 1) * B, dim, 0x5EED0013 + 7919 * rank, args.data, device=device)])
     truth = si.ground_truth(x, q_all[:B], k).cpu().numpy()
     del x
     torch.cuda.empty_cache()
@@ -228,6 +302,7 @@ def main():
     chosen = None
     sweep_log = []
     for (L, rescore) in points:
+        run_device(q_all[:B], L, rescore)          # first run of a plan pays for workspace (re)allocation
         run_device(q_all[:B], L, rescore)
         torch.cuda.synchronize(device)
         rec = recall_at_k(d_tid.cpu().numpy().view(np.uint64), truth, snap, k)
@@ -281,7 +356,8 @@ def main():
     stat_sum = np.zeros(6, np.float64)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)
+    with clocks:
         ev0.record(stream)
         for s in range(args.warmup, nb):
             run_device(q_all[s * B:(s + 1) * B], L, rescore)
@@ -306,13 +382,14 @@ def main():
     for w in range(args.warmup):
         idx.search_batch_ptrs(h_q[w * B:(w + 1) * B].data_ptr(), B, k, L, rescore, h_tid.data_ptr(), h_dist.data_ptr())
     barrier()
-    t0 = time.perf_counter()
-    for s in range(args.warmup, nb):
-        idx.search_batch_ptrs(h_q[s * B:(s + 1) * B].data_ptr(), B, k, L, rescore, h_tid.data_ptr(), h_dist.data_ptr())
-        if world > 1:
-            shard.gather_rows(torch.from_numpy(h_tid.numpy()).to(device), torch.from_numpy(h_dist.numpy()).to(device), B)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with clocks:
+        t0 = time.perf_counter()
+        for s in range(args.warmup, nb):
+            idx.search_batch_ptrs(h_q[s * B:(s + 1) * B].data_ptr(), B, k, L, rescore, h_tid.data_ptr(), h_dist.data_ptr())
+            if world > 1:
+                shard.gather_rows(torch.from_numpy(h_tid.numpy()).to(device), torch.from_numpy(h_dist.numpy()).to(device), B)
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks ---------------------------------------------------------------------
     tm = torch.tensor([dev_ms, e2e_s * 1e3, search_ms, rerank_ms], dtype=torch.float64, device=device)
@@ -337,7 +414,7 @@ def main():
     achieved = alg_bytes_launch / (search_avg_ms / 1e3) / 1e9
     rerank_bytes_launch = B * (rescore + k - 1 if rescore else 0) * dim * 4
     rerank_avg_ms = rerank_ms / args.steps
-    roofline = {"kernel": "dann_search_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"kernel": "dann_search2_kernel<u32,3> (two warps per query)" if snap.R <= 64 else "dann_search_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg_bytes_launch), "avg_launch_ms": round(search_avg_ms, 4),
                 "per_query": {"visits": round(visits_q, 1), "d_quantized": round(dq_q, 1), "code_bytes": code_bytes}}
@@ -399,8 +476,7 @@ def main():
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 popcount + f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {args.n}x{dim}-d {args.data} ('Cohere-shape' synthetic) SBQ {snap.bits}-bit "
-                               f"diskann index in HBM, batch={B} queries/GPU/step, k={k}",
+        "config": {"workload": workload_name(args, snap.bits),
                    "search_list_size": L, "rescore": rescore, "recall_at_10": round(recall, 4),
                    "parallelism": f"query-shard x{world} (replicated index, all_gather of top-k)",
                    "l2_policy": f"index {idx.hbm_bytes / 1e9:.2f} GB >> 126 MB L2, random gathers, distinct queries every step",
