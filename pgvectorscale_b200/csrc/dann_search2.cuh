@@ -305,7 +305,15 @@ struct PairSearch {
         /* bitmap flavour: clear exactly the bits this query set */
         if (a.bitmap_words) {
             __syncwarp();
-            for (uint32_t i = lane; i < nins; i += 32) bitmap[ins[i] >> 5] = 0u;
+            uint32_t i = lane;
+            for (; i + 7 * 32 < nins; i += 8 * 32) { /* 8 independent loads in flight per lane */
+                uint32_t w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[u] = ins[i + u * 32];
+#pragma unroll
+                for (int u = 0; u < 8; u++) bitmap[w[u] >> 5] = 0u;
+            }
+            for (; i < nins; i += 32) bitmap[ins[i] >> 5] = 0u;
             __threadfence_block();
         }
     }
@@ -472,8 +480,10 @@ struct PairSearch {
                 hstatus |= ctl->status_a;
                 const uint32_t p = (hk - 1) & 1;
                 const uint32_t d = H::key(head);
-                const uint32_t node = __ldcg(cnode + T::seq(head));
-                if (ctl->expect[p] != node) hstatus |= DANN_ST_INTERNAL;
+                /* the memory warp already resolved which node this pop yields (page p is its
+                 * expansion); the seq->node table is only read to cross-check, off the critical path */
+                const uint32_t node = ctl->expect[p];
+                const uint32_t node_chk = __ldcg(cnode + T::seq(head));
                 if (hstatus) break;
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
@@ -485,6 +495,7 @@ struct PairSearch {
                 if (hstatus) break;
                 visits++;
                 push_page(p);
+                if (node_chk != node) hstatus |= DANN_ST_INTERNAL;
             }
             if (hstatus) break;
             if (vis_len == 0) break;

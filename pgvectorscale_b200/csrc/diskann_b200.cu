@@ -448,7 +448,8 @@ static uint32_t env_u32(const char *name, uint32_t dflt) {
     return (uint32_t)strtoul(s, nullptr, 10);
 }
 
-static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, SearchPlan *p) {
+static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, bool keyed,
+                     SearchPlan *p) {
     const IndexView &v = ix->v;
     /* visits are about L + consumed; every visit stages at most R ids */
     uint64_t need = ((uint64_t)L + c_target + 40u) * v.R * grow;
@@ -463,10 +464,13 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
      * (<= 2 MB per warp, i.e. up to 16M nodes), else the CAS hash set */
     const bool use_bitmap = env_u32("DANN_SEARCH_BITMAP", v.n <= (16u << 20) ? 1 : 0) != 0;
     p->bitmap_words = use_bitmap ? ((v.n + 127u) / 128u) * 4u : 0u;
-    p->ins_cap = p->cand_cap;
+    /* every deduped id is recorded, also the ones a label filter then rejects: visits x R */
+    p->ins_cap = keyed ? 2 * p->cand_cap : p->cand_cap;
+    if (keyed) p->hash_cap = pow2ceil(4 * p->cand_cap);
     bool small = p->cand_cap <= 65536 && (uint64_t)v.words * 64 <= 65535;
     p->esize = small ? 4 : 8;
-    uint64_t vcap = std::max<uint64_t>(((uint64_t)L + 96u) * grow / shrink, 8);
+    /* visited holds the not-yet-consumed visits: about L, more under a label filter */
+    uint64_t vcap = std::max<uint64_t>(((uint64_t)L * (keyed ? 2 : 1) + 96u) * grow / shrink, 8);
     p->vcap = (uint32_t)((vcap + 3) & ~3ull);
     const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
@@ -533,7 +537,7 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
     uint32_t nq = (uint32_t)B;
     for (int attempt = 0;; attempt++) {
         SearchPlan p;
-        rc = make_plan(ix, nq, (uint32_t)L, c_target, grow, &p);
+        rc = make_plan(ix, nq, (uint32_t)L, c_target, grow, d_label_off != nullptr, &p);
         if (rc) return rc;
         const size_t slots = (size_t)p.grid * p.W;
         if (!p.bitmap_words) CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
@@ -585,6 +589,8 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         CK(cudaMemcpyAsync(ctl, d_ctl, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (ctl[1] == 0) break;
+        if (getenv("DANN_DEBUG_STATUS")) fprintf(stderr, "[diskann_b200] search overflow bits 0x%x (attempt %d, plan need=%u vcap=%u)\n", ctl[1], attempt, p.need, p.vcap);
+        if (ctl[1] & DANN_ST_INTERNAL) return fail(DANN_ERR_STATE, "internal error: next-node prediction mismatch in the two-warp search kernel");
         /* some queries outgrew their workspace: rerun exactly those with a larger one */
         if (attempt >= 8) return fail(DANN_ERR_CAPACITY, "search workspace still too small after %d growth steps", attempt);
         hstats.resize(B);
