@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) dann_prepare_kernel(IndexView ix, const f
 /* (distance_xor_optimized, distance/mod.rs:265-323).  G lanes share one code row with    */
 /* 128-bit no-allocate loads; UNR pairs are in flight per lane group.                     */
 template <int NCH, int UNR>
-__global__ void __launch_bounds__(256) dann_sbq_distance_kernel(const uint64_t *__restrict__ codes,
+__global__ void __launch_bounds__(512) dann_sbq_distance_kernel(const uint64_t *__restrict__ codes,
                                                                 uint32_t cw,
                                                                 const uint64_t *__restrict__ qcodes,
                                                                 const uint32_t *__restrict__ pair_q,

@@ -46,7 +46,8 @@ template <typename E, int NCH>
 struct PairSearch {
     using T = EntryTraits<E>;
     using H = RustHeap<E, T::KSHIFT>;
-    static constexpr int RPI = NCH <= 3 ? 4 : (NCH == 4 ? 2 : 1);
+    /* rows gathered per lane group per round: 6 x 8 = 48 rows (G=4) covers a typical 50-id list at once */
+    static constexpr int RPI = NCH <= 2 ? 8 : (NCH == 3 ? 6 : (NCH == 4 ? 4 : 2));
 
     const SearchArgs &a;
     const int lane;
@@ -153,22 +154,26 @@ struct PairSearch {
         __syncwarp();
     }
 
-    /* SBQ distances of page `list` -> `dl` (distance/mod.rs:265-323) */
-    __device__ __forceinline__ void distances(const uint32_t *list, uint32_t *dl, uint32_t tn) {
+    /* SBQ distances of page `list` -> `dl` (distance/mod.rs:265-323).  EXACT: every lane's NCH
+     * chunk slots exist (cw/2 == NCH*G), so the per-chunk bounds test disappears. */
+    template <bool EXACT>
+    __device__ __forceinline__ void distances_impl(const uint32_t *list, uint32_t *dl, uint32_t tn) {
         const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
         const uint32_t nchunks = a.ix.cw >> 1;
+        const size_t rowbytes = (size_t)a.ix.cw * 8;
+        const unsigned char *cbase = reinterpret_cast<const unsigned char *>(a.ix.codes) + (size_t)gl * 16;
+        const uint32_t cstep = G * 16;
         for (uint32_t b = 0; b < tn; b += RP * RPI) {
             ulonglong2 v[RPI][NCH];
 #pragma unroll
             for (int u = 0; u < RPI; u++) {
-                uint32_t r = b + u * RP + grp;
-                uint32_t node = r < tn ? list[r] : 0u;
-                const ulonglong2 *row =
-                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)node * a.ix.cw);
+                const uint32_t r = b + u * RP + grp;
+                const bool live = r < tn;
+                const unsigned char *row = cbase + (size_t)(live ? list[r] : 0u) * rowbytes;
 #pragma unroll
                 for (int i = 0; i < NCH; i++) {
-                    uint32_t c = gl + i * G;
-                    v[u][i] = (r < tn && c < nchunks) ? ldg_stream_u128(row + c) : qc[i];
+                    const bool ok = live && (EXACT || gl + i * G < nchunks);
+                    v[u][i] = ok ? ldg_stream_u128(row + i * cstep) : qc[i];
                 }
             }
 #pragma unroll
@@ -178,11 +183,15 @@ struct PairSearch {
                 for (int i = 0; i < NCH; i++)
                     s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
                 for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
-                uint32_t r = b + u * RP + grp;
+                const uint32_t r = b + u * RP + grp;
                 if (gl == 0 && r < tn) dl[r] = s;
             }
         }
         __syncwarp();
+    }
+    __device__ __forceinline__ void distances(const uint32_t *list, uint32_t *dl, uint32_t tn) {
+        if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
+        else distances_impl<false>(list, dl, tn);
     }
 
     __device__ __forceinline__ void run_memory(uint32_t q) {
@@ -529,7 +538,7 @@ struct PairSearch {
 };
 
 template <typename E, int NCH>
-__global__ void __launch_bounds__(512, 1) dann_search2_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char dann_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, role = warp & 1;
     const int P = blockDim.x >> 6;

@@ -122,6 +122,12 @@ struct dann_scan {
 };
 
 /* ------------------------------------------------------------------------------------ */
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *s = getenv(name);
+    if (!s || !*s) return dflt;
+    return (uint32_t)strtoul(s, nullptr, 10);
+}
+
 static uint32_t pow2ceil(uint32_t x) {
     uint32_t p = 1;
     while (p < x) p <<= 1;
@@ -367,13 +373,35 @@ extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int 
     return DANN_OK;
 }
 
+template <int NCH, int UNR>
+static void launch_sbq_u(dann_index *ix, const uint64_t *q, const uint32_t *pq, const uint32_t *pn, size_t np,
+                         uint32_t *out, cudaStream_t st) {
+    const int threads = (int)env_u32("DANN_SBQ_THREADS", 256);
+    /* one full wave of resident CTAs (grid-stride loop inside): no partial last wave */
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dann_sbq_distance_kernel<NCH, UNR>, threads, 0) != cudaSuccess || occ < 1)
+        occ = 4;
+    int blocks = ix->sm_count * (int)env_u32("DANN_SBQ_BLOCKS_PER_SM", (uint32_t)occ);
+    dann_sbq_distance_kernel<NCH, UNR><<<blocks, threads, 0, st>>>(ix->v.codes, ix->v.cw, q, pq, pn, np, out, ix->G,
+                                                                  ix->Gshift);
+}
+
 template <int NCH>
 static void launch_sbq(dann_index *ix, const uint64_t *q, const uint32_t *pq, const uint32_t *pn, size_t np,
                        uint32_t *out, cudaStream_t st) {
-    constexpr int UNR = NCH <= 3 ? 4 : (NCH == 4 ? 2 : 1);
-    int blocks = ix->sm_count * 8;
-    dann_sbq_distance_kernel<NCH, UNR><<<blocks, 256, 0, st>>>(ix->v.codes, ix->v.cw, q, pq, pn, np, out,
-                                                              ix->G, ix->Gshift);
+    /* pairs in flight per lane group.  Measured on B200 (tools/bench_sbq.py, 192-B codes): UNR=2 -> 40
+     * registers, 5.04 TB/s; UNR=4 -> 64 registers, 4.36 TB/s; UNR=8 -> 128 registers, 3.79 TB/s:
+     * occupancy beats per-thread memory-level parallelism for these random row gathers. */
+    constexpr int UNR = NCH <= 4 ? 2 : 1;
+    if (NCH <= 3) {
+        switch (env_u32("DANN_SBQ_UNR", UNR)) {
+            case 1: return launch_sbq_u<NCH, 1>(ix, q, pq, pn, np, out, st);
+            case 4: return launch_sbq_u<NCH, 4>(ix, q, pq, pn, np, out, st);
+            case 8: return launch_sbq_u<NCH, 8>(ix, q, pq, pn, np, out, st);
+            default: break;
+        }
+    }
+    launch_sbq_u<NCH, UNR>(ix, q, pq, pn, np, out, st);
 }
 
 extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const uint32_t *d_pair_q,
@@ -442,11 +470,6 @@ struct SearchPlan {
     bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
 };
 
-static uint32_t env_u32(const char *name, uint32_t dflt) {
-    const char *s = getenv(name);
-    if (!s || !*s) return dflt;
-    return (uint32_t)strtoul(s, nullptr, 10);
-}
 
 static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, bool keyed,
                      SearchPlan *p) {
@@ -475,7 +498,7 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
     p->pairs = v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
-    const uint32_t wmax = p->pairs ? 8u : 12u; /* __launch_bounds__ of the two kernels */
+    const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
     if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
     uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
