@@ -104,17 +104,23 @@ struct RustHeap {
     /* ---- 1-based storage forms (slot p holds Rust's data[p-1]; parent p>>1, children 2p, 2p+1).
      * Child pairs are then 8-byte aligned, so the pop's descent reads both children with one
      * 64-bit load, and the ancestor index of lane j is simply p >> j. ------------------------ */
-    template <typename Store>
+    /* PSM: the caller guarantees that every PARENT slot on the path is in shared memory (true
+     * whenever the leaf slot is < 2*hs), so only lane 0's leaf store may go to the HBM tail. */
+    template <bool PSM = false, typename Store>
     static __device__ __forceinline__ void sift_up_warp1(Store &s, uint32_t p, E elem, int lane) {
         const uint32_t k = key(elem);
         const uint32_t ast = p >> lane; /* slot at height `lane` on the path (0 = above the root) */
         const uint32_t ald = ast >> 1;  /* its parent */
         E av = 0;
-        if (ald) av = s.get(ald);
+        if (ald) av = PSM ? s.get_sm(ald) : s.get(ald);
         const unsigned above = __ballot_sync(0xFFFFFFFFu, ald != 0 && key(av) > k);
         const unsigned tm = above & ~(above + 1u); /* trailing ones: the ancestors the element passes */
         const unsigned wm = tm | (tm + 1u);        /* lanes 0..rise write */
-        if ((wm >> lane) & 1u) s.set(ast, ((tm >> lane) & 1u) ? av : elem);
+        if ((wm >> lane) & 1u) {
+            const E val = ((tm >> lane) & 1u) ? av : elem;
+            if (PSM && lane > 0) s.set_sm(ast, val);
+            else s.set(ast, val);
+        }
         __syncwarp();
     }
 
@@ -148,7 +154,7 @@ struct RustHeap {
         p = __shfl_sync(0xFFFFFFFFu, p, 0);
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         __syncwarp();
-        sift_up_warp1(s, p, item, lane);
+        sift_up_warp1<false>(s, p, item, lane);
     }
 
     /* len must be > 0 */
@@ -187,6 +193,8 @@ struct ArrayStore {
     E *p;
     __device__ __forceinline__ E get(uint32_t i) const { return p[i]; }
     __device__ __forceinline__ void set(uint32_t i, E v) { p[i] = v; }
+    __device__ __forceinline__ E get_sm(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ void set_sm(uint32_t i, E v) { p[i] = v; }
     /* entries i and i+1, i even: one aligned load of both */
     __device__ __forceinline__ void get2(uint32_t i, E &a, E &b) const {
         if constexpr (sizeof(E) == 4) {
@@ -208,6 +216,8 @@ struct SplitStore {
     E *gl;
     uint32_t hs;
     __device__ __forceinline__ E get(uint32_t i) const { return i < hs ? sm[i] : gl[i]; }
+    __device__ __forceinline__ E get_sm(uint32_t i) const { return sm[i]; } /* caller knows i < hs */
+    __device__ __forceinline__ void set_sm(uint32_t i, E v) { sm[i] = v; }
     __device__ __forceinline__ void get2(uint32_t i, E &a, E &b) const { /* hs is even: a pair never straddles */
         const E *q = i < hs ? sm + i : gl + i;
         a = q[0];

@@ -334,7 +334,7 @@ struct PairSearch {
      * Inert elements (parent key <= own key: they stay at their leaf whatever earlier pushes of
      * the batch do) are written in parallel; the others are compacted into a small queue and
      * replayed in order through the cooperative sift-up, the next one prefetched meanwhile. */
-    template <typename Store>
+    template <bool PSM, typename Store>
     __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
         const unsigned lt = (1u << lane) - 1u;
         for (uint32_t base = 0; base < tn; base += 32) {
@@ -347,7 +347,7 @@ struct PairSearch {
             if (have && slot > 1) {
                 const uint32_t parent = slot >> 1;
                 if (parent <= heap_len + base) { /* parent is settled (old, or from an earlier round) */
-                    inert = H::key(st.get(parent)) <= dmine;
+                    inert = H::key(PSM ? st.get_sm(parent) : st.get(parent)) <= dmine;
                     if (inert) st.set(slot, mine);
                 }
             }
@@ -364,9 +364,9 @@ struct PairSearch {
             uint32_t sp = cqp[0];
             for (uint32_t i = 0; i < nact; i++) {
                 const uint32_t nx = i + 1 < nact ? i + 1 : i;
-                const E en = cqe[nx];
+                const E en = cqe[nx]; /* next element fetched before this one's dependent chain */
                 const uint32_t sn = cqp[nx];
-                H::sift_up_warp1(st, sp, e, lane);
+                H::template sift_up_warp1<PSM>(st, sp, e, lane);
                 e = en;
                 sp = sn;
             }
@@ -377,11 +377,13 @@ struct PairSearch {
         const uint32_t tn = ctl->tn[p], seq0 = ctl->seq0[p];
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
         if (tn == 0) return;
-        if (heap_len + tn < heap.hs) {
+        if (heap_len + tn < heap.hs) { /* everything in shared memory */
             ArrayStore<E> sm{heap.sm};
-            push_batch(sm, dl, tn, seq0);
+            push_batch<true>(sm, dl, tn, seq0);
+        } else if (heap_len + tn < 2 * heap.hs) { /* leaves spill to HBM, every parent still in shared memory */
+            push_batch<true>(heap, dl, tn, seq0);
         } else {
-            push_batch(heap, dl, tn, seq0);
+            push_batch<false>(heap, dl, tn, seq0);
         }
         heap_len += tn;
         dq += tn;
