@@ -414,8 +414,17 @@ def main():
     achieved = alg_bytes_launch / (search_avg_ms / 1e3) / 1e9
     rerank_bytes_launch = B * (rescore + k - 1 if rescore else 0) * dim * 4
     rerank_avg_ms = rerank_ms / args.steps
+    # DRAM traffic of one search-kernel launch from the committed `ncu --set full` capture of the same
+    # operating point (profiles/r01_traffic.json); null when the capture is for another configuration
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if (tj.get("L"), tj.get("rescore"), tj.get("n"), tj.get("batch")) == (L, rescore, args.n, B):
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"kernel": "dann_search2_kernel<u32,3> (two warps per query)" if snap.R <= 64 else "dann_search_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg_bytes_launch), "avg_launch_ms": round(search_avg_ms, 4),
                 "per_query": {"visits": round(visits_q, 1), "d_quantized": round(dq_q, 1), "code_bytes": code_bytes}}
     others = {"dann_rerank_kernel": {"alg_bytes_per_launch": int(rerank_bytes_launch),
