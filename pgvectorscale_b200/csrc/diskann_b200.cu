@@ -475,7 +475,7 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
                      SearchPlan *p) {
     const IndexView &v = ix->v;
     /* visits are about L + consumed; every visit stages at most R ids */
-    uint64_t need = ((uint64_t)L + c_target + 40u) * v.R * grow;
+    uint64_t need = (((uint64_t)L + c_target) * 23 / 20 + 40u) * v.R * grow; /* 15% slack over L + consumed */
     /* test hook: start from a deliberately small workspace to exercise the growth path */
     const uint32_t shrink = std::max<uint32_t>(env_u32("DANN_DEBUG_SHRINK", 1), 1);
     need = std::max<uint64_t>(need / shrink, 256);
