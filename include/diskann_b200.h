@@ -154,6 +154,25 @@ int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const uint32_t *
 int dann_full_distance(dann_index *ix, const float *d_q_full, const uint32_t *d_nodes, int B,
                        int m, float *d_out, void *stream);
 
+/* ---- index construction (NOT the scan hot path) -----------------------------
+ * GPU batch Vamana over SBQ codes built from the scan kernels: greedy_search_for_build
+ * (graph/mod.rs:285-327) + prune_neighbors (:392-488) + back-pointers (:212-266,720-737), nodes
+ * inserted in batches.  The index must have been loaded with R == 64 neighbour slots per node
+ * (contents ignored), start_default == 0 and no labels; `vectors` may be NULL at load and supplied
+ * later.  On return every list holds <= num_neighbors ids.  The graph is a valid diskann graph but not
+ * the reference's serial insertion order, so it serves fixtures and benchmarks. */
+typedef struct {
+    uint32_t batches;
+    float search_ms, prune_ms, sort_ms, backlink_ms, total_ms;
+    double avg_degree;
+} dann_build_stats;
+int dann_build_graph(dann_index *ix, int num_neighbors, int search_list_size, float max_alpha, uint32_t max_batch,
+                     dann_build_stats *out);
+/* Copy the neighbour lists back to the host: out [n][R] with R = the snapshot's R. */
+int dann_index_download_nbrs(dann_index *ix, uint32_t *out);
+/* Supply (or replace) the heap vectors of an index loaded with vectors == NULL; [n][dim] host floats. */
+int dann_index_set_vectors(dann_index *ix, const float *vectors);
+
 /* Number of this library's kernel launches since load (bench.py "gpu_launches"). */
 uint64_t dann_kernel_launches(const dann_index *ix);
 

@@ -1,0 +1,239 @@
+// dann_build.cuh — GPU batch Vamana construction over SBQ codes.
+//
+// NOT part of the scan hot path: this is the first "next" row of the scope table, built from the
+// hot path's own kernels.  The reference builds its graph serially (graph/mod.rs:637-737: search
+// the current graph for the new node with quantized distances, alpha-prune the visited set,
+// add back-pointers and prune on overflow).  A batch of nodes is inserted here at once, the way
+// parallel DiskANN builders do:
+//   1. greedy_search_for_build (graph/mod.rs:285-327) for every node of the batch with the beam
+//      search kernel in build mode (query code = the node's own SBQ code, result = visited list);
+//   2. prune_neighbors (graph/mod.rs:392-488) per node: a warp-cooperative restatement of the
+//      two-round alpha prune over Hamming distances (sbq/mod.rs:178-190 node-to-node distances);
+//   3. update_back_pointer (graph/mod.rs:720-737): the (neighbour <- node) edges of the batch are
+//      sorted by destination, appended, and lists that outgrow the slack are pruned again.
+// The result is a valid diskann graph but not the reference's serial one (insertion is batched),
+// so it is used for fixtures/benchmarks; scan parity is always checked oracle-vs-GPU on the SAME
+// graph.
+#pragma once
+#include "dann_device.cuh"
+
+#define DANN_BUILD_CMAX 128u /* candidates considered by one prune */
+#define DANN_BUILD_SLACK 64u /* neighbour slots per node while building (the reference: ceil(1.3 R)) */
+
+/* candidate key: (distance << 32) | node id ; sorted ascending = reference's candidates.sort() up to
+ * the tie-break among equal distances (id order here, ip_distance order there) */
+
+__device__ __forceinline__ void build_bitonic_sort128(uint64_t *k, int lane) {
+    for (uint32_t size = 2; size <= DANN_BUILD_CMAX; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < DANN_BUILD_CMAX; t += 32) {
+                uint32_t u = t ^ stride;
+                if (u > t) {
+                    uint64_t a = k[t], b = k[u];
+                    bool up = (t & size) == 0;
+                    if ((a > b) == up) {
+                        k[t] = b;
+                        k[u] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+/* prune_neighbors (graph/mod.rs:392-488) for point `p`: ck[0..C) sorted candidate keys (no duplicates,
+ * p itself excluded).  cc = staging for candidate codes [C][cws] (cws odd stride), mf[C] factors.
+ * Writes up to R (id, dist) pairs; returns the count. */
+__device__ __forceinline__ uint32_t build_prune_warp(const uint64_t *__restrict__ codes, uint32_t cw, uint32_t cws,
+                                                     uint32_t p, const uint64_t *ck, float *mf, uint64_t *cc,
+                                                     uint32_t C, uint32_t R, float max_alpha, uint32_t *out_id,
+                                                     uint16_t *out_d, int lane) {
+    for (uint32_t c = 0; c < C; c++) {
+        const uint64_t *row = codes + (size_t)(uint32_t)ck[c] * cw;
+        for (uint32_t w = lane; w < cw; w += 32) cc[c * cws + w] = __ldg(row + w);
+    }
+    for (uint32_t c = lane; c < C; c += 32) mf[c] = 0.0f;
+    __syncwarp();
+    uint32_t nres = 0;
+    float alpha = 1.0f;
+    while (alpha <= max_alpha && nres < R) {
+        for (uint32_t i = 0; i < C && nres < R; i++) {
+            if (mf[i] > alpha) continue;
+            __syncwarp();
+            if (lane == 0) {
+                mf[i] = 3.0e38f; /* don't consider again */
+                out_id[nres] = (uint32_t)ck[i];
+                out_d[nres] = (uint16_t)(ck[i] >> 32);
+            }
+            nres++;
+            const uint32_t idi = (uint32_t)ck[i];
+            const uint64_t *ci = cc + i * cws;
+            for (uint32_t j = i + 1 + lane; j < C; j += 32) {
+                float f = mf[j];
+                if (f > max_alpha) continue; /* completely excluded already */
+                const uint64_t *cj = cc + j * cws;
+                uint32_t dij = 0;
+                for (uint32_t w = 0; w < cw; w++) dij += __popcll(ci[w] ^ cj[w]);
+                const uint32_t dpj = (uint32_t)(ck[j] >> 32), idj = (uint32_t)ck[j];
+                float factor; /* DistanceWithTieBreak::get_factor, neighbor_with_distance.rs:55-65 */
+                if (dij == 0) {
+                    if (dpj == 0) {
+                        float tp = (float)(idj > p ? idj - p : p - idj), te = (float)(idj > idi ? idj - idi : idi - idj);
+                        factor = tp / te;
+                    } else {
+                        factor = 3.0e38f;
+                    }
+                } else {
+                    factor = (float)dpj / (float)dij;
+                }
+                mf[j] = f > factor ? f : factor;
+            }
+            __syncwarp();
+        }
+        alpha *= 1.2f;
+    }
+    __syncwarp();
+    return nres;
+}
+
+struct BuildArgs {
+    const uint64_t *codes;
+    uint32_t cw, cws, n;
+    uint32_t *nbrs;       /* [n][SLACK] */
+    uint16_t *nbr_dist;   /* [n][SLACK] */
+    uint8_t *deg;         /* [n] */
+    uint32_t R;           /* num_neighbors */
+    float max_alpha;
+    uint32_t per_warp_smem;
+};
+
+__device__ __forceinline__ void build_smem(unsigned char *base, uint32_t cws, uint64_t *&ck, uint64_t *&cc, float *&mf,
+                                           uint32_t *&oid, uint16_t *&od) {
+    ck = reinterpret_cast<uint64_t *>(base);
+    cc = ck + DANN_BUILD_CMAX;
+    mf = reinterpret_cast<float *>(cc + (size_t)DANN_BUILD_CMAX * cws);
+    oid = reinterpret_cast<uint32_t *>(mf + DANN_BUILD_CMAX);
+    od = reinterpret_cast<uint16_t *>(oid + DANN_BUILD_SLACK);
+}
+
+__device__ __forceinline__ void build_write_list(const BuildArgs &a, uint32_t p, const uint32_t *oid, const uint16_t *od,
+                                                 uint32_t cnt, int lane) {
+    uint32_t *row = a.nbrs + (size_t)p * DANN_BUILD_SLACK;
+    uint16_t *drow = a.nbr_dist + (size_t)p * DANN_BUILD_SLACK;
+    for (uint32_t t = lane; t < DANN_BUILD_SLACK; t += 32) {
+        row[t] = t < cnt ? oid[t] : DANN_INVALID_NODE;
+        drow[t] = t < cnt ? od[t] : (uint16_t)0;
+    }
+    if (lane == 0) a.deg[p] = (uint8_t)cnt;
+}
+
+/* step 2: forward edges of the batch nodes [lo, lo+m) from their visited lists; also emits the
+ * back-link triples key = (dst << 32) | (dist << 16), val = src into [m][SLACK] slots (~0 = unused) */
+__global__ void __launch_bounds__(256) dann_build_prune_kernel(BuildArgs a, uint32_t lo, uint32_t m,
+                                                               const uint64_t *vis, const uint32_t *vis_len,
+                                                               uint32_t vis_cap, uint64_t *trip_key, uint32_t *trip_val) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    uint64_t *ck, *cc;
+    float *mf;
+    uint32_t *oid;
+    uint16_t *od;
+    build_smem(dann_smem + (size_t)warp * a.per_warp_smem, a.cws, ck, cc, mf, oid, od);
+    for (uint32_t b = blockIdx.x * W + warp; b < m; b += gridDim.x * W) {
+        const uint32_t p = lo + b;
+        uint32_t C = vis_len[b];
+        if (C > DANN_BUILD_CMAX) C = DANN_BUILD_CMAX; /* the visited list is sorted: keep the closest */
+        for (uint32_t c = lane; c < C; c += 32) ck[c] = vis[(size_t)b * vis_cap + c];
+        __syncwarp();
+        const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, C, a.R, a.max_alpha, oid, od, lane);
+        build_write_list(a, p, oid, od, cnt, lane);
+        for (uint32_t t = lane; t < DANN_BUILD_SLACK; t += 32) {
+            size_t o = (size_t)b * DANN_BUILD_SLACK + t;
+            trip_key[o] = t < cnt ? (((uint64_t)oid[t] << 32) | ((uint64_t)od[t] << 16)) : ~0ull;
+            trip_val[o] = p;
+        }
+        __syncwarp();
+    }
+}
+
+/* segment heads of the sorted triples: first entry of every destination */
+__global__ void dann_build_heads_kernel(const uint64_t *key, size_t total, uint32_t *heads, uint32_t *nheads) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t k = key[i];
+        if (k == ~0ull) continue;
+        if (i == 0 || (uint32_t)(key[i - 1] >> 32) != (uint32_t)(k >> 32)) heads[atomicAdd(nheads, 1u)] = (uint32_t)i;
+    }
+}
+
+/* step 3: back-pointers.  One warp per destination node: append the (closest 64) new sources; a list
+ * that would outgrow the slack is pruned back to R (graph/mod.rs:212-266 add_neighbors) */
+__global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, const uint64_t *key, const uint32_t *val,
+                                                                  size_t total, const uint32_t *heads, uint32_t nheads) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    uint64_t *ck, *cc;
+    float *mf;
+    uint32_t *oid;
+    uint16_t *od;
+    build_smem(dann_smem + (size_t)warp * a.per_warp_smem, a.cws, ck, cc, mf, oid, od);
+    for (uint32_t h = blockIdx.x * W + warp; h < nheads; h += gridDim.x * W) {
+        const size_t s = heads[h];
+        const uint32_t q = (uint32_t)(key[s] >> 32);
+        const uint32_t deg = a.deg[q];
+        /* additions: up to 64 entries of this destination, already sorted by distance */
+        uint32_t nadd = 0;
+        for (uint32_t t0 = 0; t0 < DANN_BUILD_SLACK; t0 += 32) {
+            size_t i = s + t0 + lane;
+            bool ok = i < total && key[i] != ~0ull && (uint32_t)(key[i] >> 32) == q;
+            unsigned mk = __ballot_sync(DANN_FULL, ok);
+            if (ok) ck[deg + t0 + lane] = (((key[i] >> 16) & 0xFFFFull) << 32) | val[i];
+            nadd += __popc(mk);
+            if (mk != DANN_FULL) break;
+        }
+        const uint32_t *row = a.nbrs + (size_t)q * DANN_BUILD_SLACK;
+        const uint16_t *drow = a.nbr_dist + (size_t)q * DANN_BUILD_SLACK;
+        for (uint32_t t = lane; t < deg; t += 32) ck[t] = ((uint64_t)drow[t] << 32) | row[t];
+        __syncwarp();
+        const uint32_t tot = deg + nadd;
+        if (tot <= DANN_BUILD_SLACK) { /* room left: plain append */
+            uint32_t *wrow = a.nbrs + (size_t)q * DANN_BUILD_SLACK;
+            uint16_t *wdrow = a.nbr_dist + (size_t)q * DANN_BUILD_SLACK;
+            for (uint32_t t = deg + lane; t < tot; t += 32) {
+                wrow[t] = (uint32_t)ck[t];
+                wdrow[t] = (uint16_t)(ck[t] >> 32);
+            }
+            if (lane == 0) a.deg[q] = (uint8_t)tot;
+        } else {
+            for (uint32_t t = tot + lane; t < DANN_BUILD_CMAX; t += 32) ck[t] = ~0ull;
+            __syncwarp();
+            build_bitonic_sort128(ck, lane);
+            const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, q, ck, mf, cc, tot, a.R, a.max_alpha, oid, od, lane);
+            build_write_list(a, q, oid, od, cnt, lane);
+        }
+        __syncwarp();
+    }
+}
+
+/* finalize_index_build (build.rs:905-960): lists longer than R are pruned to R */
+__global__ void __launch_bounds__(256) dann_build_finalize_kernel(BuildArgs a) {
+    extern __shared__ __align__(16) unsigned char dann_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    uint64_t *ck, *cc;
+    float *mf;
+    uint32_t *oid;
+    uint16_t *od;
+    build_smem(dann_smem + (size_t)warp * a.per_warp_smem, a.cws, ck, cc, mf, oid, od);
+    for (uint32_t p = blockIdx.x * W + warp; p < a.n; p += gridDim.x * W) {
+        const uint32_t deg = a.deg[p];
+        if (deg <= a.R) continue;
+        const uint32_t *row = a.nbrs + (size_t)p * DANN_BUILD_SLACK;
+        const uint16_t *drow = a.nbr_dist + (size_t)p * DANN_BUILD_SLACK;
+        for (uint32_t t = lane; t < DANN_BUILD_CMAX; t += 32) ck[t] = t < deg ? (((uint64_t)drow[t] << 32) | row[t]) : ~0ull;
+        __syncwarp();
+        build_bitonic_sort128(ck, lane);
+        const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, deg, a.R, a.max_alpha, oid, od, lane);
+        build_write_list(a, p, oid, od, cnt, lane);
+        __syncwarp();
+    }
+}

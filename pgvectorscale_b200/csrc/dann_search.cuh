@@ -64,6 +64,12 @@ struct SearchArgs {
     uint32_t G, Gshift;         /* lanes per code row (power of two) */
     uint32_t lists_unique;      /* no neighbour list repeats an id (checked at index load) */
     uint32_t per_warp_smem;
+    /* build mode (dann_build.cuh): the scan stops when visit_closest first returns None and the
+     * visited list (graph/mod.rs:285-327 greedy_search_for_build) is written out instead of a stream */
+    uint32_t build_mode;
+    uint64_t *vis_out;      /* [B][vis_out_cap] (dist << 32) | node, ascending */
+    uint32_t *vis_out_len;  /* [B] */
+    uint32_t vis_out_cap;
 };
 
 #define DANN_LIST_CAP 64u

@@ -509,6 +509,12 @@ struct PairSearch {
                 if (node_chk != node) hstatus |= DANN_ST_INTERNAL;
             }
             if (hstatus) break;
+            if (a.build_mode) { /* greedy_search_for_build: one-shot search, the visited set is the result */
+                const uint32_t nv = vis_len < a.vis_out_cap ? vis_len : a.vis_out_cap;
+                for (uint32_t i = lane; i < nv; i += 32) a.vis_out[(size_t)q * a.vis_out_cap + i] = vis[vis_head + i];
+                if (lane == 0) a.vis_out_len[q] = nv;
+                break;
+            }
             if (vis_len == 0) break;
             uint64_t e = vis[vis_head];
             __syncwarp();

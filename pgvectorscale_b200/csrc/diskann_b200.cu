@@ -20,6 +20,9 @@
 #include "dann_kernels.cuh"
 #include "dann_search.cuh"
 #include "dann_search2.cuh"
+#include "dann_build.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 /* ------------------------------------------------------------------------------------ */
 static thread_local std::string g_err;
@@ -226,7 +229,7 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
     if (words != s->words) return fail(DANN_ERR_INVALID_ARG, "words=%u but dim_index*bits needs %u", s->words, words);
     if (s->distance_type < DANN_COSINE || s->distance_type > DANN_IP)
         return fail(DANN_ERR_INVALID_ARG, "unknown distance type %d", s->distance_type);
-    if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->vectors || !s->mean))
+    if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->mean))
         return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
     if (s->has_labels && s->n && (!s->label_off || (s->label_off[s->n] && !s->labels)))
         return fail(DANN_ERR_INVALID_ARG, "has_labels set but label arrays missing");
@@ -281,7 +284,7 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
     CK(upload_padded<uint64_t>(ix, s->codes, s->n, words, v.cw, 0ull, &codes));
     CK(upload_padded<uint32_t>(ix, s->nbrs, s->n, v.R, v.Rp, DANN_INVALID_NODE, &nbrs));
     CK(upload(ix, s->heap_tid, (size_t)s->n, &tids));
-    CK(upload(ix, s->vectors, (size_t)s->n * s->dim, &vectors));
+    if (s->vectors) CK(upload(ix, s->vectors, (size_t)s->n * s->dim, &vectors)); /* NULL: supplied later (dann_index_set_vectors) */
     CK(upload(ix, v.n_start_labels ? s->start_labels : nullptr, (size_t)v.n_start_labels, &sl));
     CK(upload(ix, v.n_start_labels ? s->start_label_nodes : nullptr, (size_t)v.n_start_labels, &sln));
     if (v.has_labels && s->n) {
@@ -312,7 +315,7 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
         CK(cudaStreamSynchronize(ix->stream));
         ix->lists_unique = h == 0;
     }
-    if (s->distance_type == DANN_COSINE && s->n) {
+    if (s->distance_type == DANN_COSINE && s->n && vectors) {
         /* rerank reads the heap vector through PgVector::from_datum -> preprocess_cosine
          * (sbq/storage.rs:304-328, pg_vector.rs:153-155); the result only depends on the row,
          * so it is computed once here with the same arithmetic. */
@@ -525,42 +528,21 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     return DANN_OK;
 }
 
-/* B queries, first k rows each.  All pointers are device pointers. */
-static int search_batch_device_locked(dann_index *ix, const float *d_queries, const int16_t *d_labels,
-                                      const int32_t *d_label_off, int B, int k, int L, int rescore,
-                                      uint64_t *d_out_tid, float *d_out_dist, uint32_t *d_out_node,
-                                      uint32_t *d_out_count, dann_query_stats *d_out_stats, cudaStream_t st) {
+/* The beam search over B prepared query codes, with the invisible workspace-growth reruns.
+ * vis_out != NULL selects build mode (dann_build.cuh). */
+static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *d_labels, const int32_t *d_label_off,
+                      int B, uint32_t L, uint32_t c_target, dann_query_stats *d_stats, uint64_t *vis_out,
+                      uint32_t *vis_out_len, uint32_t vis_out_cap, cudaStream_t st) {
     const IndexView &v = ix->v;
-    if (B <= 0 || k <= 0) return fail(DANN_ERR_INVALID_ARG, "B and k must be positive");
-    if (L < 1 || L > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000 (guc.rs:11-26)", L);
-    if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000 (guc.rs:28-43)", rescore);
-    if (!d_queries || !d_out_tid) return fail(DANN_ERR_INVALID_ARG, "NULL query or output buffer");
-    /* rows needed from the approximate stream: scan.rs:255-305 */
-    const uint32_t c_target = rescore == 0 ? (uint32_t)k : (uint32_t)rescore + (uint32_t)k - 1u;
-
-    CK(ix->sc_qfull.reserve((size_t)B * v.dim * sizeof(float)));
-    CK(ix->sc_qcodes.reserve((size_t)B * v.cw * sizeof(uint64_t)));
-    CK(ix->sc_stream.reserve((size_t)B * c_target * sizeof(uint32_t)));
-    CK(ix->sc_stream_len.reserve((size_t)B * sizeof(uint32_t)));
-    CK(ix->sc_stats.reserve((size_t)B * sizeof(dann_query_stats)));
-    CK(ix->sc_qlist.reserve((size_t)B * sizeof(uint32_t)));
-    CK(ix->sc_ctl.reserve(64));
-    dann_query_stats *d_stats = d_out_stats ? d_out_stats : ix->sc_stats.as<dann_query_stats>();
     uint32_t *d_ctl = ix->sc_ctl.as<uint32_t>(); /* [0]=work counter, [1]=overflow bits */
-
-    ix->timing = dann_batch_timing{};
-    CK(cudaEventRecord(ix->ev[0], st));
-    int rc = launch_prepare(ix, d_queries, B, ix->sc_qfull.as<float>(), ix->sc_qcodes.as<uint64_t>(), st);
-    if (rc) return rc;
-    CK(cudaEventRecord(ix->ev[1], st));
-
+    int rc;
     std::vector<uint32_t> qlist;
     std::vector<dann_query_stats> hstats;
     uint32_t grow = 1;
     uint32_t nq = (uint32_t)B;
     for (int attempt = 0;; attempt++) {
         SearchPlan p;
-        rc = make_plan(ix, nq, (uint32_t)L, c_target, grow, d_label_off != nullptr, &p);
+        rc = make_plan(ix, nq, L, c_target, grow, d_label_off != nullptr, &p);
         if (rc) return rc;
         const size_t slots = (size_t)p.grid * p.W;
         if (!p.bitmap_words) CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
@@ -574,12 +556,12 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         CK(cudaMemsetAsync(d_ctl, 0, 8, st));
         SearchArgs a;
         a.ix = v;
-        a.q_codes = ix->sc_qcodes.as<uint64_t>();
+        a.q_codes = d_q_codes;
         a.q_labels = d_labels;
         a.q_label_off = d_label_off;
         a.qlist = attempt == 0 ? nullptr : ix->sc_qlist.as<uint32_t>();
         a.nq = nq;
-        a.L = (uint32_t)L;
+        a.L = L;
         a.c_target = c_target;
         a.stream = ix->sc_stream.as<uint32_t>();
         a.stream_len = ix->sc_stream_len.as<uint32_t>();
@@ -601,6 +583,10 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         a.G = ix->G;
         a.Gshift = ix->Gshift;
         a.per_warp_smem = p.per_warp;
+        a.build_mode = vis_out ? 1u : 0u;
+        a.vis_out = vis_out;
+        a.vis_out_len = vis_out_len;
+        a.vis_out_cap = vis_out_cap;
         search_fn fn = p.pairs ? (p.esize == 4 ? pick_search2<uint32_t>(ix->NCH) : pick_search2<uint64_t>(ix->NCH))
                                : (p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH));
         size_t smem = (size_t)p.per_warp * p.W;
@@ -626,6 +612,42 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
         grow *= 2;
         ix->timing.retries++;
     }
+    return DANN_OK;
+}
+
+/* B queries, first k rows each.  All pointers are device pointers. */
+static int search_batch_device_locked(dann_index *ix, const float *d_queries, const int16_t *d_labels,
+                                      const int32_t *d_label_off, int B, int k, int L, int rescore,
+                                      uint64_t *d_out_tid, float *d_out_dist, uint32_t *d_out_node,
+                                      uint32_t *d_out_count, dann_query_stats *d_out_stats, cudaStream_t st) {
+    const IndexView &v = ix->v;
+    if (B <= 0 || k <= 0) return fail(DANN_ERR_INVALID_ARG, "B and k must be positive");
+    if (L < 1 || L > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000 (guc.rs:11-26)", L);
+    if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000 (guc.rs:28-43)", rescore);
+    if (!d_queries || !d_out_tid) return fail(DANN_ERR_INVALID_ARG, "NULL query or output buffer");
+    if (rescore > 0 && v.n && !v.vectors) return fail(DANN_ERR_STATE, "index has no heap vectors yet (dann_index_set_vectors): rescore must be 0");
+    /* rows needed from the approximate stream: scan.rs:255-305 */
+    const uint32_t c_target = rescore == 0 ? (uint32_t)k : (uint32_t)rescore + (uint32_t)k - 1u;
+
+    CK(ix->sc_qfull.reserve((size_t)B * v.dim * sizeof(float)));
+    CK(ix->sc_qcodes.reserve((size_t)B * v.cw * sizeof(uint64_t)));
+    CK(ix->sc_stream.reserve((size_t)B * c_target * sizeof(uint32_t)));
+    CK(ix->sc_stream_len.reserve((size_t)B * sizeof(uint32_t)));
+    CK(ix->sc_stats.reserve((size_t)B * sizeof(dann_query_stats)));
+    CK(ix->sc_qlist.reserve((size_t)B * sizeof(uint32_t)));
+    CK(ix->sc_ctl.reserve(64));
+    dann_query_stats *d_stats = d_out_stats ? d_out_stats : ix->sc_stats.as<dann_query_stats>();
+    uint32_t *d_ctl = ix->sc_ctl.as<uint32_t>(); /* [0]=work counter, [1]=overflow bits */
+
+    ix->timing = dann_batch_timing{};
+    CK(cudaEventRecord(ix->ev[0], st));
+    int rc = launch_prepare(ix, d_queries, B, ix->sc_qfull.as<float>(), ix->sc_qcodes.as<uint64_t>(), st);
+    if (rc) return rc;
+    CK(cudaEventRecord(ix->ev[1], st));
+
+    rc = run_search(ix, ix->sc_qcodes.as<uint64_t>(), d_labels, d_label_off, B, (uint32_t)L, c_target, d_stats, nullptr,
+                    nullptr, 0, st);
+    if (rc) return rc;
     CK(cudaEventRecord(ix->ev[2], st));
 
     RerankArgs r;
@@ -736,6 +758,201 @@ extern "C" int dann_search_batch(dann_index *ix, const float *queries, const int
                                  dann_query_stats *out_stats) {
     return search_batch_host(ix, queries, labels, label_off, B, k, search_list_size, rescore, out_tid, out_dist,
                              nullptr, out_count, out_stats);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* index construction — see dann_build.cuh                            */
+
+extern "C" int dann_index_set_vectors(dann_index *ix, const float *vectors) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!vectors) return fail(DANN_ERR_INVALID_ARG, "dann_index_set_vectors: NULL vectors");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    IndexView &v = ix->v;
+    if (!v.n) return DANN_OK;
+    float *d = const_cast<float *>(v.vectors);
+    if (!d) {
+        void *p = nullptr;
+        size_t bytes = (size_t)v.n * v.dim * sizeof(float);
+        CK(cudaMalloc(&p, bytes));
+        ix->owned.push_back(p);
+        ix->hbm_bytes += bytes;
+        d = reinterpret_cast<float *>(p);
+        v.vectors = d;
+    }
+    CK(cudaMemcpy(d, vectors, (size_t)v.n * v.dim * sizeof(float), cudaMemcpyHostToDevice));
+    if (v.distance_type == DANN_COSINE) {
+        int blocks = std::min<long long>((v.n + 255) / 256, (long long)ix->sm_count * 8);
+        dann_normalize_rows_kernel<<<std::max(blocks, 1), 256, 0, ix->stream>>>(d, v.n, v.dim);
+        ix->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    return DANN_OK;
+}
+
+extern "C" int dann_index_download_nbrs(dann_index *ix, uint32_t *out) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!out) return fail(DANN_ERR_INVALID_ARG, "dann_index_download_nbrs: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const IndexView &v = ix->v;
+    if (!v.n) return DANN_OK;
+    CK(cudaMemcpy2D(out, (size_t)v.R * 4, v.nbrs, (size_t)v.Rp * 4, (size_t)v.R * 4, v.n, cudaMemcpyDeviceToHost));
+    return DANN_OK;
+}
+
+extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_list_size, float max_alpha,
+                                uint32_t max_batch, dann_build_stats *out) {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    IndexView &v = ix->v;
+    if (v.R != DANN_BUILD_SLACK || v.Rp != DANN_BUILD_SLACK)
+        return fail(DANN_ERR_INVALID_ARG, "dann_build_graph needs an index loaded with R == %u neighbour slots", DANN_BUILD_SLACK);
+    if (num_neighbors < 1 || num_neighbors > (int)DANN_BUILD_SLACK) return fail(DANN_ERR_INVALID_ARG, "num_neighbors must be 1..%u", DANN_BUILD_SLACK);
+    if (search_list_size < 1 || search_list_size > 1000) return fail(DANN_ERR_INVALID_ARG, "build search_list_size must be 1..1000");
+    if (v.has_labels) return fail(DANN_ERR_INVALID_ARG, "labeled builds are not implemented");
+    if (v.n == 0) return DANN_OK;
+    if (v.start_default != 0) return fail(DANN_ERR_INVALID_ARG, "dann_build_graph inserts in id order: start_default must be 0");
+    if (max_batch == 0) max_batch = 1u << 20;
+    cudaStream_t st = ix->stream;
+    const uint32_t n = v.n;
+    const uint32_t vis_cap = 2 * DANN_BUILD_CMAX;
+    const uint32_t mb = std::min<uint32_t>(max_batch, n);
+
+    DevBuf b_dist, b_deg, b_vis, b_vlen, b_k0, b_k1, b_v0, b_v1, b_heads, b_tmp, b_stream, b_slen, b_stats;
+    struct Cleanup {
+        std::vector<DevBuf *> v;
+        ~Cleanup() {
+            for (DevBuf *b : v) b->release();
+        }
+    } cleanup{{&b_dist, &b_deg, &b_vis, &b_vlen, &b_k0, &b_k1, &b_v0, &b_v1, &b_heads, &b_tmp, &b_stream, &b_slen, &b_stats}};
+    const size_t ntrip = (size_t)mb * DANN_BUILD_SLACK;
+    CK(b_dist.reserve((size_t)n * DANN_BUILD_SLACK * sizeof(uint16_t)));
+    CK(b_deg.reserve((size_t)n));
+    CK(b_vis.reserve((size_t)mb * vis_cap * sizeof(uint64_t)));
+    CK(b_vlen.reserve((size_t)mb * 4));
+    CK(b_k0.reserve(ntrip * 8));
+    CK(b_k1.reserve(ntrip * 8));
+    CK(b_v0.reserve(ntrip * 4));
+    CK(b_v1.reserve(ntrip * 4));
+    CK(b_heads.reserve(ntrip * 4 + 64));
+    CK(ix->sc_stream.reserve((size_t)mb * 4)); /* run_search writes stream_len / stats even in build mode */
+    CK(ix->sc_stream_len.reserve((size_t)mb * 4));
+    CK(b_stats.reserve((size_t)mb * sizeof(dann_query_stats)));
+    CK(ix->sc_qlist.reserve((size_t)mb * sizeof(uint32_t)));
+    CK(ix->sc_ctl.reserve(64));
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b_k0.as<uint64_t>(), b_k1.as<uint64_t>(), b_v0.as<uint32_t>(),
+                                       b_v1.as<uint32_t>(), ntrip, 16, 64, st));
+    CK(b_tmp.reserve(tmp_bytes));
+    uint32_t *nbrs = const_cast<uint32_t *>(v.nbrs);
+    CK(cudaMemsetAsync(nbrs, 0xFF, (size_t)n * DANN_BUILD_SLACK * 4, st));
+    CK(cudaMemsetAsync(b_deg.p, 0, n, st));
+
+    BuildArgs ba;
+    ba.codes = v.codes;
+    ba.cw = v.cw;
+    ba.cws = v.cw | 1u;
+    ba.n = n;
+    ba.nbrs = nbrs;
+    ba.nbr_dist = b_dist.as<uint16_t>();
+    ba.deg = b_deg.as<uint8_t>();
+    ba.R = (uint32_t)num_neighbors;
+    ba.max_alpha = max_alpha;
+    const size_t pw = ((size_t)DANN_BUILD_CMAX * 8 + (size_t)DANN_BUILD_CMAX * ba.cws * 8 + DANN_BUILD_CMAX * 4 +
+                       DANN_BUILD_SLACK * 4 + DANN_BUILD_SLACK * 2 + 15) & ~(size_t)15;
+    ba.per_warp_smem = (uint32_t)pw;
+    const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
+    int bw = (int)std::min<size_t>(8, budget / pw);
+    if (bw < 1) return fail(DANN_ERR_CAPACITY, "SBQ code of %u words is too wide for the prune kernel's shared memory", v.words);
+    const size_t bsmem = pw * bw;
+    CK(cudaFuncSetAttribute(dann_build_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    CK(cudaFuncSetAttribute(dann_build_backlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    CK(cudaFuncSetAttribute(dann_build_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    const int bgrid = ix->sm_count * std::max<int>(1, (int)(budget / bsmem));
+
+    dann_build_stats bs{};
+    cudaEvent_t e[5];
+    for (auto &x : e) CK(cudaEventCreate(&x));
+    struct EvGuard {
+        cudaEvent_t *e;
+        ~EvGuard() {
+            for (int i = 0; i < 5; i++) cudaEventDestroy(e[i]);
+        }
+    } evg{e};
+    const uint32_t lists_unique_saved = ix->lists_unique;
+    ix->lists_unique = 1; /* the builder never repeats an id within a list */
+    const bool verbose = getenv("DANN_BUILD_VERBOSE") != nullptr;
+    /* node 0 is the entry point (the reference's first inserted node); everything else arrives in
+     * batches that grow with the graph (at most 1/16 of it) up to max_batch */
+    for (uint32_t lo = 1; lo < n;) {
+        uint32_t m = std::max<uint32_t>(1, lo / 16);
+        m = std::min(std::min(m, mb), n - lo);
+        CK(cudaEventRecord(e[0], st));
+        rc = run_search(ix, v.codes + (size_t)lo * v.cw, nullptr, nullptr, (int)m, (uint32_t)search_list_size, 1u,
+                        b_stats.as<dann_query_stats>(), b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(), vis_cap, st);
+        if (rc) {
+            ix->lists_unique = lists_unique_saved;
+            return rc;
+        }
+        CK(cudaEventRecord(e[1], st));
+        dann_build_prune_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, lo, m, b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(), vis_cap,
+                                                              b_k0.as<uint64_t>(), b_v0.as<uint32_t>());
+        ix->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e[2], st));
+        const size_t cnt = (size_t)m * DANN_BUILD_SLACK;
+        size_t tb = b_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tb, b_k0.as<uint64_t>(), b_k1.as<uint64_t>(), b_v0.as<uint32_t>(),
+                                           b_v1.as<uint32_t>(), cnt, 16, 64, st));
+        uint32_t *d_nheads = b_heads.as<uint32_t>() + ntrip;
+        CK(cudaMemsetAsync(d_nheads, 0, 4, st));
+        dann_build_heads_kernel<<<ix->sm_count * 4, 256, 0, st>>>(b_k1.as<uint64_t>(), cnt, b_heads.as<uint32_t>(), d_nheads);
+        ix->launches += 2;
+        uint32_t nheads = 0;
+        CK(cudaMemcpyAsync(&nheads, d_nheads, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(e[3], st));
+        if (nheads) {
+            dann_build_backlink_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, b_k1.as<uint64_t>(), b_v1.as<uint32_t>(), cnt,
+                                                                     b_heads.as<uint32_t>(), nheads);
+            ix->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(e[4], st));
+        CK(cudaStreamSynchronize(st));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e[0], e[1]));
+        bs.search_ms += ms;
+        CK(cudaEventElapsedTime(&ms, e[1], e[2]));
+        bs.prune_ms += ms;
+        CK(cudaEventElapsedTime(&ms, e[2], e[3]));
+        bs.sort_ms += ms;
+        CK(cudaEventElapsedTime(&ms, e[3], e[4]));
+        bs.backlink_ms += ms;
+        bs.batches++;
+        if (verbose && (bs.batches % 16 == 0 || lo + m >= n))
+            fprintf(stderr, "[dann_build] batch %u: nodes %u..%u (m=%u, %u destinations) search %.0f prune %.0f sort %.0f backlink %.0f ms\n",
+                    bs.batches, lo, lo + m, m, nheads, bs.search_ms, bs.prune_ms, bs.sort_ms, bs.backlink_ms);
+        lo += m;
+    }
+    dann_build_finalize_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba);
+    ix->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    bs.total_ms = bs.search_ms + bs.prune_ms + bs.sort_ms + bs.backlink_ms;
+    /* average degree */
+    {
+        std::vector<uint8_t> hdeg(std::min<uint32_t>(n, 1u << 20));
+        CK(cudaMemcpy(hdeg.data(), b_deg.p, hdeg.size(), cudaMemcpyDeviceToHost));
+        double sdeg = 0;
+        for (uint8_t d : hdeg) sdeg += d;
+        bs.avg_degree = sdeg / (double)hdeg.size();
+    }
+    if (out) *out = bs;
+    return DANN_OK;
 }
 
 /* ------------------------------------------------------------------------------------ */

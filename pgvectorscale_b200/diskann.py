@@ -49,6 +49,11 @@ class _BatchTiming(C.Structure):
                 ("resort_ms", C.c_float), ("total_ms", C.c_float), ("retries", C.c_uint32)]
 
 
+class _BuildStats(C.Structure):
+    _fields_ = [("batches", C.c_uint32), ("search_ms", C.c_float), ("prune_ms", C.c_float), ("sort_ms", C.c_float),
+                ("backlink_ms", C.c_float), ("total_ms", C.c_float), ("avg_degree", C.c_double)]
+
+
 class _QueryStats(C.Structure):
     _fields_ = [("visits", C.c_uint32), ("d_quantized", C.c_uint32), ("candidates", C.c_uint32),
                 ("d_full", C.c_uint32), ("stream_len", C.c_uint32), ("status", C.c_uint32)]
@@ -64,6 +69,7 @@ EXPORTS = [
     "dann_scan_stats", "dann_scan_end", "dann_search_batch", "dann_search_batch_device",
     "dann_prepare_queries", "dann_code_stride", "dann_sbq_distance", "dann_full_distance",
     "dann_kernel_launches", "dann_last_batch_timing",
+    "dann_build_graph", "dann_index_download_nbrs", "dann_index_set_vectors",
 ]
 
 _LIB = None
@@ -104,6 +110,9 @@ def load_library(path: Optional[str] = None):
     lib.dann_sbq_distance.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp]
     lib.dann_full_distance.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
     lib.dann_last_batch_timing.argtypes = [vp, C.POINTER(_BatchTiming)]
+    lib.dann_build_graph.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(_BuildStats)]
+    lib.dann_index_download_nbrs.argtypes = [vp, vp]
+    lib.dann_index_set_vectors.argtypes = [vp, vp]
     if path is None:
         _LIB = lib
     return lib
@@ -209,6 +218,25 @@ class DiskAnnIndex:
         t = _BatchTiming()
         _check(self._lib, self._lib.dann_last_batch_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in _BatchTiming._fields_}
+
+    # -- index construction (not the scan hot path) -----------------------------
+    def build_graph(self, num_neighbors: int = 50, search_list_size: int = 100, max_alpha: float = 1.2,
+                    max_batch: int = 1 << 20) -> dict:
+        """GPU batch Vamana over the SBQ codes already in HBM (index loaded with R == 64 slots)."""
+        st = _BuildStats()
+        _check(self._lib, self._lib.dann_build_graph(self._h, int(num_neighbors), int(search_list_size),
+                                                     float(max_alpha), int(max_batch), C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _BuildStats._fields_}
+
+    def download_nbrs(self) -> np.ndarray:
+        out = np.empty((self.n, self.R), np.uint32)
+        _check(self._lib, self._lib.dann_index_download_nbrs(self._h, _np_ptr(out)))
+        return out
+
+    def set_vectors(self, vectors: np.ndarray):
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        assert v.shape == (self.n, self.dim)
+        _check(self._lib, self._lib.dann_index_set_vectors(self._h, _np_ptr(v)))
 
     # -- scan operator ----------------------------------------------------------------
     def begin_scan(self) -> "IndexScan":

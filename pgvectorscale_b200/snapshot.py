@@ -54,7 +54,7 @@ class Snapshot:
     codes: np.ndarray
     nbrs: np.ndarray
     heap_tid: np.ndarray
-    vectors: np.ndarray
+    vectors: Optional[np.ndarray]   # None: supplied after load (DiskAnnIndex.set_vectors)
     start_default: int = INVALID_NODE
     start_labels: Optional[np.ndarray] = None
     start_label_nodes: Optional[np.ndarray] = None
@@ -66,7 +66,8 @@ class Snapshot:
         assert self.codes.shape == (self.n, self.words) and self.codes.dtype == np.uint64
         assert self.nbrs.shape == (self.n, self.R) and self.nbrs.dtype == np.uint32
         assert self.heap_tid.shape == (self.n,) and self.heap_tid.dtype == np.uint64
-        assert self.vectors.shape == (self.n, self.dim) and self.vectors.dtype == np.float32
+        if self.vectors is not None:
+            assert self.vectors.shape == (self.n, self.dim) and self.vectors.dtype == np.float32
         assert self.mean.shape == (self.dim_index,)
         assert 1 <= self.dim_index <= self.dim
         if self.has_labels:

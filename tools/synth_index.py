@@ -234,3 +234,38 @@ def ground_truth(x: torch.Tensor, q: torch.Tensor, k: int, mask: torch.Tensor | 
             sc = torch.where(mask[s:e], sc, torch.full_like(sc, -4.0))
         out[s:e] = torch.topk(sc, k, dim=1).indices
     return out
+
+
+@torch.no_grad()
+def build_index_vamana(x: torch.Tensor, distance_type: int = COSINE, bits: int | None = None, R: int = 50,
+                       L_build: int = 100, alpha: float = 1.2, max_batch: int = 1 << 20, log=None, keep_index=False):
+    """Same contract as build_index(), but the graph comes from the product's GPU batch Vamana builder
+    (dann_build_graph: beam search in build mode + alpha prune + back-links, all over SBQ codes, like the
+    reference's build) instead of the exact-kNN fixture.  Scales linearly in n.
+    Returns the host Snapshot (R = 64 slots per node, lists of <= R ids); with keep_index=True also the
+    loaded DiskAnnIndex (vectors already supplied)."""
+    from pgvectorscale_b200 import diskann
+    t0 = time.time()
+    n, dim = x.shape
+    bits = default_bits(dim) if bits is None else bits
+    say = log or (lambda *a: None)
+    mean = x.mean(dim=0)
+    m2 = ((x - mean) ** 2).sum(dim=0)
+    mean_h, m2_h = mean.cpu().numpy().astype(np.float32), m2.cpu().numpy().astype(np.float32)
+    codes = quantize_nodes(x, distance_type, bits, mean_h, m2_h, n)
+    say(f"  sbq codes {time.time() - t0:.1f}s")
+    slots = 64
+    snap = Snapshot(n=n, dim=dim, dim_index=dim, bits=bits, words=code_words(dim, bits), R=slots,
+                    distance_type=distance_type, has_labels=False, count=n, mean=mean_h, m2=m2_h, codes=codes,
+                    nbrs=np.full((n, slots), INVALID_NODE, np.uint32), heap_tid=make_heap_tids(n), vectors=None,
+                    start_default=0 if n else INVALID_NODE)
+    idx = diskann.DiskAnnIndex(snap, device=x.device.index or 0)
+    st = idx.build_graph(R, L_build, alpha, max_batch)
+    say(f"  gpu vamana build {time.time() - t0:.1f}s: {st}")
+    snap.nbrs = idx.download_nbrs()
+    snap.vectors = x.cpu().numpy()
+    if keep_index:
+        idx.set_vectors(snap.vectors)
+        return snap, idx, st
+    idx.close()
+    return snap, None, st
