@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024, help="queries per GPU per step")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--data", default="lowrank", choices=["lowrank", "gaussian"])
+    ap.add_argument("--fixture", default="vamana", choices=["vamana", "knn"],
+                    help="graph of the synthetic index: the product's GPU batch Vamana builder over SBQ codes "
+                         "(restates the reference build) or the exact-kNN + alpha-prune torch fixture")
     ap.add_argument("--bits", type=int, default=0, help="SBQ bits/dim (0 = reference default)")
     ap.add_argument("--L", type=int, default=0, help="fix search_list_size (0 = sweep for 99%% recall)")
     ap.add_argument("--rescore", type=int, default=0)
@@ -59,7 +62,8 @@ def log(*a):
 
 # (search_list_size, rescore) in increasing cost (visits ~ L + rescore); recall is driven mostly by rescore
 SWEEP = [(25, 50), (50, 50), (100, 50), (50, 100), (100, 100), (64, 150), (100, 150), (64, 200), (100, 200),
-         (150, 200), (200, 200), (150, 300), (200, 300), (400, 400), (800, 400), (800, 800), (1600, 1000)]
+         (150, 200), (200, 200), (150, 250), (200, 250), (150, 300), (200, 300), (300, 300), (400, 400), (800, 400),
+         (800, 800), (1000, 1000), (1600, 1000)]
 
 
 class ClockSampler:
@@ -166,8 +170,12 @@ def build_fixture(args, device):
     from tools import synth_index as si
     t0 = time.time()
     x = si.gen_dataset(args.n, args.dim, 0x5EED0010, args.data, device=device)
-    snap = si.build_index(x, bits=args.bits or None, R=50, log=log)
-    log(f"[bench] index fixture: n={args.n} dim={args.dim} data={args.data} bits={snap.bits} built in {time.time() - t0:.1f}s")
+    if args.fixture == "vamana":
+        snap, _, st = si.build_index_vamana(x, bits=args.bits or None, R=50, L_build=100, alpha=1.2, log=log)
+    else:
+        snap = si.build_index(x, bits=args.bits or None, R=50, log=log)
+    log(f"[bench] index fixture ({args.fixture}): n={args.n} dim={args.dim} data={args.data} bits={snap.bits} "
+        f"built in {time.time() - t0:.1f}s")
     return x, snap
 
 
@@ -489,7 +497,9 @@ def main():
                    "search_list_size": L, "rescore": rescore, "recall_at_10": round(recall, 4),
                    "parallelism": f"query-shard x{world} (replicated index, all_gather of top-k)",
                    "l2_policy": f"index {idx.hbm_bytes / 1e9:.2f} GB >> 126 MB L2, random gathers, distinct queries every step",
-                   "index_fixture": "tools/synth_index.py (GPU batch builder, not the reference's serial build)"},
+                   "index_fixture": ("dann_build_graph: GPU batch Vamana over SBQ codes (R=50, L_build=100, alpha=1.2), "
+                                     "the reference's build algorithm with batched insertion" if args.fixture == "vamana"
+                                     else "tools/synth_index.py exact-kNN + alpha-prune torch fixture")},
         "recall_sweep": sweep_log,
         "parity": parity,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * dim * 4,

@@ -96,7 +96,7 @@ def nodes_of(tid):
 
 
 SWEEP = [(50, 50), (100, 50), (100, 100), (100, 150), (100, 200), (150, 200), (200, 200), (200, 300), (300, 300),
-         (400, 400), (600, 600), (800, 800)]
+         (400, 400), (600, 600), (800, 800), (1000, 1000), (1500, 1000)]
 chosen = None
 for (L, rescore) in SWEEP:
     idx.search_batch(qh, k=k, search_list_size=L, rescore=rescore)

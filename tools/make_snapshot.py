@@ -17,11 +17,15 @@ ap.add_argument("--data", default="lowrank")
 ap.add_argument("--bits", type=int, default=0)
 ap.add_argument("--queries", type=int, default=8192)
 ap.add_argument("--labels", action="store_true")
+ap.add_argument("--fixture", default="vamana", choices=["vamana", "knn"])
 ap.add_argument("--out", default="/tmp/snap")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 x = si.gen_dataset(a.n, a.dim, 0x5EED0010, a.data, device=dev)
-snap = si.build_index(x, bits=a.bits or None, labels_seed=0x5EED0040 if a.labels else None, log=print)
+if a.fixture == "vamana" and not a.labels:
+    snap, _, _ = si.build_index_vamana(x, bits=a.bits or None, log=print)
+else:
+    snap = si.build_index(x, bits=a.bits or None, labels_seed=0x5EED0040 if a.labels else None, log=print)
 q = si.gen_dataset(a.queries, a.dim, 0x5EED0011, a.data, device=dev)
 truth = si.ground_truth(x, q[:1024], 10).cpu().numpy()
 snap.save(a.out + ".npz")
