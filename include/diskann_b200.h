@@ -125,7 +125,9 @@ void dann_scan_end(dann_scan *sc);
 /* Host buffers; H2D/D2H copies are part of the call (this is the end-to-end path).
  * labels/label_off: CSR of each query's scan-key labels, label_off == NULL = no key.
  * out_tid [B*k] (block<<16|offset, DANN_INVALID_TID past out_count[b]), out_dist [B*k],
- * out_count [B] rows produced, out_stats [B] (each may be NULL except out_tid). */
+ * out_count [B] rows produced, out_stats [B] (each may be NULL except out_tid).
+ * rescore + k is bounded by the rerank kernel's shared memory (about 45 000 rows at 768 dimensions):
+ * larger requests return DANN_ERR_INVALID_ARG; the scan operator inherits the bound per scan. */
 int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
                       const int32_t *label_off, int B, int k, int search_list_size,
                       int rescore, uint64_t *out_tid, float *out_dist, uint32_t *out_count,

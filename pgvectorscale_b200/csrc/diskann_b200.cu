@@ -625,6 +625,12 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
     if (L < 1 || L > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000 (guc.rs:11-26)", L);
     if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000 (guc.rs:28-43)", rescore);
     if (!d_queries || !d_out_tid) return fail(DANN_ERR_INVALID_ARG, "NULL query or output buffer");
+    {   /* the rerank kernel keeps one f32 per streamed row + the window in shared memory */
+        const size_t need_smem = (size_t)((v.dim + 3u) & ~3u) * 4 + ((size_t)rescore + (size_t)k + 2) * 4 + (size_t)rescore * 8 + 64;
+        if (need_smem > ix->smem_optin)
+            return fail(DANN_ERR_INVALID_ARG, "k=%d rows with rescore=%d need %zu B of shared memory per scan (limit %zu): "
+                        "fetch fewer rows per scan", k, rescore, need_smem, ix->smem_optin);
+    }
     if (rescore > 0 && v.n && !v.vectors) return fail(DANN_ERR_STATE, "index has no heap vectors yet (dann_index_set_vectors): rescore must be 0");
     /* rows needed from the approximate stream: scan.rs:255-305 */
     const uint32_t c_target = rescore == 0 ? (uint32_t)k : (uint32_t)rescore + (uint32_t)k - 1u;
@@ -637,7 +643,6 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
     CK(ix->sc_qlist.reserve((size_t)B * sizeof(uint32_t)));
     CK(ix->sc_ctl.reserve(64));
     dann_query_stats *d_stats = d_out_stats ? d_out_stats : ix->sc_stats.as<dann_query_stats>();
-    uint32_t *d_ctl = ix->sc_ctl.as<uint32_t>(); /* [0]=work counter, [1]=overflow bits */
 
     ix->timing = dann_batch_timing{};
     CK(cudaEventRecord(ix->ev[0], st));

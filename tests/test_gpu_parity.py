@@ -258,3 +258,37 @@ def test_prepare_and_full_distance_kernels(lib):
                         x = oracle.preprocess_cosine(x)
                     ref = np.float32(oracle.distance(dist, x, full[b], "avx2"))
                     assert out[b, i].view(np.uint32) == ref.view(np.uint32), (dist, b, i)
+
+
+def test_argument_validation_does_not_poison_the_handle(lib):
+    s = build_case(400, 64, L2, seed=71, kind="uniform", R=12, L_build=24)
+    q = _queries(s, 4, 3, "uniform")
+    with lib.DiskAnnIndex(s) as idx:
+        for kw in (dict(k=0), dict(k=10, search_list_size=0), dict(k=10, search_list_size=10001),
+                   dict(k=10, rescore=1001), dict(k=10, rescore=-1), dict(k=2_000_000, rescore=10)):
+            with pytest.raises(lib.DiskAnnError) as e:
+                idx.search_batch(q, **kw)
+            assert e.value.code == -1, kw          # DANN_ERR_INVALID_ARG, not a CUDA error
+        _compare_batch(s, idx, q, 10, 50, 20)      # the handle still works
+        sc = idx.begin_scan()
+        with pytest.raises(lib.DiskAnnError):
+            sc.gettuple()                           # amgettuple before amrescan
+        sc.end()
+
+
+def test_index_without_vectors_then_set_vectors(lib):
+    from oracle import oracle
+    s = build_case(900, 96, COSINE, seed=73, R=16, L_build=32)
+    vec = s.vectors
+    s.vectors = None
+    q = _queries(s, 8, 4)
+    with lib.DiskAnnIndex(s) as idx:
+        with pytest.raises(lib.DiskAnnError):
+            idx.search_batch(q, k=5, rescore=10)    # no heap vectors yet: only rescore=0 scans
+        s.vectors = vec
+        g0 = idx.search_batch(q, k=5, rescore=0)
+        otid, _, _, _ = oracle.scan_batch(s, q, None, None, 100, 0, 5)
+        assert np.array_equal(g0["tid"], otid)
+        idx.set_vectors(vec)
+        _compare_batch(s, idx, q, 5, 100, 10)
+        assert np.array_equal(idx.download_nbrs(), s.nbrs)
