@@ -114,7 +114,9 @@ int dann_scan_begin(dann_index *ix, dann_scan **out);
  * GUCs diskann.query_search_list_size / diskann.query_rescore (guc.rs:3-4). */
 int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
                      int search_list_size, int rescore);
-/* Returns 1 and fills the outputs for the next row, 0 at end of scan, <0 on error.
+/* One amgettuple: resumes the scan's suspended search (its state lives in HBM between calls), pulls
+ * exactly the rows TSVResponseIterator::next_with_resort would (scan.rs:244-305), pops one.
+ * Returns 1 and fills the outputs for the next row, 0 at end of scan, <0 on error.
  * dist is the exact rerank distance (NaN when rescore == 0). Any output may be NULL. */
 int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id,
                        float *dist);
@@ -127,7 +129,7 @@ void dann_scan_end(dann_scan *sc);
  * out_tid [B*k] (block<<16|offset, DANN_INVALID_TID past out_count[b]), out_dist [B*k],
  * out_count [B] rows produced, out_stats [B] (each may be NULL except out_tid).
  * rescore + k is bounded by the rerank kernel's shared memory (about 45 000 rows at 768 dimensions):
- * larger requests return DANN_ERR_INVALID_ARG; the scan operator inherits the bound per scan. */
+ * larger requests return DANN_ERR_INVALID_ARG (the streaming scan operator has no such bound). */
 int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
                       const int32_t *label_off, int B, int k, int search_list_size,
                       int rescore, uint64_t *out_tid, float *out_dist, uint32_t *out_count,

@@ -468,3 +468,57 @@ __global__ void dann_check_unique_kernel(const uint32_t *nbrs, uint32_t n, uint3
         if (__any_sync(DANN_FULL, dup) && lane == 0) atomicOr(flag, 1u);
     }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Streaming scan (dann_scan_gettuple): one step of next_with_resort (scan.rs:244-305).       */
+/* The rerank window lives in HBM between calls: win[] is the BinaryHeap<ResortData> array,   */
+/* entries (total_cmp key of the exact distance << 32) | node.  One thread: push the rows that */
+/* just came off the approximate stream, then pop one row for the executor.                  */
+struct ScanWindow {
+    uint32_t len, d_full;
+};
+struct ScanRow {
+    uint64_t tid;
+    uint32_t node, have;
+    float dist;
+    uint32_t pad;
+};
+__global__ void dann_scan_resort_kernel(IndexView ix, ScanWindow *w, uint64_t *win, uint32_t rescore,
+                                        const uint32_t *new_nodes, const float *new_dist, uint32_t skip,
+                                        uint32_t nnew, ScanRow *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ScanRow r;
+    r.tid = DANN_INVALID_TID;
+    r.node = DANN_INVALID_NODE;
+    r.have = 0;
+    r.dist = DANN_NAN_F;
+    r.pad = 0;
+    if (rescore == 0) { /* resort_buffer.capacity() == 0: the stream order is the result (scan.rs:251-253) */
+        if (nnew > skip) {
+            r.node = new_nodes[skip];
+            r.tid = ix.tids[r.node];
+            r.have = 1;
+        }
+        *out = r;
+        return;
+    }
+    using H = RustHeap<uint64_t, 32>;
+    ArrayStore<uint64_t> store{win};
+    uint32_t len = w->len;
+    for (uint32_t i = skip; i < nnew; i++) { /* full_distance_comparisons += 1; resort_buffer.push(..) */
+        H::push(store, len, ((uint64_t)total_ukey(new_dist[i]) << 32) | new_nodes[i]);
+        w->d_full++;
+    }
+    if (len > 0) {
+        uint64_t e = H::pop(store, len);
+        uint32_t uk = (uint32_t)(e >> 32) ^ 0x80000000u; /* undo total_ukey: the transform is an involution */
+        int32_t b = (int32_t)uk;
+        b ^= (int32_t)(((uint32_t)(b >> 31)) >> 1);
+        r.node = (uint32_t)e;
+        r.dist = __int_as_float(b);
+        r.tid = ix.tids[r.node];
+        r.have = 1;
+    }
+    w->len = len;
+    *out = r;
+}

@@ -38,6 +38,11 @@
 #include "dann_device.cuh"
 #include "dann_heap.cuh"
 
+/* what a suspended scan keeps besides its HBM workspace (heap tail, inserted-set, seq->node table) */
+struct SavedScan {
+    uint32_t valid, heap_len, vis_len, ncand, nins, visits, dq, exhausted;
+};
+
 struct SearchArgs {
     IndexView ix;
     const uint64_t *q_codes;    /* [B][cw] */
@@ -64,6 +69,11 @@ struct SearchArgs {
     uint32_t G, Gshift;         /* lanes per code row (power of two) */
     uint32_t lists_unique;      /* no neighbour list repeats an id (checked at index load) */
     uint32_t per_warp_smem;
+    /* resumable scan (dann_scan_gettuple): single query, single warp; the per-scan workspace is not
+     * shared with other queries, so the state below survives between launches */
+    struct SavedScan *saved; /* NULL = one-shot */
+    void *saved_heap_sm;     /* [hs] copy of the shared-memory part of the heap */
+    uint64_t *saved_vis;     /* [vcap] */
     /* build mode (dann_build.cuh): the scan stops when visit_closest first returns None and the
      * visited list (graph/mod.rs:285-327 greedy_search_for_build) is written out instead of a stream */
     uint32_t build_mode;
@@ -362,6 +372,20 @@ struct SearchWarp {
         heap_len = vis_head = vis_len = ncand = nins = listn = 0;
         visits = dq = status = 0;
         uint32_t scount = 0;
+        const bool resumed = a.saved && a.saved->valid;
+        if (resumed) { /* pick the suspended ListSearchResult up where the last amgettuple left it */
+            heap_len = a.saved->heap_len;
+            vis_len = a.saved->vis_len;
+            ncand = a.saved->ncand;
+            nins = a.saved->nins;
+            visits = a.saved->visits;
+            dq = a.saved->dq;
+            const E *hsrc = reinterpret_cast<const E *>(a.saved_heap_sm);
+            const uint32_t hn = heap_len < heap.hs ? heap_len : heap.hs;
+            for (uint32_t i = lane; i < hn; i += 32) heap.sm[i] = hsrc[i];
+            for (uint32_t i = lane; i < vis_len; i += 32) vis[i] = a.saved_vis[i];
+            __syncwarp();
+        }
         /* query code chunks this lane compares against (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) */
         {
             const uint32_t gl = lane & (a.G - 1), nchunks = ix.cw >> 1;
@@ -373,7 +397,7 @@ struct SearchWarp {
             }
         }
         /* inserted = HashSet::new() (the bitmap flavour is already all zero) */
-        if (!a.bitmap_words) {
+        if (!a.bitmap_words && !resumed) {
             uint4 ff = make_uint4(DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE);
             uint4 *h4 = reinterpret_cast<uint4 *>(hash);
             for (uint32_t i = lane; i < a.hash_cap / 4; i += 32) h4[i] = ff;
@@ -383,13 +407,15 @@ struct SearchWarp {
         ql = nullptr;
         nql = 0;
         filter = false;
+        if (a.q_label_off) {
+            int32_t o0 = a.q_label_off[q], o1 = a.q_label_off[q + 1];
+            ql = a.q_labels + o0;
+            nql = (uint32_t)(o1 - o0);
+            filter = nql > 0; /* has_label_filter, scan.rs:189 */
+        }
         /* greedy_search_streaming_init + ListSearchResult::new (graph/mod.rs:97-124,331-354) */
-        if (ix.start_default != DANN_INVALID_NODE) {
+        if (ix.start_default != DANN_INVALID_NODE && !resumed) {
             if (a.q_label_off) { /* StartNodes::get_for_node(Some(labels)), start_nodes.rs:39-48 */
-                int32_t o0 = a.q_label_off[q], o1 = a.q_label_off[q + 1];
-                ql = a.q_labels + o0;
-                nql = (uint32_t)(o1 - o0);
-                filter = nql > 0; /* has_label_filter, scan.rs:189 */
                 for (uint32_t b = 0; b < nql && !status; b += 32) {
                     uint32_t i = b + lane, n = DANN_INVALID_NODE;
                     bool valid = false;
@@ -465,8 +491,25 @@ struct SearchWarp {
             scount++;
             if (scount == a.c_target) done = true;
         }
-        /* bitmap flavour: clear exactly the bits this query set */
-        if (a.bitmap_words) {
+        if (a.saved) { /* suspend: the inserted-set and the heap tail stay where they are */
+            __syncwarp();
+            E *hdst = reinterpret_cast<E *>(a.saved_heap_sm);
+            const uint32_t hn = heap_len < heap.hs ? heap_len : heap.hs;
+            for (uint32_t i = lane; i < hn; i += 32) hdst[i] = heap.sm[i];
+            for (uint32_t i = lane; i < vis_len; i += 32) a.saved_vis[i] = vis[vis_head + i];
+            if (lane == 0) {
+                SavedScan sv;
+                sv.valid = status ? 0u : 1u;
+                sv.heap_len = heap_len;
+                sv.vis_len = vis_len;
+                sv.ncand = ncand;
+                sv.nins = nins;
+                sv.visits = visits;
+                sv.dq = dq;
+                sv.exhausted = (!done && !status) ? 1u : 0u; /* next() returned None */
+                *a.saved = sv;
+            }
+        } else if (a.bitmap_words) { /* bitmap flavour: clear exactly the bits this query set */
             __syncwarp();
             for (uint32_t i = lane; i < nins; i += 32) bitmap[ins[i] >> 5] = 0u;
             __threadfence_block();

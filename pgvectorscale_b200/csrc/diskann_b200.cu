@@ -107,20 +107,26 @@ struct dann_index {
     uint32_t lists_unique = 0;
 };
 
+struct SearchPlan {
+    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
+    bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
+};
+
 struct dann_scan {
     dann_index *ix = nullptr;
     std::vector<float> query;
     std::vector<int16_t> labels;
     int nlabels = -1;
-    bool null_query = false;
     int L = 100, rescore = 50;
     bool active = false;
-    /* rows fetched so far (the scan re-runs with a larger LIMIT when they run out) */
-    std::vector<uint64_t> tid;
-    std::vector<float> dist;
-    std::vector<uint32_t> node;
-    uint32_t produced = 0, next = 0, k_cur = 0;
-    bool exhausted = false;
+    /* suspended search state in HBM (see SavedScan / dann_search.cuh) */
+    DevBuf d_query, d_qfull, d_qcodes, d_labels, d_label_off, d_saved, d_heap_sm, d_vis, d_heap_tail, d_cnode, d_set,
+        d_ins, d_stream, d_slen, d_stats, d_dist, d_win, d_winst, d_row, d_ctl;
+    SearchPlan plan{};
+    uint32_t grow = 1;
+    uint32_t streamed = 0;  /* rows taken off the approximate stream so far */
+    uint32_t win_len = 0;   /* rows sitting in the rerank window */
+    bool exhausted = false; /* next() returned None */
     dann_query_stats stats{};
 };
 
@@ -468,14 +474,10 @@ static search_fn pick_search2(uint32_t nch) {
     }
 }
 
-struct SearchPlan {
-    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
-    bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
-};
 
 
 static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, bool keyed,
-                     SearchPlan *p) {
+                     SearchPlan *p, bool force_single = false) {
     const IndexView &v = ix->v;
     /* visits are about L + consumed; every visit stages at most R ids */
     uint64_t need = (((uint64_t)L + c_target) * 23 / 20 + 40u) * v.R * grow; /* 15% slack over L + consumed */
@@ -500,7 +502,7 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     p->vcap = (uint32_t)((vcap + 3) & ~3ull);
     const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
-    p->pairs = v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
+    p->pairs = !force_single && v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
     if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
@@ -583,6 +585,9 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.G = ix->G;
         a.Gshift = ix->Gshift;
         a.per_warp_smem = p.per_warp;
+        a.saved = nullptr;
+        a.saved_heap_sm = nullptr;
+        a.saved_vis = nullptr;
         a.build_mode = vis_out ? 1u : 0u;
         a.vis_out = vis_out;
         a.vis_out_len = vis_out_len;
@@ -972,65 +977,216 @@ extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) {
     return DANN_OK;
 }
 
+static void scan_release(dann_scan *sc) {
+    DevBuf *bufs[] = {&sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
+                      &sc->d_heap_sm, &sc->d_vis, &sc->d_heap_tail, &sc->d_cnode, &sc->d_set, &sc->d_ins, &sc->d_stream,
+                      &sc->d_slen, &sc->d_stats, &sc->d_dist, &sc->d_win, &sc->d_winst, &sc->d_row, &sc->d_ctl};
+    for (DevBuf *b : bufs) b->release();
+}
+
+/* (re)allocate the scan's private workspace for the current plan and reset the search state */
+static int scan_reset_search(dann_scan *sc) {
+    dann_index *ix = sc->ix;
+    cudaStream_t st = ix->stream;
+    SearchPlan &p = sc->plan;
+    int rc = make_plan(ix, 1, (uint32_t)sc->L, (uint32_t)sc->rescore + 64u, sc->grow, sc->nlabels >= 0, &p, true);
+    if (rc) return rc;
+    CK(sc->d_saved.reserve(sizeof(SavedScan)));
+    CK(sc->d_heap_sm.reserve((size_t)p.hs * p.esize + 16));
+    CK(sc->d_vis.reserve((size_t)p.vcap * 8));
+    CK(sc->d_heap_tail.reserve((size_t)p.cand_cap * p.esize));
+    CK(sc->d_cnode.reserve((size_t)p.cand_cap * 4));
+    CK(sc->d_ins.reserve((size_t)p.ins_cap * 4));
+    if (p.bitmap_words) {
+        CK(sc->d_set.reserve((size_t)p.bitmap_words * 4));
+        CK(cudaMemsetAsync(sc->d_set.p, 0, (size_t)p.bitmap_words * 4, st));
+    } else {
+        CK(sc->d_set.reserve((size_t)p.hash_cap * 4));
+    }
+    CK(cudaMemsetAsync(sc->d_saved.p, 0, sizeof(SavedScan), st));
+    return DANN_OK;
+}
+
 extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
                                 int search_list_size, int rescore) {
     if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_rescan: NULL scan");
     if (search_list_size < 1 || search_list_size > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000", search_list_size);
     if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000", rescore);
     if (nlabels > 0 && !labels) return fail(DANN_ERR_INVALID_ARG, "labels is NULL but nlabels > 0");
-    const uint32_t dim = sc->ix->v.dim;
-    sc->null_query = query == nullptr;
+    dann_index *ix = sc->ix;
+    int rc = check_live(ix);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const IndexView &v = ix->v;
+    if (rescore > 0 && v.n && !v.vectors) return fail(DANN_ERR_STATE, "index has no heap vectors yet: rescore must be 0");
+    cudaStream_t st = ix->stream;
+    const uint32_t dim = v.dim;
     if (query) sc->query.assign(query, query + dim);
     else sc->query.assign(dim, 0.0f); /* NULL order-by argument: zero vector, no labels (labels/mod.rs:214-216) */
-    sc->nlabels = sc->null_query ? -1 : nlabels;
+    sc->nlabels = query ? nlabels : -1;
     sc->labels.clear();
-    if (sc->nlabels > 0) sc->labels.assign(labels, labels + nlabels);
+    if (sc->nlabels > 0) { /* LabelSet::from(Vec): sort_unstable + dedup (labels/mod.rs:30-37) */
+        sc->labels.assign(labels, labels + nlabels);
+        std::sort(sc->labels.begin(), sc->labels.end());
+        sc->labels.erase(std::unique(sc->labels.begin(), sc->labels.end()), sc->labels.end());
+    }
     sc->L = search_list_size;
     sc->rescore = rescore;
-    sc->tid.clear();
-    sc->dist.clear();
-    sc->node.clear();
-    sc->produced = sc->next = sc->k_cur = 0;
+    sc->grow = 1;
+    sc->streamed = sc->win_len = 0;
     sc->exhausted = false;
     sc->stats = dann_query_stats{};
+    /* amrescan's vector preparation runs once, here */
+    CK(sc->d_query.reserve((size_t)dim * 4));
+    CK(sc->d_qfull.reserve((size_t)dim * 4));
+    CK(sc->d_qcodes.reserve((size_t)v.cw * 8));
+    CK(sc->d_slen.reserve(16));
+    CK(sc->d_stats.reserve(sizeof(dann_query_stats)));
+    CK(sc->d_win.reserve((size_t)std::max(rescore, 1) * 8));
+    CK(sc->d_winst.reserve(sizeof(ScanWindow)));
+    CK(sc->d_row.reserve(sizeof(ScanRow)));
+    CK(sc->d_ctl.reserve(64));
+    CK(cudaMemcpyAsync(sc->d_query.p, sc->query.data(), (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+    if (sc->nlabels >= 0) {
+        int32_t off[2] = {0, (int32_t)sc->labels.size()};
+        CK(sc->d_labels.reserve(std::max<size_t>(sc->labels.size(), 1) * 2));
+        CK(sc->d_label_off.reserve(8));
+        if (!sc->labels.empty()) CK(cudaMemcpyAsync(sc->d_labels.p, sc->labels.data(), sc->labels.size() * 2, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sc->d_label_off.p, off, 8, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemsetAsync(sc->d_winst.p, 0, sizeof(ScanWindow), st));
+    rc = launch_prepare(ix, sc->d_query.as<float>(), 1, sc->d_qfull.as<float>(), sc->d_qcodes.as<uint64_t>(), st);
+    if (rc) return rc;
+    rc = scan_reset_search(sc);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
     sc->active = true;
     return DANN_OK;
 }
 
-static int scan_fetch(dann_scan *sc, uint32_t k) {
-    sc->tid.assign(k, DANN_INVALID_TID);
-    sc->dist.assign(k, 0.0f);
-    sc->node.assign(k, DANN_INVALID_NODE);
-    uint32_t count = 0;
-    int32_t off[2] = {0, sc->nlabels > 0 ? sc->nlabels : 0};
-    int rc = search_batch_host(sc->ix, sc->query.data(), sc->labels.data(), sc->nlabels >= 0 ? off : nullptr, 1,
-                               (int)k, sc->L, sc->rescore, sc->tid.data(), sc->dist.data(), sc->node.data(),
-                               &count, &sc->stats);
-    if (rc) return rc;
-    sc->produced = count;
-    sc->k_cur = k;
-    sc->exhausted = count < k;
-    return DANN_OK;
+/* Pull `need` more rows off the approximate stream into d_stream[skip ..]; returns how many came. */
+static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip_out) {
+    dann_index *ix = sc->ix;
+    const IndexView &v = ix->v;
+    cudaStream_t st = ix->stream;
+    uint32_t skip = 0; /* rows that are only re-generated because the workspace had to grow */
+    for (int attempt = 0;; attempt++) {
+        const SearchPlan &p = sc->plan;
+        const uint32_t want = skip + need;
+        CK(sc->d_stream.reserve((size_t)want * 4));
+        uint32_t *d_ctl = sc->d_ctl.as<uint32_t>();
+        CK(cudaMemsetAsync(d_ctl, 0, 8, st));
+        SearchArgs a;
+        a.ix = v;
+        a.q_codes = sc->d_qcodes.as<uint64_t>();
+        a.q_labels = sc->nlabels >= 0 ? sc->d_labels.as<int16_t>() : nullptr;
+        a.q_label_off = sc->nlabels >= 0 ? sc->d_label_off.as<int32_t>() : nullptr;
+        a.qlist = nullptr;
+        a.nq = 1;
+        a.L = (uint32_t)sc->L;
+        a.c_target = want;
+        a.stream = sc->d_stream.as<uint32_t>();
+        a.stream_len = sc->d_slen.as<uint32_t>();
+        a.stats = sc->d_stats.as<dann_query_stats>();
+        a.overflow = d_ctl + 1;
+        a.counter = d_ctl;
+        a.hash = sc->d_set.as<uint32_t>();
+        a.hash_cap = p.hash_cap;
+        a.bitmap = sc->d_set.as<uint32_t>();
+        a.bitmap_words = p.bitmap_words;
+        a.ins_list = sc->d_ins.as<uint32_t>();
+        a.ins_cap = p.ins_cap;
+        a.lists_unique = ix->lists_unique;
+        a.cand_node = sc->d_cnode.as<uint32_t>();
+        a.cand_cap = p.cand_cap;
+        a.heap_tail = sc->d_heap_tail.p;
+        a.hs = p.hs;
+        a.vcap = p.vcap;
+        a.G = ix->G;
+        a.Gshift = ix->Gshift;
+        a.per_warp_smem = p.per_warp;
+        a.saved = sc->d_saved.as<SavedScan>();
+        a.saved_heap_sm = sc->d_heap_sm.p;
+        a.saved_vis = sc->d_vis.as<uint64_t>();
+        a.build_mode = 0;
+        a.vis_out = nullptr;
+        a.vis_out_len = nullptr;
+        a.vis_out_cap = 0;
+        search_fn fn = p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
+        fn<<<1, 32, p.per_warp, st>>>(a);
+        ix->launches++;
+        CK(cudaGetLastError());
+        struct {
+            uint32_t ctl[2];
+        } h;
+        CK(cudaMemcpyAsync(h.ctl, d_ctl, 8, cudaMemcpyDeviceToHost, st));
+        uint32_t slen = 0;
+        CK(cudaMemcpyAsync(&slen, sc->d_slen.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&sc->stats, sc->d_stats.p, sizeof(dann_query_stats), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h.ctl[1] == 0) {
+            if (slen < want) sc->exhausted = true;
+            *got = slen > skip ? slen - skip : 0;
+            *skip_out = skip;
+            return DANN_OK;
+        }
+        /* the scan outgrew its workspace: rebuild it twice as large and replay the stream up to here */
+        if (attempt >= 8) return fail(DANN_ERR_CAPACITY, "scan workspace still too small after %d growth steps", attempt);
+        sc->grow *= 2;
+        int rc = scan_reset_search(sc);
+        if (rc) return rc;
+        skip = sc->streamed;
+    }
 }
 
 extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) {
     if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_gettuple: NULL scan");
     if (!sc->active) return fail(DANN_ERR_STATE, "dann_scan_gettuple before dann_scan_rescan");
-    if (sc->next >= sc->produced) {
-        if (sc->exhausted) return 0;
-        /* Rows i < k of a scan do not depend on k, so the operator materialises the first
-         * k rows and re-runs with 4x the LIMIT when the executor asks for more. */
-        uint32_t k = sc->k_cur == 0 ? 16u : sc->k_cur * 4u;
-        int rc = scan_fetch(sc, k);
+    dann_index *ix = sc->ix;
+    int rc = check_live(ix);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const IndexView &v = ix->v;
+    cudaStream_t st = ix->stream;
+    /* next_with_resort (scan.rs:244-305): `while resort_buffer.len() < resort_size { next() ... }` then pop;
+     * with resort_size == 0 it is a plain next() */
+    const uint32_t rescore = (uint32_t)sc->rescore;
+    uint32_t need = rescore == 0 ? 1u : (sc->win_len < rescore ? rescore - sc->win_len : 0u);
+    uint32_t got = 0, skip = 0;
+    if (need && !sc->exhausted) {
+        rc = scan_pull(sc, need, &got, &skip);
         if (rc) return rc;
-        if (sc->next >= sc->produced) return 0;
+        sc->streamed += got;
     }
-    uint64_t t = sc->tid[sc->next];
-    if (block) *block = (uint32_t)(t >> 16);
-    if (offset) *offset = (uint16_t)(t & 0xFFFFu);
-    if (node_id) *node_id = sc->node[sc->next];
-    if (dist) *dist = sc->dist[sc->next];
-    sc->next++;
+    if (rescore > 0 && got > 0) { /* get_full_distance_for_resort for the rows that just arrived */
+        CK(sc->d_dist.reserve((size_t)(skip + got) * 4));
+        size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(dann_full_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dann_full_distance_kernel<<<1, 128, smem, st>>>(v, sc->d_qfull.as<float>(), sc->d_stream.as<uint32_t>(),
+                                                       (int)(skip + got), sc->d_dist.as<float>());
+        ix->launches++;
+        CK(cudaGetLastError());
+    }
+    dann_scan_resort_kernel<<<1, 32, 0, st>>>(v, sc->d_winst.as<ScanWindow>(), sc->d_win.as<uint64_t>(), rescore,
+                                             sc->d_stream.as<uint32_t>(), sc->d_dist.as<float>(), skip, skip + got,
+                                             sc->d_row.as<ScanRow>());
+    ix->launches++;
+    CK(cudaGetLastError());
+    ScanRow row;
+    ScanWindow ws;
+    CK(cudaMemcpyAsync(&row, sc->d_row.p, sizeof(ScanRow), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&ws, sc->d_winst.p, sizeof(ScanWindow), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    sc->win_len = ws.len;
+    sc->stats.d_full = ws.d_full;
+    sc->stats.stream_len = sc->streamed;
+    if (!row.have) return 0;
+    if (block) *block = (uint32_t)(row.tid >> 16);
+    if (offset) *offset = (uint16_t)(row.tid & 0xFFFFu);
+    if (node_id) *node_id = row.node;
+    if (dist) *dist = row.dist;
     return 1;
 }
 
@@ -1040,4 +1196,10 @@ extern "C" int dann_scan_stats(dann_scan *sc, dann_query_stats *out) {
     return DANN_OK;
 }
 
-extern "C" void dann_scan_end(dann_scan *sc) { delete sc; }
+extern "C" void dann_scan_end(dann_scan *sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->ix->device);
+    scan_release(sc);
+    cudaGetLastError();
+    delete sc;
+}

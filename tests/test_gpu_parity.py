@@ -292,3 +292,34 @@ def test_index_without_vectors_then_set_vectors(lib):
         idx.set_vectors(vec)
         _compare_batch(s, idx, q, 5, 100, 10)
         assert np.array_equal(idx.download_nbrs(), s.nbrs)
+
+
+def test_scan_counters_after_every_gettuple(lib, monkeypatch):
+    """The scan is a suspended search in HBM, resumed by each amgettuple: after row i its counters
+    (visits / d_quantized / candidate / d_full, the ones amendscan logs, scan.rs:461-472) are what
+    the reference's would be after i rows — not those of a larger prefetched LIMIT."""
+    from oracle import oracle
+    s = build_case(2000, 128, COSINE, seed=81, labels=True, R=24, L_build=50, deleted_every=9)
+    q = _queries(s, 2, 15)
+    with lib.DiskAnnIndex(s) as idx:
+        sc = idx.begin_scan()
+        for shrink in (None, "16"):                     # second pass: the workspace must regrow mid-scan
+            if shrink:
+                monkeypatch.setenv("DANN_DEBUG_SHRINK", shrink)
+            for (labels, L, rescore) in ((None, 30, 12), ([4, 7], 20, 0), (None, 5, 3)):
+                sc.rescan(q[0], labels=labels, search_list_size=L, rescore=rescore)
+                for i in range(1, 41):
+                    row = sc.gettuple()
+                    ref = oracle.scan(s, q[0], labels, L, rescore, i)
+                    if len(ref["tid"]) < i:
+                        assert row is None
+                        break
+                    assert ((row[0] << 16) | row[1]) == int(ref["tid"][-1]) and row[2] == int(ref["node"][-1])
+                    if rescore:
+                        assert np.float32(row[3]).view(np.uint32) == ref["dist"][-1].view(np.uint32)
+                    st = sc.stats()
+                    for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len"):
+                        assert st[f] == ref["stats"][f], (f, i, labels, L, rescore, shrink)
+            if shrink:
+                monkeypatch.delenv("DANN_DEBUG_SHRINK")
+        sc.end()
