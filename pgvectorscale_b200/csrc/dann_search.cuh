@@ -25,7 +25,7 @@
 //            The inserted-set is a bitmap over node ids (one atomicOr per neighbour, cleared
 //            by replaying the list of inserted ids) when the index is small enough for
 //            one bitmap per resident warp, else an open-addressing CAS hash set.
-//   The heap entry packs (dist, seq): u32 = dist16|seq16 when both fit, else u64.
+//   The heap entry packs (dist, seq) in 4 bytes whenever it can (Ent32x21 / Ent32x16), else 8.
 //
 // Per visit the dependent memory round trips are: seq->node (L2) -> neighbour list (HBM,
 // overlapped with the pop's sift-down and the visited-list insert) -> inserted-set atomics
@@ -84,26 +84,31 @@ struct SearchArgs {
 
 #define DANN_LIST_CAP 64u
 
-template <typename E>
-struct EntryTraits;
-template <>
-struct EntryTraits<uint32_t> {
+/* Heap entry layouts: (distance << SEQ_BITS) | candidate sequence number.  Only the distance takes part in
+ * comparisons.  Ent32x21: 11-bit distances (codes of up to 2047 bits, e.g. 768-d x 2 bits = 1536) and up
+ * to 2M candidates per query in 4 bytes; Ent32x16: 16-bit distances, up to 65536 candidates; Ent64: anything. */
+struct Ent32x21 {
+    using E = uint32_t;
+    static constexpr int KSHIFT = 21;
+    static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 21) | seq; }
+    static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0x1FFFFFu; }
+};
+struct Ent32x16 {
+    using E = uint32_t;
     static constexpr int KSHIFT = 16;
     static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 16) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0xFFFFu; }
 };
-template <>
-struct EntryTraits<uint64_t> {
+struct Ent64 {
+    using E = uint64_t;
     static constexpr int KSHIFT = 32;
-    static __device__ __forceinline__ uint64_t make(uint32_t d, uint32_t seq) {
-        return ((uint64_t)d << 32) | seq;
-    }
+    static __device__ __forceinline__ uint64_t make(uint32_t d, uint32_t seq) { return ((uint64_t)d << 32) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint64_t e) { return (uint32_t)e; }
 };
 
-template <typename E, int NCH>
+template <typename T, int NCH>
 struct SearchWarp {
-    using T = EntryTraits<E>;
+    using E = typename T::E;
     using H = RustHeap<E, T::KSHIFT>;
     /* code rows gathered per lane group before reducing (16-B loads in flight = RPI*NCH):
      * with G=4 lanes per 192-B row, 8 x 8 rows = all 64 staged rows in one round */
@@ -530,13 +535,14 @@ struct SearchWarp {
     }
 };
 
-template <typename E, int NCH>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(384, 1) dann_search_kernel(const SearchArgs a) {
+    using E = typename T::E;
     extern __shared__ __align__(16) unsigned char dann_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const uint32_t slot = blockIdx.x * W + warp;
     unsigned char *base = dann_smem + (size_t)warp * a.per_warp_smem;
-    SearchWarp<E, NCH> w(a, lane);
+    SearchWarp<T, NCH> w(a, lane);
     w.vis = reinterpret_cast<uint64_t *>(base);
     E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
     w.list = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));

@@ -42,9 +42,9 @@ __device__ __forceinline__ void pair_sync(uint32_t id) {
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
-template <typename E, int NCH>
+template <typename T, int NCH>
 struct PairSearch {
-    using T = EntryTraits<E>;
+    using E = typename T::E;
     using H = RustHeap<E, T::KSHIFT>;
     /* rows gathered per lane group per round: 6 x 8 = 48 rows (G=4) covers a typical 50-id list at once */
     static constexpr int RPI = NCH <= 2 ? 8 : (NCH == 3 ? 6 : (NCH == 4 ? 4 : 2));
@@ -545,14 +545,15 @@ struct PairSearch {
     }
 };
 
-template <typename E, int NCH>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a) {
+    using E = typename T::E;
     extern __shared__ __align__(16) unsigned char dann_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, role = warp & 1;
     const int P = blockDim.x >> 6;
     const uint32_t slot = blockIdx.x * P + pair;
     unsigned char *base = dann_smem + (size_t)pair * a.per_warp_smem;
-    PairSearch<E, NCH> w(a, lane, 1u + (uint32_t)pair);
+    PairSearch<T, NCH> w(a, lane, 1u + (uint32_t)pair);
     w.vis = reinterpret_cast<uint64_t *>(base);
     E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
     w.listp = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));

@@ -109,6 +109,7 @@ struct dann_index {
 
 struct SearchPlan {
     uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
+    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64 */
     bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
 };
 
@@ -452,26 +453,29 @@ extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const u
 /* ------------------------------------------------------------------------------------ */
 /* search kernel dispatch                                                                */
 typedef void (*search_fn)(const SearchArgs);
-template <typename E>
+template <typename T>
 static search_fn pick_search(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search_kernel<E, 1>;
-        case 2: return dann_search_kernel<E, 2>;
-        case 3: return dann_search_kernel<E, 3>;
-        case 4: return dann_search_kernel<E, 4>;
-        default: return dann_search_kernel<E, 8>;
+        case 1: return dann_search_kernel<T, 1>;
+        case 2: return dann_search_kernel<T, 2>;
+        case 3: return dann_search_kernel<T, 3>;
+        case 4: return dann_search_kernel<T, 4>;
+        default: return dann_search_kernel<T, 8>;
     }
 }
-
-template <typename E>
+template <typename T>
 static search_fn pick_search2(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search2_kernel<E, 1>;
-        case 2: return dann_search2_kernel<E, 2>;
-        case 3: return dann_search2_kernel<E, 3>;
-        case 4: return dann_search2_kernel<E, 4>;
-        default: return dann_search2_kernel<E, 8>;
+        case 1: return dann_search2_kernel<T, 1>;
+        case 2: return dann_search2_kernel<T, 2>;
+        case 3: return dann_search2_kernel<T, 3>;
+        case 4: return dann_search2_kernel<T, 4>;
+        default: return dann_search2_kernel<T, 8>;
     }
+}
+static search_fn pick_kernel(bool pairs, int entry, uint32_t nch) {
+    if (pairs) return entry == 0 ? pick_search2<Ent32x21>(nch) : entry == 1 ? pick_search2<Ent32x16>(nch) : pick_search2<Ent64>(nch);
+    return entry == 0 ? pick_search<Ent32x21>(nch) : entry == 1 ? pick_search<Ent32x16>(nch) : pick_search<Ent64>(nch);
 }
 
 
@@ -495,8 +499,13 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     /* every deduped id is recorded, also the ones a label filter then rejects: visits x R */
     p->ins_cap = keyed ? 2 * p->cand_cap : p->cand_cap;
     if (keyed) p->hash_cap = pow2ceil(4 * p->cand_cap);
-    bool small = p->cand_cap <= 65536 && (uint64_t)v.words * 64 <= 65535;
-    p->esize = small ? 4 : 8;
+    /* heap entry layout (dann_search.cuh): 4 bytes whenever the distance and the sequence number fit */
+    const uint64_t maxdist = (uint64_t)v.words * 64;
+    if (maxdist < 2048 && p->cand_cap <= (1u << 21)) p->entry = 0;
+    else if (maxdist < 65536 && p->cand_cap <= 65536) p->entry = 1;
+    else p->entry = 2;
+    p->entry = (int)env_u32("DANN_SEARCH_ENTRY", (uint32_t)p->entry); /* test hook */
+    p->esize = p->entry == 2 ? 8 : 4;
     /* visited holds the not-yet-consumed visits: about L, more under a label filter */
     uint64_t vcap = std::max<uint64_t>(((uint64_t)L * (keyed ? 2 : 1) + 96u) * grow / shrink, 8);
     p->vcap = (uint32_t)((vcap + 3) & ~3ull);
@@ -592,8 +601,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.vis_out = vis_out;
         a.vis_out_len = vis_out_len;
         a.vis_out_cap = vis_out_cap;
-        search_fn fn = p.pairs ? (p.esize == 4 ? pick_search2<uint32_t>(ix->NCH) : pick_search2<uint64_t>(ix->NCH))
-                               : (p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH));
+        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);
@@ -1112,7 +1120,7 @@ static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip
         a.vis_out = nullptr;
         a.vis_out_len = nullptr;
         a.vis_out_cap = 0;
-        search_fn fn = p.esize == 4 ? pick_search<uint32_t>(ix->NCH) : pick_search<uint64_t>(ix->NCH);
+        search_fn fn = pick_kernel(false, p.entry, ix->NCH);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
         fn<<<1, 32, p.per_warp, st>>>(a);
         ix->launches++;

@@ -177,6 +177,14 @@ def test_single_warp_kernel_and_wide_lists(lib, monkeypatch):
         _compare_batch(s, idx, q, 10, 100, 50)
         _compare_batch(s, idx, q, 10, 40, 20, labels=[[1 + (i % 16), 5] for i in range(24)])
         monkeypatch.delenv("DANN_SEARCH_BITMAP")
+        # all three heap-entry layouts (4 B dist11|seq21, 4 B dist16|seq16, 8 B), both kernels
+        for entry in ("0", "1", "2"):
+            monkeypatch.setenv("DANN_SEARCH_ENTRY", entry)
+            _compare_batch(s, idx, q[:12], 10, 100, 50)
+            monkeypatch.setenv("DANN_SEARCH_KERNEL", "1")
+            _compare_batch(s, idx, q[:12], 10, 60, 20)
+            monkeypatch.delenv("DANN_SEARCH_KERNEL")
+        monkeypatch.delenv("DANN_SEARCH_ENTRY")
     s = build_case(1200, 64, L2, seed=23, kind="uniform", R=70, L_build=80)
     with lib.DiskAnnIndex(s) as idx:
         _compare_batch(s, idx, _queries(s, 16, 6, "uniform"), 10, 60, 30)
