@@ -60,6 +60,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one),
+# so fd 1 is pointed at stderr for the whole run and only emit() writes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 # (search_list_size, rescore) in increasing cost (visits ~ L + rescore); recall is driven mostly by rescore
 SWEEP = [(25, 50), (50, 50), (100, 50), (50, 100), (100, 100), (64, 150), (100, 150), (64, 200), (100, 200),
          (150, 200), (200, 200), (150, 250), (200, 250), (150, 300), (200, 300), (300, 300), (400, 400), (800, 400),
@@ -258,7 +268,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -512,7 +522,7 @@ def main():
                                    f"(oracle/oracle.cpp, -O2 -mavx2 -mfma -mpopcnt); single-thread: {cpu1_qps:.0f} q/s"},
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
