@@ -9,8 +9,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdiskann_b200.so")
 SOURCES = ["diskann_b200.cu"]
-HEADERS = ["dann_device.cuh", "dann_heap.cuh", "dann_kernels.cuh", "dann_search.cuh",
-           os.path.join("..", "..", "include", "diskann_b200.h")]
+
+
+def _dependencies():
+    """Every source the library is compiled from: all of csrc/ plus the public header."""
+    import glob
+    deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+    deps += glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+    deps.append(os.path.abspath(__file__))      # flag changes rebuild too
+    return deps
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # Blackwell B200 only, no PTX fallback for other parts
@@ -31,8 +39,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in _dependencies())
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -1,6 +1,8 @@
-// dann_search2.cuh — two-warp StreamingDiskANN beam search (sm_100a): one MEMORY warp and one
+// dann_search2.cuh — two-warp StreamingDiskANN beam search (sm_100a): one MEMORY/CONTROL warp and one
 // HEAP warp per query, so that the HBM/L2 round trips of visit i+1 run under the heap pushes of
-// visit i.  Same algorithm, same results and counters as dann_search.cuh (the single-warp
+// visit i.  The memory warp drives the scan (visit_closest's stop test, the visited list, consume, the
+// deleted-tuple skip, the stream output, neighbour fetch, dedupe, label filter, SBQ distances); the heap
+// warp is a pure BinaryHeap engine (pop, ordered pushes) that reports the root the next pop will leave.  Same algorithm, same results and counters as dann_search.cuh (the single-warp
 // kernel, kept for R > 64 and as the cross-check in tests); see that file for the reference map.
 //
 // Why the split is exact.  The reference's loop is pop -> expand -> push* -> pop ... .  The
@@ -15,9 +17,9 @@
 // — three loads, available BEFORE the pop's sift-down runs.  So the memory warp can start
 // fetching the neighbour list, the inserted-set bits and the SBQ codes of visit i+1 while the
 // heap warp is still pushing the batch of visit i.  The prediction is certain, not speculative;
-// it is only wasted when the scan ends first (the heap warp counts d_quantized at push time, so
-// counters are unaffected).  The heap warp still checks every prediction against the node it
-// actually pops and reports DANN_ST_INTERNAL on a mismatch.
+// the memory warp therefore also evaluates the stop test itself and only expands nodes the reference
+// would visit.  The heap warp still checks every prediction against the node it actually pops and
+// reports DANN_ST_INTERNAL on a mismatch.
 //
 // Hand-off: double-buffered (list, dist) pages and control words in shared memory, one named
 // barrier (bar.sync id, 64) per visit.
@@ -35,8 +37,12 @@ struct PairCtl {
     uint32_t root_valid[2]; /* heap root as it will be just before page p's successor is pushed */
     uint32_t root_key[2];
     uint32_t root_seq[2];
-    uint32_t go[2];         /* 0 = the scan is over */
+    uint32_t cmd[2];        /* memory warp -> heap warp: 0 = scan over, 1 = pop then push page p, 2 = push page p (start nodes) */
+    uint32_t status_b;      /* heap warp's cross-check failures */
+    uint32_t pad_;          /* keeps sizeof a multiple of 8: the push queue behind it holds 8-byte entries */
 };
+
+static_assert(sizeof(PairCtl) % 8 == 0, "PairCtl must keep 8-byte alignment for what follows it");
 
 __device__ __forceinline__ void pair_sync(uint32_t id) {
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
@@ -67,6 +73,7 @@ struct PairSearch {
     ulonglong2 qc[NCH];
     const int16_t *ql;
     uint32_t nql, ncand, nins, listn, status;
+    uint32_t vis_head, vis_len; /* the visited list belongs to the controller (memory) warp */
     bool filter;
 
     __device__ __forceinline__ bool hash_insert(uint32_t n) {
@@ -225,78 +232,42 @@ struct PairSearch {
             filter = nql > 0;
             nstart_pages = nql ? (nql + 63) / 64 : 1;
         }
-        for (uint32_t k = 0;; k++) {
+        vis_head = vis_len = 0;
+        uint32_t visits = 0, scount = 0, k = 0;
+        /* ---- start nodes (graph/mod.rs:97-124, start_nodes.rs:39-48): 64 per page, never label-checked */
+        for (; k < nstart_pages; k++) {
             const uint32_t p = k & 1;
             uint32_t *list = listp + p * DANN_LIST_CAP, *dl = dlp + p * DANN_LIST_CAP;
-            uint32_t expect = DANN_INVALID_NODE;
             listn = 0;
-            if (k < nstart_pages) {
-                /* start nodes (graph/mod.rs:97-124, start_nodes.rs:39-48): 64 per page, never label-checked */
-                if (have_graph && !status) {
-                    if (a.q_label_off) {
-                        uint32_t n[2];
-                        bool v[2];
+            if (have_graph && !status) {
+                if (a.q_label_off) {
+                    uint32_t n[2];
+                    bool v[2];
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            uint32_t i = k * 64 + h * 32 + lane;
-                            n[h] = DANN_INVALID_NODE;
-                            v[h] = false;
-                            if (i < nql) {
-                                int16_t lab = __ldg(ql + i);
-                                uint32_t lo = 0, hi = ix.n_start_labels;
-                                while (lo < hi) {
-                                    uint32_t mid = (lo + hi) >> 1;
-                                    if (__ldg(ix.start_labels + mid) < lab) lo = mid + 1;
-                                    else hi = mid;
-                                }
-                                if (lo < ix.n_start_labels && __ldg(ix.start_labels + lo) == lab) {
-                                    n[h] = __ldg(ix.start_label_nodes + lo);
-                                    v[h] = true;
-                                }
+                    for (int h = 0; h < 2; h++) {
+                        uint32_t i = k * 64 + h * 32 + lane;
+                        n[h] = DANN_INVALID_NODE;
+                        v[h] = false;
+                        if (i < nql) {
+                            int16_t lab = __ldg(ql + i);
+                            uint32_t lo = 0, hi = ix.n_start_labels;
+                            while (lo < hi) {
+                                uint32_t mid = (lo + hi) >> 1;
+                                if (__ldg(ix.start_labels + mid) < lab) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            if (lo < ix.n_start_labels && __ldg(ix.start_labels + lo) == lab) {
+                                n[h] = __ldg(ix.start_label_nodes + lo);
+                                v[h] = true;
                             }
                         }
-                        /* two start nodes may coincide across the halves: keep list order */
-                        stage(list, n[0], v[0], DANN_INVALID_NODE, false, false);
-                        if (!status) stage(list, n[1], v[1], DANN_INVALID_NODE, false, false);
-                    } else {
-                        stage(list, lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, DANN_INVALID_NODE,
-                              false, false);
                     }
-                }
-            } else {
-                /* which node does the heap warp pop next?  (see the header comment) */
-                const uint32_t pp = (k - 1) & 1;
-                const uint32_t *pl = listp + pp * DANN_LIST_CAP, *pd = dlp + pp * DANN_LIST_CAP;
-                const uint32_t ptn = ctl->tn[pp];
-                uint32_t d0 = lane < ptn ? pd[lane] : 0xFFFFFFFFu;
-                uint32_t d1 = lane + 32 < ptn ? pd[lane + 32] : 0xFFFFFFFFu;
-                uint32_t m = min(d0, d1);
-                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
-                uint32_t node = DANN_INVALID_NODE;
-                const bool rv = ctl->root_valid[pp] != 0;
-                if (ptn && (!rv || m < ctl->root_key[pp])) {
-                    unsigned e0 = __ballot_sync(DANN_FULL, d0 == m), e1 = __ballot_sync(DANN_FULL, d1 == m);
-                    uint32_t idx = e0 ? (uint32_t)(__ffs(e0) - 1) : 32u + (uint32_t)(__ffs(e1) - 1);
-                    node = pl[idx];
-                } else if (rv) {
-                    node = cnode[ctl->root_seq[pp]];
-                }
-                expect = node;
-                if (node != DANN_INVALID_NODE && !status) { /* sbq/storage.rs:135-190 */
-                    const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
-                    uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
-                    uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
-                    const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
-                    const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
-                    const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
-                    const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
-                    const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-                    if (a.lists_unique) {
-                        stage(list, n0, v0, n1, v1, filter);
-                    } else {
-                        stage(list, n0, v0, DANN_INVALID_NODE, false, filter);
-                        if (!status) stage(list, n1, v1, DANN_INVALID_NODE, false, filter);
-                    }
+                    /* two start nodes may coincide across the halves: keep list order */
+                    stage(list, n[0], v[0], DANN_INVALID_NODE, false, false);
+                    if (!status) stage(list, n[1], v[1], DANN_INVALID_NODE, false, false);
+                } else {
+                    stage(list, lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, DANN_INVALID_NODE, false,
+                          false);
                 }
             }
             if (status) listn = 0;
@@ -304,13 +275,99 @@ struct PairSearch {
             if (lane == 0) {
                 ctl->tn[p] = listn;
                 ctl->seq0[p] = ncand;
-                ctl->expect[p] = expect;
-                ctl->status_a = status;
+                ctl->expect[p] = DANN_INVALID_NODE;
+                ctl->cmd[p] = 2u;
             }
             ncand += listn;
-            pair_sync(bar); /* page p is ready; the heap warp has published ctl[p] */
-            if (!ctl->go[p]) break;
+            pair_sync(bar); /* page p handed over; the heap warp has published root[p] */
         }
+        /* ---- TSVResponseIterator::next (scan.rs:210-242) driven from here: this warp knows the next
+         * root of the heap (node and key) as soon as the previous page's distances exist */
+        for (;; k++) {
+            const uint32_t p = k & 1, pp = (k - 1) & 1;
+            const uint32_t *pl = listp + pp * DANN_LIST_CAP, *pd = dlp + pp * DANN_LIST_CAP;
+            const uint32_t ptn = ctl->tn[pp];
+            uint32_t d0 = lane < ptn ? pd[lane] : 0xFFFFFFFFu;
+            uint32_t d1 = lane + 32 < ptn ? pd[lane + 32] : 0xFFFFFFFFu;
+            uint32_t m = min(d0, d1);
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
+            uint32_t node = DANN_INVALID_NODE, key = 0;
+            const bool rv = ctl->root_valid[pp] != 0;
+            if (ptn && (!rv || m < ctl->root_key[pp])) { /* first element of the batch attaining a strictly smaller minimum */
+                unsigned e0 = __ballot_sync(DANN_FULL, d0 == m), e1 = __ballot_sync(DANN_FULL, d1 == m);
+                uint32_t idx = e0 ? (uint32_t)(__ffs(e0) - 1) : 32u + (uint32_t)(__ffs(e1) - 1);
+                node = pl[idx];
+                key = m;
+            } else if (rv) { /* the root the pop left behind stays on top */
+                node = cnode[ctl->root_seq[pp]];
+                key = ctl->root_key[pp];
+            }
+            const bool have = node != DANN_INVALID_NODE;
+            bool visit = false;
+            while (!status) {
+                /* visit_closest (graph/mod.rs:153-170): candidates empty -> None; strictly more than L
+                 * visited and head >= visited[L-1] -> None; else pop */
+                if (have && !(vis_len > a.L && key >= (uint32_t)(vis[vis_head + a.L - 1] >> 32))) {
+                    visit = true;
+                    break;
+                }
+                if (a.build_mode) { /* greedy_search_for_build: one-shot search, the visited set is the result */
+                    const uint32_t nv = vis_len < a.vis_out_cap ? vis_len : a.vis_out_cap;
+                    for (uint32_t i = lane; i < nv; i += 32) a.vis_out[(size_t)q * a.vis_out_cap + i] = vis[vis_head + i];
+                    if (lane == 0) a.vis_out_len[q] = nv;
+                    break;
+                }
+                if (vis_len == 0) break;        /* consume() -> None */
+                const uint64_t e = vis[vis_head]; /* visited.remove(0), graph/mod.rs:174-184 */
+                __syncwarp();
+                vis_head++;
+                vis_len--;
+                const uint32_t cn = (uint32_t)e;
+                const uint64_t tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
+                if ((tid & 0xFFFFull) == 0) continue;     /* InvalidOffsetNumber: deleted tuple, scan.rs:231-234 */
+                if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = cn;
+                scount++;
+                if (scount == a.c_target) break;
+            }
+            if (!visit) { /* the scan is over (enough rows, stream exhausted, or a workspace overflow) */
+                if (lane == 0) ctl->cmd[p] = 0u;
+                pair_sync(bar);
+                break;
+            }
+            /* sbq/storage.rs:135-190: expand `node`; its neighbour list is fetched first so that the
+             * visited-list insert runs under that latency */
+            const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
+            uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+            uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
+            visited_insert(key, node);
+            visits++;
+            uint32_t *list = listp + p * DANN_LIST_CAP, *dl = dlp + p * DANN_LIST_CAP;
+            listn = 0;
+            if (!status) {
+                const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
+                const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
+                const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
+                const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
+                const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
+                if (a.lists_unique) {
+                    stage(list, n0, v0, n1, v1, filter);
+                } else {
+                    stage(list, n0, v0, DANN_INVALID_NODE, false, filter);
+                    if (!status) stage(list, n1, v1, DANN_INVALID_NODE, false, filter);
+                }
+            }
+            if (status) listn = 0;
+            distances(list, dl, listn);
+            if (lane == 0) {
+                ctl->tn[p] = listn;
+                ctl->seq0[p] = ncand;
+                ctl->expect[p] = node;
+                ctl->cmd[p] = 1u; /* pop (it will be `node`) and push this page */
+            }
+            ncand += listn;
+            pair_sync(bar);
+        }
+        status |= ctl->status_b;
         /* bitmap flavour: clear exactly the bits this query set */
         if (a.bitmap_words) {
             __syncwarp();
@@ -325,10 +382,23 @@ struct PairSearch {
             for (; i < nins; i += 32) bitmap[ins[i] >> 5] = 0u;
             __threadfence_block();
         }
+        if (lane == 0) {
+            a.stream_len[q] = scount;
+            dann_query_stats st;
+            st.visits = visits;
+            st.d_quantized = ncand; /* every staged candidate was pushed */
+            st.candidates = ncand;
+            st.d_full = 0;
+            st.stream_len = scount;
+            st.status = status;
+            a.stats[q] = st;
+            if (status) atomicOr(a.overflow, status);
+        }
+        __syncwarp();
     }
 
     /* ================================= heap warp ======================================= */
-    uint32_t heap_len, vis_head, vis_len, visits, dq, hstatus, hk;
+    uint32_t heap_len, hk;
 
     /* BinaryHeap::push x tn in list order (insert_neighbor, graph/mod.rs:144-147); 1-based slots.
      * Inert elements (parent key <= own key: they stay at their leaf whatever earlier pushes of
@@ -386,13 +456,12 @@ struct PairSearch {
             push_batch<false>(heap, dl, tn, seq0);
         }
         heap_len += tn;
-        dq += tn;
     }
 
     __device__ __forceinline__ void visited_insert(uint32_t d, uint32_t node) {
         if (vis_head + vis_len + 1 > a.vcap) {
             if (vis_len + 1 > a.vcap) {
-                hstatus |= DANN_ST_VIS;
+                status |= DANN_ST_VIS;
                 return;
             }
             for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
@@ -426,11 +495,10 @@ struct PairSearch {
         __syncwarp();
     }
 
-    /* publish the control words of hand-off k and meet the memory warp */
-    __device__ __forceinline__ void handoff(uint32_t go, bool rv, E root) {
+    /* publish the heap root as it stands before page k is pushed, and meet the memory warp */
+    __device__ __forceinline__ void handoff(bool rv, E root) {
         const uint32_t p = hk & 1;
         if (lane == 0) {
-            ctl->go[p] = go;
             ctl->root_valid[p] = rv ? 1u : 0u;
             ctl->root_key[p] = H::key(root);
             ctl->root_seq[p] = T::seq(root);
@@ -440,108 +508,59 @@ struct PairSearch {
     }
 
     __device__ __forceinline__ void run_heap(uint32_t q) {
-        const IndexView &ix = a.ix;
-        heap_len = vis_head = vis_len = visits = dq = hstatus = hk = 0;
-        uint32_t scount = 0;
+        heap_len = hk = 0;
         uint32_t nstart_pages = 1;
         if (a.q_label_off) {
             uint32_t nql_ = (uint32_t)(a.q_label_off[q + 1] - a.q_label_off[q]);
             nstart_pages = nql_ ? (nql_ + 63) / 64 : 1;
         }
-        for (uint32_t k = 0; k < nstart_pages; k++) {
-            E root = 0;
-            if (heap_len) root = heap.get(1);
-            handoff(1u, heap_len != 0, root);
-            hstatus |= ctl->status_a;
-            push_page((hk - 1) & 1);
-        }
-        bool done = false;
-        while (!done && !hstatus) { /* TSVResponseIterator::next, scan.rs:210-242 */
-            while (true) {          /* greedy_search_iterate */
-                E head = 0, after = 0;
-                int go = 0, av = 0;
-                if (lane == 0 && heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
-                    head = heap.get(1);
-                    go = 1;
-                    if (vis_len > a.L) {
-                        uint64_t at = vis[vis_head + a.L - 1];
-                        if (H::key(head) >= (uint32_t)(at >> 32)) go = 0;
-                    }
-                    if (go && heap_len > 1) { /* root of the heap once this pop is done */
-                        const uint32_t m = heap_len - 1; /* elements left */
-                        const E last = heap.get(heap_len);
-                        E c = last;
-                        if (m >= 2) {
-                            c = heap.get(2);
-                            if (m >= 3) {
-                                E cr = heap.get(3);
-                                if (H::key(cr) <= H::key(c)) c = cr;
-                            }
+        for (uint32_t k = 0;; k++) {
+            const uint32_t p = k & 1;
+            E head = 0, pub = 0;
+            int pv = 0;
+            if (lane == 0 && heap_len > 0) {
+                head = heap.get(1);
+                if (k < nstart_pages) { /* a start page is pushed without a pop: the root is the root */
+                    pub = head;
+                    pv = 1;
+                } else if (heap_len > 1) { /* root of the heap once the coming pop is done (header comment) */
+                    const uint32_t m = heap_len - 1;
+                    const E last = heap.get(heap_len);
+                    E c = last;
+                    if (m >= 2) {
+                        c = heap.get(2);
+                        if (m >= 3) {
+                            E cr = heap.get(3);
+                            if (H::key(cr) <= H::key(c)) c = cr;
                         }
-                        after = (m >= 2 && H::key(last) < H::key(c)) ? last : c;
-                        av = 1;
                     }
+                    pub = (m >= 2 && H::key(last) < H::key(c)) ? last : c;
+                    pv = 1;
                 }
-                go = __shfl_sync(DANN_FULL, go, 0);
-                if (!go) break;
-                head = __shfl_sync(DANN_FULL, head, 0);
-                after = __shfl_sync(DANN_FULL, after, 0);
-                av = __shfl_sync(DANN_FULL, av, 0);
-                handoff(1u, av != 0, after);
-                hstatus |= ctl->status_a;
-                const uint32_t p = (hk - 1) & 1;
-                const uint32_t d = H::key(head);
-                /* the memory warp already resolved which node this pop yields (page p is its
-                 * expansion); the seq->node table is only read to cross-check, off the critical path */
-                const uint32_t node = ctl->expect[p];
-                const uint32_t node_chk = __ldcg(cnode + T::seq(head));
-                if (hstatus) break;
+            }
+            head = __shfl_sync(DANN_FULL, head, 0);
+            pub = __shfl_sync(DANN_FULL, pub, 0);
+            pv = __shfl_sync(DANN_FULL, pv, 0);
+            handoff(pv != 0, pub);
+            const uint32_t cmd = ctl->cmd[p];
+            if (cmd == 0) break;
+            uint32_t node_chk = DANN_INVALID_NODE;
+            if (cmd == 1) { /* candidates.pop(): the memory warp already knows which node this is */
+                if (heap_len == 0) {
+                    if (lane == 0) ctl->status_b = DANN_ST_INTERNAL;
+                    continue;
+                }
+                node_chk = __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
                     H::pop_warp1(sm, heap_len, lane);
                 } else {
                     H::pop_warp1(heap, heap_len, lane);
                 }
-                visited_insert(d, node);
-                if (hstatus) break;
-                visits++;
-                push_page(p);
-                if (node_chk != node) hstatus |= DANN_ST_INTERNAL;
             }
-            if (hstatus) break;
-            if (a.build_mode) { /* greedy_search_for_build: one-shot search, the visited set is the result */
-                const uint32_t nv = vis_len < a.vis_out_cap ? vis_len : a.vis_out_cap;
-                for (uint32_t i = lane; i < nv; i += 32) a.vis_out[(size_t)q * a.vis_out_cap + i] = vis[vis_head + i];
-                if (lane == 0) a.vis_out_len[q] = nv;
-                break;
-            }
-            if (vis_len == 0) break;
-            uint64_t e = vis[vis_head];
-            __syncwarp();
-            vis_head++;
-            vis_len--;
-            uint32_t node = (uint32_t)e;
-            uint64_t tid = __ldg(ix.tids + node);
-            if ((tid & 0xFFFFull) == 0) continue;
-            if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = node;
-            scount++;
-            if (scount == a.c_target) done = true;
+            push_page(p);
+            if (cmd == 1 && node_chk != ctl->expect[p] && lane == 0) ctl->status_b = DANN_ST_INTERNAL;
         }
-        handoff(0u, false, 0); /* releases the memory warp */
-        hstatus |= ctl->status_a;
-        if (lane == 0) {
-            a.stream_len[q] = scount;
-            dann_query_stats st;
-            st.visits = visits;
-            st.d_quantized = dq;
-            st.candidates = dq;
-            st.d_full = 0;
-            st.stream_len = scount;
-            st.status = hstatus;
-            a.stats[q] = st;
-            if (hstatus) atomicOr(a.overflow, hstatus);
-        }
-        __syncwarp();
     }
 };
 
@@ -573,6 +592,7 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
             uint32_t qi = atomicAdd(a.counter, 1u);
             w.ctl->q = qi < a.nq ? (a.qlist ? a.qlist[qi] : qi) : 0xFFFFFFFFu;
             w.ctl->status_a = 0;
+            w.ctl->status_b = 0;
         }
         pair_sync(w.bar);
         const uint32_t q = w.ctl->q;

@@ -331,3 +331,34 @@ def test_scan_counters_after_every_gettuple(lib, monkeypatch):
             if shrink:
                 monkeypatch.delenv("DANN_DEBUG_SHRINK")
         sc.end()
+
+
+def test_device_buffer_entry_point_matches_host_entry_point(lib):
+    """dann_search_batch_device (buffers already in HBM, caller's stream) == dann_search_batch."""
+    import torch
+    s = build_case(2000, 128, COSINE, seed=91, labels=True, R=24, L_build=50)
+    q = _queries(s, 40, 17)
+    with lib.DiskAnnIndex(s) as idx:
+        dev = torch.device("cuda", 0)
+        h = idx.search_batch(q, k=10, search_list_size=60, rescore=25)
+        d_q = torch.from_numpy(q).to(dev)
+        d_tid = torch.empty((40, 10), dtype=torch.int64, device=dev)
+        d_dist = torch.empty((40, 10), dtype=torch.float32, device=dev)
+        d_cnt = torch.empty(40, dtype=torch.int32, device=dev)
+        d_st = torch.empty((40, 6), dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            idx.search_batch_device(d_q, 10, 60, 25, d_tid, d_dist, d_cnt, d_st, stream=side.cuda_stream)
+        side.synchronize()
+        assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), h["tid"])
+        assert np.array_equal(d_dist.cpu().numpy().view(np.uint32), h["dist"].view(np.uint32))
+        assert np.array_equal(d_cnt.cpu().numpy().view(np.uint32), h["count"])
+        assert np.array_equal(d_st.cpu().numpy().view(np.uint32)[:, 0], h["stats"]["visits"])
+        # keyed variant: labels must be sorted + dedup per query on the device path
+        keys = [[3, 9] for _ in range(40)]
+        hk = idx.search_batch(q, labels=keys, k=10, search_list_size=60, rescore=25)
+        d_lab = torch.tensor([3, 9] * 40, dtype=torch.int16, device=dev)
+        d_off = torch.arange(0, 82, 2, dtype=torch.int32, device=dev)
+        idx.search_batch_device(d_q, 10, 60, 25, d_tid, d_dist, d_cnt, d_st, d_labels=d_lab, d_label_off=d_off)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), hk["tid"])
