@@ -441,7 +441,7 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "dann_search2_kernel<u32,3> (two warps per query)" if snap.R <= 64 else "dann_search_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"kernel": "dann_search2_kernel<Ent32x21,3> (two warps per query)" if snap.R <= 64 else "dann_search_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg_bytes_launch), "avg_launch_ms": round(search_avg_ms, 4),
                 "per_query": {"visits": round(visits_q, 1), "d_quantized": round(dq_q, 1), "code_bytes": code_bytes}}
