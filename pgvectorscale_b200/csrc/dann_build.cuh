@@ -17,6 +17,26 @@
 #pragma once
 #include "dann_device.cuh"
 
+/* labels/mod.rs:84-111 LabelSet::contains_intersection: is (a ∩ b) ⊆ c ?  (sorted i16 arrays) */
+__device__ __forceinline__ bool labels_contains_intersection(const int16_t *c, uint32_t nc, const int16_t *a, uint32_t na,
+                                                             const int16_t *b, uint32_t nb) {
+    uint32_t i = 0, j = 0, k = 0;
+    while (i < na && j < nb) {
+        int16_t x = __ldg(a + i), y = __ldg(b + j);
+        if (x == y) {
+            while (k < nc && __ldg(c + k) < x) k++;
+            if (k == nc || __ldg(c + k) > x) return false;
+            i++;
+            j++;
+        } else if (x < y) {
+            i++;
+        } else {
+            j++;
+        }
+    }
+    return true;
+}
+
 #define DANN_BUILD_CMAX 128u /* candidates considered by one prune */
 #define DANN_BUILD_SLACK 64u /* neighbour slots per node while building (the reference: ceil(1.3 R)) */
 
@@ -48,7 +68,15 @@ __device__ __forceinline__ void build_bitonic_sort128(uint64_t *k, int lane) {
 __device__ __forceinline__ uint32_t build_prune_warp(const uint64_t *__restrict__ codes, uint32_t cw, uint32_t cws,
                                                      uint32_t p, const uint64_t *ck, float *mf, uint64_t *cc,
                                                      uint32_t C, uint32_t R, float max_alpha, uint32_t *out_id,
-                                                     uint16_t *out_d, int lane) {
+                                                     uint16_t *out_d, int lane, const uint32_t *label_off = nullptr,
+                                                     const int16_t *labels = nullptr) {
+    const int16_t *pl = nullptr;
+    uint32_t npl = 0;
+    if (label_off) {
+        uint32_t o0 = __ldg(label_off + p);
+        pl = labels + o0;
+        npl = __ldg(label_off + p + 1) - o0;
+    }
     for (uint32_t c = 0; c < C; c++) {
         const uint64_t *row = codes + (size_t)(uint32_t)ck[c] * cw;
         for (uint32_t w = lane; w < cw; w += 32) cc[c * cws + w] = __ldg(row + w);
@@ -69,9 +97,21 @@ __device__ __forceinline__ uint32_t build_prune_warp(const uint64_t *__restrict_
             nres++;
             const uint32_t idi = (uint32_t)ck[i];
             const uint64_t *ci = cc + i * cws;
+            const int16_t *il = nullptr;
+            uint32_t nil = 0;
+            if (label_off) {
+                uint32_t o0 = __ldg(label_off + idi);
+                il = labels + o0;
+                nil = __ldg(label_off + idi + 1) - o0;
+            }
             for (uint32_t j = i + 1 + lane; j < C; j += 32) {
                 float f = mf[j];
                 if (f > max_alpha) continue; /* completely excluded already */
+                if (label_off) { /* does the kept neighbour carry every label the candidate shares with the point? */
+                    const uint32_t idj0 = (uint32_t)ck[j];
+                    uint32_t o0 = __ldg(label_off + idj0);
+                    if (!labels_contains_intersection(il, nil, labels + o0, __ldg(label_off + idj0 + 1) - o0, pl, npl)) continue;
+                }
                 const uint64_t *cj = cc + j * cws;
                 uint32_t dij = 0;
                 for (uint32_t w = 0; w < cw; w++) dij += __popcll(ci[w] ^ cj[w]);
@@ -106,6 +146,8 @@ struct BuildArgs {
     uint32_t R;           /* num_neighbors */
     float max_alpha;
     uint32_t per_warp_smem;
+    const uint32_t *label_off; /* NULL: unlabeled index */
+    const int16_t *labels;
 };
 
 __device__ __forceinline__ void build_smem(unsigned char *base, uint32_t cws, uint64_t *&ck, uint64_t *&cc, float *&mf,
@@ -142,11 +184,45 @@ __global__ void __launch_bounds__(256) dann_build_prune_kernel(BuildArgs a, uint
     build_smem(dann_smem + (size_t)warp * a.per_warp_smem, a.cws, ck, cc, mf, oid, od);
     for (uint32_t b = blockIdx.x * W + warp; b < m; b += gridDim.x * W) {
         const uint32_t p = lo + b;
-        uint32_t C = vis_len[b];
-        if (C > DANN_BUILD_CMAX) C = DANN_BUILD_CMAX; /* the visited list is sorted: keep the closest */
-        for (uint32_t c = lane; c < C; c += 32) ck[c] = vis[(size_t)b * vis_cap + c];
+        /* add_neighbors (graph/mod.rs:212-266): candidates = current neighbours of p (from the filtered pass of a
+         * labeled insert) + the visited set, without duplicates and without p itself */
+        const uint32_t deg = a.deg[p];
+        uint32_t nv = vis_len[b];
+        if (nv > DANN_BUILD_CMAX - deg) nv = DANN_BUILD_CMAX - deg; /* the visited list is sorted: keep the closest */
+        const uint32_t *row = a.nbrs + (size_t)p * DANN_BUILD_SLACK;
+        const uint16_t *drow = a.nbr_dist + (size_t)p * DANN_BUILD_SLACK;
+        for (uint32_t c = lane; c < DANN_BUILD_CMAX; c += 32) {
+            uint64_t k = ~0ull;
+            if (c < deg) k = ((uint64_t)drow[c] << 32) | row[c];
+            else if (c < deg + nv) k = vis[(size_t)b * vis_cap + (c - deg)];
+            if ((uint32_t)k == p) k = ~0ull; /* prevent self-loops */
+            ck[c] = k;
+        }
         __syncwarp();
-        const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, C, a.R, a.max_alpha, oid, od, lane);
+        build_bitonic_sort128(ck, lane);
+        /* equal keys are adjacent after the sort: drop repeats, compact */
+        uint32_t C = 0;
+        for (uint32_t c0 = 0; c0 < DANN_BUILD_CMAX; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint64_t k = ck[c];
+            const bool keep = k != ~0ull && (c == 0 || ck[c - 1] != k);
+            const unsigned mk = __ballot_sync(DANN_FULL, keep);
+            __syncwarp();
+            if (keep) ck[C + __popc(mk & ((1u << lane) - 1u))] = k;
+            C += __popc(mk);
+            __syncwarp();
+        }
+        uint32_t cnt;
+        if (C <= DANN_BUILD_SLACK) { /* not more than max_neighbors_during_build: keep them all */
+            for (uint32_t t = lane; t < C; t += 32) {
+                oid[t] = (uint32_t)ck[t];
+                od[t] = (uint16_t)(ck[t] >> 32);
+            }
+            cnt = C;
+            __syncwarp();
+        } else {
+            cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, C, a.R, a.max_alpha, oid, od, lane, a.label_off, a.labels);
+        }
         build_write_list(a, p, oid, od, cnt, lane);
         for (uint32_t t = lane; t < DANN_BUILD_SLACK; t += 32) {
             size_t o = (size_t)b * DANN_BUILD_SLACK + t;
@@ -196,7 +272,7 @@ __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, c
         for (uint32_t t = lane; t < deg; t += 32) ck[t] = ((uint64_t)drow[t] << 32) | row[t];
         __syncwarp();
         const uint32_t tot = deg + nadd;
-        if (tot <= DANN_BUILD_SLACK) { /* room left: plain append */
+        if (tot <= DANN_BUILD_SLACK && !a.label_off) { /* room left and no repeats possible: plain append */
             uint32_t *wrow = a.nbrs + (size_t)q * DANN_BUILD_SLACK;
             uint16_t *wdrow = a.nbr_dist + (size_t)q * DANN_BUILD_SLACK;
             for (uint32_t t = deg + lane; t < tot; t += 32) {
@@ -208,7 +284,29 @@ __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, c
             for (uint32_t t = tot + lane; t < DANN_BUILD_CMAX; t += 32) ck[t] = ~0ull;
             __syncwarp();
             build_bitonic_sort128(ck, lane);
-            const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, q, ck, mf, cc, tot, a.R, a.max_alpha, oid, od, lane);
+            /* a source may already be a neighbour (second pass of a labeled insert): equal keys are adjacent */
+            uint32_t C = 0;
+            for (uint32_t c0 = 0; c0 < DANN_BUILD_CMAX; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                const uint64_t k = ck[c];
+                const bool keep = k != ~0ull && (c == 0 || ck[c - 1] != k);
+                const unsigned mk = __ballot_sync(DANN_FULL, keep);
+                __syncwarp();
+                if (keep) ck[C + __popc(mk & ((1u << lane) - 1u))] = k;
+                C += __popc(mk);
+                __syncwarp();
+            }
+            uint32_t cnt;
+            if (C <= DANN_BUILD_SLACK) {
+                for (uint32_t t = lane; t < C; t += 32) {
+                    oid[t] = (uint32_t)ck[t];
+                    od[t] = (uint16_t)(ck[t] >> 32);
+                }
+                cnt = C;
+                __syncwarp();
+            } else {
+                cnt = build_prune_warp(a.codes, a.cw, a.cws, q, ck, mf, cc, C, a.R, a.max_alpha, oid, od, lane, a.label_off, a.labels);
+            }
             build_write_list(a, q, oid, od, cnt, lane);
         }
         __syncwarp();
@@ -232,7 +330,7 @@ __global__ void __launch_bounds__(256) dann_build_finalize_kernel(BuildArgs a) {
         for (uint32_t t = lane; t < DANN_BUILD_CMAX; t += 32) ck[t] = t < deg ? (((uint64_t)drow[t] << 32) | row[t]) : ~0ull;
         __syncwarp();
         build_bitonic_sort128(ck, lane);
-        const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, deg, a.R, a.max_alpha, oid, od, lane);
+        const uint32_t cnt = build_prune_warp(a.codes, a.cw, a.cws, p, ck, mf, cc, deg, a.R, a.max_alpha, oid, od, lane, a.label_off, a.labels);
         build_write_list(a, p, oid, od, cnt, lane);
         __syncwarp();
     }

@@ -830,7 +830,8 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
         return fail(DANN_ERR_INVALID_ARG, "dann_build_graph needs an index loaded with R == %u neighbour slots", DANN_BUILD_SLACK);
     if (num_neighbors < 1 || num_neighbors > (int)DANN_BUILD_SLACK) return fail(DANN_ERR_INVALID_ARG, "num_neighbors must be 1..%u", DANN_BUILD_SLACK);
     if (search_list_size < 1 || search_list_size > 1000) return fail(DANN_ERR_INVALID_ARG, "build search_list_size must be 1..1000");
-    if (v.has_labels) return fail(DANN_ERR_INVALID_ARG, "labeled builds are not implemented");
+    if (v.has_labels && v.n_start_labels == 0)
+        return fail(DANN_ERR_INVALID_ARG, "a labeled build needs the per-label start nodes (first node carrying each label)");
     if (v.n == 0) return DANN_OK;
     if (v.start_default != 0) return fail(DANN_ERR_INVALID_ARG, "dann_build_graph inserts in id order: start_default must be 0");
     if (max_batch == 0) max_batch = 1u << 20;
@@ -879,6 +880,8 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     ba.deg = b_deg.as<uint8_t>();
     ba.R = (uint32_t)num_neighbors;
     ba.max_alpha = max_alpha;
+    ba.label_off = v.has_labels ? v.label_off : nullptr;
+    ba.labels = v.has_labels ? v.labels : nullptr;
     const size_t pw = ((size_t)DANN_BUILD_CMAX * 8 + (size_t)DANN_BUILD_CMAX * ba.cws * 8 + DANN_BUILD_CMAX * 4 +
                        DANN_BUILD_SLACK * 4 + DANN_BUILD_SLACK * 2 + 15) & ~(size_t)15;
     ba.per_warp_smem = (uint32_t)pw;
@@ -908,48 +911,55 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     for (uint32_t lo = 1; lo < n;) {
         uint32_t m = std::max<uint32_t>(1, lo / 16);
         m = std::min(std::min(m, mb), n - lo);
-        CK(cudaEventRecord(e[0], st));
-        rc = run_search(ix, v.codes + (size_t)lo * v.cw, nullptr, nullptr, (int)m, (uint32_t)search_list_size, 1u,
-                        b_stats.as<dann_query_stats>(), b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(), vis_cap, st);
-        if (rc) {
-            ix->lists_unique = lists_unique_saved;
-            return rc;
-        }
-        CK(cudaEventRecord(e[1], st));
-        dann_build_prune_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, lo, m, b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(), vis_cap,
-                                                              b_k0.as<uint64_t>(), b_v0.as<uint32_t>());
-        ix->launches++;
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(e[2], st));
-        const size_t cnt = (size_t)m * DANN_BUILD_SLACK;
-        size_t tb = b_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tb, b_k0.as<uint64_t>(), b_k1.as<uint64_t>(), b_v0.as<uint32_t>(),
-                                           b_v1.as<uint32_t>(), cnt, 16, 64, st));
-        uint32_t *d_nheads = b_heads.as<uint32_t>() + ntrip;
-        CK(cudaMemsetAsync(d_nheads, 0, 4, st));
-        dann_build_heads_kernel<<<ix->sm_count * 4, 256, 0, st>>>(b_k1.as<uint64_t>(), cnt, b_heads.as<uint32_t>(), d_nheads);
-        ix->launches += 2;
+        /* graph/mod.rs:637-660: a labeled node is inserted twice — first from the label start nodes with the
+         * label filter on, then from the default start node without it; the second pass merges with the
+         * neighbours the first one left (add_neighbors) */
         uint32_t nheads = 0;
-        CK(cudaMemcpyAsync(&nheads, d_nheads, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaEventRecord(e[3], st));
-        if (nheads) {
-            dann_build_backlink_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, b_k1.as<uint64_t>(), b_v1.as<uint32_t>(), cnt,
-                                                                     b_heads.as<uint32_t>(), nheads);
+        for (int pass = v.has_labels ? 0 : 1; pass < 2; pass++) {
+            const int16_t *qlab = pass == 0 ? v.labels : nullptr;
+            const int32_t *qoff = pass == 0 ? reinterpret_cast<const int32_t *>(v.label_off + lo) : nullptr;
+            CK(cudaEventRecord(e[0], st));
+            rc = run_search(ix, v.codes + (size_t)lo * v.cw, qlab, qoff, (int)m, (uint32_t)search_list_size, 1u,
+                            b_stats.as<dann_query_stats>(), b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(), vis_cap, st);
+            if (rc) {
+                ix->lists_unique = lists_unique_saved;
+                return rc;
+            }
+            CK(cudaEventRecord(e[1], st));
+            dann_build_prune_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, lo, m, b_vis.as<uint64_t>(), b_vlen.as<uint32_t>(),
+                                                                  vis_cap, b_k0.as<uint64_t>(), b_v0.as<uint32_t>());
             ix->launches++;
             CK(cudaGetLastError());
+            CK(cudaEventRecord(e[2], st));
+            const size_t cnt = (size_t)m * DANN_BUILD_SLACK;
+            size_t tb = b_tmp.cap;
+            CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tb, b_k0.as<uint64_t>(), b_k1.as<uint64_t>(), b_v0.as<uint32_t>(),
+                                               b_v1.as<uint32_t>(), cnt, 16, 64, st));
+            uint32_t *d_nheads = b_heads.as<uint32_t>() + ntrip;
+            CK(cudaMemsetAsync(d_nheads, 0, 4, st));
+            dann_build_heads_kernel<<<ix->sm_count * 4, 256, 0, st>>>(b_k1.as<uint64_t>(), cnt, b_heads.as<uint32_t>(), d_nheads);
+            ix->launches += 2;
+            CK(cudaMemcpyAsync(&nheads, d_nheads, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaEventRecord(e[3], st));
+            if (nheads) {
+                dann_build_backlink_kernel<<<bgrid, bw * 32, bsmem, st>>>(ba, b_k1.as<uint64_t>(), b_v1.as<uint32_t>(), cnt,
+                                                                         b_heads.as<uint32_t>(), nheads);
+                ix->launches++;
+                CK(cudaGetLastError());
+            }
+            CK(cudaEventRecord(e[4], st));
+            CK(cudaStreamSynchronize(st));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e[0], e[1]));
+            bs.search_ms += ms;
+            CK(cudaEventElapsedTime(&ms, e[1], e[2]));
+            bs.prune_ms += ms;
+            CK(cudaEventElapsedTime(&ms, e[2], e[3]));
+            bs.sort_ms += ms;
+            CK(cudaEventElapsedTime(&ms, e[3], e[4]));
+            bs.backlink_ms += ms;
         }
-        CK(cudaEventRecord(e[4], st));
-        CK(cudaStreamSynchronize(st));
-        float ms;
-        CK(cudaEventElapsedTime(&ms, e[0], e[1]));
-        bs.search_ms += ms;
-        CK(cudaEventElapsedTime(&ms, e[1], e[2]));
-        bs.prune_ms += ms;
-        CK(cudaEventElapsedTime(&ms, e[2], e[3]));
-        bs.sort_ms += ms;
-        CK(cudaEventElapsedTime(&ms, e[3], e[4]));
-        bs.backlink_ms += ms;
         bs.batches++;
         if (verbose && (bs.batches % 16 == 0 || lo + m >= n))
             fprintf(stderr, "[dann_build] batch %u: nodes %u..%u (m=%u, %u destinations) search %.0f prune %.0f sort %.0f backlink %.0f ms\n",

@@ -237,8 +237,18 @@ def ground_truth(x: torch.Tensor, q: torch.Tensor, k: int, mask: torch.Tensor | 
 
 
 @torch.no_grad()
+def label_start_nodes(label_off: np.ndarray, labels: np.ndarray):
+    """First node (in heap order) carrying each label: graph/mod.rs:490-533 update_start_nodes."""
+    n = len(label_off) - 1
+    node_of = np.repeat(np.arange(n, dtype=np.uint32), np.diff(label_off).astype(np.int64))
+    sl, first_idx = np.unique(labels, return_index=True)
+    return sl.astype(np.int16), node_of[first_idx].astype(np.uint32)
+
+
+@torch.no_grad()
 def build_index_vamana(x: torch.Tensor, distance_type: int = COSINE, bits: int | None = None, R: int = 50,
-                       L_build: int = 100, alpha: float = 1.2, max_batch: int = 1 << 20, log=None, keep_index=False):
+                       L_build: int = 100, alpha: float = 1.2, max_batch: int = 1 << 20, log=None, keep_index=False,
+                       labels_seed: int | None = None):
     """Same contract as build_index(), but the graph comes from the product's GPU batch Vamana builder
     (dann_build_graph: beam search in build mode + alpha prune + back-links, all over SBQ codes, like the
     reference's build) instead of the exact-kNN fixture.  Scales linearly in n.
@@ -255,10 +265,15 @@ def build_index_vamana(x: torch.Tensor, distance_type: int = COSINE, bits: int |
     codes = quantize_nodes(x, distance_type, bits, mean_h, m2_h, n)
     say(f"  sbq codes {time.time() - t0:.1f}s")
     slots = 64
+    label_off = labels = sl = sn = None
+    if labels_seed is not None:
+        label_off, labels = gen_labels(n, labels_seed, device=x.device)
+        sl, sn = label_start_nodes(label_off, labels)
     snap = Snapshot(n=n, dim=dim, dim_index=dim, bits=bits, words=code_words(dim, bits), R=slots,
-                    distance_type=distance_type, has_labels=False, count=n, mean=mean_h, m2=m2_h, codes=codes,
-                    nbrs=np.full((n, slots), INVALID_NODE, np.uint32), heap_tid=make_heap_tids(n), vectors=None,
-                    start_default=0 if n else INVALID_NODE)
+                    distance_type=distance_type, has_labels=labels_seed is not None, count=n, mean=mean_h, m2=m2_h,
+                    codes=codes, nbrs=np.full((n, slots), INVALID_NODE, np.uint32), heap_tid=make_heap_tids(n),
+                    vectors=None, start_default=0 if n else INVALID_NODE, start_labels=sl, start_label_nodes=sn,
+                    label_off=label_off, labels=labels)
     idx = diskann.DiskAnnIndex(snap, device=x.device.index or 0)
     st = idx.build_graph(R, L_build, alpha, max_batch)
     say(f"  gpu vamana build {time.time() - t0:.1f}s: {st}")
