@@ -103,7 +103,8 @@ int dann_device_count(void);
  * reference's preprocess_cosine arithmetic, distance/mod.rs:225-253). */
 int dann_index_load(const dann_snapshot_desc *snap, int device, dann_index **out);
 void dann_index_free(dann_index *ix);
-/* Bytes of HBM held by the index arrays (codes, nbrs, tids, vectors, labels, means). */
+/* `vectors` may be NULL in the snapshot (see dann_index_set_vectors); scans then need rescore == 0.
+ * Bytes of HBM held by the index arrays (codes, nbrs, tids, vectors, labels, means): */
 uint64_t dann_index_hbm_bytes(const dann_index *ix);
 
 /* ---- scan operator: one row at a time, amgettuple order ------------------------ */
@@ -162,9 +163,12 @@ int dann_full_distance(dann_index *ix, const float *d_q_full, const uint32_t *d_
  * GPU batch Vamana over SBQ codes built from the scan kernels: greedy_search_for_build
  * (graph/mod.rs:285-327) + prune_neighbors (:392-488) + back-pointers (:212-266,720-737), nodes
  * inserted in batches.  The index must have been loaded with R == 64 neighbour slots per node
- * (contents ignored), start_default == 0 and no labels; `vectors` may be NULL at load and supplied
- * later.  On return every list holds <= num_neighbors ids.  The graph is a valid diskann graph but not
- * the reference's serial insertion order, so it serves fixtures and benchmarks. */
+ * (contents ignored) and start_default == 0; `vectors` may be NULL at load and supplied later.  A labeled
+ * index (has_labels, with start_labels/start_label_nodes = the first node carrying each label) is built
+ * the reference's way: a label-filtered insertion pass from the label start nodes, then the unfiltered
+ * one (graph/mod.rs:637-660), with the label-aware prune (:445-455).  On return every list holds
+ * <= num_neighbors ids.  The graph is a valid diskann graph but not the reference's serial insertion
+ * order, so it serves bulk builds, fixtures and benchmarks. */
 typedef struct {
     uint32_t batches;
     float search_ms, prune_ms, sort_ms, backlink_ms, total_ms;
