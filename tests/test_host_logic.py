@@ -31,3 +31,22 @@ def test_snapshot_roundtrip(tmp_path):
 def test_heap_tids_have_valid_offsets():
     t = snapshot.make_heap_tids(1000)
     assert ((t & np.uint64(0xFFFF)) >= 1).all() and len(set(t.tolist())) == 1000
+
+
+def test_bench_keeps_stdout_for_the_json_line():
+    """bench.py points fd 1 at stderr so that only its final JSON line reaches the real stdout
+    (libraries such as NCCL print banners there)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert r.stdout == ""
+    assert "--impl" in r.stderr and "--gpus" in r.stderr
+
+
+def test_shard_bounds_and_recall_helper_shapes():
+    from pgvectorscale_b200.group import shard_bounds
+    assert shard_bounds(1024, 8, 0) == (0, 128) and shard_bounds(1024, 8, 7) == (896, 1024)
+    assert shard_bounds(10, 4, 1) == (3, 6)
