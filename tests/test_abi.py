@@ -64,3 +64,26 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "oracle.h" not in text, f
+
+
+def test_plain_c_program_links_and_fails_loudly_without_a_device(lib_built, tmp_path):
+    """include/diskann_b200.h is a self-contained C99 header; harness/executor_harness.c drives the scan operator
+    the way the pgrx shim would.  Without a GPU it must report DANN_ERR_NO_DEVICE (exit code 3), not crash."""
+    import shutil
+    import subprocess
+    from pgvectorscale_b200 import diskann
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "executor_harness")
+    libdir = os.path.dirname(lib_built)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "harness", "executor_harness.c"), "-L" + libdir, "-ldiskann_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if diskann.device_count() > 0:
+        assert r.returncode == 0, r.stderr
+        assert "rows" in r.stdout
+    else:
+        assert r.returncode == 3
+        assert "no CPU path" in r.stderr
