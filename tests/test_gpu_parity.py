@@ -363,21 +363,3 @@ def test_device_buffer_entry_point_matches_host_entry_point(lib):
         torch.cuda.synchronize()
         assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), hk["tid"])
 
-
-def test_plain_c_executor_harness_runs_a_scan(lib, lib_built, tmp_path):
-    """The C99 harness (the pgrx shim's call sequence) loads an index and streams every row of a scan."""
-    import os
-    import shutil
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    gcc = shutil.which("gcc")
-    if gcc is None:
-        pytest.skip("gcc not available")
-    exe = str(tmp_path / "executor_harness")
-    libdir = os.path.dirname(lib_built)
-    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
-                    os.path.join(root, "harness", "executor_harness.c"), "-L" + libdir, "-ldiskann_b200",
-                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "rows; visits=" in r.stdout
