@@ -64,3 +64,24 @@ def make_index(vectors, distance_type=COSINE, bits=None, R=50, L_build=100, alph
                     start_labels=sl if label_off is not None else None,
                     start_label_nodes=sn if label_off is not None else None,
                     label_off=label_off, labels=labels)
+
+
+def to_plain(s):
+    """Re-express an SBQ fixture as a plain-storage index over the same graph: each node keeps the f32 vector
+    PlainStorage would have stored (plain/node.rs:17-22 via pg_vector.rs:143-148: truncated to dim_index, and
+    cosine-normalised after truncation).  The reference rejects inner product and labels for this layout
+    (build.rs:264-290); the graph itself would be built on exact distances there - any valid graph serves
+    scan parity."""
+    import copy
+    from . import oracle
+    p = copy.copy(s)
+    iv = np.ascontiguousarray(s.vectors[:, :s.dim_index], dtype=np.float32).copy()
+    if s.distance_type == COSINE:
+        for i in range(len(iv)):
+            iv[i] = oracle.preprocess_cosine(iv[i])
+    p.storage_type = 1
+    p.index_vectors = iv
+    p.has_labels = 0
+    p.label_off = p.labels = None
+    p.start_labels = p.start_label_nodes = None
+    return p

@@ -486,9 +486,22 @@ static inline const int16_t *node_labels(const orc_snapshot *s, uint32_t n, uint
 }
 
 /* sbq/storage.rs:365-391 create_lsn_for_start_node + graph/mod.rs:117-122 */
+/* plain/mod.rs:22-32 PlainDistanceMeasure::calculate_distance: distance_fn(query.to_index_slice(), node.vector) */
+static inline float plain_distance(const QueryCtx &q, Lsr &l, uint32_t node) {
+    const orc_snapshot *s = q.s;
+    l.stats.d_full++; /* record_full_distance_comparison */
+    return orc_distance_avx2(s->distance_type, q.q_index.data(), s->index_vectors + (size_t)node * s->dim_index,
+                             s->dim_index);
+}
+
 static void lsr_add_start(const QueryCtx &q, Lsr &l, uint32_t node) {
     if (!l.prepare_insert(node)) return;
     const orc_snapshot *s = q.s;
+    if (s->storage_type == ORC_STORAGE_PLAIN) { /* plain/storage.rs:223-252 */
+        float d = plain_distance(q, l, node);
+        l.insert_neighbor(Lsn{node, Dwtb{d, 0}});
+        return;
+    }
     l.stats.d_quantized++;
     float d = (float)orc_hamming(s->codes + (size_t)node * s->words, q.q_code.data(), s->words);
     l.insert_neighbor(Lsn{node, Dwtb{d, 0}});
@@ -502,6 +515,11 @@ static void visit_lsn(const QueryCtx &q, Lsr &l, uint32_t visiting, bool no_filt
         uint32_t n = nb[j];
         if (n == ORC_INVALID_NODE) break; /* sbq/node.rs:261-285 */
         if (!l.prepare_insert(n)) continue;
+        if (s->storage_type == ORC_STORAGE_PLAIN) { /* plain/storage.rs:254-299 (asserts no_filter) */
+            float d = plain_distance(q, l, n);
+            l.insert_neighbor(Lsn{n, Dwtb{d, 0}});
+            continue;
+        }
         if (q.labels_some) {
             if (!no_filter) {
                 uint32_t cnt;
@@ -574,10 +592,16 @@ struct Scan { /* scan.rs TSVResponseIterator :162-306 */
         /* graph/mod.rs:331-354 greedy_search_streaming_init */
         lsr.inserted.reset(4096);
         if (s->start_default == ORC_INVALID_NODE) return; /* no nodes in the graph */
-        /* sbq/mod.rs:145-148 */
-        q.q_code.assign(s->words, 0);
-        orc_quantize(q.q_index.data(), s->dim_index, s->bits, s->mean, s->m2, s->count,
-                     q.q_code.data());
+        if (s->storage_type == ORC_STORAGE_PLAIN) {
+            /* plain storage does not support label filters (plain/storage.rs:260): the key is ignored here */
+            q.labels_some = false;
+            q.labels.clear();
+            q.has_label_filter = false;
+        } else {
+            /* sbq/mod.rs:145-148 */
+            q.q_code.assign(s->words, 0);
+            orc_quantize(q.q_index.data(), s->dim_index, s->bits, s->mean, s->m2, s->count, q.q_code.data());
+        }
         /* start_nodes.rs:39-48 */
         if (q.labels_some) {
             for (int16_t lab : q.labels) {
@@ -617,7 +641,9 @@ struct Scan { /* scan.rs TSVResponseIterator :162-306 */
 
     /* scan.rs:244-305 next_with_resort */
     bool next_with_resort(uint64_t *tid, uint32_t *node, float *dist) {
-        if (resort_size == 0) { /* resort_buffer.capacity() == 0 */
+        /* scan.rs:392-403: plain storage only resorts when the index holds fewer dimensions than the heap */
+        const bool plain_no_resort = q.s->storage_type == ORC_STORAGE_PLAIN && q.s->dim == q.s->dim_index;
+        if (resort_size == 0 || plain_no_resort) { /* resort_buffer.capacity() == 0 */
             *dist = std::nanf("");
             return next(tid, node);
         }

@@ -56,7 +56,14 @@ typedef struct {
     const uint32_t *start_label_nodes;
     const uint32_t *label_off; /* [n+1] CSR into labels, only if has_labels */
     const int16_t *labels;     /* sorted+dedup per node */
+    /* storage_layout (storage.rs:144-169).  ORC_STORAGE_PLAIN: the node holds the f32 vector it was built
+     * from (truncated to dim_index, cosine-normalised at insert, plain/node.rs:17-22) and the beam search
+     * compares the query against it directly (plain/storage.rs:223-299); no label filters. */
+    int32_t storage_type;        /* ORC_STORAGE_SBQ (0) / ORC_STORAGE_PLAIN (1) */
+    const float *index_vectors;  /* [n*dim_index], plain storage only */
 } orc_snapshot;
+
+enum { ORC_STORAGE_SBQ = 0, ORC_STORAGE_PLAIN = 1 };
 
 typedef struct {
     uint64_t visits;      /* stats.visits           (stats.rs record_visit)   */

@@ -29,6 +29,7 @@ class _Snapshot(C.Structure):
         ("start_default", C.c_uint32), ("n_start_labels", C.c_uint32),
         ("start_labels", C.c_void_p), ("start_label_nodes", C.c_void_p),
         ("label_off", C.c_void_p), ("labels", C.c_void_p),
+        ("storage_type", C.c_int32), ("index_vectors", C.c_void_p),
     ]
 
 
@@ -216,6 +217,8 @@ def _snapshot_struct(s):
     st.start_label_nodes = arr(s.start_label_nodes, np.uint32)
     st.label_off = arr(s.label_off, np.uint32)
     st.labels = arr(s.labels, np.int16)
+    st.storage_type = int(getattr(s, "storage_type", 0) or 0)
+    st.index_vectors = arr(getattr(s, "index_vectors", None), np.float32)
     return st, _Keep(keep)
 
 

@@ -149,6 +149,10 @@ class DiskAnnIndex:
         self._lib = load_library()
         snapshot.validate()
         s = snapshot
+        if int(getattr(s, "storage_type", 0) or 0) != 0:
+            # storage_layout = plain (storage.rs:144-169) is restated in the oracle only; no CUDA scan for it yet
+            # and, as everywhere in the product path, no CPU fallback.
+            raise DiskAnnError(-1, "storage_layout=plain snapshots are not supported by the CUDA scan path")
         keep = []
 
         def arr(a, dt):

@@ -60,6 +60,11 @@ class Snapshot:
     start_label_nodes: Optional[np.ndarray] = None
     label_off: Optional[np.ndarray] = None
     labels: Optional[np.ndarray] = None
+    # storage_layout (storage.rs:144-169): 0 = SBQ ("memory_optimized", the default and the only layout the CUDA
+    # path scans today), 1 = plain: nodes hold index_vectors[n, dim_index] f32 (plain/node.rs:17-22).  The
+    # oracle restates both; the plain scan kernel is the next scope row.
+    storage_type: int = 0
+    index_vectors: Optional[np.ndarray] = None
 
     def validate(self) -> None:
         assert self.words == code_words(self.dim_index, self.bits)

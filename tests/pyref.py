@@ -194,14 +194,24 @@ def scan(s, query, labels, L, rescore, max_rows):
             return []
         return list(s.labels[s.label_off[n]:s.label_off[n + 1]])
 
+    plain = int(getattr(s, "storage_type", 0) or 0) == 1
+    if plain:                                   # plain/storage.rs:260 asserts no_filter
+        labels = None
+        has_filter = False
+
     def add(n):
-        stats["d_quantized"] += 1
-        d = float(hamming(s.codes[n], qcode))
+        if plain:                               # plain/mod.rs:22-32, plain/storage.rs:223-299
+            stats["d_full"] += 1
+            d = float(distance(s.distance_type, q_index, np.array(s.index_vectors[n], f)))
+        else:
+            stats["d_quantized"] += 1
+            d = float(hamming(s.codes[n], qcode))
         stats["candidates"] += 1
         cand.push((d, n))
 
     if s.start_default != INVALID:
-        qcode = quantize(q_index, s.bits, s.mean, s.m2, s.count, s.words)
+        if not plain:
+            qcode = quantize(q_index, s.bits, s.mean, s.m2, s.count, s.words)
         if labels is None:
             starts = [s.start_default]
         else:
@@ -264,7 +274,7 @@ def scan(s, query, labels, L, rescore, max_rows):
     resort = RustBinaryHeap(lambda a, b: total_key(b[0]) <= total_key(a[0]))
     rows = []
     while len(rows) < max_rows:
-        if rescore == 0:
+        if rescore == 0 or (plain and s.dim == s.dim_index):    # scan.rs:392-403
             r = nxt()
             if r is None:
                 break

@@ -50,3 +50,15 @@ def test_shard_bounds_and_recall_helper_shapes():
     from pgvectorscale_b200.group import shard_bounds
     assert shard_bounds(1024, 8, 0) == (0, 128) and shard_bounds(1024, 8, 7) == (896, 1024)
     assert shard_bounds(10, 4, 1) == (3, 6)
+
+
+def test_plain_storage_snapshot_is_refused_not_emulated():
+    """The plain layout exists in the oracle only: the product path must refuse it rather
+    than route anywhere else."""
+    import pytest
+    from conftest import build_case
+    from oracle import fixtures
+    from pgvectorscale_b200.diskann import DiskAnnError, DiskAnnIndex
+    s = fixtures.to_plain(build_case(64, 16, 1, seed=2, R=8, L_build=16))
+    with pytest.raises(DiskAnnError, match="plain"):
+        DiskAnnIndex(s)

@@ -263,6 +263,43 @@ def test_cpp_oracle_equals_python_restatement(dist, bits, labels, dim_index):
             assert a["stats"] == b_stats
 
 
+# ---- plain storage layout (oracle groundwork, no CUDA path yet) ---------------
+@pytest.mark.parametrize("dist,dim_index", [(COSINE, None), (L2, None), (COSINE, 40), (L2, 40)])
+def test_plain_storage_scan_cpp_equals_python(dist, dim_index):
+    s = fixtures.to_plain(build_case(300, 64, dist, seed=21 + dist, kind="normal", R=12, L_build=24,
+                                     dim_index=dim_index, deleted_every=9))
+    q = fixtures.gen_vectors(4, 64, 77, "normal")
+    for i in range(4):
+        for (L, rescore, rows) in ((20, 10, 15), (5, 0, 25), (30, 40, 12)):
+            a = oracle.scan(s, q[i], None, L, rescore, rows)
+            b_rows, b_stats = pyref.scan(s, q[i], None, L, rescore, rows)
+            assert a["node"].tolist() == [r[1] for r in b_rows]
+            assert a["stats"] == b_stats
+            assert a["stats"]["d_quantized"] == 0
+            resorts = rescore > 0 and s.dim != s.dim_index          # scan.rs:392-403
+            if resorts:
+                assert a["dist"].view(np.uint32).tolist() == \
+                    np.array([r[2] for r in b_rows], np.float32).view(np.uint32).tolist()
+                assert a["stats"]["d_full"] > a["stats"]["candidates"]
+            else:
+                assert a["stats"]["d_full"] == a["stats"]["candidates"]  # every comparison is a full distance
+
+
+def test_plain_storage_l2_sanity_kat():       # build.rs:1475-1516 run with storage_layout = plain (plain/tests.rs)
+    s, v = _three_vector_index(L2)
+    p = fixtures.to_plain(s)
+    for q in ([1, 1, 1], [2, 2, 2], [3, 3, 3]):
+        assert _top1(p, v, q, rescore=0) == q   # exact distances: no rescore needed, unlike the SBQ layout
+
+
+def test_plain_storage_exact_order_on_full_graph_walk():
+    s = fixtures.to_plain(build_case(200, 32, L2, seed=5, kind="normal", R=16, L_build=40))
+    q = fixtures.gen_vectors(1, 32, 6, "normal")[0]
+    r = oracle.scan(s, q, None, 400, 0, 200)     # L >= n: the stream is the exact order of every reachable node
+    d = np.array([oracle.distance(L2, q, s.index_vectors[n]) for n in r["node"]], np.float32)
+    assert len(r["node"]) == 200 and np.all(np.diff(d) >= 0)
+
+
 # ---- committed golden vectors -----------------------------------------------------------------
 def test_golden_vectors():
     path = os.path.join(os.path.dirname(__file__), "golden", "scan_golden.npz")
