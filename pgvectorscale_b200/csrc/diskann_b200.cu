@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -93,7 +94,7 @@ struct dann_index {
     std::mutex mu;
     int sm_count = 0;
     size_t smem_optin = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0}; /* bumped by entry points that do not take `mu` too */
     bool poisoned = false;
     /* per-warp-slot search workspace */
     DevBuf ws_hash, ws_cand, ws_heap, ws_bitmap, ws_ins;
@@ -222,26 +223,55 @@ extern "C" void dann_index_free(dann_index *ix) {
     delete ix;
 }
 
-extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
-    dann_index *ix = nullptr;
-    if (!s || !out) return fail(DANN_ERR_INVALID_ARG, "dann_index_load: NULL argument");
-    *out = nullptr;
-    int ndev = dann_device_count();
-    if (ndev <= 0) return fail(DANN_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
-    if (device < 0 || device >= ndev) return fail(DANN_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+/* Everything the kernels index with comes from the snapshot: reject ids and offsets that would send a
+ * gather out of bounds here, on the host, before anything is copied (the reference gets the same guarantee
+ * from Postgres' page/item bounds checks, util/page.rs:254-290). */
+static int validate_snapshot(const dann_snapshot_desc *s, uint32_t *words_out) {
     if (s->dim == 0 || s->dim_index == 0 || s->dim_index > s->dim || s->bits == 0 || s->R == 0)
         return fail(DANN_ERR_INVALID_ARG, "bad snapshot geometry");
     uint64_t nb = (uint64_t)s->dim_index * s->bits;
     uint32_t words = (uint32_t)(nb % 64 == 0 ? nb / 64 : nb / 64 + 1); /* quantize.rs:38-46 */
     if (words != s->words) return fail(DANN_ERR_INVALID_ARG, "words=%u but dim_index*bits needs %u", s->words, words);
+    *words_out = words;
     if (s->distance_type < DANN_COSINE || s->distance_type > DANN_IP)
         return fail(DANN_ERR_INVALID_ARG, "unknown distance type %d", s->distance_type);
+    if (s->n == DANN_INVALID_NODE) return fail(DANN_ERR_INVALID_ARG, "n collides with the invalid-node sentinel");
     if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->mean))
         return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
+    if (s->bits > 1 && s->n && !s->m2) return fail(DANN_ERR_INVALID_ARG, "m2 is required when bits > 1 (sbq/quantize.rs:73-101)");
     if (s->has_labels && s->n && (!s->label_off || (s->label_off[s->n] && !s->labels)))
         return fail(DANN_ERR_INVALID_ARG, "has_labels set but label arrays missing");
     if (s->start_default != DANN_INVALID_NODE && s->start_default >= s->n)
         return fail(DANN_ERR_INVALID_ARG, "start_default out of range");
+    if (s->n_start_labels && s->start_labels && s->start_label_nodes) {
+        for (uint32_t i = 0; i < s->n_start_labels; i++) {
+            if (s->start_label_nodes[i] >= s->n) return fail(DANN_ERR_INVALID_ARG, "start node of label %d out of range", (int)s->start_labels[i]);
+            if (i && s->start_labels[i] <= s->start_labels[i - 1]) return fail(DANN_ERR_INVALID_ARG, "start_labels must be strictly ascending");
+        }
+    }
+    for (size_t r = 0; r < s->n; r++) { /* a list ends at its first invalid id (sbq/node.rs:260-273) */
+        const uint32_t *row = s->nbrs + r * s->R;
+        for (uint32_t j = 0; j < s->R && row[j] != DANN_INVALID_NODE; j++)
+            if (row[j] >= s->n) return fail(DANN_ERR_INVALID_ARG, "neighbour %u of node %zu is %u, outside the index (n=%u)", j, r, row[j], s->n);
+    }
+    if (s->has_labels && s->n) {
+        if (s->label_off[0] != 0) return fail(DANN_ERR_INVALID_ARG, "label_off[0] must be 0");
+        for (size_t r = 0; r < s->n; r++)
+            if (s->label_off[r + 1] < s->label_off[r]) return fail(DANN_ERR_INVALID_ARG, "label_off is not monotone at node %zu", r);
+    }
+    return DANN_OK;
+}
+
+extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
+    dann_index *ix = nullptr;
+    if (!s || !out) return fail(DANN_ERR_INVALID_ARG, "dann_index_load: NULL argument");
+    *out = nullptr;
+    uint32_t words = 0;
+    int vrc = validate_snapshot(s, &words);
+    if (vrc) return vrc;
+    int ndev = dann_device_count();
+    if (ndev <= 0) return fail(DANN_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(DANN_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
 
     ix = new (std::nothrow) dann_index();
     if (!ix) return fail(DANN_ERR_OOM, "host allocation failed");
@@ -338,7 +368,7 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
 }
 
 extern "C" uint64_t dann_index_hbm_bytes(const dann_index *ix) { return ix ? ix->hbm_bytes : 0; }
-extern "C" uint64_t dann_kernel_launches(const dann_index *ix) { return ix ? ix->launches : 0; }
+extern "C" uint64_t dann_kernel_launches(const dann_index *ix) { return ix ? ix->launches.load() : 0; }
 extern "C" uint32_t dann_code_stride(const dann_index *ix) { return ix ? ix->v.cw : 0; }
 
 extern "C" int dann_last_batch_timing(dann_index *ix, dann_batch_timing *out) {
@@ -741,6 +771,8 @@ static int search_batch_host(dann_index *ix, const float *queries, const int16_t
         /* LabelSet::from(Vec): sort_unstable + dedup per query (labels/mod.rs:30-37) */
         no.resize((size_t)B + 1);
         no[0] = 0;
+        if (label_off[0] < 0) return fail(DANN_ERR_INVALID_ARG, "label_off[0] is negative");
+        if (label_off[B] > label_off[0] && !labels) return fail(DANN_ERR_INVALID_ARG, "labels is NULL but label_off describes a non-empty key");
         for (int b = 0; b < B; b++) {
             int32_t o0 = label_off[b], o1 = label_off[b + 1];
             if (o1 < o0) return fail(DANN_ERR_INVALID_ARG, "label_off is not monotone");

@@ -49,6 +49,41 @@ def test_no_cpu_fallback_without_device(lib_built):
     assert "no CPU path" in str(e.value)
 
 
+def _tiny_snapshot(**over):
+    from pgvectorscale_b200.snapshot import Snapshot, make_heap_tids
+    n, dim = 4, 8
+    kw = dict(n=n, dim=dim, dim_index=dim, bits=2, words=1, R=4, distance_type=1, has_labels=False,
+              count=n, mean=np.zeros(dim, np.float32), m2=np.ones(dim, np.float32),
+              codes=np.zeros((n, 1), np.uint64), nbrs=np.full((n, 4), 0xFFFFFFFF, np.uint32),
+              heap_tid=make_heap_tids(n), vectors=np.zeros((n, dim), np.float32), start_default=0)
+    kw.update(over)
+    return Snapshot(**kw)
+
+
+@pytest.mark.parametrize("over,msg", [
+    (dict(nbrs=np.array([[1, 2, 0xFFFFFFFF, 9]] * 4, np.uint32)), None),            # ids after the sentinel are ignored
+    (dict(nbrs=np.array([[1, 4, 0xFFFFFFFF, 0]] * 4, np.uint32)), "outside the index"),
+    (dict(start_default=4), "start_default"),
+    (dict(has_labels=True, label_off=np.array([0, 2, 1, 3, 3], np.uint32), labels=np.array([1, 2, 3], np.int16),
+          start_labels=np.array([1], np.int16), start_label_nodes=np.array([0], np.uint32)), "monotone"),
+    (dict(has_labels=True, label_off=np.array([0, 1, 2, 3, 3], np.uint32), labels=np.array([1, 2, 3], np.int16),
+          start_labels=np.array([1], np.int16), start_label_nodes=np.array([7], np.uint32)), "start node"),
+])
+def test_snapshot_is_validated_on_the_host_before_any_copy(lib_built, over, msg):
+    """Out-of-range ids/offsets would become out-of-bounds gathers in the kernels: dann_index_load rejects them
+    on the host (so this runs without a GPU: a well-formed snapshot gets as far as DANN_ERR_NO_DEVICE)."""
+    from pgvectorscale_b200 import diskann
+    if diskann.device_count() > 0 and msg is None:
+        diskann.DiskAnnIndex(_tiny_snapshot(**over)).close()
+        return
+    with pytest.raises(diskann.DiskAnnError) as e:
+        diskann.DiskAnnIndex(_tiny_snapshot(**over))
+    if msg is None:
+        assert e.value.code == -3
+    else:
+        assert e.value.code == -1 and msg in str(e.value)
+
+
 def test_missing_library_raises(tmp_path):
     from pgvectorscale_b200 import diskann
     with pytest.raises(diskann.DiskAnnError):
