@@ -40,6 +40,12 @@ struct IndexView {
 };
 
 // 128-bit read-only load that does not allocate in L1 (streaming gathers of SBQ codes).
+#ifdef DANN_SIMT_EMU /* tests/simt: the same sources compiled by g++ for the CPU SIMT emulator (no PTX there) */
+__device__ __forceinline__ ulonglong2 ldg_stream_u128(const void *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) { return *reinterpret_cast<const uint32_t *>(p); }
+__device__ __forceinline__ float4 ldg_stream_f4(const void *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float ldg_stream_f1(const void *p) { return *reinterpret_cast<const float *>(p); }
+#else
 __device__ __forceinline__ ulonglong2 ldg_stream_u128(const void *p) {
     ulonglong2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];"
@@ -64,6 +70,7 @@ __device__ __forceinline__ float ldg_stream_f1(const void *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+#endif
 
 // f32::total_cmp key (core::f32::total_cmp): monotone signed-int image of the float.
 __device__ __forceinline__ int32_t total_key(float f) {

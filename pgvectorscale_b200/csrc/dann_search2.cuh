@@ -45,7 +45,11 @@ struct PairCtl {
 static_assert(sizeof(PairCtl) % 8 == 0, "PairCtl must keep 8-byte alignment for what follows it");
 
 __device__ __forceinline__ void pair_sync(uint32_t id) {
+#ifdef DANN_SIMT_EMU
+    simt::named_barrier(id, 64);
+#else
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+#endif
 }
 
 template <typename T, int NCH>

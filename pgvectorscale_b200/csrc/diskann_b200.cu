@@ -22,6 +22,7 @@
 #include "dann_search.cuh"
 #include "dann_search2.cuh"
 #include "dann_build.cuh"
+#include "dann_plan.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -108,11 +109,6 @@ struct dann_index {
     uint32_t lists_unique = 0;
 };
 
-struct SearchPlan {
-    uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
-    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64 */
-    bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
-};
 
 struct dann_scan {
     dann_index *ix = nullptr;
@@ -133,34 +129,6 @@ struct dann_scan {
 };
 
 /* ------------------------------------------------------------------------------------ */
-static uint32_t env_u32(const char *name, uint32_t dflt) {
-    const char *s = getenv(name);
-    if (!s || !*s) return dflt;
-    return (uint32_t)strtoul(s, nullptr, 10);
-}
-
-static uint32_t pow2ceil(uint32_t x) {
-    uint32_t p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
-
-static int pick_code_mapping(uint32_t cw, uint32_t *G, uint32_t *Gshift, uint32_t *NCH) {
-    uint32_t C = cw / 2;
-    uint32_t g = pow2ceil((C + 2) / 3);
-    if (g > 32) g = 32;
-    uint32_t n = (C + g - 1) / g;
-    uint32_t sup;
-    if (n <= 4) sup = n;
-    else if (n <= 8) sup = 8;
-    else return -1;
-    *G = g;
-    *Gshift = 0;
-    while ((1u << *Gshift) < g) (*Gshift)++;
-    *NCH = sup;
-    return 0;
-}
-
 template <typename Tp>
 static cudaError_t upload(dann_index *ix, const Tp *host, size_t count, Tp **out) {
     void *p = nullptr;
@@ -512,60 +480,15 @@ static search_fn pick_kernel(bool pairs, int entry, uint32_t nch) {
 
 static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, bool keyed,
                      SearchPlan *p, bool force_single = false) {
-    const IndexView &v = ix->v;
-    /* visits are about L + consumed; every visit stages at most R ids */
-    uint64_t need = (((uint64_t)L + c_target) * 23 / 20 + 40u) * v.R * grow; /* 15% slack over L + consumed */
-    /* test hook: start from a deliberately small workspace to exercise the growth path */
-    const uint32_t shrink = std::max<uint32_t>(env_u32("DANN_DEBUG_SHRINK", 1), 1);
-    need = std::max<uint64_t>(need / shrink, 256);
-    if (need > (1ull << 30)) return fail(DANN_ERR_CAPACITY, "per-query workspace would exceed 2^30 candidates");
-    p->need = (uint32_t)need;
-    p->cand_cap = (uint32_t)((need + 1023) & ~1023ull);
-    p->hash_cap = pow2ceil(2 * p->cand_cap);
-    /* inserted-set: one bitmap over node ids per resident warp while that stays small
-     * (<= 2 MB per warp, i.e. up to 16M nodes), else the CAS hash set */
-    const bool use_bitmap = env_u32("DANN_SEARCH_BITMAP", v.n <= (16u << 20) ? 1 : 0) != 0;
-    p->bitmap_words = use_bitmap ? ((v.n + 127u) / 128u) * 4u : 0u;
-    /* every deduped id is recorded, also the ones a label filter then rejects: visits x R */
-    p->ins_cap = keyed ? 2 * p->cand_cap : p->cand_cap;
-    if (keyed) p->hash_cap = pow2ceil(4 * p->cand_cap);
-    /* heap entry layout (dann_search.cuh): 4 bytes whenever the distance and the sequence number fit */
-    const uint64_t maxdist = (uint64_t)v.words * 64;
-    if (maxdist < 2048 && p->cand_cap <= (1u << 21)) p->entry = 0;
-    else if (maxdist < 65536 && p->cand_cap <= 65536) p->entry = 1;
-    else p->entry = 2;
-    p->entry = (int)env_u32("DANN_SEARCH_ENTRY", (uint32_t)p->entry); /* test hook */
-    p->esize = p->entry == 2 ? 8 : 4;
-    /* visited holds the not-yet-consumed visits: about L, more under a label filter */
-    uint64_t vcap = std::max<uint64_t>(((uint64_t)L * (keyed ? 2 : 1) + 96u) * grow / shrink, 8);
-    p->vcap = (uint32_t)((vcap + 3) & ~3ull);
-    const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
-    /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
-    p->pairs = !force_single && v.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
-    const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
-    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
-    if (fixed + 1024 > budget) return fail(DANN_ERR_CAPACITY, "visited list of %u entries does not fit shared memory", p->vcap);
-    uint32_t wneed = (nq + ix->sm_count - 1) / ix->sm_count;
-    wneed = std::min<uint32_t>(std::max<uint32_t>(wneed, 1), wmax);
-    /* Concurrency first: a batch should run in one wave (queries are latency-bound, one or two
-     * warps each), so take as many query slots per SM as the batch needs and give each slot
-     * whatever shared memory is left for the top of its heap; deeper heap levels spill to the
-     * slot's HBM tail.  Only when that would leave fewer than 2048 in-smem entries (the top 11
-     * levels) do we trade slots for shared memory. */
-    const uint32_t hs_min = (uint32_t)std::min<uint64_t>(p->cand_cap, 2048);
-    uint32_t wfit = (uint32_t)(budget / (fixed + (size_t)hs_min * p->esize));
-    uint32_t W = std::min(wneed, std::max<uint32_t>(wfit, 1));
-    W = env_u32("DANN_SEARCH_WARPS", W);
-    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), wmax);
-    while (W > 1 && budget / W < fixed + 1024) W--;
-    size_t per_warp = (budget / W) & ~(size_t)15;
-    uint32_t hs = (uint32_t)std::min<size_t>(p->cand_cap, (per_warp - fixed) / p->esize);
-    hs = env_u32("DANN_SEARCH_HS", hs);
-    hs = std::min(hs, p->cand_cap) & ~3u;
-    p->hs = hs;
-    p->W = W;
-    p->per_warp = (uint32_t)((fixed + (size_t)hs * p->esize + 15) & ~(size_t)15);
-    p->grid = std::min<uint32_t>((uint32_t)ix->sm_count, (nq + W - 1) / W);
+    PlanInputs in;
+    in.n = ix->v.n;
+    in.R = ix->v.R;
+    in.words = ix->v.words;
+    in.smem_optin = ix->smem_optin;
+    in.sm_count = ix->sm_count;
+    char err[256];
+    int rc = dann_make_plan(in, nq, L, c_target, grow, keyed, p, force_single, err, sizeof err);
+    if (rc) return fail(rc, "%s", err);
     return DANN_OK;
 }
 

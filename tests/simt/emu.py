@@ -1,0 +1,118 @@
+"""ctypes front end of the CPU SIMT-emulation harness (tests/simt/emu_search.cpp).  Test infrastructure only."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import build_emu  # noqa: E402
+from pgvectorscale_b200.diskann import _SnapshotDesc, _QueryStats  # noqa: E402  (struct layouts of include/diskann_b200.h)
+
+
+class EmuInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("retries", "entry", "W", "hs", "pairs", "grid", "cand_cap", "vcap",
+                                          "bitmap_words", "nch", "G", "pad")] + [("switches", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_emu.build())
+        _lib.emu_last_error.restype = C.c_char_p
+        _lib.emu_search.restype = C.c_int
+    return _lib
+
+
+def _desc(s):
+    keep = []
+
+    def arr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return C.c_void_p(a.ctypes.data)
+
+    d = _SnapshotDesc()
+    d.n, d.dim, d.dim_index, d.bits, d.words, d.R = s.n, s.dim, s.dim_index, s.bits, s.words, s.R
+    d.distance_type = int(s.distance_type)
+    d.has_labels = int(bool(s.has_labels))
+    d.count = int(s.count)
+    d.mean = arr(s.mean, np.float32)
+    d.m2 = arr(s.m2, np.float32)
+    d.codes = arr(s.codes, np.uint64)
+    d.nbrs = arr(s.nbrs, np.uint32)
+    d.heap_tid = arr(s.heap_tid, np.uint64)
+    d.vectors = arr(s.vectors, np.float32)
+    d.start_default = int(s.start_default)
+    d.n_start_labels = 0 if s.start_labels is None else len(s.start_labels)
+    d.start_labels = arr(s.start_labels, np.int16)
+    d.start_label_nodes = arr(s.start_label_nodes, np.uint32)
+    d.label_off = arr(s.label_off, np.uint32)
+    d.labels = arr(s.labels, np.int16)
+    return d, keep
+
+
+def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148, smem_optin=232448, env=None):
+    """Approximate streams of B prepared queries through the emulated search kernel.
+    labels: None, or a list (one entry per query) of sorted, de-duplicated label lists.
+    env: DANN_* test knobs applied around the call (the plan reads them with getenv).
+    -> (streams: list of np.uint32 arrays, stats: list of dicts, info dict)"""
+    q_codes = np.ascontiguousarray(q_codes, dtype=np.uint64).reshape(-1, s.words)
+    B = q_codes.shape[0]
+    d, keep = _desc(s)
+    qlab = qoff = None
+    if labels is not None:
+        off = np.zeros(B + 1, np.int32)
+        flat = []
+        for b, ls in enumerate(labels):
+            flat.extend(int(x) for x in ls)
+            off[b + 1] = len(flat)
+        qlab = np.array(flat if flat else [0], np.int16)
+        qoff = off
+    stream = np.full((B, max(c_target, 1)), 0xFFFFFFFF, np.uint32)
+    slen = np.zeros(B, np.uint32)
+    stats = (_QueryStats * B)()
+    info = EmuInfo()
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        rc = lib().emu_search(C.byref(d), C.c_void_p(q_codes.ctypes.data),
+                              C.c_void_p(qlab.ctypes.data) if qlab is not None else None,
+                              C.c_void_p(qoff.ctypes.data) if qoff is not None else None,
+                              C.c_uint32(B), C.c_uint32(L), C.c_uint32(c_target), C.c_int(1 if single_warp else 0),
+                              C.c_uint32(sm_count), C.c_uint32(smem_optin), C.c_void_p(stream.ctypes.data),
+                              C.c_void_p(slen.ctypes.data), stats, C.byref(info))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if rc != 0:
+        raise RuntimeError(f"emu_search failed ({rc}): {lib().emu_last_error().decode()}")
+    streams = [stream[b, :slen[b]].copy() for b in range(B)]
+    st = [{f: getattr(stats[b], f) for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len", "status")}
+          for b in range(B)]
+    return streams, st, {f: getattr(info, f) for f, _ in EmuInfo._fields_}
+
+
+PLAN_FIELDS = ("need", "cand_cap", "hash_cap", "vcap", "hs", "W", "grid", "per_warp", "esize", "bitmap_words", "ins_cap",
+               "entry", "pairs")
+
+
+def plan(n, R, words, nq, L, c_target, grow=1, keyed=False, force_single=False, sm_count=148, smem_optin=232448):
+    """dann_make_plan (pgvectorscale_b200/csrc/dann_plan.h) -> dict; raises on DANN_ERR_CAPACITY."""
+    out = (C.c_uint32 * 13)()
+    rc = lib().emu_plan(C.c_uint32(n), C.c_uint32(R), C.c_uint32(words), C.c_uint32(nq), C.c_uint32(L), C.c_uint32(c_target),
+                        C.c_uint32(grow), C.c_int(int(keyed)), C.c_int(int(force_single)), C.c_uint32(sm_count),
+                        C.c_uint32(smem_optin), out)
+    if rc != 0:
+        raise RuntimeError(f"plan failed ({rc}): {lib().emu_last_error().decode()}")
+    return dict(zip(PLAN_FIELDS, [int(x) for x in out]))

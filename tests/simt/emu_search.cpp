@@ -1,0 +1,227 @@
+// emu_search.cpp — runs the beam-search kernel SOURCES (pgvectorscale_b200/csrc/dann_search{,2}.cuh) under the CPU
+// SIMT emulator with the product's own workspace plan (dann_plan.h), mirroring run_search() in diskann_b200.cu:
+// same launch shape, same overflow/retry loop.  TEST INFRASTRUCTURE ONLY (see simt_emu.h); built by
+// tests/simt/build_emu.py with g++, never by build.py, never loaded by the package.
+#include <cuda_runtime.h> /* resolves to tests/simt/shim/cuda_runtime.h */
+
+#include <string>
+#include <vector>
+
+#include "dann_search2.cuh"
+#include "dann_plan.h"
+
+alignas(128) unsigned char dann_smem[256 * 1024];
+
+typedef void (*emu_kernel)(const SearchArgs);
+
+template <typename T>
+static emu_kernel pick1(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search_kernel<T, 1>;
+        case 2: return dann_search_kernel<T, 2>;
+        case 3: return dann_search_kernel<T, 3>;
+        default: return nullptr;
+    }
+}
+template <typename T>
+static emu_kernel pick2(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search2_kernel<T, 1>;
+        case 2: return dann_search2_kernel<T, 2>;
+        case 3: return dann_search2_kernel<T, 3>;
+        default: return nullptr;
+    }
+}
+static emu_kernel pick(bool pairs, int entry, uint32_t nch) {
+    if (pairs) return entry == 0 ? pick2<Ent32x21>(nch) : entry == 1 ? pick2<Ent32x16>(nch) : pick2<Ent64>(nch);
+    return entry == 0 ? pick1<Ent32x21>(nch) : entry == 1 ? pick1<Ent32x16>(nch) : pick1<Ent64>(nch);
+}
+
+static std::string g_emu_err;
+extern "C" const char *emu_last_error(void) { return g_emu_err.c_str(); }
+
+struct emu_info {
+    uint32_t retries, entry, W, hs, pairs, grid, cand_cap, vcap, bitmap_words, nch, G;
+    uint32_t pad;
+    uint64_t switches;
+};
+
+/* One dann_search_batch-style search pass (no rerank): the approximate stream of every query.
+ * q_codes [B][s->words]; qoff NULL = no scan key.  Returns 0, or a negative dann_status. */
+extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, const int16_t *qlab, const int32_t *qoff,
+                          uint32_t B, uint32_t L, uint32_t c_target, int force_single, uint32_t sm_count,
+                          uint32_t smem_optin, uint32_t *stream, uint32_t *stream_len, dann_query_stats *stats,
+                          emu_info *info) {
+    IndexView v{};
+    v.n = s->n;
+    v.dim = s->dim;
+    v.dim_index = s->dim_index;
+    v.bits = s->bits;
+    v.words = s->words;
+    v.cw = (s->words + 1u) & ~1u;
+    v.R = s->R;
+    v.Rp = (s->R + 7u) & ~7u;
+    v.distance_type = s->distance_type;
+    v.has_labels = s->has_labels ? 1 : 0;
+    v.count = s->count;
+    v.start_default = s->n ? s->start_default : DANN_INVALID_NODE;
+    v.n_start_labels = s->start_labels && s->start_label_nodes ? s->n_start_labels : 0;
+    uint32_t G = 1, Gshift = 0, NCH = 1;
+    if (pick_code_mapping(v.cw, &G, &Gshift, &NCH) != 0) {
+        g_emu_err = "code too wide";
+        return DANN_ERR_INVALID_ARG;
+    }
+    /* HBM layout of dann_index_load: padded code rows and neighbour rows (16-byte aligned like cudaMalloc) */
+    std::vector<ulonglong2> codes_store(((size_t)s->n * v.cw + 1) / 2 + 1);
+    uint64_t *codes = reinterpret_cast<uint64_t *>(codes_store.data());
+    for (size_t i = 0; i < s->n; i++)
+        for (uint32_t w = 0; w < v.cw; w++) codes[i * v.cw + w] = w < s->words ? s->codes[i * s->words + w] : 0ull;
+    std::vector<uint32_t> nbrs((size_t)s->n * v.Rp + 4, DANN_INVALID_NODE);
+    uint32_t lists_unique = 1;
+    for (size_t i = 0; i < s->n; i++) {
+        for (uint32_t j = 0; j < s->R; j++) nbrs[i * v.Rp + j] = s->nbrs[i * s->R + j];
+        for (uint32_t j = 0; j < s->R && s->nbrs[i * s->R + j] != DANN_INVALID_NODE; j++)
+            for (uint32_t k = 0; k < j; k++)
+                if (s->nbrs[i * s->R + k] == s->nbrs[i * s->R + j]) lists_unique = 0;
+    }
+    if (s->R > 64) lists_unique = 0;
+    std::vector<ulonglong2> q_store(((size_t)B * v.cw + 1) / 2 + 1);
+    uint64_t *qc = reinterpret_cast<uint64_t *>(q_store.data());
+    for (size_t b = 0; b < B; b++)
+        for (uint32_t w = 0; w < v.cw; w++) qc[b * v.cw + w] = w < s->words ? q_codes[b * s->words + w] : 0ull;
+    v.codes = codes;
+    v.nbrs = nbrs.data();
+    v.tids = s->heap_tid;
+    v.vectors = s->vectors;
+    v.mean = s->mean;
+    v.m2 = s->m2;
+    v.start_labels = s->start_labels;
+    v.start_label_nodes = s->start_label_nodes;
+    v.label_off = s->label_off;
+    v.labels = s->labels;
+    if (!v.has_labels) v.label_off = nullptr, v.labels = nullptr;
+
+    PlanInputs in;
+    in.n = v.n;
+    in.R = v.R;
+    in.words = v.words;
+    in.smem_optin = smem_optin;
+    in.sm_count = (int)sm_count;
+
+    std::vector<uint32_t> qlist;
+    uint32_t nq = B, grow = 1, retries = 0;
+    uint32_t ctl[2];
+    SearchPlan p{};
+    const uint64_t sw0 = simt::total_switches();
+    for (int attempt = 0;; attempt++) {
+        char err[256];
+        int rc = dann_make_plan(in, nq, L, c_target, grow, qoff != nullptr, &p, force_single != 0, err, sizeof err);
+        if (rc) {
+            g_emu_err = err;
+            return rc;
+        }
+        if ((size_t)p.per_warp * p.W > sizeof dann_smem) {
+            g_emu_err = "plan needs more shared memory than the emulator provides";
+            return DANN_ERR_CAPACITY;
+        }
+        const size_t slots = (size_t)p.grid * p.W;
+        std::vector<uint4> hash_store(p.bitmap_words ? 1 : slots * p.hash_cap / 4 + 1);
+        std::vector<uint32_t> cand(slots * p.cand_cap), bitmap(slots * (size_t)p.bitmap_words + 1, 0u),
+            ins(p.bitmap_words ? slots * (size_t)p.ins_cap : 1);
+        std::vector<ulonglong2> heap_store(slots * p.cand_cap * (size_t)p.esize / 16 + 1);
+        ctl[0] = ctl[1] = 0;
+        SearchArgs a{};
+        a.ix = v;
+        a.q_codes = qc;
+        a.q_labels = qlab;
+        a.q_label_off = qoff;
+        a.qlist = attempt == 0 ? nullptr : qlist.data();
+        a.nq = nq;
+        a.L = L;
+        a.c_target = c_target;
+        a.stream = stream;
+        a.stream_len = stream_len;
+        a.stats = stats;
+        a.overflow = ctl + 1;
+        a.counter = ctl;
+        a.hash = reinterpret_cast<uint32_t *>(hash_store.data());
+        a.hash_cap = p.hash_cap;
+        a.bitmap = bitmap.data();
+        a.bitmap_words = p.bitmap_words;
+        a.ins_list = ins.data();
+        a.ins_cap = p.ins_cap;
+        a.lists_unique = lists_unique;
+        a.cand_node = cand.data();
+        a.cand_cap = p.cand_cap;
+        a.heap_tail = heap_store.data();
+        a.hs = p.hs;
+        a.vcap = p.vcap;
+        a.G = G;
+        a.Gshift = Gshift;
+        a.per_warp_smem = p.per_warp;
+        emu_kernel fn = pick(p.pairs, p.entry, NCH);
+        if (!fn) {
+            g_emu_err = "this code width is not instantiated in the emulator build";
+            return DANN_ERR_INVALID_ARG;
+        }
+        simt::launch(p.grid, p.W * (p.pairs ? 64 : 32), [&] { fn(a); });
+        for (uint32_t w : bitmap)
+            if (w) {
+                g_emu_err = "inserted-set bitmap not clean after the launch";
+                return DANN_ERR_STATE;
+            }
+        if (ctl[1] == 0) break;
+        if (ctl[1] & DANN_ST_INTERNAL) {
+            g_emu_err = "next-node prediction mismatch";
+            return DANN_ERR_STATE;
+        }
+        if (attempt >= 8) {
+            g_emu_err = "workspace still too small";
+            return DANN_ERR_CAPACITY;
+        }
+        qlist.clear();
+        for (uint32_t b = 0; b < B; b++)
+            if (stats[b].status) qlist.push_back(b);
+        nq = (uint32_t)qlist.size();
+        grow *= 2;
+        retries++;
+    }
+    if (info) {
+        info->retries = retries;
+        info->entry = (uint32_t)p.entry;
+        info->W = p.W;
+        info->hs = p.hs;
+        info->pairs = p.pairs;
+        info->grid = p.grid;
+        info->cand_cap = p.cand_cap;
+        info->vcap = p.vcap;
+        info->bitmap_words = p.bitmap_words;
+        info->nch = NCH;
+        info->G = G;
+        info->switches = simt::total_switches() - sw0;
+    }
+    return 0;
+}
+
+/* the plan alone (host logic test): out[] = need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words,
+ * ins_cap, entry, pairs */
+extern "C" int emu_plan(uint32_t n, uint32_t R, uint32_t words, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow,
+                        int keyed, int force_single, uint32_t sm_count, uint32_t smem_optin, uint32_t *out) {
+    PlanInputs in;
+    in.n = n;
+    in.R = R;
+    in.words = words;
+    in.smem_optin = smem_optin;
+    in.sm_count = (int)sm_count;
+    SearchPlan p{};
+    char err[256];
+    int rc = dann_make_plan(in, nq, L, c_target, grow, keyed != 0, &p, force_single != 0, err, sizeof err);
+    if (rc) {
+        g_emu_err = err;
+        return rc;
+    }
+    const uint32_t v[13] = {p.need, p.cand_cap, p.hash_cap, p.vcap, p.hs, p.W, p.grid, p.per_warp, p.esize, p.bitmap_words,
+                            p.ins_cap, (uint32_t)p.entry, (uint32_t)p.pairs};
+    for (int i = 0; i < 13; i++) out[i] = v[i];
+    return 0;
+}

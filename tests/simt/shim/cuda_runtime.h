@@ -1,0 +1,4 @@
+// Stand-in for <cuda_runtime.h> when the kernel sources are compiled by g++ for the SIMT emulator
+// (tests/simt/simt_emu.h).  Test infrastructure only.
+#pragma once
+#include "../simt_emu.h"

@@ -1,0 +1,245 @@
+// simt_emu.cpp — fibers, scheduler and warp collectives of the SIMT emulator (see simt_emu.h).  Test infrastructure.
+#include "simt_emu.h"
+
+#if !defined(__x86_64__)
+#error "the fiber switch below is written for x86-64 System V"
+#endif
+
+extern "C" void simt_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_switch, .-simt_switch
+)");
+
+namespace simt {
+
+Block *g_blk = nullptr;
+Fiber *g_cur = nullptr;
+static uint64_t g_total_switches = 0;
+static const size_t kStack = 256 * 1024;
+
+uint64_t total_switches() { return g_total_switches; }
+
+void yield() {
+    Block *b = g_blk;
+    Fiber *f = g_cur;
+    b->switches++;
+    g_total_switches++;
+    simt_switch(&f->sp, b->sched_sp);
+}
+
+static void trampoline() {
+    Fiber *f = g_cur;
+    g_blk->body();
+    f->done = true;
+    g_blk->progress++;
+    yield();
+    fprintf(stderr, "simt: resumed a finished fiber\n");
+    abort();
+}
+
+static void prepare(Fiber &f) {
+    f.stack = (char *)aligned_alloc(64, kStack);
+    if (!f.stack) abort();
+    uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
+    void **sp = (void **)top;
+    *--sp = nullptr;             /* where a caller's return address would sit: keeps rsp = 8 (mod 16) at entry */
+    *--sp = (void *)trampoline;  /* `ret` target of the first switch */
+    for (int i = 0; i < 6; i++) *--sp = nullptr; /* rbp rbx r12 r13 r14 r15 */
+    f.sp = sp;
+}
+
+static void complete(Slot &s, unsigned nlanes_mask) {
+    uint64_t *out = s.out[s.gen & 1];
+    const unsigned mask = s.mask;
+    (void)nlanes_mask;
+    switch (s.kind) {
+        case K_SYNC:
+            break;
+        case K_BALLOT: {
+            unsigned r = 0;
+            for (int l = 0; l < 32; l++)
+                if (((mask >> l) & 1u) && s.val[l]) r |= 1u << l;
+            for (int l = 0; l < 32; l++) out[l] = r;
+            break;
+        }
+        case K_ANY:
+        case K_ALL: {
+            bool any = false, all = true;
+            for (int l = 0; l < 32; l++)
+                if ((mask >> l) & 1u) {
+                    any |= s.val[l] != 0;
+                    all &= s.val[l] != 0;
+                }
+            for (int l = 0; l < 32; l++) out[l] = s.kind == K_ANY ? any : all;
+            break;
+        }
+        case K_SHFL:
+        case K_SHFL_UP:
+        case K_SHFL_DOWN:
+        case K_SHFL_XOR:
+            for (int l = 0; l < 32; l++) {
+                if (!((mask >> l) & 1u)) continue;
+                int src = l;
+                if (s.kind == K_SHFL) src = (int)(s.aux[l] & 31u);
+                else if (s.kind == K_SHFL_UP) src = l - (int)s.aux[l] >= 0 ? l - (int)s.aux[l] : l;
+                else if (s.kind == K_SHFL_DOWN) src = l + (int)s.aux[l] <= 31 ? l + (int)s.aux[l] : l;
+                else src = (int)((unsigned)l ^ s.aux[l]) & 31;
+                if (!((mask >> src) & 1u)) {
+                    fprintf(stderr, "simt: shuffle reads lane %d which is not in mask %08x\n", src, mask);
+                    abort();
+                }
+                out[l] = s.val[src];
+            }
+            break;
+        case K_MATCH_ANY:
+            for (int l = 0; l < 32; l++) {
+                if (!((mask >> l) & 1u)) continue;
+                unsigned r = 0;
+                for (int m = 0; m < 32; m++)
+                    if (((mask >> m) & 1u) && s.val[m] == s.val[l]) r |= 1u << m;
+                out[l] = r;
+            }
+            break;
+        default:
+            abort();
+    }
+}
+
+uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
+    Block *b = g_blk;
+    Fiber *f = g_cur;
+    const unsigned lane = f->tid & 31u;
+    Warp &w = b->warps[f->tid >> 5];
+    if (!((mask >> lane) & 1u)) {
+        fprintf(stderr, "simt: lane %u calls a collective with mask %08x that excludes it\n", lane, mask);
+        abort();
+    }
+    Slot *s = nullptr;
+    for (Slot &c : w.slots)
+        if (c.arrived && c.mask == mask && !((c.arrived >> lane) & 1u)) {
+            s = &c;
+            break;
+        }
+    if (!s)
+        for (Slot &c : w.slots)
+            if (!c.arrived) {
+                s = &c;
+                s->mask = mask;
+                s->kind = kind;
+                break;
+            }
+    if (!s) {
+        fprintf(stderr, "simt: more than 4 divergent collectives in flight in one warp\n");
+        abort();
+    }
+    if (s->kind != kind) {
+        fprintf(stderr, "simt: lanes of warp %u meet in different collectives (%d vs %d, mask %08x)\n", f->tid >> 5, s->kind,
+                kind, mask);
+        abort();
+    }
+    const uint64_t mygen = s->gen;
+    s->val[lane] = val;
+    s->aux[lane] = aux;
+    s->arrived |= 1u << lane;
+    if (s->arrived == mask) {
+        complete(*s, mask);
+        s->arrived = 0;
+        s->gen++;
+        b->progress++;
+        b->collectives++;
+    } else {
+        f->blocked_on = "warp collective";
+        while (s->gen == mygen) yield();
+        f->blocked_on = nullptr;
+    }
+    return s->out[mygen & 1][lane];
+}
+
+void named_barrier(unsigned id, unsigned count) {
+    Block *b = g_blk;
+    Fiber *f = g_cur;
+    if (id >= 16) abort();
+    Barrier &br = b->bars[id];
+    if (br.arrived == 0) br.count = count;
+    else if (br.count != count) {
+        fprintf(stderr, "simt: bar.sync %u with different thread counts (%u vs %u)\n", id, br.count, count);
+        abort();
+    }
+    const uint64_t mygen = br.gen;
+    br.arrived++;
+    if (br.arrived == count) {
+        br.arrived = 0;
+        br.gen++;
+        b->progress++;
+    } else {
+        f->blocked_on = "named barrier";
+        while (br.gen == mygen) yield();
+        f->blocked_on = nullptr;
+    }
+}
+
+void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
+    for (unsigned bi = 0; bi < grid; bi++) {
+        Block b;
+        b.bidx.x = bi;
+        b.bdim.x = block;
+        b.gdim.x = grid;
+        b.body = body;
+        b.fibers.resize(block);
+        b.warps.resize((block + 31) / 32);
+        for (unsigned t = 0; t < block; t++) {
+            b.fibers[t].tid = t;
+            b.fibers[t].tidx.x = t;
+            prepare(b.fibers[t]);
+        }
+        g_blk = &b;
+        unsigned live = block;
+        uint64_t last_progress = ~0ull;
+        int idle_passes = 0;
+        while (live) {
+            for (unsigned t = 0; t < block; t++) {
+                Fiber &f = b.fibers[t];
+                if (f.done) continue;
+                g_cur = &f;
+                simt_switch(&b.sched_sp, f.sp);
+                if (f.done) live--;
+            }
+            if (b.progress == last_progress) {
+                if (++idle_passes > 4) {
+                    fprintf(stderr, "simt: deadlock in block %u:", bi);
+                    for (unsigned t = 0; t < block; t++)
+                        if (!b.fibers[t].done) fprintf(stderr, " t%u(%s)", t, b.fibers[t].blocked_on ? b.fibers[t].blocked_on : "running");
+                    fprintf(stderr, "\n");
+                    abort();
+                }
+            } else {
+                idle_passes = 0;
+                last_progress = b.progress;
+            }
+        }
+        for (unsigned t = 0; t < block; t++) free(b.fibers[t].stack);
+        g_blk = nullptr;
+        g_cur = nullptr;
+    }
+}
+
+}  // namespace simt

@@ -1,0 +1,144 @@
+"""The search-kernel SOURCES (pgvectorscale_b200/csrc/dann_search.cuh, dann_search2.cuh, dann_heap.cuh) compiled by
+g++ and run on the CPU under a SIMT emulator (tests/simt/simt_emu.h: one fiber per CUDA thread, warp collectives,
+named barriers), with the product's own workspace plan (dann_plan.h), compared with the oracle: same approximate
+stream (node ids in consume order) and same counters.
+
+This is a LOGIC check that needs no GPU; it does not replace the `-m gpu` parity tests (no memory-model or timing
+effects are modelled) and nothing in the product can reach it."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
+from conftest import build_case  # noqa: E402
+from oracle import fixtures, oracle  # noqa: E402
+
+COSINE, L2, IP = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as m
+    m.lib()
+    return m
+
+
+def qcodes(s, queries):
+    out = []
+    for x in queries:
+        v = np.array(x[:s.dim_index], np.float32)
+        if s.distance_type == COSINE:
+            v = oracle.preprocess_cosine(v)
+        out.append(oracle.quantize(v, s.bits, s.mean, s.m2, s.count))
+    return np.stack(out)
+
+
+def check(emu, s, queries, L, c_target, labels=None, **kw):
+    norm = None if labels is None else [sorted(set(int(x) for x in ls)) for ls in labels]
+    streams, st, info = emu.search(s, qcodes(s, queries), L, c_target, labels=norm, **kw)
+    for b, q in enumerate(queries):
+        r = oracle.scan(s, q, None if labels is None else labels[b], L, 0, c_target)
+        assert streams[b].tolist() == r["node"].tolist(), (b, info)
+        for f in ("visits", "d_quantized", "candidates", "stream_len"):
+            assert st[b][f] == r["stats"][f], (b, f, info)
+        assert st[b]["status"] == 0
+    return info
+
+
+@pytest.mark.parametrize("single_warp", [False, True])
+@pytest.mark.parametrize("dist,bits,dim", [(COSINE, 2, 96), (L2, 1, 200), (IP, 2, 40)])
+def test_emulated_kernels_equal_oracle(emu, single_warp, dist, bits, dim):
+    s = build_case(500, dim, dist, bits=bits, seed=11 + dim, kind="normal", R=20, L_build=40, deleted_every=9)
+    q = fixtures.gen_vectors(4, dim, 5, "normal")
+    info = check(emu, s, q, 25, 30, single_warp=single_warp)
+    assert info["pairs"] == (0 if single_warp else 1)
+
+
+def test_emulated_reference_shape_768d_2bit(emu):
+    """768 dimensions x 2 bits = 24 words: the NCH=3, G=4 code mapping the benchmarks run."""
+    s = build_case(300, 768, COSINE, seed=2, kind="normal", R=32, L_build=48)
+    q = fixtures.gen_vectors(2, 768, 8, "normal")
+    info = check(emu, s, q, 20, 29)
+    assert (info["nch"], info["G"]) == (3, 4)
+
+
+@pytest.mark.parametrize("entry", [0, 1, 2])
+@pytest.mark.parametrize("single_warp", [False, True])
+def test_emulated_heap_entry_layouts(emu, entry, single_warp):
+    s = build_case(400, 64, L2, seed=21, kind="normal", R=16, L_build=32)
+    q = fixtures.gen_vectors(3, 64, 6, "normal")
+    info = check(emu, s, q, 30, 40, single_warp=single_warp, env={"DANN_SEARCH_ENTRY": entry})
+    assert info["entry"] == entry
+
+
+@pytest.mark.parametrize("hs", [8, 64, 256])
+@pytest.mark.parametrize("single_warp", [False, True])
+def test_emulated_heap_tail_in_global_memory(emu, hs, single_warp):
+    """A tiny shared-memory heap top forces every SplitStore path: leaves in the tail, parents in the tail, the pop's
+    descent crossing from shared to global memory."""
+    s = build_case(500, 64, COSINE, seed=5, kind="normal", R=24, L_build=48)
+    q = fixtures.gen_vectors(3, 64, 7, "normal")
+    info = check(emu, s, q, 40, 50, single_warp=single_warp, env={"DANN_SEARCH_HS": hs})
+    assert info["hs"] == hs
+
+
+@pytest.mark.parametrize("single_warp", [False, True])
+def test_emulated_label_filtered_scan_and_hash_set(emu, single_warp):
+    s = build_case(600, 48, L2, seed=31, kind="normal", R=24, L_build=48, labels=True, deleted_every=13)
+    q = fixtures.gen_vectors(4, 48, 3, "normal")
+    labs = [[3], [7, 1, 7], [], [16, 2, 9, 4]]
+    check(emu, s, q, 30, 25, labels=labs, single_warp=single_warp)
+    info = check(emu, s, q, 30, 25, labels=labs, single_warp=single_warp, env={"DANN_SEARCH_BITMAP": 0})
+    assert info["bitmap_words"] == 0
+
+
+@pytest.mark.parametrize("single_warp", [False, True])
+def test_emulated_workspace_growth_retries(emu, single_warp):
+    s = build_case(500, 64, COSINE, seed=41, kind="normal", R=24, L_build=48)
+    q = fixtures.gen_vectors(3, 64, 4, "normal")
+    info = check(emu, s, q, 40, 60, single_warp=single_warp, env={"DANN_DEBUG_SHRINK": 16})
+    assert info["retries"] >= 1
+
+
+def test_emulated_several_pairs_per_block_and_stream_exhaustion(emu):
+    """sm_count=1 packs 7 query slots (14 warps, 7 named barriers) into one block; c_target > n drains the graph."""
+    s = build_case(150, 32, L2, seed=51, kind="normal", R=12, L_build=24, deleted_every=5)
+    q = fixtures.gen_vectors(9, 32, 2, "normal")
+    info = check(emu, s, q, 10, 400, sm_count=1)
+    assert info["grid"] == 1 and info["W"] == 7
+
+
+def test_emulated_lists_with_repeated_ids(emu):
+    s = build_case(300, 32, L2, seed=61, kind="normal", R=16, L_build=32)
+    nb = s.nbrs.copy()
+    nb[:, 5] = nb[:, 1]                 # the same id twice in every list: the per-list dedupe must keep list order
+    nb[::3, 9] = nb[::3, 0]
+    s.nbrs = nb
+    q = fixtures.gen_vectors(3, 32, 12, "normal")
+    check(emu, s, q, 20, 30)
+    check(emu, s, q, 20, 30, single_warp=True)
+
+
+# ---- the workspace plan itself (host logic of diskann_b200.cu, shared through dann_plan.h) ----------------
+def test_plan_benchmark_shape_is_one_wave_of_seven_pairs(emu):
+    p = emu.plan(n=1_000_000, R=64, words=24, nq=1024, L=150, c_target=259)
+    assert p["pairs"] == 1 and p["W"] == 7 and p["grid"] == 147          # ceil(1024 / 7) blocks, one per SM
+    assert p["entry"] == 0 and p["esize"] == 4                            # 1536-bit codes, < 2M candidates: 4-byte entries
+    assert p["bitmap_words"] == (1_000_000 + 127) // 128 * 4
+    assert p["per_warp"] * p["W"] <= 232448 - 1024
+    assert p["hs"] >= 2048 and p["hs"] % 4 == 0
+    assert p["cand_cap"] % 1024 == 0 and p["cand_cap"] >= (150 + 259) * 64
+
+
+def test_plan_scales_with_growth_and_keys(emu):
+    a = emu.plan(n=50_000_000, R=64, words=24, nq=4096, L=1000, c_target=1009)
+    assert a["bitmap_words"] == 0 and a["hash_cap"] >= 2 * a["cand_cap"]   # > 16M nodes: CAS hash set
+    b = emu.plan(n=50_000_000, R=64, words=24, nq=4096, L=1000, c_target=1009, grow=2, keyed=True)
+    assert b["cand_cap"] >= 2 * a["cand_cap"] - 1024 and b["vcap"] > 2 * a["vcap"] - 8
+    assert b["hash_cap"] >= 4 * b["cand_cap"]
+    c = emu.plan(n=1000, R=100, words=24, nq=10, L=100, c_target=59)        # R > 64: single-warp kernel
+    assert c["pairs"] == 0
+    with pytest.raises(RuntimeError, match="2\\^30"):
+        emu.plan(n=1000, R=64, words=24, nq=1, L=10000, c_target=1009, grow=1 << 12)
