@@ -14,6 +14,7 @@ struct SearchPlan {
     uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
     int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64 */
     bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
+    int hv;     /* heap-warp engine of the two-warp kernel (dann_search2.cuh: 0 = round-1 path, 1 = DANN_HEAP_V2) */
 };
 
 /* what the plan depends on besides the request */
@@ -88,6 +89,7 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     const size_t budget = in.smem_optin > 1024 ? in.smem_optin - 1024 : in.smem_optin;
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
     p->pairs = !force_single && in.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
+    p->hv = p->pairs && env_u32("DANN_HEAP_V2", 0) == 1 ? 1 : 0;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
     if (fixed + 1024 > budget) {

@@ -52,7 +52,11 @@ __device__ __forceinline__ void pair_sync(uint32_t id) {
 #endif
 }
 
-template <typename T, int NCH>
+/* HV selects the heap warp's engine: 0 = cooperative sift-up per active push + one-level pop descent (the measured
+ * round-1 path), 1 = register-resident push path + look-ahead pop (push_batch_v2 / pop_warp1_la below: same heap
+ * array after every page, checked under the CPU SIMT emulator in tests/test_simt_emulation.py; selected with
+ * DANN_HEAP_V2=1 until it has been timed on hardware). */
+template <typename T, int NCH, int HV = 0>
 struct PairSearch {
     using E = typename T::E;
     using H = RustHeap<E, T::KSHIFT>;
@@ -447,10 +451,84 @@ struct PairSearch {
         }
     }
 
+    /* The same pushes with the root-ward path of the current leaf held in registers: lane j owns the slot at height
+     * j above the leaf (lane 0 = the leaf itself), so a push is one ballot ("which ancestors does the element
+     * pass"), one shuffle (those ancestors move one level down) and a select - no memory access on the dependent
+     * chain.  When the leaf advances to the next slot only the lanes whose ancestor changes (heights <= ctz(slot))
+     * write their slot back and take the right-hand neighbour, which they prefetched when they entered the old one.
+     * Exactness: a slot at height j of the current leaf level is read and written by lane j only (so program
+     * order is the only ordering needed) until the leaf level changes at a power-of-two slot, where every lane
+     * writes back, the warp syncs and reloads.  Requires heap_len >= 64 >= tn: every ancestor of a new slot is then an old
+     * slot, never a slot of this batch. */
+    template <typename Store>
+    __device__ __forceinline__ void push_batch_v2(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
+        constexpr E KM = (E(1) << T::KSHIFT) - E(1);
+        const uint32_t lanebit = 1u << lane, lanebit2 = lanebit << 1;
+        uint32_t pos = heap_len + 1;
+        uint32_t node = pos >> lane;
+        E val = 0, nxt = 0;
+        bool dirty = false;
+        if (lane >= 1 && node != 0) {
+            val = st.get(node);
+            if (node + 1 <= heap_len) nxt = st.get(node + 1);
+        }
+        for (uint32_t base = 0; base < tn; base += 32) {
+            const uint32_t r = base + lane;
+            const E mine = T::make(r < tn ? dl[r] : 0u, seq0 + r);
+            const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const E e = __shfl_sync(DANN_FULL, mine, (int)i);
+                const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
+                const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
+                const unsigned tm1 = x & ~(x + 1u); /* bit 0 (the leaf) and the consecutive ancestors passed: lanes 0..rise */
+                const E up = __shfl_down_sync(DANN_FULL, val, 1);
+                if (tm1 & lanebit2) val = up;     /* lanes below `rise`: the ancestor above moves down into this slot */
+                else if (tm1 & lanebit) val = e;  /* lane `rise`: the element lands */
+                dirty = dirty || (tm1 & lanebit) != 0;
+                if (base + i + 1 < tn) { /* move the path to the next leaf */
+                    const uint32_t pos1 = pos + 1;
+                    if ((pos1 & pos) == 0) { /* new leaf level: every slot changes owner */
+                        if (dirty) st.set(node, val);
+                        __syncwarp();
+                        node = pos1 >> lane;
+                        dirty = false;
+                        val = nxt = 0;
+                        if (lane >= 1 && node != 0) {
+                            val = st.get(node);
+                            if (node + 1 <= heap_len) nxt = st.get(node + 1);
+                        }
+                    } else { /* heights 0..ctz(pos1) step to the right (written for predication, not branches) */
+                        const bool adv = lanebit <= (pos1 & (0u - pos1));
+                        if (adv && dirty) st.set(node, val);
+                        node += adv ? 1u : 0u;
+                        val = adv ? nxt : val;
+                        dirty = dirty && !adv;
+                        if (adv && lane >= 1 && node + 1 <= heap_len) nxt = st.get(node + 1);
+                    }
+                    pos = pos1;
+                }
+            }
+        }
+        if (dirty) st.set(node, val);
+        __syncwarp();
+    }
+
     __device__ __forceinline__ void push_page(uint32_t p) {
         const uint32_t tn = ctl->tn[p], seq0 = ctl->seq0[p];
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
         if (tn == 0) return;
+        if constexpr (HV == 1) {
+            if (heap_len >= 64) {
+                if (heap_len + tn < heap.hs) {
+                    ArrayStore<E> sm{heap.sm};
+                    push_batch_v2(sm, dl, tn, seq0);
+                } else {
+                    push_batch_v2(heap, dl, tn, seq0);
+                }
+                heap_len += tn;
+                return;
+            }
+        }
         if (heap_len + tn < heap.hs) { /* everything in shared memory */
             ArrayStore<E> sm{heap.sm};
             push_batch<true>(sm, dl, tn, seq0);
@@ -557,9 +635,11 @@ struct PairSearch {
                 node_chk = __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
-                    H::pop_warp1(sm, heap_len, lane);
+                    if constexpr (HV == 1) H::pop_warp1_la(sm, heap_len, lane);
+                    else H::pop_warp1(sm, heap_len, lane);
                 } else {
-                    H::pop_warp1(heap, heap_len, lane);
+                    if constexpr (HV == 1) H::pop_warp1_la(heap, heap_len, lane);
+                    else H::pop_warp1(heap, heap_len, lane);
                 }
             }
             push_page(p);
@@ -568,7 +648,7 @@ struct PairSearch {
     }
 };
 
-template <typename T, int NCH>
+template <typename T, int NCH, int HV = 0>
 __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a) {
     using E = typename T::E;
     extern __shared__ __align__(16) unsigned char dann_smem[];
@@ -576,7 +656,7 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
     const int P = blockDim.x >> 6;
     const uint32_t slot = blockIdx.x * P + pair;
     unsigned char *base = dann_smem + (size_t)pair * a.per_warp_smem;
-    PairSearch<T, NCH> w(a, lane, 1u + (uint32_t)pair);
+    PairSearch<T, NCH, HV> w(a, lane, 1u + (uint32_t)pair);
     w.vis = reinterpret_cast<uint64_t *>(base);
     E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
     w.listp = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));

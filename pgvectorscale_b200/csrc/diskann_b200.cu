@@ -461,18 +461,19 @@ static search_fn pick_search(uint32_t nch) {
         default: return dann_search_kernel<T, 8>;
     }
 }
-template <typename T>
+template <typename T, int HV>
 static search_fn pick_search2(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search2_kernel<T, 1>;
-        case 2: return dann_search2_kernel<T, 2>;
-        case 3: return dann_search2_kernel<T, 3>;
-        case 4: return dann_search2_kernel<T, 4>;
-        default: return dann_search2_kernel<T, 8>;
+        case 1: return dann_search2_kernel<T, 1, HV>;
+        case 2: return dann_search2_kernel<T, 2, HV>;
+        case 3: return dann_search2_kernel<T, 3, HV>;
+        case 4: return dann_search2_kernel<T, 4, HV>;
+        default: return dann_search2_kernel<T, 8, HV>;
     }
 }
-static search_fn pick_kernel(bool pairs, int entry, uint32_t nch) {
-    if (pairs) return entry == 0 ? pick_search2<Ent32x21>(nch) : entry == 1 ? pick_search2<Ent32x16>(nch) : pick_search2<Ent64>(nch);
+static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0) {
+    if (pairs && hv == 1) return entry == 0 ? pick_search2<Ent32x21, 1>(nch) : entry == 1 ? pick_search2<Ent32x16, 1>(nch) : pick_search2<Ent64, 1>(nch);
+    if (pairs) return entry == 0 ? pick_search2<Ent32x21, 0>(nch) : entry == 1 ? pick_search2<Ent32x16, 0>(nch) : pick_search2<Ent64, 0>(nch);
     return entry == 0 ? pick_search<Ent32x21>(nch) : entry == 1 ? pick_search<Ent32x16>(nch) : pick_search<Ent64>(nch);
 }
 
@@ -554,7 +555,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.vis_out = vis_out;
         a.vis_out_len = vis_out_len;
         a.vis_out_cap = vis_out_cap;
-        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH);
+        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH, p.hv);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);

@@ -12,7 +12,7 @@ from pgvectorscale_b200.diskann import _SnapshotDesc, _QueryStats  # noqa: E402 
 
 class EmuInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("retries", "entry", "W", "hs", "pairs", "grid", "cand_cap", "vcap",
-                                          "bitmap_words", "nch", "G", "pad")] + [("switches", C.c_uint64)]
+                                          "bitmap_words", "nch", "G", "hv")] + [("switches", C.c_uint64)]
 
 
 _lib = None
@@ -116,3 +116,25 @@ def plan(n, R, words, nq, L, c_target, grow=1, keyed=False, force_single=False, 
     if rc != 0:
         raise RuntimeError(f"plan failed ({rc}): {lib().emu_last_error().decode()}")
     return dict(zip(PLAN_FIELDS, [int(x) for x in out]))
+
+
+KSHIFT = {0: 21, 1: 16, 2: 32}
+
+
+def heap_script(ops, entry=0, hv=0, hs=64, cap=1 << 16):
+    """ops: list of ("push", [keys...]) (<= 64 keys: one page) or ("pop",).  Runs the heap warp's engine under the
+    emulator.  -> (heap as list of (key, seq) for slots 1..len, popped sequence numbers)"""
+    kinds = np.array([0 if o[0] == "push" else 1 for o in ops], np.uint32)
+    n = np.array([len(o[1]) if o[0] == "push" else 0 for o in ops], np.uint32)
+    keys = np.array([k for o in ops if o[0] == "push" for k in o[1]] or [0], np.uint32)
+    out = np.zeros(cap, np.uint64)
+    olen = np.zeros(1, np.uint32)
+    pops = np.zeros(max(1, int((kinds == 1).sum())), np.uint32)
+    rc = lib().emu_heap_script(C.c_int(entry), C.c_int(hv), C.c_void_p(kinds.ctypes.data), C.c_void_p(n.ctypes.data),
+                               C.c_uint32(len(ops)), C.c_void_p(keys.ctypes.data), C.c_uint32(hs), C.c_uint32(cap),
+                               C.c_void_p(out.ctypes.data), C.c_void_p(olen.ctypes.data), C.c_void_p(pops.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"emu_heap_script failed ({rc}): {lib().emu_last_error().decode()}")
+    sh = KSHIFT[entry]
+    heap = [(int(e) >> sh, int(e) & ((1 << sh) - 1)) for e in out[:int(olen[0])]]
+    return heap, pops

@@ -23,17 +23,18 @@ static emu_kernel pick1(uint32_t nch) {
         default: return nullptr;
     }
 }
-template <typename T>
+template <typename T, int HV>
 static emu_kernel pick2(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search2_kernel<T, 1>;
-        case 2: return dann_search2_kernel<T, 2>;
-        case 3: return dann_search2_kernel<T, 3>;
+        case 1: return dann_search2_kernel<T, 1, HV>;
+        case 2: return dann_search2_kernel<T, 2, HV>;
+        case 3: return dann_search2_kernel<T, 3, HV>;
         default: return nullptr;
     }
 }
-static emu_kernel pick(bool pairs, int entry, uint32_t nch) {
-    if (pairs) return entry == 0 ? pick2<Ent32x21>(nch) : entry == 1 ? pick2<Ent32x16>(nch) : pick2<Ent64>(nch);
+static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv) {
+    if (pairs && hv == 1) return entry == 0 ? pick2<Ent32x21, 1>(nch) : entry == 1 ? pick2<Ent32x16, 1>(nch) : pick2<Ent64, 1>(nch);
+    if (pairs) return entry == 0 ? pick2<Ent32x21, 0>(nch) : entry == 1 ? pick2<Ent32x16, 0>(nch) : pick2<Ent64, 0>(nch);
     return entry == 0 ? pick1<Ent32x21>(nch) : entry == 1 ? pick1<Ent32x16>(nch) : pick1<Ent64>(nch);
 }
 
@@ -42,7 +43,7 @@ extern "C" const char *emu_last_error(void) { return g_emu_err.c_str(); }
 
 struct emu_info {
     uint32_t retries, entry, W, hs, pairs, grid, cand_cap, vcap, bitmap_words, nch, G;
-    uint32_t pad;
+    uint32_t hv;
     uint64_t switches;
 };
 
@@ -159,7 +160,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.G = G;
         a.Gshift = Gshift;
         a.per_warp_smem = p.per_warp;
-        emu_kernel fn = pick(p.pairs, p.entry, NCH);
+        emu_kernel fn = pick(p.pairs, p.entry, NCH, p.hv);
         if (!fn) {
             g_emu_err = "this code width is not instantiated in the emulator build";
             return DANN_ERR_INVALID_ARG;
@@ -198,6 +199,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         info->bitmap_words = p.bitmap_words;
         info->nch = NCH;
         info->G = G;
+        info->hv = (uint32_t)p.hv;
         info->switches = simt::total_switches() - sw0;
     }
     return 0;
@@ -223,5 +225,87 @@ extern "C" int emu_plan(uint32_t n, uint32_t R, uint32_t words, uint32_t nq, uin
     const uint32_t v[13] = {p.need, p.cand_cap, p.hash_cap, p.vcap, p.hs, p.W, p.grid, p.per_warp, p.esize, p.bitmap_words,
                             p.ins_cap, (uint32_t)p.entry, (uint32_t)p.pairs};
     for (int i = 0; i < 13; i++) out[i] = v[i];
+    return 0;
+}
+
+/* ---- the heap warp's engine alone: a script of push pages and pops run through PairSearch::push_page and the pop of
+ * run_heap, one warp, dumped after the last operation.  kinds[i]: 0 = push page of n[i] keys (taken from keys[] in
+ * order), 1 = pop.  out_heap[len] receives the packed entries of slots 1..len, pops_seq[] the sequence number of
+ * every popped root.  hs = entries kept in "shared memory", the rest in the tail. */
+template <typename T, int HV>
+static void heap_script_warp(const uint32_t *kinds, const uint32_t *n, uint32_t nops, const uint32_t *keys, uint32_t hs,
+                             uint32_t cap, uint64_t *out_heap, uint32_t *out_len, uint32_t *pops_seq, SearchArgs &a,
+                             typename T::E *tail) {
+    using E = typename T::E;
+    using H = RustHeap<E, T::KSHIFT>;
+    const int lane = threadIdx.x & 31;
+    unsigned char *base = dann_smem;
+    PairSearch<T, 1, HV> w(a, lane, 1u);
+    E *hsm = reinterpret_cast<E *>(base);
+    w.listp = reinterpret_cast<uint32_t *>(base + (size_t)hs * sizeof(E));
+    w.dlp = w.listp + 2 * DANN_LIST_CAP;
+    w.ctl = reinterpret_cast<PairCtl *>(w.dlp + 2 * DANN_LIST_CAP);
+    w.cqp = reinterpret_cast<uint32_t *>(w.ctl + 1);
+    w.cqe = reinterpret_cast<E *>(w.cqp + 32);
+    w.heap.sm = hsm;
+    w.heap.gl = tail;
+    w.heap.hs = hs;
+    w.heap_len = 0;
+    uint32_t seq = 0, kpos = 0, npop = 0;
+    for (uint32_t i = 0; i < nops; i++) {
+        if (kinds[i] == 0) {
+            for (uint32_t r = lane; r < n[i]; r += 32) w.dlp[r] = keys[kpos + r];
+            if (lane == 0) {
+                w.ctl->tn[0] = n[i];
+                w.ctl->seq0[0] = seq;
+            }
+            __syncwarp();
+            w.push_page(0);
+            __syncwarp();
+            seq += n[i];
+            kpos += n[i];
+        } else if (w.heap_len > 0) {
+            if (lane == 0) pops_seq[npop] = T::seq(w.heap.get(1));
+            npop++;
+            __syncwarp();
+            if (w.heap_len < w.heap.hs) {
+                ArrayStore<E> sm{w.heap.sm};
+                if constexpr (HV == 1) H::pop_warp1_la(sm, w.heap_len, lane);
+                else H::pop_warp1(sm, w.heap_len, lane);
+            } else {
+                if constexpr (HV == 1) H::pop_warp1_la(w.heap, w.heap_len, lane);
+                else H::pop_warp1(w.heap, w.heap_len, lane);
+            }
+            __syncwarp();
+        }
+    }
+    for (uint32_t s = 1 + lane; s <= w.heap_len; s += 32) out_heap[s - 1] = (uint64_t)w.heap.get(s);
+    if (lane == 0) *out_len = w.heap_len;
+    (void)cap;
+}
+
+extern "C" int emu_heap_script(int entry, int hv, const uint32_t *kinds, const uint32_t *n, uint32_t nops, const uint32_t *keys,
+                               uint32_t hs, uint32_t cap, uint64_t *out_heap, uint32_t *out_len, uint32_t *pops_seq) {
+    if (hs % 4 || (size_t)hs * 8 + 4096 > sizeof dann_smem) {
+        g_emu_err = "bad hs";
+        return DANN_ERR_INVALID_ARG;
+    }
+    SearchArgs a{};
+    std::vector<ulonglong2> tail((size_t)cap / 2 + 2);
+    auto run = [&](auto tag, auto hvtag) {
+        using T = decltype(tag);
+        constexpr int HV = decltype(hvtag)::value;
+        simt::launch(1, 32, [&] {
+            heap_script_warp<T, HV>(kinds, n, nops, keys, hs, cap, out_heap, out_len, pops_seq, a,
+                                    reinterpret_cast<typename T::E *>(tail.data()));
+        });
+    };
+    auto by_hv = [&](auto tag) {
+        if (hv == 1) run(tag, std::integral_constant<int, 1>{});
+        else run(tag, std::integral_constant<int, 0>{});
+    };
+    if (entry == 0) by_hv(Ent32x21{});
+    else if (entry == 1) by_hv(Ent32x16{});
+    else by_hv(Ent64{});
     return 0;
 }

@@ -1,6 +1,8 @@
 // simt_emu.cpp — fibers, scheduler and warp collectives of the SIMT emulator (see simt_emu.h).  Test infrastructure.
 #include "simt_emu.h"
 
+#include <algorithm>
+
 #if !defined(__x86_64__)
 #error "the fiber switch below is written for x86-64 System V"
 #endif
@@ -215,8 +217,24 @@ void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
         unsigned live = block;
         uint64_t last_progress = ~0ull;
         int idle_passes = 0;
+        /* fiber visiting order per pass: SIMT_SCHED=0 ascending thread ids, 1 descending, 2 a fresh pseudo-random
+         * permutation every pass (seed SIMT_SEED).  Collectives make results independent of the order unless the
+         * kernel has an intra-warp race (a shared-memory exchange without __syncwarp), which one of the orders
+         * then exposes. */
+        const char *se = getenv("SIMT_SCHED");
+        const int sched = se ? atoi(se) : 0;
+        const char *sd = getenv("SIMT_SEED");
+        uint64_t rng = (sd ? strtoull(sd, nullptr, 10) : 1) * 0x9E3779B97F4A7C15ull + bi;
+        std::vector<unsigned> order(block);
+        for (unsigned t = 0; t < block; t++) order[t] = sched == 1 ? block - 1 - t : t;
         while (live) {
-            for (unsigned t = 0; t < block; t++) {
+            if (sched == 2)
+                for (unsigned t = block; t > 1; t--) {
+                    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                    std::swap(order[t - 1], order[(rng >> 33) % t]);
+                }
+            for (unsigned oi = 0; oi < block; oi++) {
+                const unsigned t = order[oi];
                 Fiber &f = b.fibers[t];
                 if (f.done) continue;
                 g_cur = &f;

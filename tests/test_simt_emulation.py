@@ -121,6 +121,98 @@ def test_emulated_lists_with_repeated_ids(emu):
     check(emu, s, q, 20, 30, single_warp=True)
 
 
+# ---- heap-warp engine v2 (DANN_HEAP_V2=1: register-resident push path + look-ahead pop) ----------------------
+@pytest.mark.parametrize("entry", [0, 1, 2])
+@pytest.mark.parametrize("hs", [None, 16, 128, 1024])
+def test_emulated_heap_engine_v2_equals_oracle(emu, entry, hs):
+    """Long scans so that the heap crosses several leaf levels (power-of-two slots) and, with a small shared-memory
+    top, runs its leaves / parents / pop descent out of the global tail."""
+    s = build_case(2500, 64, COSINE, seed=71, kind="normal", R=32, L_build=64, deleted_every=17)
+    q = fixtures.gen_vectors(3, 64, 13, "normal")
+    env = {"DANN_HEAP_V2": 1, "DANN_SEARCH_ENTRY": entry}
+    if hs is not None:
+        env["DANN_SEARCH_HS"] = hs
+    info = check(emu, s, q, 80, 150, env=env)
+    assert info["hv"] == 1 and info["entry"] == entry and info["cand_cap"] >= 4096
+
+
+def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
+    s = build_case(800, 48, L2, seed=81, kind="normal", R=24, L_build=48, labels=True, deleted_every=13)
+    q = fixtures.gen_vectors(8, 48, 3, "normal")
+    labs = [[3], [7, 1, 7], [], [16, 2, 9, 4], [5], [1, 2], [11], [8, 3]]
+    info = check(emu, s, q, 40, 60, labels=labs, sm_count=1, env={"DANN_HEAP_V2": 1, "DANN_DEBUG_SHRINK": 8})
+    assert info["hv"] == 1 and info["W"] == 7 and info["retries"] >= 1
+    info = check(emu, s, q, 40, 60, labels=labs, sm_count=1, env={"DANN_HEAP_V2": 1, "DANN_SEARCH_BITMAP": 0})
+    assert info["hv"] == 1 and info["bitmap_words"] == 0
+
+
+def test_emulated_heap_engine_v2_reference_shape(emu):
+    s = build_case(400, 768, COSINE, seed=2, kind="normal", R=48, L_build=64)
+    q = fixtures.gen_vectors(2, 768, 8, "normal")
+    info = check(emu, s, q, 50, 59, env={"DANN_HEAP_V2": 1})
+    assert (info["nch"], info["G"], info["hv"]) == (3, 4, 1)
+
+
+# ---- the heap warp's engine alone, differential against the Python clone of Rust's BinaryHeap -----------------
+def _model(ops):
+    import pyref
+    h = pyref.RustBinaryHeap(lambda a, b: b[0] <= a[0])      # Reverse<(key, seq)> with ties Equal
+    seq, pops = 0, []
+    for o in ops:
+        if o[0] == "push":
+            for k in o[1]:
+                h.push((int(k), seq))
+                seq += 1
+        elif len(h):
+            pops.append(h.pop()[1])
+    return list(h.data), pops
+
+
+def _random_script(rng, nops, key_range, pop_share, first=None):
+    ops = [("push", first)] if first else []
+    for _ in range(nops):
+        if rng.random() < pop_share:
+            ops.append(("pop",))
+        else:
+            ops.append(("push", [int(x) for x in rng.integers(0, key_range, size=int(rng.integers(1, 65)))]))
+    return ops
+
+
+@pytest.mark.parametrize("hv", [0, 1])
+@pytest.mark.parametrize("entry,key_range", [(0, 4), (0, 1500), (1, 40), (2, 3)])
+@pytest.mark.parametrize("hs", [8, 256, 16384])
+def test_emulated_heap_engine_equals_rust_heap_model(emu, monkeypatch, hv, entry, key_range, hs):
+    """Random pages of pushes and pops with few distinct keys (ties everywhere, elements racing to the root, pages
+    that straddle a leaf-level change): the heap ARRAY after the script and every popped element must equal the
+    sequential std algorithm's, for the shared-memory part and the global tail, under all three lane schedules."""
+    rng = np.random.default_rng(1000 * hv + 100 * entry + key_range + hs)
+    for sched in (0, 1, 2):
+        monkeypatch.setenv("SIMT_SCHED", str(sched))
+        ops = _random_script(rng, 120, key_range, 0.45)
+        heap, pops = emu.heap_script(ops, entry=entry, hv=hv, hs=hs)
+        want_heap, want_pops = _model(ops)
+        assert heap == want_heap
+        assert pops[:len(want_pops)].tolist() == want_pops
+
+
+@pytest.mark.parametrize("hv", [0, 1])
+def test_emulated_heap_engine_root_handover_at_leaf_level_change(emu, monkeypatch, hv):
+    """The push that fills slot 2^d - 1 rises to the root, and the next page starts a new leaf level: the root slot
+    changes owner lane exactly there (engine v2 needs its write-back / sync / reload)."""
+    for sched in (0, 1, 2):
+        monkeypatch.setenv("SIMT_SCHED", str(sched))
+        for d in (7, 8, 10):
+            n0 = (1 << d) - 1 - 40
+            ops = [("push", [1000] * 64) for _ in range(n0 // 64)] + [("push", [1000] * (n0 % 64))]
+            # one page: 39 large keys, then a new minimum at slot 2^d - 1, then smaller and smaller keys beyond it
+            ops.append(("push", [900] * 39 + [5] + [4, 3, 3, 2, 900, 1, 0, 0]))
+            ops.append(("pop",))
+            ops.append(("push", [0, 7, 0]))
+            heap, pops = emu.heap_script([o for o in ops if o[0] == "pop" or len(o[1])], entry=0, hv=hv, hs=4096)
+            want_heap, want_pops = _model([o for o in ops if o[0] == "pop" or len(o[1])])
+            assert heap == want_heap and pops[:len(want_pops)].tolist() == want_pops
+
+
 # ---- the workspace plan itself (host logic of diskann_b200.cu, shared through dann_plan.h) ----------------
 def test_plan_benchmark_shape_is_one_wave_of_seven_pairs(emu):
     p = emu.plan(n=1_000_000, R=64, words=24, nq=1024, L=150, c_target=259)
