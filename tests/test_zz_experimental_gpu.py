@@ -1,0 +1,61 @@
+"""GPU parity of code paths that exist but have NOT been run on hardware yet (this round's GPU minutes were spent
+before they were written).  They are bit-exact under the CPU SIMT emulator (tests/test_simt_emulation.py); these
+tests are the hardware check and only run when DANN_RUN_EXPERIMENTAL=1 is set, so that an unverified path can never
+turn the regular `-m gpu` run red.  First thing to run next round:
+
+    DANN_RUN_EXPERIMENTAL=1 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import build_case
+from test_gpu_parity import _compare_batch, _queries
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DANN_RUN_EXPERIMENTAL") != "1",
+                                 reason="opt-in: set DANN_RUN_EXPERIMENTAL=1 (paths not yet verified on hardware)")]
+
+COSINE, L2, IP = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def lib(lib_built):
+    from pgvectorscale_b200 import diskann
+    if diskann.device_count() < 1:
+        pytest.fail("no CUDA device visible: -m gpu tests need the B200 box")
+    return diskann
+
+
+@pytest.fixture()
+def heap_v2(monkeypatch):
+    monkeypatch.setenv("DANN_HEAP_V2", "1")
+
+
+@pytest.mark.parametrize("dist,bits", [(COSINE, 2), (L2, 1)])
+def test_heap_engine_v2_batch_matches_oracle(lib, heap_v2, dist, bits):
+    s = build_case(3000, 768, dist, bits=bits, seed=11 + dist + bits, kind="normal")
+    with lib.DiskAnnIndex(s) as idx:
+        q = _queries(s, 64, 77)
+        _compare_batch(s, idx, q, k=10, L=100, rescore=50)
+        _compare_batch(s, idx, q[:16], k=10, L=25, rescore=0)
+        _compare_batch(s, idx, q[:32], k=20, L=300, rescore=200)
+
+
+@pytest.mark.parametrize("entry", [1, 2])
+def test_heap_engine_v2_entry_layouts_and_tail(lib, heap_v2, monkeypatch, entry):
+    monkeypatch.setenv("DANN_SEARCH_ENTRY", str(entry))
+    monkeypatch.setenv("DANN_SEARCH_HS", "256")       # most of the heap in the HBM tail
+    s = build_case(3000, 256, COSINE, seed=5, kind="normal")
+    with lib.DiskAnnIndex(s) as idx:
+        _compare_batch(s, idx, _queries(s, 48, 3), k=10, L=150, rescore=100)
+
+
+def test_heap_engine_v2_labels(lib, heap_v2):
+    s = build_case(3000, 128, L2, seed=6, kind="uniform", labels=True)
+    rng = np.random.default_rng(4)
+    with lib.DiskAnnIndex(s) as idx:
+        q = _queries(s, 64, 9, "uniform")
+        labels = [[int(x) for x in rng.integers(1, 17, size=int(rng.integers(1, 4)))] for _ in range(64)]
+        _compare_batch(s, idx, q, k=10, L=100, rescore=50, labels=labels)
