@@ -170,7 +170,38 @@ struct PairSearch {
     }
 
     /* SBQ distances of page `list` -> `dl` (distance/mod.rs:265-323).  EXACT: every lane's NCH
-     * chunk slots exist (cw/2 == NCH*G), so the per-chunk bounds test disappears. */
+     * chunk slots exist (cw/2 == NCH*G), so the per-chunk bounds test disappears.
+     * One round = NU row slots per lane group: all 16-byte loads first, then XOR + popcount + group reduction. */
+    template <bool EXACT, int NU>
+    __device__ __forceinline__ void distances_round(const uint32_t *list, uint32_t *dl, uint32_t tn, uint32_t b) {
+        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
+        const uint32_t nchunks = a.ix.cw >> 1;
+        const size_t rowbytes = (size_t)a.ix.cw * 8;
+        const unsigned char *cbase = reinterpret_cast<const unsigned char *>(a.ix.codes) + (size_t)gl * 16;
+        const uint32_t cstep = G * 16;
+        ulonglong2 v[NU][NCH];
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const uint32_t r = b + u * RP + grp;
+            const bool live = r < tn;
+            const unsigned char *row = cbase + (size_t)(live ? list[r] : 0u) * rowbytes;
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                const bool ok = live && (EXACT || gl + i * G < nchunks);
+                v[u][i] = ok ? ldg_stream_u128(row + i * cstep) : qc[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int i = 0; i < NCH; i++)
+                s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
+            for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+            const uint32_t r = b + u * RP + grp;
+            if (gl == 0 && r < tn) dl[r] = s;
+        }
+    }
     template <bool EXACT>
     __device__ __forceinline__ void distances_impl(const uint32_t *list, uint32_t *dl, uint32_t tn) {
         const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
@@ -204,9 +235,31 @@ struct PairSearch {
         }
         __syncwarp();
     }
+    /* HV == 1: row slots past the end of the page are not computed at all (a 50-id page is 7 of the 12 slots of its
+     * two rounds).  Three round sizes keep every v[][] index a compile-time constant (registers, no local memory). */
+    template <bool EXACT>
+    __device__ __forceinline__ void distances_impl2(const uint32_t *list, uint32_t *dl, uint32_t tn) {
+        const uint32_t RP = 32u >> a.Gshift;
+        for (uint32_t b = 0; b < tn; b += RP * RPI) {
+            if constexpr (RPI >= 4) {
+                const uint32_t nu = (tn - b + RP - 1) / RP;
+                if (nu > (uint32_t)RPI * 2 / 3) distances_round<EXACT, RPI>(list, dl, tn, b);
+                else if (nu > (uint32_t)RPI / 3) distances_round<EXACT, RPI * 2 / 3>(list, dl, tn, b);
+                else distances_round<EXACT, RPI / 3>(list, dl, tn, b);
+            } else {
+                distances_round<EXACT, RPI>(list, dl, tn, b);
+            }
+        }
+        __syncwarp();
+    }
     __device__ __forceinline__ void distances(const uint32_t *list, uint32_t *dl, uint32_t tn) {
-        if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
-        else distances_impl<false>(list, dl, tn);
+        if constexpr (HV == 1) {
+            if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl2<true>(list, dl, tn);
+            else distances_impl2<false>(list, dl, tn);
+        } else {
+            if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
+            else distances_impl<false>(list, dl, tn);
+        }
     }
 
     __device__ __forceinline__ void run_memory(uint32_t q) {
