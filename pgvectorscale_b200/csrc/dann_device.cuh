@@ -72,6 +72,15 @@ __device__ __forceinline__ float ldg_stream_f1(const void *p) {
 }
 #endif
 
+// Hint: bring the 128-byte line holding p into L2 (no register, no dependency; a wrong guess costs one line of traffic).
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#ifdef DANN_SIMT_EMU
+    (void)p;
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // f32::total_cmp key (core::f32::total_cmp): monotone signed-int image of the float.
 __device__ __forceinline__ int32_t total_key(float f) {
     int32_t b = __float_as_int(f);

@@ -110,6 +110,20 @@ struct PairSearch {
         unsigned m1 = __match_any_sync(DANN_FULL, n1);
         const bool f0 = v0 && ((__ffs(m0) - 1) == lane);
         const bool f1 = v1 && ((__ffs(m1) - 1) == lane);
+        if constexpr (HV == 1) {
+            /* the SBQ code rows are needed one L2 round trip from now (after the inserted-set answers): start pulling
+             * them into L2 already; rows of ids that turn out to be known are the only wasted traffic */
+            const size_t rowbytes = (size_t)a.ix.cw * 8;
+            const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
+            if (f0) {
+                prefetch_l2(cb + (size_t)n0 * rowbytes);
+                if (rowbytes > 128) prefetch_l2(cb + (size_t)n0 * rowbytes + 128);
+            }
+            if (f1) {
+                prefetch_l2(cb + (size_t)n1 * rowbytes);
+                if (rowbytes > 128) prefetch_l2(cb + (size_t)n1 * rowbytes + 128);
+            }
+        }
         bool new0 = false, new1 = false;
         if (a.bitmap_words) {
             uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
@@ -362,6 +376,17 @@ struct PairSearch {
             } else if (rv) { /* the root the pop left behind stays on top */
                 node = cnode[ctl->root_seq[pp]];
                 key = ctl->root_key[pp];
+            }
+            if constexpr (HV == 1) {
+                /* the best new candidate of the page is not visited now (the old root wins) but very likely soon:
+                 * pull its neighbour row into L2 (lanes 0..: one 128-byte line each) */
+                if (ptn && rv && !(m < ctl->root_key[pp])) {
+                    unsigned e0 = __ballot_sync(DANN_FULL, d0 == m), e1 = __ballot_sync(DANN_FULL, d1 == m);
+                    const uint32_t idx = e0 ? (uint32_t)(__ffs(e0) - 1) : 32u + (uint32_t)(__ffs(e1) - 1);
+                    const uint32_t rb = ix.Rp * 4u;
+                    if ((uint32_t)lane * 128u < rb)
+                        prefetch_l2(reinterpret_cast<const unsigned char *>(ix.nbrs + (size_t)pl[idx] * ix.Rp) + lane * 128);
+                }
             }
             const bool have = node != DANN_INVALID_NODE;
             bool visit = false;
