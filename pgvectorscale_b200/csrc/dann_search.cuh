@@ -80,7 +80,16 @@ struct SearchArgs {
     uint64_t *vis_out;      /* [B][vis_out_cap] (dist << 32) | node, ascending */
     uint32_t *vis_out_len;  /* [B] */
     uint32_t vis_out_cap;
+    /* dann_search2_kernel<.., HV=1> only: which of its alternatives run (DANN_HV_FLAGS, default all), so that each can
+     * be timed alone: 1 register-path pushes, 2 look-ahead pop, 4 page-sized distance rounds, 8 code-row L2
+     * prefetch, 16 neighbour-row L2 prefetch.  Kept last: the offsets of the fields above are unchanged. */
+    uint32_t hv_flags;
 };
+#define DANN_HV_PUSH 1u
+#define DANN_HV_POP 2u
+#define DANN_HV_DIST 4u
+#define DANN_HV_PF_CODES 8u
+#define DANN_HV_PF_NBRS 16u
 
 #define DANN_LIST_CAP 64u
 

@@ -110,7 +110,7 @@ struct PairSearch {
         unsigned m1 = __match_any_sync(DANN_FULL, n1);
         const bool f0 = v0 && ((__ffs(m0) - 1) == lane);
         const bool f1 = v1 && ((__ffs(m1) - 1) == lane);
-        if constexpr (HV == 1) {
+        if (HV == 1 && (a.hv_flags & DANN_HV_PF_CODES)) {
             /* the SBQ code rows are needed one L2 round trip from now (after the inserted-set answers): start pulling
              * them into L2 already; rows of ids that turn out to be known are the only wasted traffic */
             const size_t rowbytes = (size_t)a.ix.cw * 8;
@@ -268,12 +268,14 @@ struct PairSearch {
     }
     __device__ __forceinline__ void distances(const uint32_t *list, uint32_t *dl, uint32_t tn) {
         if constexpr (HV == 1) {
-            if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl2<true>(list, dl, tn);
-            else distances_impl2<false>(list, dl, tn);
-        } else {
-            if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
-            else distances_impl<false>(list, dl, tn);
+            if (a.hv_flags & DANN_HV_DIST) {
+                if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl2<true>(list, dl, tn);
+                else distances_impl2<false>(list, dl, tn);
+                return;
+            }
         }
+        if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
+        else distances_impl<false>(list, dl, tn);
     }
 
     __device__ __forceinline__ void run_memory(uint32_t q) {
@@ -380,7 +382,7 @@ struct PairSearch {
             if constexpr (HV == 1) {
                 /* the best new candidate of the page is not visited now (the old root wins) but very likely soon:
                  * pull its neighbour row into L2 (lanes 0..: one 128-byte line each) */
-                if (ptn && rv && !(m < ctl->root_key[pp])) {
+                if ((a.hv_flags & DANN_HV_PF_NBRS) && ptn && rv && !(m < ctl->root_key[pp])) {
                     unsigned e0 = __ballot_sync(DANN_FULL, d0 == m), e1 = __ballot_sync(DANN_FULL, d1 == m);
                     const uint32_t idx = e0 ? (uint32_t)(__ffs(e0) - 1) : 32u + (uint32_t)(__ffs(e1) - 1);
                     const uint32_t rb = ix.Rp * 4u;
@@ -596,7 +598,7 @@ struct PairSearch {
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
         if (tn == 0) return;
         if constexpr (HV == 1) {
-            if (heap_len >= 64) {
+            if (heap_len >= 64 && (a.hv_flags & DANN_HV_PUSH)) {
                 if (heap_len + tn < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
                     push_batch_v2(sm, dl, tn, seq0);
@@ -713,10 +715,10 @@ struct PairSearch {
                 node_chk = __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
-                    if constexpr (HV == 1) H::pop_warp1_la(sm, heap_len, lane);
+                    if (HV == 1 && (a.hv_flags & DANN_HV_POP)) H::pop_warp1_la(sm, heap_len, lane);
                     else H::pop_warp1(sm, heap_len, lane);
                 } else {
-                    if constexpr (HV == 1) H::pop_warp1_la(heap, heap_len, lane);
+                    if (HV == 1 && (a.hv_flags & DANN_HV_POP)) H::pop_warp1_la(heap, heap_len, lane);
                     else H::pop_warp1(heap, heap_len, lane);
                 }
             }

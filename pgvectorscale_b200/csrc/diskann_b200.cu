@@ -555,6 +555,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.vis_out = vis_out;
         a.vis_out_len = vis_out_len;
         a.vis_out_cap = vis_out_cap;
+        a.hv_flags = env_u32("DANN_HV_FLAGS", 31);
         search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH, p.hv);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1086,6 +1087,7 @@ static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip
         a.vis_out = nullptr;
         a.vis_out_len = nullptr;
         a.vis_out_cap = 0;
+        a.hv_flags = 0;
         search_fn fn = pick_kernel(false, p.entry, ix->NCH);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
         fn<<<1, 32, p.per_warp, st>>>(a);

@@ -160,6 +160,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.G = G;
         a.Gshift = Gshift;
         a.per_warp_smem = p.per_warp;
+        a.hv_flags = env_u32("DANN_HV_FLAGS", 31);
         emu_kernel fn = pick(p.pairs, p.entry, NCH, p.hv);
         if (!fn) {
             g_emu_err = "this code width is not instantiated in the emulator build";
@@ -291,6 +292,7 @@ extern "C" int emu_heap_script(int entry, int hv, const uint32_t *kinds, const u
         return DANN_ERR_INVALID_ARG;
     }
     SearchArgs a{};
+    a.hv_flags = env_u32("DANN_HV_FLAGS", 31);
     std::vector<ulonglong2> tail((size_t)cap / 2 + 2);
     auto run = [&](auto tag, auto hvtag) {
         using T = decltype(tag);

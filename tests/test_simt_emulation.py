@@ -146,6 +146,15 @@ def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
     assert info["hv"] == 1 and info["bitmap_words"] == 0
 
 
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 3, 28])
+def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
+    """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
+    s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
+    q = fixtures.gen_vectors(3, 96, 17, "normal")
+    info = check(emu, s, q, 60, 90, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags, "DANN_SEARCH_HS": 512})
+    assert info["hv"] == 1
+
+
 def test_emulated_heap_engine_v2_reference_shape(emu):
     s = build_case(400, 768, COSINE, seed=2, kind="normal", R=48, L_build=64)
     q = fixtures.gen_vectors(2, 768, 8, "normal")
