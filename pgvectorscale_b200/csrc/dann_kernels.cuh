@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include "dann_device.cuh"
+#include "dann_distance.cuh"
 #include "dann_heap.cuh"
 
 /* f32::NAN (0x7fc00000): the "no distance" value of padded / unrescored rows */
@@ -100,6 +101,49 @@ __global__ void __launch_bounds__(128) dann_prepare_kernel(IndexView ix, const f
     }
 }
 
+/* Plain storage layout: amrescan's vector preparation without a quantizer (pg_vector.rs:125-157): the full copy and
+ * the copy truncated to dim_index, each cosine-normalised on its own.  One CTA per query. */
+__global__ void __launch_bounds__(128) dann_prepare_plain_kernel(uint32_t dim, uint32_t dim_index, int cosine,
+                                                                 const float *queries, float *q_full_out,
+                                                                 float *q_index_out) {
+    __shared__ float s_div[2];
+    const int q = blockIdx.x;
+    const float *src = queries + (size_t)q * dim;
+    if (cosine) {
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const uint32_t len = threadIdx.x == 0 ? dim : dim_index;
+            float norm = 0.0f;
+            for (uint32_t i = 0; i < len; i++) {
+                float v = src[i];
+                norm = __fadd_rn(norm, __fmul_rn(v, v));
+            }
+            s_div[threadIdx.x >> 5] = cosine_divisor_from_norm(norm, len);
+        }
+    } else if (threadIdx.x == 0) {
+        s_div[0] = 0.0f;
+        s_div[1] = 0.0f;
+    }
+    __syncthreads();
+    const float dfull = s_div[0], dindex = s_div[1];
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        float v = src[i];
+        q_full_out[(size_t)q * dim + i] = dfull != 0.0f ? __fdiv_rn(v, dfull) : v;
+        if (i < dim_index) q_index_out[(size_t)q * dim_index + i] = dindex != 0.0f ? __fdiv_rn(v, dindex) : v;
+    }
+}
+
+/* Plain storage layout, after the rerank kernel: every comparison of the beam search was a full-distance comparison
+ * (plain/storage.rs:238,288), so d_full = candidates + reranked rows and d_quantized = 0.  Only launched when the
+ * rerank ran (num_dimensions_to_index < num_dimensions, scan.rs:392-403). */
+__global__ void dann_plain_stats_kernel(dann_query_stats *stats, int B) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    dann_query_stats st = stats[q];
+    st.d_full = st.candidates + st.d_full; /* the rerank kernel left the number of reranked rows here */
+    st.d_quantized = 0;
+    stats[q] = st;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Stand-alone SBQ distance: out[i] = popcount(code[pair_node[i]] ^ qcode[pair_q[i]])     */
 /* (distance_xor_optimized, distance/mod.rs:265-323).  G lanes share one code row with    */
@@ -152,84 +196,6 @@ __global__ void __launch_bounds__(512) dann_sbq_distance_kernel(const uint64_t *
             if (gl == 0 && p0 + u < npairs) out[p0 + u] = s;
         }
     }
-}
-
-/* ------------------------------------------------------------------------------------ */
-/* Exact distance with the reference's AVX2 summation order.                             */
-/* distance_l2_simd_body! / inner_product_simd_body! (distance/mod.rs:325-434) with       */
-/* S = Avx2: element e = 32*i + 8*k + j goes to accumulator k, lane j, steps i in order.  */
-/* Here 8 GPU lanes share one row: lane m (0..7) owns the four accumulator slots          */
-/* 4m..4m+3 (k = m/2, j = 4*(m%2)+t), i.e. one float4 per 32-element stride, so the 8      */
-/* lanes read 128 contiguous bytes per step.  `y` is the query (shared memory).           */
-/* Returns the finished distance on every lane of the 8-lane group.                      */
-template <bool VEC4>
-__device__ __forceinline__ float full_distance_group8(int type, const float *__restrict__ x,
-                                                      const float *__restrict__ y, uint32_t n,
-                                                      uint32_t m, unsigned gmask_base_lane) {
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    const uint32_t nfull = n >> 5;
-    const bool l2 = type == DANN_L2;
-    constexpr int UN = 8;
-    for (uint32_t i0 = 0; i0 < nfull; i0 += UN) {
-        float4 xv[UN];
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-            uint32_t i = i0 + u;
-            if (i < nfull) {
-                const float *px = x + 32 * i + 4 * m;
-                if (VEC4) xv[u] = ldg_stream_f4(px);
-                else xv[u] = make_float4(ldg_stream_f1(px), ldg_stream_f1(px + 1), ldg_stream_f1(px + 2),
-                                         ldg_stream_f1(px + 3));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-            uint32_t i = i0 + u;
-            if (i < nfull) {
-                const float *py = y + 32 * i + 4 * m;
-                float4 yv = VEC4 ? *reinterpret_cast<const float4 *>(py) : make_float4(py[0], py[1], py[2], py[3]);
-                if (l2) { /* accum = accum + ((x - y) * (x - y)) : separate sub, mul, add */
-                    float d0 = __fsub_rn(xv[u].x, yv.x), d1 = __fsub_rn(xv[u].y, yv.y);
-                    float d2 = __fsub_rn(xv[u].z, yv.z), d3 = __fsub_rn(xv[u].w, yv.w);
-                    a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
-                    a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
-                    a2 = __fadd_rn(a2, __fmul_rn(d2, d2));
-                    a3 = __fadd_rn(a3, __fmul_rn(d3, d3));
-                } else { /* accum = fmadd(x, y, accum) */
-                    a0 = __fmaf_rn(xv[u].x, yv.x, a0);
-                    a1 = __fmaf_rn(xv[u].y, yv.y, a1);
-                    a2 = __fmaf_rn(xv[u].z, yv.z, a2);
-                    a3 = __fmaf_rn(xv[u].w, yv.w, a3);
-                }
-            }
-        }
-    }
-    /* simdeez Avx2::horizontal_add_ps: ((a0+a4)+(a1+a5)) + ((a2+a6)+(a3+a7)); the pair of
-     * lanes (2k, 2k+1) holds accumulator k: lane 2k has j=0..3, lane 2k+1 has j=4..7. */
-    float v0 = __fadd_rn(a0, __shfl_xor_sync(DANN_FULL, a0, 1));
-    float v1 = __fadd_rn(a1, __shfl_xor_sync(DANN_FULL, a1, 1));
-    float v2 = __fadd_rn(a2, __shfl_xor_sync(DANN_FULL, a2, 1));
-    float v3 = __fadd_rn(a3, __shfl_xor_sync(DANN_FULL, a3, 1));
-    float h = __fadd_rn(__fadd_rn(v0, v1), __fadd_rn(v2, v3));
-    float h0 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 0);
-    float h1 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 2);
-    float h2 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 4);
-    float h3 = __shfl_sync(DANN_FULL, h, gmask_base_lane + 6);
-    float dist = __fadd_rn(__fadd_rn(__fadd_rn(h0, h1), h2), h3);
-    /* scalar tail, in order (every lane of the group computes the same chain) */
-    for (uint32_t i = nfull << 5; i < n; i++) {
-        float xi = ldg_stream_f1(x + i), yi = y[i];
-        if (l2) {
-            float diff = __fsub_rn(xi, yi);
-            dist = __fadd_rn(dist, __fmul_rn(diff, diff));
-        } else {
-            dist = __fadd_rn(dist, __fmul_rn(xi, yi));
-        }
-    }
-    if (type == DANN_L2) return dist;                 /* distance/mod.rs:88-104 (no sqrt) */
-    if (type == DANN_IP) return -dist;                /* :175-190 */
-    float r = __fsub_rn(1.0f, dist);                  /* distance_x86.rs:34-36 (1.0 - ip).max(0.0) */
-    return r > 0.0f ? r : 0.0f;
 }
 
 /* ---- 1-D TMA bulk copy (cp.async.bulk) of one query row into shared memory ---------- */

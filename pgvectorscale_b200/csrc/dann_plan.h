@@ -22,6 +22,7 @@ struct PlanInputs {
     uint32_t n, R, words; /* nodes, neighbour slots per node, u64 words per SBQ code */
     size_t smem_optin;    /* cudaDeviceProp::sharedMemPerBlockOptin */
     int sm_count;
+    uint32_t plain_dim;   /* 0 = SBQ layout; else num_dimensions_to_index of a plain-storage index */
 };
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
@@ -82,16 +83,18 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     else if (maxdist < 65536 && p->cand_cap <= 65536) p->entry = 1;
     else p->entry = 2;
     p->entry = (int)env_u32("DANN_SEARCH_ENTRY", (uint32_t)p->entry); /* test hook */
+    if (in.plain_dim) p->entry = 2; /* f32 keys need the 32-bit key field of Ent64 */
     p->esize = p->entry == 2 ? 8 : 4;
     /* visited holds the not-yet-consumed visits: about L, more under a label filter */
     uint64_t vcap = std::max<uint64_t>(((uint64_t)L * (keyed ? 2 : 1) + 96u) * grow / shrink, 8);
     p->vcap = (uint32_t)((vcap + 3) & ~3ull);
     const size_t budget = in.smem_optin > 1024 ? in.smem_optin - 1024 : in.smem_optin;
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
-    p->pairs = !force_single && in.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1;
+    p->pairs = !force_single && in.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1 && !in.plain_dim;
     p->hv = p->pairs && env_u32("DANN_HEAP_V2", 0) == 1 ? 1 : 0;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
-    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4);
+    const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4) +
+                         (size_t)((in.plain_dim + 3u) & ~3u) * 4; /* plain layout: the query's index slice */
     if (fixed + 1024 > budget) {
         snprintf(err, errlen, "visited list of %u entries does not fit shared memory", p->vcap);
         return DANN_ERR_CAPACITY;

@@ -36,6 +36,7 @@
 // order, by the warp-cooperative sift-up of dann_heap.cuh (one lane per tree level).
 #pragma once
 #include "dann_device.cuh"
+#include "dann_distance.cuh"
 #include "dann_heap.cuh"
 
 /* what a suspended scan keeps besides its HBM workspace (heap tail, inserted-set, seq->node table) */
@@ -84,6 +85,11 @@ struct SearchArgs {
      * be timed alone: 1 register-path pushes, 2 look-ahead pop, 4 page-sized distance rounds, 8 code-row L2
      * prefetch, 16 neighbour-row L2 prefetch.  Kept last: the offsets of the fields above are unchanged. */
     uint32_t hv_flags;
+    /* plain storage layout (SearchWarp<.., PLAIN=1> only; storage.rs:144-169, plain/storage.rs:223-299): the beam
+     * search compares the query's index slice with the f32 vector each node stores.  Kept after everything else. */
+    const float *plain_vectors; /* [n][plain_dim] */
+    const float *q_index;       /* [B][plain_dim] prepared (truncated, cosine-normalised) queries */
+    uint32_t plain_dim;         /* num_dimensions_to_index */
 };
 #define DANN_HV_PUSH 1u
 #define DANN_HV_POP 2u
@@ -115,7 +121,9 @@ struct Ent64 {
     static __device__ __forceinline__ uint32_t seq(uint64_t e) { return (uint32_t)e; }
 };
 
-template <typename T, int NCH>
+/* PLAIN = 1: the plain storage layout.  Keys are total_ukey(f32 distance) (Ent64 entries), every comparison is a
+ * full-distance comparison (counted as d_full), there is no label filter (plain/storage.rs:260). */
+template <typename T, int NCH, int PLAIN = 0>
 struct SearchWarp {
     using E = typename T::E;
     using H = RustHeap<E, T::KSHIFT>;
@@ -130,6 +138,7 @@ struct SearchWarp {
     uint32_t *list, *dl;
     uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
+    float *qrow; /* PLAIN: this query's index slice in shared memory */
     /* query */
     ulonglong2 qc[NCH];
     const int16_t *ql;
@@ -275,6 +284,29 @@ struct SearchWarp {
             listn = 0;
             return;
         }
+        if constexpr (PLAIN == 1) {
+            /* PlainDistanceMeasure::calculate_distance (plain/mod.rs:22-32): distance_fn(query.to_index_slice(),
+             * node.vector), 8 lanes per row, the AVX2 summation order of dann_distance.cuh; the heap key is the
+             * total order image of the f32 (-0.0 folded into +0.0: DistanceWithTieBreak treats them as equal,
+             * graph/neighbor_with_distance.rs:31-43) */
+            const uint32_t mm = lane & 7, gbase = lane & 24, grp8 = lane >> 3;
+            const bool vec4 = (a.plain_dim & 3u) == 0;
+            for (uint32_t b = 0; b < tn; b += 4) {
+                const uint32_t r = b + grp8;
+                const uint32_t node = r < tn ? list[r] : 0u;
+                const float *x = a.plain_vectors + (size_t)node * a.plain_dim;
+                const float d = vec4 ? full_distance_group8<true>(a.ix.distance_type, x, qrow, a.plain_dim, mm, gbase)
+                                     : full_distance_group8<false>(a.ix.distance_type, x, qrow, a.plain_dim, mm, gbase);
+                if (mm == 0 && r < tn) dl[r] = total_ukey(__fadd_rn(d, 0.0f));
+            }
+            __syncwarp();
+            push_batch(heap, tn);
+            heap_len += tn;
+            ncand += tn;
+            dq += tn;
+            listn = 0;
+            return;
+        }
         const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
         const uint32_t nchunks = a.ix.cw >> 1;
         for (uint32_t b = 0; b < tn; b += RP * RPI) {
@@ -400,8 +432,13 @@ struct SearchWarp {
             for (uint32_t i = lane; i < vis_len; i += 32) vis[i] = a.saved_vis[i];
             __syncwarp();
         }
+        if constexpr (PLAIN == 1) { /* the query's index slice, read by every distance of this scan */
+            const float *src = a.q_index + (size_t)q * a.plain_dim;
+            for (uint32_t i = lane; i < a.plain_dim; i += 32) qrow[i] = src[i];
+            __syncwarp();
+        }
         /* query code chunks this lane compares against (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) */
-        {
+        if constexpr (PLAIN == 0) {
             const uint32_t gl = lane & (a.G - 1), nchunks = ix.cw >> 1;
             const ulonglong2 *qrow = reinterpret_cast<const ulonglong2 *>(a.q_codes + (size_t)q * ix.cw);
 #pragma unroll
@@ -532,9 +569,9 @@ struct SearchWarp {
             a.stream_len[q] = scount;
             dann_query_stats st;
             st.visits = visits;
-            st.d_quantized = dq;
+            st.d_quantized = PLAIN == 1 ? 0u : dq;
             st.candidates = dq;
-            st.d_full = 0;
+            st.d_full = PLAIN == 1 ? dq : 0u; /* record_full_distance_comparison, plain/storage.rs:238,288 */
             st.stream_len = scount;
             st.status = status;
             a.stats[q] = st;
@@ -544,18 +581,19 @@ struct SearchWarp {
     }
 };
 
-template <typename T, int NCH>
+template <typename T, int NCH, int PLAIN = 0>
 __global__ void __launch_bounds__(384, 1) dann_search_kernel(const SearchArgs a) {
     using E = typename T::E;
     extern __shared__ __align__(16) unsigned char dann_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const uint32_t slot = blockIdx.x * W + warp;
     unsigned char *base = dann_smem + (size_t)warp * a.per_warp_smem;
-    SearchWarp<T, NCH> w(a, lane);
+    SearchWarp<T, NCH, PLAIN> w(a, lane);
     w.vis = reinterpret_cast<uint64_t *>(base);
     E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
     w.list = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));
     w.dl = w.list + DANN_LIST_CAP;
+    w.qrow = reinterpret_cast<float *>(w.dl + DANN_LIST_CAP); /* PLAIN only: [plain_dim rounded up to 4] */
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.ins = a.ins_list + (size_t)slot * a.ins_cap;

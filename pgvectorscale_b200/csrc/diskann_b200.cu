@@ -107,6 +107,10 @@ struct dann_index {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t G = 1, Gshift = 0, NCH = 1;
     uint32_t lists_unique = 0;
+    /* plain storage layout (experimental): nodes carry their f32 index vector, no SBQ codes */
+    bool plain = false;
+    const float *index_vectors = nullptr; /* [n][dim_index] in HBM */
+    DevBuf sc_qindex;
 };
 
 
@@ -118,6 +122,7 @@ struct dann_scan {
     int L = 100, rescore = 50;
     bool active = false;
     /* suspended search state in HBM (see SavedScan / dann_search.cuh) */
+    DevBuf d_qindex; /* plain layout: the prepared index slice */
     DevBuf d_query, d_qfull, d_qcodes, d_labels, d_label_off, d_saved, d_heap_sm, d_vis, d_heap_tail, d_cnode, d_set,
         d_ins, d_stream, d_slen, d_stats, d_dist, d_win, d_winst, d_row, d_ctl;
     SearchPlan plan{};
@@ -181,7 +186,7 @@ extern "C" void dann_index_free(dann_index *ix) {
     for (void *p : ix->owned) cudaFree(p);
     DevBuf *bufs[] = {&ix->ws_hash, &ix->ws_cand, &ix->ws_heap, &ix->ws_bitmap, &ix->ws_ins, &ix->sc_qfull, &ix->sc_qcodes,
                       &ix->sc_stream, &ix->sc_stream_len, &ix->sc_stats, &ix->sc_qlist, &ix->sc_ctl,
-                      &ix->sc_node, &ix->st_queries, &ix->st_labels, &ix->st_label_off, &ix->st_tid,
+                      &ix->sc_node, &ix->sc_qindex, &ix->st_queries, &ix->st_labels, &ix->st_label_off, &ix->st_tid,
                       &ix->st_dist, &ix->st_count, &ix->st_stats};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : ix->ev)
@@ -194,19 +199,29 @@ extern "C" void dann_index_free(dann_index *ix) {
 /* Everything the kernels index with comes from the snapshot: reject ids and offsets that would send a
  * gather out of bounds here, on the host, before anything is copied (the reference gets the same guarantee
  * from Postgres' page/item bounds checks, util/page.rs:254-290). */
-static int validate_snapshot(const dann_snapshot_desc *s, uint32_t *words_out) {
-    if (s->dim == 0 || s->dim_index == 0 || s->dim_index > s->dim || s->bits == 0 || s->R == 0)
+static int validate_snapshot(const dann_snapshot_desc *s, uint32_t *words_out, bool plain) {
+    if (s->dim == 0 || s->dim_index == 0 || s->dim_index > s->dim || s->R == 0 || (!plain && s->bits == 0))
         return fail(DANN_ERR_INVALID_ARG, "bad snapshot geometry");
-    uint64_t nb = (uint64_t)s->dim_index * s->bits;
-    uint32_t words = (uint32_t)(nb % 64 == 0 ? nb / 64 : nb / 64 + 1); /* quantize.rs:38-46 */
-    if (words != s->words) return fail(DANN_ERR_INVALID_ARG, "words=%u but dim_index*bits needs %u", s->words, words);
+    uint32_t words = 0;
+    if (!plain) {
+        uint64_t nb = (uint64_t)s->dim_index * s->bits;
+        words = (uint32_t)(nb % 64 == 0 ? nb / 64 : nb / 64 + 1); /* quantize.rs:38-46 */
+        if (words != s->words) return fail(DANN_ERR_INVALID_ARG, "words=%u but dim_index*bits needs %u", s->words, words);
+    }
     *words_out = words;
     if (s->distance_type < DANN_COSINE || s->distance_type > DANN_IP)
         return fail(DANN_ERR_INVALID_ARG, "unknown distance type %d", s->distance_type);
     if (s->n == DANN_INVALID_NODE) return fail(DANN_ERR_INVALID_ARG, "n collides with the invalid-node sentinel");
-    if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->mean))
-        return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
-    if (s->bits > 1 && s->n && !s->m2) return fail(DANN_ERR_INVALID_ARG, "m2 is required when bits > 1 (sbq/quantize.rs:73-101)");
+    if (plain) { /* build.rs:264-290: what CREATE INDEX rejects for storage_layout = plain */
+        if (s->distance_type == DANN_IP) return fail(DANN_ERR_INVALID_ARG, "inner product distance is not supported with plain storage");
+        if (s->has_labels) return fail(DANN_ERR_INVALID_ARG, "labeled filtering is not supported with plain storage");
+        if (s->dim_index > 2000) return fail(DANN_ERR_INVALID_ARG, "too many dimensions to index with plain storage (max is 2000)");
+        if (s->n && (!s->nbrs || !s->heap_tid)) return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
+    } else {
+        if (s->n && (!s->codes || !s->nbrs || !s->heap_tid || !s->mean))
+            return fail(DANN_ERR_INVALID_ARG, "snapshot arrays missing");
+        if (s->bits > 1 && s->n && !s->m2) return fail(DANN_ERR_INVALID_ARG, "m2 is required when bits > 1 (sbq/quantize.rs:73-101)");
+    }
     if (s->has_labels && s->n && (!s->label_off || (s->label_off[s->n] && !s->labels)))
         return fail(DANN_ERR_INVALID_ARG, "has_labels set but label arrays missing");
     if (s->start_default != DANN_INVALID_NODE && s->start_default >= s->n)
@@ -230,12 +245,13 @@ static int validate_snapshot(const dann_snapshot_desc *s, uint32_t *words_out) {
     return DANN_OK;
 }
 
-extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
+static int index_load_impl(const dann_snapshot_desc *s, const float *index_vectors, int device, dann_index **out) {
     dann_index *ix = nullptr;
     if (!s || !out) return fail(DANN_ERR_INVALID_ARG, "dann_index_load: NULL argument");
     *out = nullptr;
+    const bool plain = index_vectors != nullptr;
     uint32_t words = 0;
-    int vrc = validate_snapshot(s, &words);
+    int vrc = validate_snapshot(s, &words, plain);
     if (vrc) return vrc;
     int ndev = dann_device_count();
     if (ndev <= 0) return fail(DANN_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
@@ -277,16 +293,23 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
     v.count = s->count;
     v.start_default = s->n ? s->start_default : DANN_INVALID_NODE;
     v.n_start_labels = s->start_labels && s->start_label_nodes ? s->n_start_labels : 0;
-    if (pick_code_mapping(v.cw, &ix->G, &ix->Gshift, &ix->NCH) != 0)
+    if (!plain && pick_code_mapping(v.cw, &ix->G, &ix->Gshift, &ix->NCH) != 0)
         return fail(DANN_ERR_INVALID_ARG, "SBQ code of %u words is wider than this build supports", words);
+    ix->plain = plain;
 
     float *mean = nullptr, *m2 = nullptr, *vectors = nullptr;
     uint64_t *codes = nullptr, *tids = nullptr;
     uint32_t *nbrs = nullptr, *sln = nullptr, *loff = nullptr;
     int16_t *sl = nullptr, *labs = nullptr;
-    CK(upload(ix, s->mean, (size_t)s->dim_index, &mean));
-    CK(upload(ix, s->bits > 1 ? s->m2 : nullptr, (size_t)s->dim_index, &m2));
-    CK(upload_padded<uint64_t>(ix, s->codes, s->n, words, v.cw, 0ull, &codes));
+    if (plain) { /* nodes carry their f32 index vector instead of an SBQ code (plain/node.rs:17-22) */
+        float *iv = nullptr;
+        CK(upload(ix, index_vectors, (size_t)s->n * s->dim_index, &iv));
+        ix->index_vectors = iv;
+    } else {
+        CK(upload(ix, s->mean, (size_t)s->dim_index, &mean));
+        CK(upload(ix, s->bits > 1 ? s->m2 : nullptr, (size_t)s->dim_index, &m2));
+        CK(upload_padded<uint64_t>(ix, s->codes, s->n, words, v.cw, 0ull, &codes));
+    }
     CK(upload_padded<uint32_t>(ix, s->nbrs, s->n, v.R, v.Rp, DANN_INVALID_NODE, &nbrs));
     CK(upload(ix, s->heap_tid, (size_t)s->n, &tids));
     if (s->vectors) CK(upload(ix, s->vectors, (size_t)s->n * s->dim, &vectors)); /* NULL: supplied later (dann_index_set_vectors) */
@@ -335,6 +358,19 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
     return DANN_OK;
 }
 
+extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
+    return index_load_impl(s, nullptr, device, out);
+}
+
+extern "C" int dann_index_load_plain(const dann_snapshot_desc *s, const float *index_vectors, int device, dann_index **out) {
+    if (!index_vectors && s && s->n) return fail(DANN_ERR_INVALID_ARG, "dann_index_load_plain: NULL index_vectors");
+    /* Bit-exact against the oracle under the CPU SIMT emulator, not yet run on hardware: opt-in until it has been. */
+    if (env_u32("DANN_EXPERIMENTAL_PLAIN", 0) != 1)
+        return fail(DANN_ERR_INVALID_ARG, "storage_layout=plain scans are experimental: set DANN_EXPERIMENTAL_PLAIN=1");
+    static const float dummy = 0.0f;
+    return index_load_impl(s, index_vectors ? index_vectors : &dummy, device, out);
+}
+
 extern "C" uint64_t dann_index_hbm_bytes(const dann_index *ix) { return ix ? ix->hbm_bytes : 0; }
 extern "C" uint64_t dann_kernel_launches(const dann_index *ix) { return ix ? ix->launches.load() : 0; }
 extern "C" uint32_t dann_code_stride(const dann_index *ix) { return ix ? ix->v.cw : 0; }
@@ -373,6 +409,7 @@ extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int 
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_queries || !d_q_codes || B <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_prepare_queries: bad argument");
+    if (ix->plain) return fail(DANN_ERR_STATE, "dann_prepare_queries: a plain-storage index has no quantizer");
     std::lock_guard<std::mutex> lk(ix->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     rc = launch_prepare(ix, d_queries, B, d_q_full, d_q_codes, st);
@@ -417,6 +454,7 @@ extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_qcodes || !d_pair_q || !d_pair_node || !d_out) return fail(DANN_ERR_INVALID_ARG, "dann_sbq_distance: NULL buffer");
+    if (ix->plain) return fail(DANN_ERR_STATE, "dann_sbq_distance: a plain-storage index has no SBQ codes");
     if (npairs == 0) return DANN_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     switch (ix->NCH) {
@@ -471,7 +509,8 @@ static search_fn pick_search2(uint32_t nch) {
         default: return dann_search2_kernel<T, 8, HV>;
     }
 }
-static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0) {
+static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0, bool plain = false) {
+    if (plain) return dann_search_kernel<Ent64, 1, 1>;
     if (pairs && hv == 1) return entry == 0 ? pick_search2<Ent32x21, 1>(nch) : entry == 1 ? pick_search2<Ent32x16, 1>(nch) : pick_search2<Ent64, 1>(nch);
     if (pairs) return entry == 0 ? pick_search2<Ent32x21, 0>(nch) : entry == 1 ? pick_search2<Ent32x16, 0>(nch) : pick_search2<Ent64, 0>(nch);
     return entry == 0 ? pick_search<Ent32x21>(nch) : entry == 1 ? pick_search<Ent32x16>(nch) : pick_search<Ent64>(nch);
@@ -487,6 +526,7 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     in.words = ix->v.words;
     in.smem_optin = ix->smem_optin;
     in.sm_count = ix->sm_count;
+    in.plain_dim = ix->plain ? ix->v.dim_index : 0;
     char err[256];
     int rc = dann_make_plan(in, nq, L, c_target, grow, keyed, p, force_single, err, sizeof err);
     if (rc) return fail(rc, "%s", err);
@@ -497,7 +537,7 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
  * vis_out != NULL selects build mode (dann_build.cuh). */
 static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *d_labels, const int32_t *d_label_off,
                       int B, uint32_t L, uint32_t c_target, dann_query_stats *d_stats, uint64_t *vis_out,
-                      uint32_t *vis_out_len, uint32_t vis_out_cap, cudaStream_t st) {
+                      uint32_t *vis_out_len, uint32_t vis_out_cap, cudaStream_t st, const float *d_q_index = nullptr) {
     const IndexView &v = ix->v;
     uint32_t *d_ctl = ix->sc_ctl.as<uint32_t>(); /* [0]=work counter, [1]=overflow bits */
     int rc;
@@ -556,7 +596,10 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.vis_out_len = vis_out_len;
         a.vis_out_cap = vis_out_cap;
         a.hv_flags = env_u32("DANN_HV_FLAGS", 31);
-        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH, p.hv);
+        a.plain_vectors = ix->index_vectors;
+        a.q_index = d_q_index;
+        a.plain_dim = ix->plain ? v.dim_index : 0;
+        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH, p.hv, ix->plain);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);
@@ -599,6 +642,11 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
             return fail(DANN_ERR_INVALID_ARG, "k=%d rows with rescore=%d need %zu B of shared memory per scan (limit %zu): "
                         "fetch fewer rows per scan", k, rescore, need_smem, ix->smem_optin);
     }
+    if (ix->plain) {
+        if (d_label_off) return fail(DANN_ERR_INVALID_ARG, "plain storage does not support label filters (plain/storage.rs:260)");
+        /* scan.rs:392-403: a plain index only resorts when it holds fewer dimensions than the heap column */
+        if (v.dim == v.dim_index) rescore = 0;
+    }
     if (rescore > 0 && v.n && !v.vectors) return fail(DANN_ERR_STATE, "index has no heap vectors yet (dann_index_set_vectors): rescore must be 0");
     /* rows needed from the approximate stream: scan.rs:255-305 */
     const uint32_t c_target = rescore == 0 ? (uint32_t)k : (uint32_t)rescore + (uint32_t)k - 1u;
@@ -614,12 +662,21 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
 
     ix->timing = dann_batch_timing{};
     CK(cudaEventRecord(ix->ev[0], st));
-    int rc = launch_prepare(ix, d_queries, B, ix->sc_qfull.as<float>(), ix->sc_qcodes.as<uint64_t>(), st);
-    if (rc) return rc;
+    int rc;
+    if (ix->plain) {
+        CK(ix->sc_qindex.reserve((size_t)B * v.dim_index * sizeof(float)));
+        dann_prepare_plain_kernel<<<B, 128, 0, st>>>(v.dim, v.dim_index, v.distance_type == DANN_COSINE, d_queries,
+                                                    ix->sc_qfull.as<float>(), ix->sc_qindex.as<float>());
+        ix->launches++;
+        CK(cudaGetLastError());
+    } else {
+        rc = launch_prepare(ix, d_queries, B, ix->sc_qfull.as<float>(), ix->sc_qcodes.as<uint64_t>(), st);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(ix->ev[1], st));
 
     rc = run_search(ix, ix->sc_qcodes.as<uint64_t>(), d_labels, d_label_off, B, (uint32_t)L, c_target, d_stats, nullptr,
-                    nullptr, 0, st);
+                    nullptr, 0, st, ix->sc_qindex.as<float>());
     if (rc) return rc;
     CK(cudaEventRecord(ix->ev[2], st));
 
@@ -642,6 +699,11 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
     dann_rerank_kernel<<<B, 128, smem, st>>>(r);
     ix->launches++;
     CK(cudaGetLastError());
+    if (ix->plain && rescore > 0) {
+        dann_plain_stats_kernel<<<(B + 127) / 128, 128, 0, st>>>(d_stats, B);
+        ix->launches++;
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ix->ev[3], st));
     CK(cudaStreamSynchronize(st));
     float ms = 0;
@@ -783,6 +845,7 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
     IndexView &v = ix->v;
+    if (ix->plain) return fail(DANN_ERR_STATE, "dann_build_graph builds over SBQ codes: not available for a plain-storage index");
     if (v.R != DANN_BUILD_SLACK || v.Rp != DANN_BUILD_SLACK)
         return fail(DANN_ERR_INVALID_ARG, "dann_build_graph needs an index loaded with R == %u neighbour slots", DANN_BUILD_SLACK);
     if (num_neighbors < 1 || num_neighbors > (int)DANN_BUILD_SLACK) return fail(DANN_ERR_INVALID_ARG, "num_neighbors must be 1..%u", DANN_BUILD_SLACK);
@@ -953,7 +1016,7 @@ extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) {
 }
 
 static void scan_release(dann_scan *sc) {
-    DevBuf *bufs[] = {&sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
+    DevBuf *bufs[] = {&sc->d_qindex, &sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
                       &sc->d_heap_sm, &sc->d_vis, &sc->d_heap_tail, &sc->d_cnode, &sc->d_set, &sc->d_ins, &sc->d_stream,
                       &sc->d_slen, &sc->d_stats, &sc->d_dist, &sc->d_win, &sc->d_winst, &sc->d_row, &sc->d_ctl};
     for (DevBuf *b : bufs) b->release();
@@ -993,6 +1056,10 @@ extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
     const IndexView &v = ix->v;
+    if (ix->plain) {
+        if (query && nlabels >= 0) return fail(DANN_ERR_INVALID_ARG, "plain storage does not support label filters (plain/storage.rs:260)");
+        if (v.dim == v.dim_index) rescore = 0; /* scan.rs:392-403: next() instead of next_with_resort */
+    }
     if (rescore > 0 && v.n && !v.vectors) return fail(DANN_ERR_STATE, "index has no heap vectors yet: rescore must be 0");
     cudaStream_t st = ix->stream;
     const uint32_t dim = v.dim;
@@ -1030,8 +1097,16 @@ extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t
         CK(cudaMemcpyAsync(sc->d_label_off.p, off, 8, cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemsetAsync(sc->d_winst.p, 0, sizeof(ScanWindow), st));
-    rc = launch_prepare(ix, sc->d_query.as<float>(), 1, sc->d_qfull.as<float>(), sc->d_qcodes.as<uint64_t>(), st);
-    if (rc) return rc;
+    if (ix->plain) {
+        CK(sc->d_qindex.reserve((size_t)v.dim_index * 4));
+        dann_prepare_plain_kernel<<<1, 128, 0, st>>>(v.dim, v.dim_index, v.distance_type == DANN_COSINE, sc->d_query.as<float>(),
+                                                    sc->d_qfull.as<float>(), sc->d_qindex.as<float>());
+        ix->launches++;
+        CK(cudaGetLastError());
+    } else {
+        rc = launch_prepare(ix, sc->d_query.as<float>(), 1, sc->d_qfull.as<float>(), sc->d_qcodes.as<uint64_t>(), st);
+        if (rc) return rc;
+    }
     rc = scan_reset_search(sc);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
@@ -1088,7 +1163,10 @@ static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip
         a.vis_out_len = nullptr;
         a.vis_out_cap = 0;
         a.hv_flags = 0;
-        search_fn fn = pick_kernel(false, p.entry, ix->NCH);
+        a.plain_vectors = ix->index_vectors;
+        a.q_index = sc->d_qindex.as<float>();
+        a.plain_dim = ix->plain ? v.dim_index : 0;
+        search_fn fn = pick_kernel(false, p.entry, ix->NCH, 0, ix->plain);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
         fn<<<1, 32, p.per_warp, st>>>(a);
         ix->launches++;
@@ -1157,6 +1235,10 @@ extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offs
     CK(cudaStreamSynchronize(st));
     sc->win_len = ws.len;
     sc->stats.d_full = ws.d_full;
+    if (ix->plain) { /* every comparison of the beam search was a full-distance comparison (plain/storage.rs:238,288) */
+        sc->stats.d_full += sc->stats.candidates;
+        sc->stats.d_quantized = 0;
+    }
     sc->stats.stream_len = sc->streamed;
     if (!row.have) return 0;
     if (block) *block = (uint32_t)(row.tid >> 16);

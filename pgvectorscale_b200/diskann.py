@@ -64,7 +64,7 @@ STATS_DTYPE = np.dtype([("visits", "<u4"), ("d_quantized", "<u4"), ("candidates"
 
 # every symbol include/diskann_b200.h declares
 EXPORTS = [
-    "dann_last_error", "dann_device_count", "dann_index_load", "dann_index_free",
+    "dann_last_error", "dann_device_count", "dann_index_load", "dann_index_load_plain", "dann_index_free",
     "dann_index_hbm_bytes", "dann_scan_begin", "dann_scan_rescan", "dann_scan_gettuple",
     "dann_scan_stats", "dann_scan_end", "dann_search_batch", "dann_search_batch_device",
     "dann_prepare_queries", "dann_code_stride", "dann_sbq_distance", "dann_full_distance",
@@ -89,6 +89,7 @@ def load_library(path: Optional[str] = None):
     lib.dann_last_error.restype = C.c_char_p
     lib.dann_device_count.restype = C.c_int
     lib.dann_index_load.argtypes = [C.POINTER(_SnapshotDesc), C.c_int, C.POINTER(vp)]
+    lib.dann_index_load_plain.argtypes = [C.POINTER(_SnapshotDesc), vp, C.c_int, C.POINTER(vp)]
     lib.dann_index_free.argtypes = [vp]
     lib.dann_index_free.restype = None
     lib.dann_index_hbm_bytes.argtypes = [vp]
@@ -149,10 +150,12 @@ class DiskAnnIndex:
         self._lib = load_library()
         snapshot.validate()
         s = snapshot
-        if int(getattr(s, "storage_type", 0) or 0) != 0:
-            # storage_layout = plain (storage.rs:144-169) is restated in the oracle only; no CUDA scan for it yet
-            # and, as everywhere in the product path, no CPU fallback.
-            raise DiskAnnError(-1, "storage_layout=plain snapshots are not supported by the CUDA scan path")
+        plain = int(getattr(s, "storage_type", 0) or 0) != 0
+        if plain and os.environ.get("DANN_EXPERIMENTAL_PLAIN") != "1":
+            # storage_layout = plain (storage.rs:144-169): the kernel flavour exists (dann_index_load_plain) but has only
+            # been checked under CPU emulation so far; it is refused unless explicitly enabled.  No CPU fallback either way.
+            raise DiskAnnError(-1, "storage_layout=plain snapshots are not supported by the CUDA scan path "
+                                   "(experimental: set DANN_EXPERIMENTAL_PLAIN=1)")
         keep = []
 
         def arr(a, dt):
@@ -180,7 +183,14 @@ class DiskAnnIndex:
         d.label_off = arr(s.label_off, np.uint32)
         d.labels = arr(s.labels, np.int16)
         h = C.c_void_p()
-        _check(self._lib, self._lib.dann_index_load(C.byref(d), int(device), C.byref(h)))
+        if plain:
+            iv = np.ascontiguousarray(s.index_vectors, dtype=np.float32)
+            assert iv.shape == (s.n, s.dim_index)
+            keep.append(iv)
+            _check(self._lib, self._lib.dann_index_load_plain(C.byref(d), C.c_void_p(iv.ctypes.data), int(device),
+                                                              C.byref(h)))
+        else:
+            _check(self._lib, self._lib.dann_index_load(C.byref(d), int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
         self.n, self.dim, self.dim_index = s.n, s.dim, s.dim_index

@@ -28,7 +28,7 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-DDANN_SIMT_EMU", "-Wall", "-Wno-unknown-pragmas",
-           "-Wno-unused-function", "-Wno-unused-variable", "-Wno-sign-compare", "-fno-omit-frame-pointer",
+           "-Wno-unused-function", "-Wno-unused-variable", "-Wno-sign-compare", "-fno-omit-frame-pointer", "-ffp-contract=off",
            "-I", os.path.join(HERE, "shim"), "-I", CSRC, "-x", "c++"] + sources() + ["-o", OUT]
     subprocess.run(cmd, check=True)
     return OUT

@@ -57,13 +57,21 @@ def _desc(s):
     return d, keep
 
 
-def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148, smem_optin=232448, env=None):
+def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148, smem_optin=232448, env=None,
+           q_index=None):
     """Approximate streams of B prepared queries through the emulated search kernel.
     labels: None, or a list (one entry per query) of sorted, de-duplicated label lists.
     env: DANN_* test knobs applied around the call (the plan reads them with getenv).
     -> (streams: list of np.uint32 arrays, stats: list of dicts, info dict)"""
-    q_codes = np.ascontiguousarray(q_codes, dtype=np.uint64).reshape(-1, s.words)
-    B = q_codes.shape[0]
+    plain = q_index is not None   # plain storage layout: the kernel reads s.index_vectors / q_index, no codes
+    if plain:
+        q_index = np.ascontiguousarray(q_index, dtype=np.float32).reshape(-1, s.dim_index)
+        iv = np.ascontiguousarray(s.index_vectors, dtype=np.float32)
+        B = q_index.shape[0]
+        q_codes = np.zeros((B, max(s.words, 1)), np.uint64)
+    else:
+        q_codes = np.ascontiguousarray(q_codes, dtype=np.uint64).reshape(-1, s.words)
+        B = q_codes.shape[0]
     d, keep = _desc(s)
     qlab = qoff = None
     if labels is not None:
@@ -88,7 +96,9 @@ def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148
                               C.c_void_p(qoff.ctypes.data) if qoff is not None else None,
                               C.c_uint32(B), C.c_uint32(L), C.c_uint32(c_target), C.c_int(1 if single_warp else 0),
                               C.c_uint32(sm_count), C.c_uint32(smem_optin), C.c_void_p(stream.ctypes.data),
-                              C.c_void_p(slen.ctypes.data), stats, C.byref(info))
+                              C.c_void_p(slen.ctypes.data), stats, C.byref(info),
+                              C.c_void_p(iv.ctypes.data) if plain else None,
+                              C.c_void_p(q_index.ctypes.data) if plain else None)
     finally:
         for k, v in old.items():
             if v is None:

@@ -32,7 +32,8 @@ static emu_kernel pick2(uint32_t nch) {
         default: return nullptr;
     }
 }
-static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv) {
+static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv, bool plain = false) {
+    if (plain) return dann_search_kernel<Ent64, 1, 1>;
     if (pairs && hv == 1) return entry == 0 ? pick2<Ent32x21, 1>(nch) : entry == 1 ? pick2<Ent32x16, 1>(nch) : pick2<Ent64, 1>(nch);
     if (pairs) return entry == 0 ? pick2<Ent32x21, 0>(nch) : entry == 1 ? pick2<Ent32x16, 0>(nch) : pick2<Ent64, 0>(nch);
     return entry == 0 ? pick1<Ent32x21>(nch) : entry == 1 ? pick1<Ent32x16>(nch) : pick1<Ent64>(nch);
@@ -52,7 +53,8 @@ struct emu_info {
 extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, const int16_t *qlab, const int32_t *qoff,
                           uint32_t B, uint32_t L, uint32_t c_target, int force_single, uint32_t sm_count,
                           uint32_t smem_optin, uint32_t *stream, uint32_t *stream_len, dann_query_stats *stats,
-                          emu_info *info) {
+                          emu_info *info, const float *index_vectors, const float *q_index) {
+    const bool plain = index_vectors != nullptr; /* plain storage layout: q_codes / s->codes are not read */
     IndexView v{};
     v.n = s->n;
     v.dim = s->dim;
@@ -68,14 +70,14 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
     v.start_default = s->n ? s->start_default : DANN_INVALID_NODE;
     v.n_start_labels = s->start_labels && s->start_label_nodes ? s->n_start_labels : 0;
     uint32_t G = 1, Gshift = 0, NCH = 1;
-    if (pick_code_mapping(v.cw, &G, &Gshift, &NCH) != 0) {
+    if (!plain && pick_code_mapping(v.cw, &G, &Gshift, &NCH) != 0) {
         g_emu_err = "code too wide";
         return DANN_ERR_INVALID_ARG;
     }
     /* HBM layout of dann_index_load: padded code rows and neighbour rows (16-byte aligned like cudaMalloc) */
     std::vector<ulonglong2> codes_store(((size_t)s->n * v.cw + 1) / 2 + 1);
     uint64_t *codes = reinterpret_cast<uint64_t *>(codes_store.data());
-    for (size_t i = 0; i < s->n; i++)
+    for (size_t i = 0; i < s->n && !plain; i++)
         for (uint32_t w = 0; w < v.cw; w++) codes[i * v.cw + w] = w < s->words ? s->codes[i * s->words + w] : 0ull;
     std::vector<uint32_t> nbrs((size_t)s->n * v.Rp + 4, DANN_INVALID_NODE);
     uint32_t lists_unique = 1;
@@ -88,7 +90,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
     if (s->R > 64) lists_unique = 0;
     std::vector<ulonglong2> q_store(((size_t)B * v.cw + 1) / 2 + 1);
     uint64_t *qc = reinterpret_cast<uint64_t *>(q_store.data());
-    for (size_t b = 0; b < B; b++)
+    for (size_t b = 0; b < B && !plain; b++)
         for (uint32_t w = 0; w < v.cw; w++) qc[b * v.cw + w] = w < s->words ? q_codes[b * s->words + w] : 0ull;
     v.codes = codes;
     v.nbrs = nbrs.data();
@@ -108,6 +110,18 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
     in.words = v.words;
     in.smem_optin = smem_optin;
     in.sm_count = (int)sm_count;
+    in.plain_dim = plain ? s->dim_index : 0;
+    /* 16-byte aligned copies of the f32 rows, like cudaMalloc'ed memory */
+    std::vector<float4> iv_store, qi_store;
+    const float *ivp = nullptr, *qip = nullptr;
+    if (plain) {
+        iv_store.resize(((size_t)s->n * s->dim_index + 3) / 4 + 1);
+        qi_store.resize(((size_t)B * s->dim_index + 3) / 4 + 1);
+        memcpy(iv_store.data(), index_vectors, (size_t)s->n * s->dim_index * 4);
+        memcpy(qi_store.data(), q_index, (size_t)B * s->dim_index * 4);
+        ivp = reinterpret_cast<const float *>(iv_store.data());
+        qip = reinterpret_cast<const float *>(qi_store.data());
+    }
 
     std::vector<uint32_t> qlist;
     uint32_t nq = B, grow = 1, retries = 0;
@@ -161,7 +175,10 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.Gshift = Gshift;
         a.per_warp_smem = p.per_warp;
         a.hv_flags = env_u32("DANN_HV_FLAGS", 31);
-        emu_kernel fn = pick(p.pairs, p.entry, NCH, p.hv);
+        a.plain_vectors = ivp;
+        a.q_index = qip;
+        a.plain_dim = in.plain_dim;
+        emu_kernel fn = pick(p.pairs, p.entry, NCH, p.hv, plain);
         if (!fn) {
             g_emu_err = "this code width is not instantiated in the emulator build";
             return DANN_ERR_INVALID_ARG;
@@ -216,6 +233,7 @@ extern "C" int emu_plan(uint32_t n, uint32_t R, uint32_t words, uint32_t nq, uin
     in.words = words;
     in.smem_optin = smem_optin;
     in.sm_count = (int)sm_count;
+    in.plain_dim = 0;
     SearchPlan p{};
     char err[256];
     int rc = dann_make_plan(in, nq, L, c_target, grow, keyed != 0, &p, force_single != 0, err, sizeof err);

@@ -155,6 +155,12 @@ template <typename T>
 inline T __ldcg(const T *p) {
     return *p;
 }
+/* explicit-rounding f32 arithmetic: plain IEEE ops (the emulator is built with -ffp-contract=off) */
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
 

@@ -222,6 +222,48 @@ def test_emulated_heap_engine_root_handover_at_leaf_level_change(emu, monkeypatc
             assert heap == want_heap and pops[:len(want_pops)].tolist() == want_pops
 
 
+# ---- plain storage layout: SearchWarp<Ent64, 1, PLAIN=1> (f32 keys, exact distances inside the beam search) ----
+def qindex(s, queries):
+    out = []
+    for x in queries:
+        v = np.array(x[:s.dim_index], np.float32)
+        if s.distance_type == COSINE:
+            v = oracle.preprocess_cosine(v)
+        out.append(v)
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("dist,dim,dim_index", [(COSINE, 64, None), (L2, 64, None), (COSINE, 96, 40), (L2, 70, 38),
+                                                (L2, 33, None), (COSINE, 20, 7)])
+def test_emulated_plain_storage_scan_equals_oracle(emu, monkeypatch, dist, dim, dim_index):
+    """Vector widths with and without whole 32-element strides, multiples of 4 or not (vector vs scalar loads, the
+    scalar tail), truncated index slices; deleted tuples; all three lane schedules."""
+    s = fixtures.to_plain(build_case(500, dim, dist, seed=3 + dim, kind="normal", R=24, L_build=48, deleted_every=11,
+                                     dim_index=dim_index))
+    q = fixtures.gen_vectors(4, dim, 9, "normal")
+    for sched in (0, 1, 2):
+        monkeypatch.setenv("SIMT_SCHED", str(sched))
+        streams, st, info = emu.search(s, None, 30, 40, q_index=qindex(s, q))
+        assert info["entry"] == 2 and info["pairs"] == 0
+        for b in range(len(q)):
+            r = oracle.scan(s, q[b], None, 30, 0, 40)
+            assert streams[b].tolist() == r["node"].tolist()
+            assert st[b]["d_quantized"] == 0 and st[b]["status"] == 0
+            # rescore=0 in the oracle call: its d_full is exactly the beam search's comparisons
+            for f in ("visits", "candidates", "d_full", "stream_len"):
+                assert st[b][f] == r["stats"][f], f
+
+
+def test_emulated_plain_storage_tail_and_retries(emu):
+    s = fixtures.to_plain(build_case(900, 48, L2, seed=15, kind="normal", R=32, L_build=64))
+    q = fixtures.gen_vectors(3, 48, 4, "normal")
+    streams, st, info = emu.search(s, None, 60, 120, q_index=qindex(s, q),
+                                   env={"DANN_SEARCH_HS": 32, "DANN_DEBUG_SHRINK": 16, "DANN_SEARCH_BITMAP": 0})
+    assert info["retries"] >= 1 and info["hs"] == 32 and info["bitmap_words"] == 0
+    for b in range(len(q)):
+        assert streams[b].tolist() == oracle.scan(s, q[b], None, 60, 0, 120)["node"].tolist()
+
+
 # ---- the workspace plan itself (host logic of diskann_b200.cu, shared through dann_plan.h) ----------------
 def test_plan_benchmark_shape_is_one_wave_of_seven_pairs(emu):
     p = emu.plan(n=1_000_000, R=64, words=24, nq=1024, L=150, c_target=259)

@@ -59,3 +59,54 @@ def test_heap_engine_v2_labels(lib, heap_v2):
         q = _queries(s, 64, 9, "uniform")
         labels = [[int(x) for x in rng.integers(1, 17, size=int(rng.integers(1, 4)))] for _ in range(64)]
         _compare_batch(s, idx, q, k=10, L=100, rescore=50, labels=labels)
+
+
+# ---- plain storage layout (dann_index_load_plain, DANN_EXPERIMENTAL_PLAIN=1) ------------------------------------
+def _compare_plain(s, idx, q, k, L, rescore):
+    from oracle import oracle
+    g = idx.search_batch(q, k=k, search_list_size=L, rescore=rescore)
+    for b in range(q.shape[0]):
+        r = oracle.scan(s, q[b], None, L, rescore, k)
+        n = len(r["tid"])
+        assert int(g["count"][b]) == n
+        assert g["tid"][b, :n].tolist() == r["tid"].tolist()
+        if rescore and s.dim != s.dim_index:       # scan.rs:392-403: only then is there a rerank and a distance
+            assert g["dist"][b, :n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
+        for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len"):
+            assert int(g["stats"][f][b]) == r["stats"][f], f
+
+
+@pytest.mark.parametrize("dist,dim,dim_index", [(COSINE, 768, None), (L2, 256, None), (COSINE, 256, 100), (L2, 70, 38)])
+def test_plain_storage_batch_and_scan_match_oracle(lib, monkeypatch, dist, dim, dim_index):
+    from oracle import fixtures, oracle
+    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
+    s = fixtures.to_plain(build_case(2000, dim, dist, seed=8, kind="normal", R=32, L_build=64, deleted_every=13,
+                                     dim_index=dim_index))
+    q = _queries(s, 24, 5)
+    with lib.DiskAnnIndex(s) as idx:
+        _compare_plain(s, idx, q, k=10, L=50, rescore=20)
+        _compare_plain(s, idx, q[:8], k=15, L=20, rescore=0)
+        scan = idx.begin_scan()                       # the streaming operator, counters after every row
+        scan.rescan(q[0], search_list_size=40, rescore=10)
+        want = oracle.scan(s, q[0], None, 40, 10, 30)
+        got = []
+        for _ in range(30):
+            row = scan.gettuple()
+            if row is None:
+                break
+            got.append((row[0] << 16) | row[1])
+        assert got == want["tid"].tolist()
+        st = scan.stats()
+        for f in ("visits", "d_quantized", "candidates", "d_full"):
+            assert st[f] == want["stats"][f], f
+        scan.end()
+        with pytest.raises(lib.DiskAnnError, match="label"):
+            idx.search_batch(q[:2], labels=[[1], [2]], k=5)
+
+
+def test_plain_storage_is_refused_without_the_opt_in(lib, monkeypatch):
+    from oracle import fixtures
+    monkeypatch.delenv("DANN_EXPERIMENTAL_PLAIN", raising=False)
+    s = fixtures.to_plain(build_case(64, 16, L2, seed=2, R=8, L_build=16))
+    with pytest.raises(lib.DiskAnnError, match="plain"):
+        lib.DiskAnnIndex(s)
