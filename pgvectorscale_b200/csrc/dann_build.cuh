@@ -175,7 +175,7 @@ __device__ __forceinline__ void build_write_list(const BuildArgs &a, uint32_t p,
 __global__ void __launch_bounds__(256) dann_build_prune_kernel(BuildArgs a, uint32_t lo, uint32_t m,
                                                                const uint64_t *vis, const uint32_t *vis_len,
                                                                uint32_t vis_cap, uint64_t *trip_key, uint32_t *trip_val) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     uint64_t *ck, *cc;
     float *mf;
@@ -246,7 +246,7 @@ __global__ void dann_build_heads_kernel(const uint64_t *key, size_t total, uint3
  * that would outgrow the slack is pruned back to R (graph/mod.rs:212-266 add_neighbors) */
 __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, const uint64_t *key, const uint32_t *val,
                                                                   size_t total, const uint32_t *heads, uint32_t nheads) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     uint64_t *ck, *cc;
     float *mf;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, c
 
 /* finalize_index_build (build.rs:905-960): lists longer than R are pruned to R */
 __global__ void __launch_bounds__(256) dann_build_finalize_kernel(BuildArgs a) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     uint64_t *ck, *cc;
     float *mf;

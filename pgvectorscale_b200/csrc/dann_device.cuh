@@ -18,6 +18,16 @@
 
 #define DANN_FULL 0xFFFFFFFFu
 
+/* the kernel's dynamic shared memory window; static __shared__ variables are spelled DANN_STATIC_SMEM so that the CPU
+ * SIMT emulator (tests/simt, -DDANN_SIMT_EMU) can give both a meaning without touching the CUDA build */
+#ifdef DANN_SIMT_EMU
+#define DANN_DYN_SMEM(name) extern unsigned char name[]
+#define DANN_STATIC_SMEM static
+#else
+#define DANN_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define DANN_STATIC_SMEM __shared__
+#endif
+
 // per-query internal status bits (retried by the host with a larger workspace)
 #define DANN_ST_HEAP 1u
 #define DANN_ST_HASH 2u

@@ -54,9 +54,9 @@ __device__ __forceinline__ uint32_t sbq_count_ones(float v, float mean, float m2
  * sbq/mod.rs:145-148 (quantize the index copy). */
 __global__ void __launch_bounds__(128) dann_prepare_kernel(IndexView ix, const float *queries, int B,
                                                            float *q_full_out, uint64_t *q_codes_out) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     float *qi = reinterpret_cast<float *>(dann_smem); /* [dim_index] normalised index copy */
-    __shared__ float s_div[2];
+    DANN_STATIC_SMEM float s_div[2];
     const int q = blockIdx.x;
     const float *src = queries + (size_t)q * ix.dim;
     const bool cosine = ix.distance_type == DANN_COSINE;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) dann_prepare_kernel(IndexView ix, const f
 __global__ void __launch_bounds__(128) dann_prepare_plain_kernel(uint32_t dim, uint32_t dim_index, int cosine,
                                                                  const float *queries, float *q_full_out,
                                                                  float *q_index_out) {
-    __shared__ float s_div[2];
+    DANN_STATIC_SMEM float s_div[2];
     const int q = blockIdx.x;
     const float *src = queries + (size_t)q * dim;
     if (cosine) {
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(512) dann_sbq_distance_kernel(const uint64_t *
 }
 
 /* ---- 1-D TMA bulk copy (cp.async.bulk) of one query row into shared memory ---------- */
+#ifndef DANN_SIMT_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -229,16 +230,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         : "memory");
 }
 
+#endif /* !DANN_SIMT_EMU */
+
 /* Stage query row `src` [n floats] into shared `dst`: TMA bulk copy when the row is a
  * multiple of 16 B and 16-B aligned, plain loads otherwise.  Block-wide. */
 __device__ __forceinline__ void stage_query_row(float *dst, const float *src, uint32_t n, uint64_t *bar) {
+#ifndef DANN_SIMT_EMU
     const bool tma_ok = (n & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
     if (tma_ok) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) tma_load_1d(dst, src, n * 4u, bar);
         mbar_wait(bar, 0);
-    } else {
+    } else
+#else
+    (void)bar; /* no TMA under the CPU emulator: the plain-copy branch below */
+#endif
+    {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
@@ -247,9 +255,9 @@ __device__ __forceinline__ void stage_query_row(float *dst, const float *src, ui
 /* out[b*m+i] = distance_fn(vectors[nodes[b*m+i]], q_full[b]) ; one CTA per query */
 __global__ void __launch_bounds__(128) dann_full_distance_kernel(IndexView ix, const float *q_full,
                                                                  const uint32_t *nodes, int m, float *out) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     float *qs = reinterpret_cast<float *>(dann_smem);
-    __shared__ uint64_t bar;
+    DANN_STATIC_SMEM uint64_t bar;
     const int q = blockIdx.x;
     stage_query_row(qs, q_full + (size_t)q * ix.dim, ix.dim, &bar);
     const uint32_t lane = threadIdx.x & 31, mm = lane & 7, gbase = lane & 24;
@@ -287,13 +295,13 @@ struct RerankArgs {
 };
 
 __global__ void __launch_bounds__(128) dann_rerank_kernel(const RerankArgs a) {
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const IndexView &ix = a.ix;
     float *qs = reinterpret_cast<float *>(dann_smem);                    /* [dim rounded to 4] */
     const uint32_t dim4 = (ix.dim + 3u) & ~3u;
     float *ds = qs + dim4;                                              /* [c_target] */
     uint64_t *hp = reinterpret_cast<uint64_t *>(ds + ((a.c_target + 1u) & ~1u)); /* [rescore] */
-    __shared__ uint64_t bar;
+    DANN_STATIC_SMEM uint64_t bar;
     const int q = blockIdx.x;
     const uint32_t sl = a.stream_len[q];
     const uint32_t *st = a.stream + (size_t)q * a.c_target;
@@ -358,8 +366,8 @@ __global__ void __launch_bounds__(128) dann_rerank_kernel(const RerankArgs a) {
 /* (sequential sum per row).  Each warp takes 32 rows: coalesced 128-B row segments go     */
 /* through a padded shared tile so that every lane runs the sequential chain of one row.  */
 __global__ void __launch_bounds__(256) dann_normalize_rows_kernel(float *vectors, uint32_t n, uint32_t dim) {
-    __shared__ float tile[8][32][33];
-    __shared__ float divs[8][32];
+    DANN_STATIC_SMEM float tile[8][32][33];
+    DANN_STATIC_SMEM float divs[8][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblocks32 = (n + 31) / 32;
     for (uint32_t blk = blockIdx.x * 8 + warp; blk < nblocks32; blk += gridDim.x * 8) {

@@ -584,7 +584,7 @@ struct SearchWarp {
 template <typename T, int NCH, int PLAIN = 0>
 __global__ void __launch_bounds__(384, 1) dann_search_kernel(const SearchArgs a) {
     using E = typename T::E;
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const uint32_t slot = blockIdx.x * W + warp;
     unsigned char *base = dann_smem + (size_t)warp * a.per_warp_smem;

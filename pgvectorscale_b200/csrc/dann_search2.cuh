@@ -731,7 +731,7 @@ struct PairSearch {
 template <typename T, int NCH, int HV = 0>
 __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a) {
     using E = typename T::E;
-    extern __shared__ __align__(16) unsigned char dann_smem[];
+    DANN_DYN_SMEM(dann_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, role = warp & 1;
     const int P = blockDim.x >> 6;
     const uint32_t slot = blockIdx.x * P + pair;

@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "_build", "libemu_search.so")
 
 
 def sources():
-    return [os.path.join(HERE, "emu_search.cpp"), os.path.join(HERE, "simt_emu.cpp")]
+    return [os.path.join(HERE, "emu_search.cpp"), os.path.join(HERE, "emu_kernels.cpp"), os.path.join(HERE, "simt_emu.cpp")]
 
 
 def is_stale():

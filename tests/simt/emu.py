@@ -148,3 +148,60 @@ def heap_script(ops, entry=0, hv=0, hs=64, cap=1 << 16):
     sh = KSHIFT[entry]
     heap = [(int(e) >> sh, int(e) & ((1 << sh) - 1)) for e in out[:int(olen[0])]]
     return heap, pops
+
+
+def prepare(s, queries):
+    """dann_prepare_kernel under emulation -> (q_full [B, dim], q_codes [B, words])"""
+    queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, s.dim)
+    B = queries.shape[0]
+    d, keep = _desc(s)
+    q_full = np.zeros((B, s.dim), np.float32)
+    q_codes = np.zeros((B, s.words), np.uint64)
+    rc = lib().emu_prepare(C.byref(d), C.c_void_p(queries.ctypes.data), C.c_int(B), C.c_void_p(q_full.ctypes.data),
+                           C.c_void_p(q_codes.ctypes.data))
+    assert rc == 0
+    return q_full, q_codes
+
+
+def prepare_plain(s, queries):
+    """dann_prepare_plain_kernel under emulation -> (q_full [B, dim], q_index [B, dim_index])"""
+    queries = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, s.dim)
+    B = queries.shape[0]
+    q_full = np.zeros((B, s.dim), np.float32)
+    q_index = np.zeros((B, s.dim_index), np.float32)
+    rc = lib().emu_prepare_plain(C.c_uint32(s.dim), C.c_uint32(s.dim_index), C.c_int(int(s.distance_type == 0)),
+                                 C.c_void_p(queries.ctypes.data), C.c_int(B), C.c_void_p(q_full.ctypes.data),
+                                 C.c_void_p(q_index.ctypes.data))
+    assert rc == 0
+    return q_full, q_index
+
+
+def rerank(s, q_full, streams, c_target, k, rescore, stats=None, plain=False):
+    """dann_rerank_kernel (after dann_normalize_rows_kernel for cosine) under emulation.
+    -> dict(tid [B,k], dist [B,k], node [B,k], count [B], d_full [B])"""
+    B = len(streams)
+    d, keep = _desc(s)
+    q_full = np.ascontiguousarray(q_full, dtype=np.float32)
+    st = np.full((B, max(c_target, 1)), 0xFFFFFFFF, np.uint32)
+    sl = np.zeros(B, np.uint32)
+    for b, x in enumerate(streams):
+        st[b, :len(x)] = x
+        sl[b] = len(x)
+    tid = np.zeros((B, k), np.uint64)
+    dist = np.zeros((B, k), np.float32)
+    node = np.zeros((B, k), np.uint32)
+    count = np.zeros(B, np.uint32)
+    qs = (_QueryStats * B)()
+    if stats is not None:
+        for b in range(B):
+            for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len", "status"):
+                setattr(qs[b], f, stats[b][f])
+    rc = lib().emu_rerank(C.byref(d), C.c_void_p(q_full.ctypes.data), C.c_void_p(st.ctypes.data), C.c_void_p(sl.ctypes.data),
+                          C.c_int(B), C.c_uint32(c_target), C.c_uint32(k), C.c_uint32(rescore), C.c_void_p(tid.ctypes.data),
+                          C.c_void_p(dist.ctypes.data), C.c_void_p(node.ctypes.data), C.c_void_p(count.ctypes.data), qs)
+    assert rc == 0
+    if plain and rescore > 0:
+        assert lib().emu_plain_stats(qs, C.c_int(B)) == 0
+    return dict(tid=tid, dist=dist, node=node, count=count,
+                stats=[{f: getattr(qs[b], f) for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len")}
+                       for b in range(B)])

@@ -12,6 +12,7 @@
 // collectives (legal under independent thread scheduling), which flags code that silently relies on
 // warp-synchronous execution.  Not modelled: memory ordering weaker than sequential consistency, timing.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -161,6 +162,8 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { return __builtin_sqrtf(a); } /* IEEE sqrt is correctly rounded */
+inline float __ull2float_rn(unsigned long long v) { return (float)v; }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
 

@@ -264,6 +264,67 @@ def test_emulated_plain_storage_tail_and_retries(emu):
         assert streams[b].tolist() == oracle.scan(s, q[b], None, 60, 0, 120)["node"].tolist()
 
 
+# ---- a whole dann_search_batch call replayed on the CPU: prepare -> search -> rerank kernels under emulation ------
+def _batch_under_emulation(emu, s, q, k, L, rescore, labels=None, plain=False, env=None):
+    """Mirrors search_batch_device_locked (diskann_b200.cu): same kernels, same order, same stream/rerank sizes."""
+    if plain and s.dim == s.dim_index:
+        rescore = 0                                         # scan.rs:392-403
+    c_target = k if rescore == 0 else rescore + k - 1       # scan.rs:255-305
+    if plain:
+        q_full, q_index = emu.prepare_plain(s, q)
+        streams, st, _ = emu.search(s, None, L, c_target, q_index=q_index, env=env)
+    else:
+        q_full, q_codes = emu.prepare(s, q)
+        norm = None if labels is None else [sorted(set(int(x) for x in ls)) for ls in labels]
+        streams, st, _ = emu.search(s, q_codes, L, c_target, labels=norm, env=env)
+    return emu.rerank(s, q_full, streams, c_target, k, rescore, stats=st, plain=plain)
+
+
+def _assert_batch_equals_oracle(s, q, g, k, L, rescore, labels=None, dist_bits=True):
+    for b in range(len(q)):
+        r = oracle.scan(s, q[b], None if labels is None else labels[b], L, rescore, k)
+        n = len(r["tid"])
+        assert int(g["count"][b]) == n
+        assert g["tid"][b, :n].tolist() == r["tid"].tolist()
+        assert g["node"][b, :n].tolist() == r["node"].tolist()
+        if dist_bits:
+            assert g["dist"][b, :n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
+        for f in ("visits", "d_quantized", "candidates", "d_full", "stream_len"):
+            assert g["stats"][b][f] == r["stats"][f], f
+
+
+@pytest.mark.parametrize("dist,bits,dim,dim_index", [(COSINE, 2, 96, None), (L2, 1, 70, None), (IP, 2, 64, 40),
+                                                     (COSINE, 2, 48, 33)])
+def test_emulated_whole_batch_call_equals_oracle(emu, dist, bits, dim, dim_index):
+    """Row ids, rerank distance BITS and every counter of a full batch call, with no GPU in the box."""
+    s = build_case(600, dim, dist, bits=bits, seed=7 + dim, kind="normal", R=24, L_build=48, deleted_every=9,
+                   dim_index=dim_index)
+    q = fixtures.gen_vectors(4, dim, 21, "normal")
+    for (k, L, rescore) in ((10, 30, 20), (5, 10, 0), (12, 40, 64)):
+        g = _batch_under_emulation(emu, s, q, k, L, rescore)
+        _assert_batch_equals_oracle(s, q, g, k, L, rescore, dist_bits=rescore > 0)
+
+
+def test_emulated_whole_batch_call_with_label_keys(emu):
+    s = build_case(700, 48, L2, seed=31, kind="normal", R=24, L_build=48, labels=True, deleted_every=13)
+    q = fixtures.gen_vectors(4, 48, 3, "normal")
+    labs = [[3], [7, 1, 7], [], [16, 2, 9, 4]]
+    g = _batch_under_emulation(emu, s, q, 10, 30, 25, labels=labs)
+    _assert_batch_equals_oracle(s, q, g, 10, 30, 25, labels=labs)
+
+
+@pytest.mark.parametrize("dist,dim,dim_index", [(COSINE, 64, None), (L2, 70, 38), (COSINE, 96, 40)])
+def test_emulated_whole_plain_storage_batch_call_equals_oracle(emu, dist, dim, dim_index):
+    """Plain layout end to end: plain prepare kernel, PLAIN search kernel, rerank only when the index slice is
+    shorter than the heap vector, counters d_quantized = 0 / d_full = candidates + reranked."""
+    s = fixtures.to_plain(build_case(500, dim, dist, seed=5 + dim, kind="normal", R=24, L_build=48, deleted_every=11,
+                                     dim_index=dim_index))
+    q = fixtures.gen_vectors(4, dim, 17, "normal")
+    for (k, L, rescore) in ((10, 30, 20), (8, 15, 0)):
+        g = _batch_under_emulation(emu, s, q, k, L, rescore, plain=True)
+        _assert_batch_equals_oracle(s, q, g, k, L, rescore, dist_bits=rescore > 0 and s.dim != s.dim_index)
+
+
 # ---- the workspace plan itself (host logic of diskann_b200.cu, shared through dann_plan.h) ----------------
 def test_plan_benchmark_shape_is_one_wave_of_seven_pairs(emu):
     p = emu.plan(n=1_000_000, R=64, words=24, nq=1024, L=150, c_target=259)
