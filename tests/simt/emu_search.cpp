@@ -140,10 +140,32 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
             return DANN_ERR_CAPACITY;
         }
         const size_t slots = (size_t)p.grid * p.W;
-        std::vector<uint4> hash_store(p.bitmap_words ? 1 : slots * p.hash_cap / 4 + 1);
-        std::vector<uint32_t> cand(slots * p.cand_cap), bitmap(slots * (size_t)p.bitmap_words + 1, 0u),
-            ins(p.bitmap_words ? slots * (size_t)p.ins_cap : 1);
-        std::vector<ulonglong2> heap_store(slots * p.cand_cap * (size_t)p.esize / 16 + 1);
+        /* every workspace array sits between two guard zones that must come back untouched: an out-of-bounds
+         * store of a kernel (heap tail, seq->node table, inserted-id list, hash set, stream) fails the run */
+        const size_t GUARD = 256; /* bytes, keeps 16-byte alignment */
+        struct Guarded {
+            std::vector<ulonglong2> mem;
+            size_t bytes = 0;
+            void init(size_t nbytes, unsigned char fill) {
+                bytes = nbytes;
+                mem.assign((nbytes + 2 * 256 + 15) / 16 + 1, ulonglong2{0, 0});
+                memset(mem.data(), 0xA5, mem.size() * 16);
+                memset(reinterpret_cast<unsigned char *>(mem.data()) + 256, fill, nbytes);
+            }
+            unsigned char *p() { return reinterpret_cast<unsigned char *>(mem.data()) + 256; }
+            bool intact() const {
+                const unsigned char *b = reinterpret_cast<const unsigned char *>(mem.data());
+                for (size_t i = 0; i < 256; i++)
+                    if (b[i] != 0xA5 || b[256 + bytes + i] != 0xA5) return false;
+                return true;
+            }
+        } g_hash, g_cand, g_bitmap, g_ins, g_heap;
+        (void)GUARD;
+        g_hash.init(p.bitmap_words ? 16 : slots * (size_t)p.hash_cap * 4, 0);
+        g_cand.init(slots * (size_t)p.cand_cap * 4, 0);
+        g_bitmap.init(slots * (size_t)p.bitmap_words * 4 + 16, 0);
+        g_ins.init(p.bitmap_words ? slots * (size_t)p.ins_cap * 4 : 16, 0);
+        g_heap.init(slots * (size_t)p.cand_cap * p.esize, 0);
         ctl[0] = ctl[1] = 0;
         SearchArgs a{};
         a.ix = v;
@@ -159,16 +181,16 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.stats = stats;
         a.overflow = ctl + 1;
         a.counter = ctl;
-        a.hash = reinterpret_cast<uint32_t *>(hash_store.data());
+        a.hash = reinterpret_cast<uint32_t *>(g_hash.p());
         a.hash_cap = p.hash_cap;
-        a.bitmap = bitmap.data();
+        a.bitmap = reinterpret_cast<uint32_t *>(g_bitmap.p());
         a.bitmap_words = p.bitmap_words;
-        a.ins_list = ins.data();
+        a.ins_list = reinterpret_cast<uint32_t *>(g_ins.p());
         a.ins_cap = p.ins_cap;
         a.lists_unique = lists_unique;
-        a.cand_node = cand.data();
+        a.cand_node = reinterpret_cast<uint32_t *>(g_cand.p());
         a.cand_cap = p.cand_cap;
-        a.heap_tail = heap_store.data();
+        a.heap_tail = g_heap.p();
         a.hs = p.hs;
         a.vcap = p.vcap;
         a.G = G;
@@ -184,11 +206,15 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
             return DANN_ERR_INVALID_ARG;
         }
         simt::launch(p.grid, p.W * (p.pairs ? 64 : 32), [&] { fn(a); });
-        for (uint32_t w : bitmap)
-            if (w) {
+        for (size_t i = 0; i < slots * (size_t)p.bitmap_words; i++)
+            if (a.bitmap[i]) {
                 g_emu_err = "inserted-set bitmap not clean after the launch";
                 return DANN_ERR_STATE;
             }
+        if (!g_hash.intact() || !g_cand.intact() || !g_bitmap.intact() || !g_ins.intact() || !g_heap.intact()) {
+            g_emu_err = "a kernel wrote outside one of its workspace arrays (guard zone damaged)";
+            return DANN_ERR_STATE;
+        }
         if (ctl[1] == 0) break;
         if (ctl[1] & DANN_ST_INTERNAL) {
             g_emu_err = "next-node prediction mismatch";
