@@ -1,0 +1,23 @@
+#!/bin/bash
+# First GPU call of the next round: hardware verdict on everything that was written after this round's GPU minutes
+# were spent (bit-exact under CPU emulation only so far), then the A/B timing that decides what becomes the default.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Output lands in gpurun_out/ (r2_*.log / .json / .ncu-rep).
+mkdir -p gpurun_out
+# 1. regular parity suite must still be green (default kernels are byte-identical, profiles/r01_sass_signature.txt)
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>&1; tail -2 gpurun_out/r2_gpu_tests.log
+# 2. the opt-in paths: heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout
+DANN_RUN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q > gpurun_out/r2_experimental.log 2>&1
+tail -3 gpurun_out/r2_experimental.log
+# 3. A/B timing on the benchmark fixture at the benchmark's operating point, each alternative alone
+python tools/make_snapshot.py --out /tmp/snap > gpurun_out/r2_mk.log 2>&1; tail -1 gpurun_out/r2_mk.log
+timeout 600 python tools/hv_ab.py --snap /tmp/snap --L 150 --rescore 250 --steps 20 > gpurun_out/r2_hv_ab.jsonl 2> gpurun_out/r2_hv_ab.err
+cat gpurun_out/r2_hv_ab.jsonl
+# 4. bench lines: default, and the full HV=1 flavour
+timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.log
+DANN_HEAP_V2=1 timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/r2_bench_hv1.json 2> gpurun_out/r2_bench_hv1.log
+cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_hv1.json
+# 5. one ncu capture of the HV=1 kernel (source-level stalls) for the profile-driven next step
+DANN_HEAP_V2=1 timeout 900 ncu --set full --import-source on --clock-control none -k regex:dann_search2_kernel -c 1 \
+    -o gpurun_out/r2_search2_hv1 python tools/profile_search.py --snap /tmp/snap --L 150 --rescore 250 --steps 2 \
+    > gpurun_out/r2_ncu.log 2>&1; tail -2 gpurun_out/r2_ncu.log
