@@ -638,10 +638,27 @@ struct PairSearch {
         }
         uint64_t *w = vis + vis_head;
         uint32_t idx = 0;
-        for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
-            uint32_t i = i0 + lane;
-            bool lt = i < vis_len && (uint32_t)(w[i] >> 32) < d;
-            idx += __popc(__ballot_sync(DANN_FULL, lt));
+        if (HV == 1 && (a.hv_flags & DANN_HV_VIS)) {
+            /* partition_point(x < d) on the sorted list with a 32-ary search: one probe per lane at the end of its
+             * stride finds the boundary stride, a second ballot counts inside it - 2 ballots instead of len/32 */
+            const uint32_t stride = (vis_len + 31u) >> 5;
+            const uint32_t s0 = (uint32_t)lane * stride;
+            uint32_t pe = s0 + stride < vis_len ? s0 + stride : vis_len; /* end of this lane's stride */
+            const bool whole = s0 < vis_len && (uint32_t)(w[pe - 1] >> 32) < d;
+            const uint32_t c = __popc(__ballot_sync(DANN_FULL, whole));
+            idx = c * stride < vis_len ? c * stride : vis_len; /* the last stride may be short */
+            const uint32_t b0 = idx, b1 = b0 + stride < vis_len ? b0 + stride : vis_len;
+            for (uint32_t i0 = b0; i0 < b1; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool lt = i < b1 && (uint32_t)(w[i] >> 32) < d;
+                idx += __popc(__ballot_sync(DANN_FULL, lt));
+            }
+        } else {
+            for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
+                uint32_t i = i0 + lane;
+                bool lt = i < vis_len && (uint32_t)(w[i] >> 32) < d;
+                idx += __popc(__ballot_sync(DANN_FULL, lt));
+            }
         }
         for (int hi = (int)vis_len; hi > (int)idx; hi -= 32) {
             int i = hi - 1 - lane;

@@ -146,12 +146,21 @@ def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
     assert info["hv"] == 1 and info["bitmap_words"] == 0
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 3, 28])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 3, 60, 63])
 def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
     """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
     s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
     q = fixtures.gen_vectors(3, 96, 17, "normal")
     info = check(emu, s, q, 60, 90, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags, "DANN_SEARCH_HS": 512})
+    assert info["hv"] == 1
+
+
+@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 64, 200, 1100])
+def test_emulated_hv1_visited_search_list_sizes(emu, L):
+    """The 32-ary visited-list search at list lengths around its stride boundaries (and > 1024 entries)."""
+    s = build_case(1500, 32, L2, seed=23, kind="normal", R=16, L_build=32)
+    q = fixtures.gen_vectors(2, 32, 29, "normal")
+    info = check(emu, s, q, L, 40, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": 32})
     assert info["hv"] == 1
 
 
