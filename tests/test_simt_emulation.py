@@ -334,6 +334,27 @@ def test_emulated_whole_plain_storage_batch_call_equals_oracle(emu, dist, dim, d
         _assert_batch_equals_oracle(s, q, g, k, L, rescore, dist_bits=rescore > 0 and s.dim != s.dim_index)
 
 
+@pytest.mark.parametrize("name", ["plain_cos128", "plain_l2_96x40", "plain_cos70x38"])
+def test_plain_golden_vectors_oracle_and_emulated_kernels(emu, name):
+    """tests/golden/plain_golden.npz: the oracle still gives the frozen answers, and so do the kernels under emulation."""
+    from golden.make_plain_golden import CASES, make_case, run_case
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "plain_golden.npz"))
+    now = run_case(name)
+    for key, val in now.items():
+        assert np.array_equal(z[f"{name}/{key}"], val), key
+    s, q, L, rescore, k = make_case(name)
+    g = _batch_under_emulation(emu, s, q, k, L, rescore, plain=True)
+    resorts = rescore > 0 and s.dim != s.dim_index
+    for b in range(len(q)):
+        n = int(z[f"{name}/count"][b])
+        assert int(g["count"][b]) == n
+        assert g["tid"][b, :n].tolist() == z[f"{name}/tid"][b, :n].tolist()
+        if resorts:
+            assert g["dist"][b, :n].view(np.uint32).tolist() == z[f"{name}/dist_bits"][b, :n].tolist()
+        assert g["stats"][b]["visits"] == int(z[f"{name}/visits"][b])
+        assert g["stats"][b]["d_full"] == int(z[f"{name}/d_full"][b])
+
+
 # ---- the workspace plan itself (host logic of diskann_b200.cu, shared through dann_plan.h) ----------------
 def test_plan_benchmark_shape_is_one_wave_of_seven_pairs(emu):
     p = emu.plan(n=1_000_000, R=64, words=24, nq=1024, L=150, c_target=259)

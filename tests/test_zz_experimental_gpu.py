@@ -110,3 +110,22 @@ def test_plain_storage_is_refused_without_the_opt_in(lib, monkeypatch):
     s = fixtures.to_plain(build_case(64, 16, L2, seed=2, R=8, L_build=16))
     with pytest.raises(lib.DiskAnnError, match="plain"):
         lib.DiskAnnIndex(s)
+
+
+@pytest.mark.parametrize("name", ["plain_cos128", "plain_l2_96x40", "plain_cos70x38"])
+def test_plain_storage_golden_vectors(lib, monkeypatch, name):
+    import os as _os
+    from golden.make_plain_golden import make_case
+    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
+    z = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "plain_golden.npz"))
+    s, q, L, rescore, k = make_case(name)
+    with lib.DiskAnnIndex(s) as idx:
+        g = idx.search_batch(q, k=k, search_list_size=L, rescore=rescore)
+    assert np.array_equal(g["count"], z[f"{name}/count"])
+    assert np.array_equal(g["tid"], z[f"{name}/tid"])
+    if rescore > 0 and s.dim != s.dim_index:
+        for b in range(len(q)):
+            n = int(g["count"][b])
+            assert g["dist"][b, :n].view(np.uint32).tolist() == z[f"{name}/dist_bits"][b, :n].tolist()
+    assert np.array_equal(g["stats"]["visits"], z[f"{name}/visits"])
+    assert np.array_equal(g["stats"]["d_full"], z[f"{name}/d_full"])
