@@ -334,6 +334,23 @@ def test_emulated_whole_plain_storage_batch_call_equals_oracle(emu, dist, dim, d
         _assert_batch_equals_oracle(s, q, g, k, L, rescore, dist_bits=rescore > 0 and s.dim != s.dim_index)
 
 
+@pytest.mark.parametrize("name", ["cos768b2", "l2_768b1", "ip100lab"])
+def test_sbq_golden_vectors_emulated_kernels(emu, name):
+    """tests/golden/scan_golden.npz (the vectors the GPU parity test uses) reproduced by the emulated kernels."""
+    from golden.make_golden import CASES, make_case
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "scan_golden.npz"))
+    s, q, lab, L, rescore, k = make_case(name)
+    g = _batch_under_emulation(emu, s, q, k, L, rescore, labels=lab)
+    assert np.array_equal(g["count"], z[f"{name}/count"])
+    assert np.array_equal(g["tid"], z[f"{name}/tid"])
+    if rescore:
+        for b in range(len(q)):
+            n = int(g["count"][b])
+            assert g["dist"][b, :n].view(np.uint32).tolist() == z[f"{name}/dist_bits"][b, :n].tolist()
+    assert [x["visits"] for x in g["stats"]] == z[f"{name}/visits"].tolist()
+    assert [x["d_quantized"] for x in g["stats"]] == z[f"{name}/d_quantized"].tolist()
+
+
 @pytest.mark.parametrize("name", ["plain_cos128", "plain_l2_96x40", "plain_cos70x38"])
 def test_plain_golden_vectors_oracle_and_emulated_kernels(emu, name):
     """tests/golden/plain_golden.npz: the oracle still gives the frozen answers, and so do the kernels under emulation."""
