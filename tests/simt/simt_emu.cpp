@@ -36,7 +36,7 @@ namespace simt {
 Block *g_blk = nullptr;
 Fiber *g_cur = nullptr;
 static uint64_t g_total_switches = 0;
-static const size_t kStack = 256 * 1024;
+static const size_t kStack = 128 * 1024;
 
 uint64_t total_switches() { return g_total_switches; }
 
@@ -48,19 +48,32 @@ void yield() {
     simt_switch(&f->sp, b->sched_sp);
 }
 
+static void complete(Slot &s, unsigned nlanes_mask);
+
 static void trampoline() {
     Fiber *f = g_cur;
     g_blk->body();
     f->done = true;
     g_blk->progress++;
+    { /* a thread that has returned no longer takes part in its warp's collectives */
+        Warp &w = g_blk->warps[f->tid >> 5];
+        w.exited |= 1u << (f->tid & 31u);
+        for (Slot &c : w.slots)
+            if (c.arrived && ((c.arrived | w.exited) & c.mask) == c.mask) {
+                complete(c, c.mask);
+                c.arrived = 0;
+                c.gen++;
+                g_blk->progress++;
+                g_blk->collectives++;
+            }
+    }
     yield();
     fprintf(stderr, "simt: resumed a finished fiber\n");
     abort();
 }
 
-static void prepare(Fiber &f) {
-    f.stack = (char *)aligned_alloc(64, kStack);
-    if (!f.stack) abort();
+static void prepare(Fiber &f, char *stack) {
+    f.stack = stack;
     uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
     void **sp = (void **)top;
     *--sp = nullptr;             /* where a caller's return address would sit: keeps rsp = 8 (mod 16) at entry */
@@ -79,7 +92,7 @@ static void complete(Slot &s, unsigned nlanes_mask) {
         case K_BALLOT: {
             unsigned r = 0;
             for (int l = 0; l < 32; l++)
-                if (((mask >> l) & 1u) && s.val[l]) r |= 1u << l;
+                if (((s.arrived >> l) & 1u) && s.val[l]) r |= 1u << l;
             for (int l = 0; l < 32; l++) out[l] = r;
             break;
         }
@@ -87,7 +100,7 @@ static void complete(Slot &s, unsigned nlanes_mask) {
         case K_ALL: {
             bool any = false, all = true;
             for (int l = 0; l < 32; l++)
-                if ((mask >> l) & 1u) {
+                if ((s.arrived >> l) & 1u) {
                     any |= s.val[l] != 0;
                     all &= s.val[l] != 0;
                 }
@@ -99,7 +112,7 @@ static void complete(Slot &s, unsigned nlanes_mask) {
         case K_SHFL_DOWN:
         case K_SHFL_XOR:
             for (int l = 0; l < 32; l++) {
-                if (!((mask >> l) & 1u)) continue;
+                if (!((s.arrived >> l) & 1u)) continue;
                 int src = l;
                 if (s.kind == K_SHFL) src = (int)(s.aux[l] & 31u);
                 else if (s.kind == K_SHFL_UP) src = l - (int)s.aux[l] >= 0 ? l - (int)s.aux[l] : l;
@@ -109,15 +122,16 @@ static void complete(Slot &s, unsigned nlanes_mask) {
                     fprintf(stderr, "simt: shuffle reads lane %d which is not in mask %08x\n", src, mask);
                     abort();
                 }
-                out[l] = s.val[src];
+                /* reading a lane that has exited is undefined in CUDA; give the reader its own value back */
+                out[l] = ((s.arrived >> src) & 1u) ? s.val[src] : s.val[l];
             }
             break;
         case K_MATCH_ANY:
             for (int l = 0; l < 32; l++) {
-                if (!((mask >> l) & 1u)) continue;
+                if (!((s.arrived >> l) & 1u)) continue;
                 unsigned r = 0;
                 for (int m = 0; m < 32; m++)
-                    if (((mask >> m) & 1u) && s.val[m] == s.val[l]) r |= 1u << m;
+                    if (((s.arrived >> m) & 1u) && s.val[m] == s.val[l]) r |= 1u << m;
                 out[l] = r;
             }
             break;
@@ -162,7 +176,7 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
     s->val[lane] = val;
     s->aux[lane] = aux;
     s->arrived |= 1u << lane;
-    if (s->arrived == mask) {
+    if (((s->arrived | w.exited) & mask) == mask) {
         complete(*s, mask);
         s->arrived = 0;
         s->gen++;
@@ -200,6 +214,9 @@ void named_barrier(unsigned id, unsigned count) {
 }
 
 void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
+    /* one set of fiber stacks per launch, reused by every block (blocks run one after the other) */
+    char *stacks = (char *)aligned_alloc(64, (size_t)block * kStack);
+    if (!stacks) abort();
     for (unsigned bi = 0; bi < grid; bi++) {
         Block b;
         b.bidx.x = bi;
@@ -211,7 +228,7 @@ void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
         for (unsigned t = 0; t < block; t++) {
             b.fibers[t].tid = t;
             b.fibers[t].tidx.x = t;
-            prepare(b.fibers[t]);
+            prepare(b.fibers[t], stacks + (size_t)t * kStack);
         }
         g_blk = &b;
         unsigned live = block;
@@ -254,10 +271,10 @@ void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
                 last_progress = b.progress;
             }
         }
-        for (unsigned t = 0; t < block; t++) free(b.fibers[t].stack);
         g_blk = nullptr;
         g_cur = nullptr;
     }
+    free(stacks);
 }
 
 }  // namespace simt

@@ -39,6 +39,8 @@ struct Slot {
 
 struct Warp {
     Slot slots[4];
+    unsigned exited = 0; /* lanes whose thread has returned: collectives do not wait for them (CUDA: "all NON-EXITED
+                            threads named in mask must execute the same intrinsic") */
 };
 
 struct Barrier {

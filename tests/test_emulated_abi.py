@@ -1,0 +1,53 @@
+"""The `-m gpu` parity tests, run on the CPU box against the product's own C ABI built for the SIMT emulator
+(tests/simt: diskann_b200.cu with its launches rewritten by cu2cpp.py + every kernel source + a fake CUDA runtime ->
+tests/simt/_build/libdiskann_b200_emu.so).  Host logic (plans, growth retries, the scan operator's suspend / resume,
+argument validation, the plain-layout routing) and kernel logic are exercised TOGETHER by the very tests the B200 box
+runs, including the opt-in ones for code that has not been on hardware yet.
+
+It is a logic check, not a substitute for hardware: no memory model, no timing, and the emulated library is a test
+artifact that the package never looks for (conftest.lib_built loads it by explicit path under DANN_EMULATE=1).
+Runs in a subprocess so that the emulated library never shares a process with the tests of the real one."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(files, extra_env=None, workers=4, timeout=1500):
+    env = dict(os.environ)
+    env.update({"DANN_EMULATE": "1", "SIMT_SM_COUNT": "8"})
+    env.update(extra_env or {})
+    # build once here: the xdist workers would otherwise race on the same output file
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    import build_emu
+    build_emu.build_abi()
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-n", str(workers)] + files
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m, tail
+    return int(m.group(1)), r.stdout
+
+
+def test_gpu_parity_suite_passes_under_emulation():
+    passed, out = _run(["tests/test_gpu_parity.py", "tests/test_gpu_build_small.py"])
+    assert passed >= 23 and "skipped" not in out.splitlines()[-1], out[-500:]
+
+
+def test_not_yet_on_hardware_paths_pass_under_emulation():
+    """Heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout, through the real host code."""
+    passed, out = _run(["tests/test_zz_experimental_gpu.py"], {"DANN_RUN_EXPERIMENTAL": "1"})
+    assert passed >= 13 and "skipped" not in out.splitlines()[-1], out[-500:]
+
+
+@pytest.mark.parametrize("sched", ["1", "2"])
+def test_parity_under_other_lane_schedules(sched):
+    """Descending and shuffled fiber order (exposes missing __syncwarp()s) on a slice of the parity suite."""
+    passed, _ = _run(["tests/test_gpu_parity.py", "-k", "batch_768d or scan_operator or labeled or counters"],
+                     {"SIMT_SCHED": sched})
+    assert passed >= 5

@@ -1,0 +1,107 @@
+"""dann_build_graph on a small index whose inputs come from the oracle (numpy only): structural validity, recall of
+scans over the built graph, parity oracle vs CUDA on the built snapshot - unlabeled and labeled.  Small enough to run
+under CPU emulation too (tests/test_emulated_abi.py), where it is the only check of the builder's kernels."""
+import numpy as np
+import pytest
+
+from conftest import build_case
+
+pytestmark = pytest.mark.gpu
+
+L2 = 1
+
+
+def _build(lib, n, dim, labels, R=24, L_build=48):
+    from oracle import fixtures
+    from pgvectorscale_b200.snapshot import INVALID_NODE
+    s = build_case(n, dim, L2, seed=77, kind="normal", R=8, L_build=16, labels=labels)   # codes/means/labels from the oracle
+    slots = 64
+    s.R = slots
+    s.nbrs = np.full((n, slots), INVALID_NODE, np.uint32)
+    s.start_default = 0
+    if labels:                      # per-label start node = first node carrying the label (graph/start_nodes.rs)
+        first = {}
+        for i in range(n):
+            for l in s.labels[s.label_off[i]:s.label_off[i + 1]]:
+                first.setdefault(int(l), i)
+        ks = sorted(first)
+        s.start_labels = np.array(ks, np.int16)
+        s.start_label_nodes = np.array([first[k] for k in ks], np.uint32)
+    idx = lib.DiskAnnIndex(s)
+    st = idx.build_graph(R, L_build, 1.2, 256)
+    s.nbrs = idx.download_nbrs()
+    return s, idx, st
+
+
+def _check_structure(s, R):
+    n = s.n
+    nb = s.nbrs
+    valid = nb != 0xFFFFFFFF
+    deg = valid.sum(1)
+    assert deg.max() <= R and deg[1:].min() >= 1
+    assert (valid[:, :-1] >= valid[:, 1:]).all()                      # INVALID-terminated prefixes
+    assert (nb[valid] < n).all()
+    assert not (nb == np.arange(n, dtype=np.uint32)[:, None]).any()   # no self loops
+    for i in range(n):                                                # no duplicates
+        row = nb[i][valid[i]]
+        assert len(set(row.tolist())) == len(row)
+
+
+@pytest.fixture(scope="module")
+def lib(lib_built):
+    from pgvectorscale_b200 import diskann
+    if diskann.device_count() < 1:
+        pytest.fail("no CUDA device visible: -m gpu tests need the B200 box")
+    return diskann
+
+
+def test_small_built_graph_valid_recall_parity(lib):
+    from oracle import fixtures, oracle
+    n, dim, R = 1500, 48, 24
+    s, idx, st = _build(lib, n, dim, labels=False, R=R)
+    try:
+        _check_structure(s, R)
+        assert st["batches"] >= 5 and st["avg_degree"] > 0.5 * R
+        q = fixtures.gen_vectors(32, dim, 5, "normal")
+        g = idx.search_batch(q, k=10, search_list_size=60, rescore=60)
+        otid, odist, _, ostats = oracle.scan_batch(s, q, None, None, 60, 60, 10)
+        assert np.array_equal(g["tid"], otid)
+        assert np.array_equal(g["dist"].view(np.uint32), odist.view(np.uint32))
+        assert np.array_equal(g["stats"]["visits"].astype(np.uint64), ostats["visits"])
+        node_of = {int(t): i for i, t in enumerate(s.heap_tid)}
+        hits = 0
+        for b in range(len(q)):
+            d = ((s.vectors - q[b]) ** 2).sum(1)
+            truth = set(np.argsort(d, kind="stable")[:10].tolist())
+            hits += len(truth & set(node_of[int(t)] for t in g["tid"][b, :int(g["count"][b])]))
+        # iid Gaussian vectors are a hard case for SBQ; the yardstick is the reference's SERIAL build on the same data
+        ser = build_case(n, dim, L2, seed=77, kind="normal", R=R, L_build=48)
+        ser_hits = 0
+        for b in range(len(q)):
+            d = ((s.vectors - q[b]) ** 2).sum(1)
+            truth = set(np.argsort(d, kind="stable")[:10].tolist())
+            ser_hits += len(truth & set(oracle.scan(ser, q[b], None, 60, 60, 10)["node"].tolist()))
+        assert hits >= ser_hits - 0.1 * 10 * len(q), (hits, ser_hits)
+    finally:
+        idx.close()
+
+
+def test_small_built_labeled_graph_valid_and_parity(lib):
+    from oracle import fixtures, oracle
+    n, dim, R = 1200, 32, 24
+    s, idx, st = _build(lib, n, dim, labels=True, R=R)
+    try:
+        _check_structure(s, R)
+        q = fixtures.gen_vectors(16, dim, 6, "normal")
+        labels = [[1 + (i % 16)] for i in range(16)]
+        off = np.arange(17, dtype=np.int32)
+        lab = np.array([l[0] for l in labels], np.int16)
+        g = idx.search_batch(q, labels=labels, k=10, search_list_size=60, rescore=40)
+        otid, odist, ocount, _ = oracle.scan_batch(s, q, lab, off, 60, 40, 10)
+        assert np.array_equal(g["count"], ocount) and np.array_equal(g["tid"], otid)
+        for b in range(16):                                   # every returned row carries the label
+            for t in g["tid"][b, :int(g["count"][b])]:
+                node = int(np.nonzero(s.heap_tid == t)[0][0])
+                assert labels[b][0] in s.labels[s.label_off[node]:s.label_off[node + 1]]
+    finally:
+        idx.close()

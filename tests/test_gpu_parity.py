@@ -5,7 +5,7 @@ Bar: bit-exact row ids (TIDs), bit-exact rerank distances, equal counters
 import numpy as np
 import pytest
 
-from conftest import build_case
+from conftest import buffer_device, build_case, dptr, emulating
 
 pytestmark = pytest.mark.gpu
 
@@ -211,7 +211,7 @@ def test_sbq_distance_kernel(lib):
     import torch
     s = build_case(3000, 768, COSINE, bits=2, seed=13)
     with lib.DiskAnnIndex(s) as idx:
-        dev = torch.device("cuda", 0)
+        dev = buffer_device()
         Q, npairs = 33, 200003
         rng = np.random.default_rng(0)
         qcodes = rng.integers(0, 2**63, size=(Q, idx.code_stride), dtype=np.uint64)
@@ -222,7 +222,7 @@ def test_sbq_distance_kernel(lib):
         d_pq = torch.from_numpy(pq.view(np.int32)).to(dev)
         d_pn = torch.from_numpy(pn.view(np.int32)).to(dev)
         d_out = torch.empty(npairs, dtype=torch.int32, device=dev)
-        idx.sbq_distance(d_q, d_pq, d_pn, d_out)
+        idx.sbq_distance(dptr(d_q), dptr(d_pq), dptr(d_pn), dptr(d_out))
         x = s.codes[pn] ^ qcodes[pq][:, :s.words]
         ref = np.unpackbits(x.view(np.uint8), axis=1).sum(1).astype(np.int32)
         assert np.array_equal(d_out.cpu().numpy(), ref)
@@ -234,14 +234,14 @@ def test_prepare_and_full_distance_kernels(lib):
     for dist, dim, dim_index in ((COSINE, 768, 768), (L2, 100, 64), (IP, 130, 130)):
         s = build_case(500, dim, dist, seed=61 + dim, kind="uniform", R=16, L_build=32, dim_index=dim_index)
         with lib.DiskAnnIndex(s) as idx:
-            dev = torch.device("cuda", 0)
+            dev = buffer_device()
             B, m = 9, 21
             q = _queries(s, B, 14, "uniform") * 3.0
             q[0] = 0.0
             d_q = torch.from_numpy(q).to(dev)
             d_full = torch.empty((B, dim), dtype=torch.float32, device=dev)
             d_codes = torch.empty((B, idx.code_stride), dtype=torch.int64, device=dev)
-            idx.prepare_queries(d_q, d_full, d_codes)
+            idx.prepare_queries(dptr(d_q), dptr(d_full), dptr(d_codes))
             full = d_full.cpu().numpy()
             codes = d_codes.cpu().numpy().view(np.uint64)
             for b in range(B):
@@ -257,7 +257,7 @@ def test_prepare_and_full_distance_kernels(lib):
             nodes = rng.integers(0, s.n, size=(B, m), dtype=np.uint32)
             d_nodes = torch.from_numpy(nodes.view(np.int32)).to(dev)
             d_out = torch.empty((B, m), dtype=torch.float32, device=dev)
-            idx.full_distance(d_full, d_nodes, d_out)
+            idx.full_distance(dptr(d_full), dptr(d_nodes), dptr(d_out))
             out = d_out.cpu().numpy()
             for b in range(B):
                 for i in range(m):
@@ -339,17 +339,20 @@ def test_device_buffer_entry_point_matches_host_entry_point(lib):
     s = build_case(2000, 128, COSINE, seed=91, labels=True, R=24, L_build=50)
     q = _queries(s, 40, 17)
     with lib.DiskAnnIndex(s) as idx:
-        dev = torch.device("cuda", 0)
+        dev = buffer_device()
         h = idx.search_batch(q, k=10, search_list_size=60, rescore=25)
         d_q = torch.from_numpy(q).to(dev)
         d_tid = torch.empty((40, 10), dtype=torch.int64, device=dev)
         d_dist = torch.empty((40, 10), dtype=torch.float32, device=dev)
         d_cnt = torch.empty(40, dtype=torch.int32, device=dev)
         d_st = torch.empty((40, 6), dtype=torch.int32, device=dev)
-        side = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(side):
-            idx.search_batch_device(d_q, 10, 60, 25, d_tid, d_dist, d_cnt, d_st, stream=side.cuda_stream)
-        side.synchronize()
+        if emulating():
+            idx.search_batch_device(dptr(d_q), 10, 60, 25, dptr(d_tid), dptr(d_dist), dptr(d_cnt), dptr(d_st))
+        else:
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                idx.search_batch_device(d_q, 10, 60, 25, d_tid, d_dist, d_cnt, d_st, stream=side.cuda_stream)
+            side.synchronize()
         assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), h["tid"])
         assert np.array_equal(d_dist.cpu().numpy().view(np.uint32), h["dist"].view(np.uint32))
         assert np.array_equal(d_cnt.cpu().numpy().view(np.uint32), h["count"])
@@ -359,7 +362,9 @@ def test_device_buffer_entry_point_matches_host_entry_point(lib):
         hk = idx.search_batch(q, labels=keys, k=10, search_list_size=60, rescore=25)
         d_lab = torch.tensor([3, 9] * 40, dtype=torch.int16, device=dev)
         d_off = torch.arange(0, 82, 2, dtype=torch.int32, device=dev)
-        idx.search_batch_device(d_q, 10, 60, 25, d_tid, d_dist, d_cnt, d_st, d_labels=d_lab, d_label_off=d_off)
-        torch.cuda.synchronize()
+        idx.search_batch_device(dptr(d_q), 10, 60, 25, dptr(d_tid), dptr(d_dist), dptr(d_cnt), dptr(d_st),
+                                d_labels=dptr(d_lab), d_label_off=dptr(d_off))
+        if not emulating():
+            torch.cuda.synchronize()
         assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), hk["tid"])
 
