@@ -25,7 +25,7 @@ def test_plain_c_executor_harness_runs_a_scan(lib, lib_built, tmp_path):
     exe = str(tmp_path / "executor_harness")
     libdir = os.path.dirname(lib_built)
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
-                    os.path.join(root, "harness", "executor_harness.c"), "-L" + libdir, "-ldiskann_b200",
+                    os.path.join(root, "harness", "executor_harness.c"), "-L" + libdir, "-l:" + os.path.basename(lib_built),
                     "-Wl,-rpath," + libdir, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
