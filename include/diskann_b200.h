@@ -191,6 +191,22 @@ int dann_index_download_nbrs(dann_index *ix, uint32_t *out);
 /* Supply (or replace) the heap vectors of an index loaded with vectors == NULL; [n][dim] host floats. */
 int dann_index_set_vectors(dann_index *ix, const float *vectors);
 
+/* ---- query coalescing (multi-process serving, the in-process half) ----------------------
+ * Postgres is process-per-connection with amcanparallel = false (mod.rs:63): one scan per backend at a time, while
+ * the engine's throughput comes from batches.  A coalescer owns a dispatcher thread; any number of host threads (one
+ * per connected backend in a sidecar that holds the HBM-resident index) call dann_coalescer_search with ONE query and
+ * block; requests that arrive within max_wait_us of the first one (at most max_batch, same k / search_list_size /
+ * rescore, all keyed or all unkeyed) become one dann_search_batch call.  Each caller receives exactly the rows,
+ * distances and counters a private dann_search_batch of its query returns.  nlabels < 0 = no scan key.
+ * The socket / shared-memory transport between backends and the sidecar is not part of this library. */
+typedef struct dann_coalescer dann_coalescer;
+int dann_coalescer_create(dann_index *ix, int max_batch, int max_wait_us, dann_coalescer **out);
+int dann_coalescer_search(dann_coalescer *c, const float *query, const int16_t *labels, int nlabels, int k,
+                          int search_list_size, int rescore, uint64_t *out_tid, float *out_dist,
+                          uint32_t *out_count, dann_query_stats *out_stats);
+int dann_coalescer_stats(dann_coalescer *c, uint64_t *batches, uint64_t *queries, uint64_t *largest_batch);
+void dann_coalescer_destroy(dann_coalescer *c); /* drains what is queued, then stops; destroy before dann_index_free */
+
 /* Number of this library's kernel launches since load (bench.py "gpu_launches"). */
 uint64_t dann_kernel_launches(const dann_index *ix);
 

@@ -1261,3 +1261,7 @@ extern "C" void dann_scan_end(dann_scan *sc) {
     cudaGetLastError();
     delete sc;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* query coalescing for process-per-connection hosts                */
+#include "dann_coalescer.h"

@@ -65,6 +65,7 @@ STATS_DTYPE = np.dtype([("visits", "<u4"), ("d_quantized", "<u4"), ("candidates"
 # every symbol include/diskann_b200.h declares
 EXPORTS = [
     "dann_last_error", "dann_device_count", "dann_index_load", "dann_index_load_plain", "dann_index_free",
+    "dann_coalescer_create", "dann_coalescer_search", "dann_coalescer_stats", "dann_coalescer_destroy",
     "dann_index_hbm_bytes", "dann_scan_begin", "dann_scan_rescan", "dann_scan_gettuple",
     "dann_scan_stats", "dann_scan_end", "dann_search_batch", "dann_search_batch_device",
     "dann_prepare_queries", "dann_code_stride", "dann_sbq_distance", "dann_full_distance",
@@ -114,6 +115,11 @@ def load_library(path: Optional[str] = None):
     lib.dann_build_graph.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(_BuildStats)]
     lib.dann_index_download_nbrs.argtypes = [vp, vp]
     lib.dann_index_set_vectors.argtypes = [vp, vp]
+    lib.dann_coalescer_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.dann_coalescer_search.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.dann_coalescer_stats.argtypes = [vp, vp, vp, vp]
+    lib.dann_coalescer_destroy.argtypes = [vp]
+    lib.dann_coalescer_destroy.restype = None
     if path is None:
         _LIB = lib
     return lib
@@ -381,5 +387,55 @@ class IndexScan:
     def __del__(self):
         try:
             self.end()
+        except Exception:
+            pass
+
+
+class Coalescer:
+    """dann_coalescer: single-query callers (one thread per connected backend in a sidecar) coalesced into batch calls
+    (SURVEY.md §8f row 4).  search() blocks and may be called from many threads at once (ctypes drops the GIL)."""
+
+    def __init__(self, index: DiskAnnIndex, max_batch: int = 256, max_wait_us: int = 200):
+        self._lib = index._lib
+        self._index = index
+        h = C.c_void_p()
+        _check(self._lib, self._lib.dann_coalescer_create(index._h, int(max_batch), int(max_wait_us), C.byref(h)))
+        self._h = h
+
+    def search(self, query, labels: Optional[Sequence[int]] = None, k: int = 10,
+               search_list_size: int = QUERY_SEARCH_LIST_SIZE_DEFAULT, rescore: int = QUERY_RESCORE_DEFAULT) -> dict:
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.shape != (self._index.dim,):
+            raise ValueError(f"query must have {self._index.dim} dimensions")
+        lab = None if labels is None else np.asarray(list(labels), dtype=np.int16)
+        tid = np.full(k, 0xFFFFFFFFFFFFFFFF, np.uint64)
+        dist = np.zeros(k, np.float32)
+        count = C.c_uint32()
+        st = _QueryStats()
+        _check(self._lib, self._lib.dann_coalescer_search(
+            self._h, _np_ptr(q), _np_ptr(lab) if lab is not None and len(lab) else None, -1 if lab is None else len(lab),
+            int(k), int(search_list_size), int(rescore), _np_ptr(tid), _np_ptr(dist), C.byref(count), C.byref(st)))
+        return dict(tid=tid, dist=dist, count=int(count.value),
+                    stats={f: int(getattr(st, f)) for f, _ in _QueryStats._fields_})
+
+    def stats(self) -> dict:
+        b, q, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._lib, self._lib.dann_coalescer_stats(self._h, C.byref(b), C.byref(q), C.byref(m)))
+        return dict(batches=int(b.value), queries=int(q.value), largest_batch=int(m.value))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dann_coalescer_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

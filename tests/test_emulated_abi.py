@@ -35,8 +35,9 @@ def _run(files, extra_env=None, workers=4, timeout=1500):
 
 
 def test_gpu_parity_suite_passes_under_emulation():
-    passed, out = _run(["tests/test_gpu_parity.py", "tests/test_gpu_build_small.py", "tests/test_zz_c_harness_gpu.py"])
-    assert passed >= 24 and "skipped" not in out.splitlines()[-1], out[-500:]
+    passed, out = _run(["tests/test_gpu_parity.py", "tests/test_zz_c_harness_gpu.py", "tests/test_zz_d_build_small_gpu.py",
+                        "tests/test_zz_e_coalescer_gpu.py"])
+    assert passed >= 25 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
 def test_not_yet_on_hardware_paths_pass_under_emulation():

@@ -367,4 +367,3 @@ def test_device_buffer_entry_point_matches_host_entry_point(lib):
         if not emulating():
             torch.cuda.synchronize()
         assert np.array_equal(d_tid.cpu().numpy().view(np.uint64), hk["tid"])
-

@@ -1,6 +1,7 @@
 """dann_build_graph on a small index whose inputs come from the oracle (numpy only): structural validity, recall of
 scans over the built graph, parity oracle vs CUDA on the built snapshot - unlabeled and labeled.  Small enough to run
-under CPU emulation too (tests/test_emulated_abi.py), where it is the only check of the builder's kernels."""
+under CPU emulation too (tests/test_emulated_abi.py), where it is the only check of the builder's kernels.
+Written after this round's GPU minutes were spent; the file name sorts it after the tests that have been on hardware."""
 import numpy as np
 import pytest
 
