@@ -104,12 +104,21 @@ struct PairSearch {
 
     /* dedupe + label filter of up to 64 ids, appended to page `list` (see SearchWarp::stage) */
     __device__ __forceinline__ void stage(uint32_t *list, uint32_t n0, bool v0, uint32_t n1, bool v1,
-                                          bool apply_filter) {
+                                          bool apply_filter, bool known_unique = false) {
         if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
-        unsigned m0 = __match_any_sync(DANN_FULL, n0);
-        unsigned m1 = __match_any_sync(DANN_FULL, n1);
-        const bool f0 = v0 && ((__ffs(m0) - 1) == lane);
-        const bool f1 = v1 && ((__ffs(m1) - 1) == lane);
+        bool f0, f1;
+        if (HV == 1 && known_unique && (a.hv_flags & DANN_HV_NOMATCH)) {
+            /* the index was checked at load to have no repeated id within a neighbour list (lists_unique): the
+             * intra-list dedupe - two MATCH.ANY on the path between the list's arrival and the inserted-set
+             * atomics - has nothing to find */
+            f0 = v0;
+            f1 = v1;
+        } else {
+            unsigned m0 = __match_any_sync(DANN_FULL, n0);
+            unsigned m1 = __match_any_sync(DANN_FULL, n1);
+            f0 = v0 && ((__ffs(m0) - 1) == lane);
+            f1 = v1 && ((__ffs(m1) - 1) == lane);
+        }
         if (HV == 1 && (a.hv_flags & DANN_HV_PF_CODES)) {
             /* the SBQ code rows are needed one L2 round trip from now (after the inserted-set answers): start pulling
              * them into L2 already; rows of ids that turn out to be known are the only wasted traffic */
@@ -438,7 +447,7 @@ struct PairSearch {
                 const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
                 const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
                 if (a.lists_unique) {
-                    stage(list, n0, v0, n1, v1, filter);
+                    stage(list, n0, v0, n1, v1, filter, true);
                 } else {
                     stage(list, n0, v0, DANN_INVALID_NODE, false, filter);
                     if (!status) stage(list, n1, v1, DANN_INVALID_NODE, false, filter);
