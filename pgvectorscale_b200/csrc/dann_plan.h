@@ -94,7 +94,8 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     p->hv = p->pairs && env_u32("DANN_HEAP_V2", 0) == 1 ? 1 : 0;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4) +
-                         (size_t)((in.plain_dim + 3u) & ~3u) * 4; /* plain layout: the query's index slice */
+                         (size_t)((in.plain_dim + 3u) & ~3u) * 4 + /* plain layout: the query's index slice */
+                         (p->hv == 1 ? 16u : 0u);                  /* HV == 1: published root node ids */
     if (fixed + 1024 > budget) {
         snprintf(err, errlen, "visited list of %u entries does not fit shared memory", p->vcap);
         return DANN_ERR_CAPACITY;

@@ -84,7 +84,8 @@ struct SearchArgs {
     /* dann_search2_kernel<.., HV=1> only: which of its alternatives run (DANN_HV_FLAGS, default all), so that each can
      * be timed alone: 1 register-path pushes, 2 look-ahead pop, 4 page-sized distance rounds, 8 code-row L2
      * prefetch, 16 neighbour-row L2 prefetch, 32 32-ary visited-list search, 64 no intra-list dedupe when the
-     * index's lists are known to be duplicate-free.  Kept last: the offsets of the fields above are unchanged. */
+     * index's lists are known to be duplicate-free, 128 the heap warp resolves (and prefetches the neighbour row of) the
+     * root's node id.  Kept last: the offsets of the fields above are unchanged. */
     uint32_t hv_flags;
     /* plain storage layout (SearchWarp<.., PLAIN=1> only; storage.rs:144-169, plain/storage.rs:223-299): the beam
      * search compares the query's index slice with the f32 vector each node stores.  Kept after everything else. */
@@ -99,6 +100,7 @@ struct SearchArgs {
 #define DANN_HV_PF_NBRS 16u
 #define DANN_HV_VIS 32u
 #define DANN_HV_NOMATCH 64u
+#define DANN_HV_ROOTNODE 128u
 
 #define DANN_LIST_CAP 64u
 

@@ -70,6 +70,7 @@ struct PairSearch {
     uint32_t *listp, *dlp; /* [2][64] */
     PairCtl *ctl;
     E *cqe;         /* [32] compacted active pushes: entry */
+    uint32_t *xroot; /* HV == 1: [2] node id of the published root (+2 spare words), behind cqe */
     uint32_t *cqp;  /* [32]                          : 1-based slot */
     uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
@@ -385,7 +386,8 @@ struct PairSearch {
                 node = pl[idx];
                 key = m;
             } else if (rv) { /* the root the pop left behind stays on top */
-                node = cnode[ctl->root_seq[pp]];
+                if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) node = xroot[pp];
+                else node = cnode[ctl->root_seq[pp]];
                 key = ctl->root_key[pp];
             }
             if constexpr (HV == 1) {
@@ -686,6 +688,18 @@ struct PairSearch {
     /* publish the heap root as it stands before page k is pushed, and meet the memory warp */
     __device__ __forceinline__ void handoff(bool rv, E root) {
         const uint32_t p = hk & 1;
+        if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) {
+            /* the heap warp is ahead of the controller here: translate the root's sequence number into its node id
+             * (a global load the controller would otherwise wait for before it can even ask for the neighbour list)
+             * and start pulling that node's neighbour row into L2 - it is the next visit unless the page being
+             * built beats it */
+            if (rv) {
+                const uint32_t rn = __ldcg(cnode + T::seq(root));
+                if (lane == 0) xroot[p] = rn;
+                if ((uint32_t)lane * 128u < a.ix.Rp * 4u)
+                    prefetch_l2(reinterpret_cast<const unsigned char *>(a.ix.nbrs + (size_t)rn * a.ix.Rp) + lane * 128);
+            }
+        }
         if (lane == 0) {
             ctl->root_valid[p] = rv ? 1u : 0u;
             ctl->root_key[p] = H::key(root);
@@ -770,6 +784,7 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
     w.ctl = reinterpret_cast<PairCtl *>(w.dlp + 2 * DANN_LIST_CAP);
     w.cqp = reinterpret_cast<uint32_t *>(w.ctl + 1);
     w.cqe = reinterpret_cast<E *>(w.cqp + 32);
+    w.xroot = reinterpret_cast<uint32_t *>(w.cqe + 32); /* the plan reserves these 16 bytes only for HV == 1 */
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.ins = a.ins_list + (size_t)slot * a.ins_cap;
