@@ -321,6 +321,8 @@ struct PairSearch {
         }
         vis_head = vis_len = 0;
         uint32_t visits = 0, scount = 0, k = 0;
+        uint32_t pf_node = DANN_INVALID_NODE; /* HV == 1: node whose TID is already in pf_tid */
+        uint64_t pf_tid = 0;
         /* ---- start nodes (graph/mod.rs:97-124, start_nodes.rs:39-48): 64 per page, never label-checked */
         for (; k < nstart_pages; k++) {
             const uint32_t p = k & 1;
@@ -422,7 +424,18 @@ struct PairSearch {
                 vis_head++;
                 vis_len--;
                 const uint32_t cn = (uint32_t)e;
-                const uint64_t tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
+                uint64_t tid;
+                if (HV == 1 && (a.hv_flags & DANN_HV_TIDPF)) {
+                    /* the head of the visited list is known a whole visit before it is consumed: its TID was asked for
+                     * then (below), so this dependent HBM load is off the consume -> visit path */
+                    tid = cn == pf_node ? pf_tid : __ldg(ix.tids + cn);
+                    if (vis_len) { /* the next head, for a burst of consumes */
+                        pf_node = (uint32_t)vis[vis_head];
+                        pf_tid = __ldg(ix.tids + pf_node);
+                    }
+                } else {
+                    tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
+                }
                 if ((tid & 0xFFFFull) == 0) continue;     /* InvalidOffsetNumber: deleted tuple, scan.rs:231-234 */
                 if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = cn;
                 scount++;
@@ -439,6 +452,13 @@ struct PairSearch {
             uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
             uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
             visited_insert(key, node);
+            if (HV == 1 && (a.hv_flags & DANN_HV_TIDPF) && !status) {
+                const uint32_t hn = (uint32_t)vis[vis_head]; /* vis_len >= 1 after the insert */
+                if (hn != pf_node) {
+                    pf_node = hn;
+                    pf_tid = __ldg(ix.tids + hn);
+                }
+            }
             visits++;
             uint32_t *list = listp + p * DANN_LIST_CAP, *dl = dlp + p * DANN_LIST_CAP;
             listn = 0;

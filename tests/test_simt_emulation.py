@@ -146,7 +146,7 @@ def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
     assert info["hv"] == 1 and info["bitmap_words"] == 0
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 3, 124, 131, 255])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 3, 380, 131, 511])
 def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
     """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
     s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
