@@ -321,8 +321,8 @@ struct PairSearch {
         }
         vis_head = vis_len = 0;
         uint32_t visits = 0, scount = 0, k = 0;
-        uint32_t pf_node = DANN_INVALID_NODE; /* HV == 1: node whose TID is already in pf_tid */
-        uint64_t pf_tid = 0;
+        uint32_t pf_node = DANN_INVALID_NODE; /* HV == 1: node whose TID offset is already in pf_off */
+        uint32_t pf_off = 0;                  /* its heap offset number (0 = deleted tuple) */
         /* ---- start nodes (graph/mod.rs:97-124, start_nodes.rs:39-48): 64 per page, never label-checked */
         for (; k < nstart_pages; k++) {
             const uint32_t p = k & 1;
@@ -426,12 +426,14 @@ struct PairSearch {
                 const uint32_t cn = (uint32_t)e;
                 uint64_t tid;
                 if (HV == 1 && (a.hv_flags & DANN_HV_TIDPF)) {
-                    /* the head of the visited list is known a whole visit before it is consumed: its TID was asked for
-                     * then (below), so this dependent HBM load is off the consume -> visit path */
-                    tid = cn == pf_node ? pf_tid : __ldg(ix.tids + cn);
+                    /* the head of the visited list is known a whole visit before it is consumed: the offset half of
+                     * its TID (all that the deleted-tuple test needs; little-endian low 16 bits) was asked for then
+                     * (below), so this dependent HBM load is off the consume -> visit path */
+                    const unsigned short *off16 = reinterpret_cast<const unsigned short *>(ix.tids);
+                    tid = cn == pf_node ? pf_off : __ldg(off16 + (size_t)cn * 4);
                     if (vis_len) { /* the next head, for a burst of consumes */
                         pf_node = (uint32_t)vis[vis_head];
-                        pf_tid = __ldg(ix.tids + pf_node);
+                        pf_off = __ldg(off16 + (size_t)pf_node * 4);
                     }
                 } else {
                     tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
@@ -456,7 +458,7 @@ struct PairSearch {
                 const uint32_t hn = (uint32_t)vis[vis_head]; /* vis_len >= 1 after the insert */
                 if (hn != pf_node) {
                     pf_node = hn;
-                    pf_tid = __ldg(ix.tids + hn);
+                    pf_off = __ldg(reinterpret_cast<const unsigned short *>(ix.tids) + (size_t)hn * 4);
                 }
             }
             visits++;
