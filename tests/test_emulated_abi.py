@@ -36,14 +36,23 @@ def _run(files, extra_env=None, workers=4, timeout=1500):
 
 def test_gpu_parity_suite_passes_under_emulation():
     passed, out = _run(["tests/test_gpu_parity.py", "tests/test_zz_c_harness_gpu.py", "tests/test_zz_d_build_small_gpu.py",
-                        "tests/test_zz_e_coalescer_gpu.py"])
-    assert passed >= 25 and "skipped" not in out.splitlines()[-1], out[-500:]
+                        "tests/test_zz_e_coalescer_gpu.py", "tests/test_zz_f_fuzz_gpu.py"])
+    assert passed >= 65 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
 def test_not_yet_on_hardware_paths_pass_under_emulation():
     """Heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout, through the real host code."""
     passed, out = _run(["tests/test_zz_experimental_gpu.py"], {"DANN_RUN_EXPERIMENTAL": "1"})
     assert passed >= 13 and "skipped" not in out.splitlines()[-1], out[-500:]
+
+
+def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "200", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16",
+                                                       "DANN_DEBUG_SHRINK": "8", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"})
+    assert passed == 200
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "200", "DANN_SEARCH_KERNEL": "1",
+                                                       "DANN_SEARCH_BITMAP": "0", "SIMT_SCHED": "1"})
+    assert passed == 200
 
 
 @pytest.mark.parametrize("sched", ["1", "2"])
