@@ -129,3 +129,42 @@ def test_plain_storage_golden_vectors(lib, monkeypatch, name):
             assert g["dist"][b, :n].view(np.uint32).tolist() == z[f"{name}/dist_bits"][b, :n].tolist()
     assert np.array_equal(g["stats"]["visits"], z[f"{name}/visits"])
     assert np.array_equal(g["stats"]["d_full"], z[f"{name}/d_full"])
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_plain_storage_random_small_indexes(lib, monkeypatch, seed):
+    """Edge-case fuzz of the plain layout: tiny graphs, 1..100 dimensions, truncated slices, deleted tuples."""
+    from oracle import fixtures, oracle
+    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.choice([1, 2, 5, 33, 200]))
+    dim = int(rng.choice([1, 2, 3, 8, 31, 33, 64, 100]))
+    dist = int(rng.choice([COSINE, L2]))
+    dim_index = None if dim < 3 or rng.random() < 0.5 else int(rng.integers(1, dim))
+    R = int(rng.choice([1, 3, 16, 40, 70]))
+    s = fixtures.to_plain(build_case(n, dim, dist, seed=seed, kind="normal", R=R, L_build=max(2 * R, 8),
+                                     dim_index=dim_index, deleted_every=int(rng.choice([0, 0, 3, 1]))))
+    B = int(rng.integers(1, 5))
+    q = fixtures.gen_vectors(B, dim, 300 + seed, "normal")
+    if rng.random() < 0.3:
+        q[0] = 0.0
+    with lib.DiskAnnIndex(s) as idx:
+        for _ in range(2):
+            _compare_plain(s, idx, q, k=int(rng.choice([1, 3, 20])), L=int(rng.choice([1, 2, 5, 50])),
+                           rescore=int(rng.choice([0, 1, 7, 100])))
+        L, rescore = int(rng.choice([1, 4, 30])), int(rng.choice([0, 2, 50]))
+        want = oracle.scan(s, q[0], None, L, rescore, 10_000)
+        sc = idx.begin_scan()
+        sc.rescan(q[0], search_list_size=L, rescore=rescore)
+        got = []
+        while True:
+            row = sc.gettuple()
+            if row is None:
+                break
+            got.append((row[0] << 16) | row[1])
+            assert len(got) <= n
+        assert got == want["tid"].tolist()
+        st = sc.stats()
+        for f in ("visits", "d_quantized", "candidates", "d_full"):
+            assert st[f] == want["stats"][f], f
+        sc.end()
