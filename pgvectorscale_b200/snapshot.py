@@ -86,6 +86,30 @@ class Snapshot:
                 d[f.name] = v
         np.savez(path, **d)
 
+    RAW_MAGIC = b"DANNSNP1"
+    RAW_ARRAYS = (("mean", np.float32), ("m2", np.float32), ("codes", np.uint64), ("nbrs", np.uint32),
+                  ("heap_tid", np.uint64), ("vectors", np.float32), ("start_labels", np.int16),
+                  ("start_label_nodes", np.uint32), ("label_off", np.uint32), ("labels", np.int16),
+                  ("index_vectors", np.float32))
+
+    def save_raw(self, path: str) -> None:
+        """Flat binary form for C hosts (harness/snapshot_raw.h reads it into a dann_snapshot_desc):
+        8-byte magic, 16 little-endian u64 header words, then every array of RAW_ARRAYS in order, each preceded by its
+        byte length (u64) and padded to a multiple of 64 bytes (absent arrays have length 0)."""
+        hdr = np.zeros(16, np.uint64)
+        hdr[:12] = [self.n, self.dim, self.dim_index, self.bits, self.words, self.R, int(self.distance_type) & 0xFFFFFFFF,
+                    int(bool(self.has_labels)), int(self.count), int(self.start_default),
+                    0 if self.start_labels is None else len(self.start_labels), int(self.storage_type or 0)]
+        with open(path, "wb") as f:
+            f.write(self.RAW_MAGIC)
+            f.write(hdr.tobytes())
+            for name, dt in self.RAW_ARRAYS:
+                v = getattr(self, name)
+                b = b"" if v is None else np.ascontiguousarray(v, dtype=dt).tobytes()
+                f.write(np.uint64(len(b)).tobytes())
+                f.write(b)
+                f.write(b"\0" * ((-len(b)) % 64))
+
     @classmethod
     def load(cls, path: str) -> "Snapshot":
         z = np.load(path)

@@ -62,3 +62,48 @@ def test_plain_storage_snapshot_is_refused_not_emulated():
     s = fixtures.to_plain(build_case(64, 16, 1, seed=2, R=8, L_build=16))
     with pytest.raises(DiskAnnError, match="plain"):
         DiskAnnIndex(s)
+
+
+def test_raw_snapshot_file_round_trips_through_the_c_reader(tmp_path):
+    """Snapshot.save_raw -> harness/snapshot_raw.h (C99): every header field and array arrives intact."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import build_case
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    s = build_case(200, 24, 1, seed=3, R=8, L_build=16, labels=True, deleted_every=7)
+    s.save_raw(str(tmp_path / "s.raw"))
+    (tmp_path / "t.c").write_text(r'''
+#include "snapshot_raw.h"
+int main(int argc, char **argv) {
+    dann_snapshot_desc s; const float *iv = 0;
+    (void)argc;
+    void *b = dann_snapshot_raw_read(argv[1], &s, &iv);
+    if (!b) return 1;
+    unsigned long long h = 1469598103934665603ull;
+    #define MIX(p, bytes) for (size_t i = 0; i < (size_t)(bytes); i++) h = (h ^ ((const unsigned char *)(p))[i]) * 1099511628211ull
+    MIX(s.mean, s.dim_index * 4); MIX(s.m2, s.dim_index * 4); MIX(s.codes, (size_t)s.n * s.words * 8);
+    MIX(s.nbrs, (size_t)s.n * s.R * 4); MIX(s.heap_tid, (size_t)s.n * 8); MIX(s.vectors, (size_t)s.n * s.dim * 4);
+    MIX(s.start_labels, s.n_start_labels * 2); MIX(s.start_label_nodes, s.n_start_labels * 4);
+    MIX(s.label_off, ((size_t)s.n + 1) * 4); MIX(s.labels, (size_t)s.label_off[s.n] * 2);
+    printf("%u %u %u %u %u %u %d %d %llu %u %u %d %llu\n", s.n, s.dim, s.dim_index, s.bits, s.words, s.R, s.distance_type,
+           s.has_labels, (unsigned long long)s.count, s.start_default, s.n_start_labels, iv != 0, h);
+    free(b); return 0;
+}''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "t")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    "-I" + os.path.join(root, "harness"), str(tmp_path / "t.c"), "-o", exe], check=True)
+    out = subprocess.run([exe, str(tmp_path / "s.raw")], capture_output=True, text=True, check=True).stdout.split()
+    h = 1469598103934665603
+    for a, dt in ((s.mean, np.float32), (s.m2, np.float32), (s.codes, np.uint64), (s.nbrs, np.uint32), (s.heap_tid, np.uint64),
+                  (s.vectors, np.float32), (s.start_labels, np.int16), (s.start_label_nodes, np.uint32),
+                  (s.label_off, np.uint32), (s.labels, np.int16)):
+        for byte in np.ascontiguousarray(a, dtype=dt).tobytes():
+            h = ((h ^ byte) * 1099511628211) % (1 << 64)
+    want = [s.n, s.dim, s.dim_index, s.bits, s.words, s.R, int(s.distance_type), 1, int(s.count), int(s.start_default),
+            len(s.start_labels), 0, h]
+    assert [int(x) for x in out] == want

@@ -60,3 +60,39 @@ def test_coalescer_concurrent_single_query_callers_get_private_scan_results(lib)
             assert g["dist"][:n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
         for f in ("visits", "d_quantized", "candidates", "d_full"):
             assert g["stats"][f] == r["stats"][f], (i, f)
+
+
+def test_c_load_generator_through_the_coalescer(lib, lib_built, tmp_path):
+    """harness/coalescer_load.c: pthread clients over the C ABI, index from the raw snapshot file (harness/snapshot_raw.h);
+    the checksum of every returned TID equals the oracle's private scans."""
+    import json
+    import os
+    import shutil
+    import subprocess
+    from oracle import fixtures, oracle
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "coalescer_load")
+    libdir = os.path.dirname(lib_built)
+    subprocess.run([gcc, "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    "-I" + os.path.join(root, "harness"), os.path.join(root, "harness", "coalescer_load.c"), "-L" + libdir,
+                    "-l:" + os.path.basename(lib_built), "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    s = build_case(1500, 64, COSINE, seed=4, kind="normal", R=24, L_build=48)
+    s.save_raw(str(tmp_path / "snap.raw"))
+    q = fixtures.gen_vectors(64, 64, 8, "normal")
+    q.astype(np.float32).tofile(str(tmp_path / "q.f32"))
+    T, per, L, rescore, k = 8, 8, 40, 20, 10
+    r = subprocess.run([exe, str(tmp_path / "snap.raw"), str(tmp_path / "q.f32"), str(T), str(per), str(L), str(rescore), str(k),
+                        "16", "20000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout)
+    assert d["queries"] == T * per and d["batches"] < T * per
+    chk = 0
+    for t in range(T):
+        for i in range(per):
+            o = oracle.scan(s, q[(t * per + i) % 64], None, L, rescore, k)
+            for x in list(o["tid"]) + [0xFFFFFFFFFFFFFFFF] * (k - len(o["tid"])):
+                chk = (chk * 1099511628211 + int(x)) % (1 << 64)
+    assert chk == d["tid_checksum"]

@@ -19,6 +19,7 @@ ap.add_argument("--queries", type=int, default=8192)
 ap.add_argument("--labels", action="store_true")
 ap.add_argument("--fixture", default="vamana", choices=["vamana", "knn"])
 ap.add_argument("--out", default="/tmp/snap")
+ap.add_argument("--raw", action="store_true", help="also write <out>.raw / <out>_q.f32 for the C harnesses")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 x = si.gen_dataset(a.n, a.dim, 0x5EED0010, a.data, device=dev)
@@ -31,4 +32,7 @@ truth = si.ground_truth(x, q[:1024], 10).cpu().numpy()
 snap.save(a.out + ".npz")
 np.save(a.out + "_q.npy", q.cpu().numpy())
 np.save(a.out + "_truth.npy", truth)
+if a.raw:
+    snap.save_raw(a.out + ".raw")
+    q.cpu().numpy().astype(np.float32).tofile(a.out + "_q.f32")
 print("saved", a.out)

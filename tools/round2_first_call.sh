@@ -10,7 +10,7 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>
 DANN_RUN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q > gpurun_out/r2_experimental.log 2>&1
 tail -3 gpurun_out/r2_experimental.log
 # 3. A/B timing on the benchmark fixture at the benchmark's operating point, each alternative alone
-python tools/make_snapshot.py --out /tmp/snap > gpurun_out/r2_mk.log 2>&1; tail -1 gpurun_out/r2_mk.log
+python tools/make_snapshot.py --out /tmp/snap --raw > gpurun_out/r2_mk.log 2>&1; tail -1 gpurun_out/r2_mk.log
 timeout 600 python tools/hv_ab.py --snap /tmp/snap --L 150 --rescore 250 --steps 20 > gpurun_out/r2_hv_ab.jsonl 2> gpurun_out/r2_hv_ab.err
 cat gpurun_out/r2_hv_ab.jsonl
 # 4. bench lines: default, and the full HV=1 flavour
@@ -21,3 +21,10 @@ cat gpurun_out/r2_bench_default.json gpurun_out/r2_bench_hv1.json
 DANN_HEAP_V2=1 timeout 900 ncu --set full --import-source on --clock-control none -k regex:dann_search2_kernel -c 1 \
     -o gpurun_out/r2_search2_hv1 python tools/profile_search.py --snap /tmp/snap --L 150 --rescore 250 --steps 2 \
     > gpurun_out/r2_ncu.log 2>&1; tail -2 gpurun_out/r2_ncu.log
+# 6. query coalescer: C pthread clients (stand-ins for backends) -> batches; how much of the batch throughput survives
+gcc -std=c99 -O2 -Iinclude -Iharness harness/coalescer_load.c -Lpgvectorscale_b200 -l:libdiskann_b200.so \
+    -Wl,-rpath,$PWD/pgvectorscale_b200 -lpthread -o /tmp/coalescer_load
+for T in 64 256 1024; do
+  /tmp/coalescer_load /tmp/snap.raw /tmp/snap_q.f32 $T 64 150 250 10 1024 200 >> gpurun_out/r2_coalescer.jsonl 2>> gpurun_out/r2_coalescer.err
+done
+cat gpurun_out/r2_coalescer.jsonl
