@@ -507,6 +507,9 @@ def main():
                    "search_list_size": L, "rescore": rescore, "recall_at_10": round(recall, 4),
                    "parallelism": f"query-shard x{world} (replicated index, all_gather of top-k)",
                    "l2_policy": f"index {idx.hbm_bytes / 1e9:.2f} GB >> 126 MB L2, random gathers, distinct queries every step",
+                   "search_kernel": ("dann_search2_kernel<HV=1> DANN_HV_FLAGS=%s (alternative engine, see DESIGN.md)"
+                                     % os.environ.get("DANN_HV_FLAGS", "all") if os.environ.get("DANN_HEAP_V2") == "1"
+                                     else "dann_search2_kernel<HV=0> (the round-1 measured kernel)"),
                    "index_fixture": ("dann_build_graph: GPU batch Vamana over SBQ codes (R=50, L_build=100, alpha=1.2), "
                                      "the reference's build algorithm with batched insertion" if args.fixture == "vamana"
                                      else "tools/synth_index.py exact-kNN + alpha-prune torch fixture")},
