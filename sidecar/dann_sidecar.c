@@ -1,0 +1,181 @@
+/* dann_sidecar.c — the process that owns the GPU on a Postgres host.
+ *
+ * Postgres backends are separate processes and cannot share a CUDA context; each would otherwise hold its own copy of
+ * the index in HBM and run one lonely scan at a time.  The sidecar loads the index once (DANNSNP1 file written by the
+ * Rust-side exporter), listens on a Unix-domain socket, and gives every connection (= one backend)
+ * a thread that forwards its scans to the library's coalescer: whatever the backends ask for within one window runs as
+ * one batch on the GPU.  Plain C99 + pthreads over include/diskann_b200.h.
+ *
+ *   dann_sidecar <snapshot.raw> <socket path> [max_batch=1024] [max_wait_us=200]
+ *
+ * Wire protocol (little-endian, one request -> one reply, any number per connection):
+ *   request : u32 magic 'DANQ', i32 k, i32 search_list_size, i32 rescore, i32 nlabels (-1 = no scan key),
+ *             f32 query[dim], i16 labels[max(nlabels,0)]
+ *   reply   : i32 status (dann_status), u32 count, then if status == 0: u64 tid[k], f32 dist[k],
+ *             u32 stats[6] (visits, d_quantized, candidates, d_full, stream_len, status); else u32 len + message.
+ * The first message on a connection is the server's hello: u32 magic 'DANH', u32 dim, u32 n.
+ * A backend's amrescan sends one request with k = the rows it expects to need (a LIMIT hint or a chunk size) and
+ * amgettuple serves rows from the reply; running past k re-requests with a larger k (scans are deterministic, so the
+ * first k rows repeat). */
+#define _POSIX_C_SOURCE 200809L
+#include <errno.h>
+#include <pthread.h>
+#include <signal.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+#include "../harness/snapshot_raw.h"
+
+static dann_coalescer *g_co;
+static uint32_t g_dim, g_n;
+static volatile sig_atomic_t g_stop;
+
+static int read_full(int fd, void *buf, size_t n) {
+    unsigned char *p = (unsigned char *)buf;
+    while (n) {
+        ssize_t r = read(fd, p, n);
+        if (r == 0) return -1;
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        p += r;
+        n -= (size_t)r;
+    }
+    return 0;
+}
+static int write_full(int fd, const void *buf, size_t n) {
+    const unsigned char *p = (const unsigned char *)buf;
+    while (n) {
+        ssize_t r = write(fd, p, n);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        p += r;
+        n -= (size_t)r;
+    }
+    return 0;
+}
+
+static void *serve(void *arg) {
+    const int fd = (int)(intptr_t)arg;
+    const uint32_t hello[3] = {0x484E4144u /* 'DANH' */, g_dim, g_n};
+    float *query = (float *)malloc((size_t)g_dim * sizeof(float));
+    if (!query || write_full(fd, hello, sizeof hello) != 0) goto out;
+    for (;;) {
+        int32_t h[5];
+        if (read_full(fd, h, sizeof h) != 0) break;
+        if ((uint32_t)h[0] != 0x514E4144u /* 'DANQ' */ || h[1] < 1 || h[1] > 65536 || h[4] < -1 || h[4] > 32767) break;
+        const int k = h[1], nlabels = h[4];
+        int16_t labels[64];
+        int16_t *lab = labels, *big = NULL;
+        if (read_full(fd, query, (size_t)g_dim * sizeof(float)) != 0) break;
+        if (nlabels > 64) lab = big = (int16_t *)malloc((size_t)nlabels * 2);
+        if (nlabels > 0 && (!lab || read_full(fd, lab, (size_t)nlabels * 2) != 0)) {
+            free(big);
+            break;
+        }
+        uint64_t *tid = (uint64_t *)malloc((size_t)k * 8);
+        float *dist = (float *)malloc((size_t)k * 4);
+        uint32_t count = 0;
+        dann_query_stats st;
+        memset(&st, 0, sizeof st);
+        int32_t rc = tid && dist ? dann_coalescer_search(g_co, query, lab, nlabels, k, h[2], h[3], tid, dist, &count, &st)
+                                 : DANN_ERR_OOM;
+        int bad = 0;
+        int32_t head[2] = {rc, (int32_t)count};
+        bad |= write_full(fd, head, sizeof head);
+        if (rc == DANN_OK) {
+            bad |= write_full(fd, tid, (size_t)k * 8);
+            bad |= write_full(fd, dist, (size_t)k * 4);
+            bad |= write_full(fd, &st, sizeof st);
+        } else {
+            const char *msg = dann_last_error();
+            uint32_t len = (uint32_t)strlen(msg);
+            bad |= write_full(fd, &len, 4);
+            bad |= write_full(fd, msg, len);
+        }
+        free(tid);
+        free(dist);
+        free(big);
+        if (bad) break;
+    }
+out:
+    free(query);
+    close(fd);
+    return NULL;
+}
+
+static void on_term(int sig) {
+    (void)sig;
+    g_stop = 1;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s snapshot.raw socket_path [max_batch] [max_wait_us]\n", argv[0]);
+        return 2;
+    }
+    dann_snapshot_desc s;
+    const float *iv = NULL;
+    void *buf = dann_snapshot_raw_read(argv[1], &s, &iv);
+    if (!buf) {
+        fprintf(stderr, "dann_sidecar: cannot read %s\n", argv[1]);
+        return 1;
+    }
+    dann_index *ix = NULL;
+    int rc = iv ? dann_index_load_plain(&s, iv, 0, &ix) : dann_index_load(&s, 0, &ix);
+    g_dim = s.dim;
+    g_n = s.n;
+    free(buf);
+    if (rc != DANN_OK) {
+        fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
+        return rc == DANN_ERR_NO_DEVICE ? 3 : 1;
+    }
+    if (dann_coalescer_create(ix, argc > 3 ? atoi(argv[3]) : 1024, argc > 4 ? atoi(argv[4]) : 200, &g_co) != DANN_OK) {
+        fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
+        return 1;
+    }
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_handler = on_term;
+    sigaction(SIGTERM, &sa, NULL);
+    sigaction(SIGINT, &sa, NULL);
+    signal(SIGPIPE, SIG_IGN);
+    int ls = socket(AF_UNIX, SOCK_STREAM, 0);
+    struct sockaddr_un addr;
+    memset(&addr, 0, sizeof addr);
+    addr.sun_family = AF_UNIX;
+    strncpy(addr.sun_path, argv[2], sizeof addr.sun_path - 1);
+    unlink(argv[2]);
+    if (ls < 0 || bind(ls, (struct sockaddr *)&addr, sizeof addr) != 0 || listen(ls, 512) != 0) {
+        perror("dann_sidecar: socket");
+        return 1;
+    }
+    fprintf(stderr, "dann_sidecar: %u nodes x %u dims in HBM (%.2f GB), listening on %s\n", g_n, g_dim,
+            (double)dann_index_hbm_bytes(ix) / 1e9, argv[2]);
+    while (!g_stop) {
+        int fd = accept(ls, NULL, NULL);
+        if (fd < 0) {
+            if (errno == EINTR) continue;
+            break;
+        }
+        pthread_t th;
+        if (pthread_create(&th, NULL, serve, (void *)(intptr_t)fd) == 0) pthread_detach(th);
+        else close(fd);
+    }
+    close(ls);
+    unlink(argv[2]);
+    uint64_t batches = 0, queries = 0, largest = 0;
+    dann_coalescer_stats(g_co, &batches, &queries, &largest);
+    fprintf(stderr, "dann_sidecar: %llu queries in %llu batches (largest %llu)\n", (unsigned long long)queries,
+            (unsigned long long)batches, (unsigned long long)largest);
+    dann_coalescer_destroy(g_co);
+    dann_index_free(ix);
+    return 0;
+}

@@ -96,3 +96,68 @@ def test_c_load_generator_through_the_coalescer(lib, lib_built, tmp_path):
             for x in list(o["tid"]) + [0xFFFFFFFFFFFFFFFF] * (k - len(o["tid"])):
                 chk = (chk * 1099511628211 + int(x)) % (1 << 64)
     assert chk == d["tid_checksum"]
+
+
+def test_sidecar_process_serves_concurrent_backends(lib, lib_built, tmp_path):
+    """sidecar/dann_sidecar.c: one process owns the index, every connection is a backend; concurrent clients get
+    exactly the oracle's private scans (rows, distance bits, counters), keyed and unkeyed."""
+    import os
+    import shutil
+    import signal
+    import subprocess
+    import threading
+    import time
+    from oracle import fixtures, oracle
+    from pgvectorscale_b200.sidecar_client import SidecarClient
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dann_sidecar")
+    libdir = os.path.dirname(lib_built)
+    subprocess.run([gcc, "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "sidecar", "dann_sidecar.c"), "-L" + libdir, "-l:" + os.path.basename(lib_built),
+                    "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    s = build_case(1200, 48, COSINE, seed=12, kind="normal", R=24, L_build=48, labels=True, deleted_every=10)
+    s.save_raw(str(tmp_path / "snap.raw"))
+    sock = str(tmp_path / "dann.sock")
+    proc = subprocess.Popen([exe, str(tmp_path / "snap.raw"), sock, "32", "20000"], stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock) or proc.poll() is not None:
+                break
+            time.sleep(0.05)
+        assert proc.poll() is None and os.path.exists(sock), proc.stderr.read() if proc.poll() is not None else "no socket"
+        q = fixtures.gen_vectors(24, 48, 31, "normal")
+        out, errors = {}, []
+
+        def backend(t):
+            try:
+                with SidecarClient(sock) as c:
+                    assert (c.dim, c.n) == (48, 1200)
+                    for j in range(4):
+                        i = t * 4 + j
+                        key = [3, 9] if i % 2 else None
+                        out[i] = c.scan(q[i], labels=key, k=10, search_list_size=40, rescore=15)
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        th = [threading.Thread(target=backend, args=(t,)) for t in range(6)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert not errors, errors
+        for i in range(24):
+            r = oracle.scan(s, q[i], [3, 9] if i % 2 else None, 40, 15, 10)
+            n = len(r["tid"])
+            assert out[i]["count"] == n and out[i]["tid"][:n].tolist() == r["tid"].tolist()
+            assert out[i]["dist"][:n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
+            assert out[i]["stats"]["visits"] == r["stats"]["visits"]
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+    assert "queries in" in proc.stderr.read()
