@@ -288,6 +288,101 @@ struct PairSearch {
         else distances_impl<false>(list, dl, tn);
     }
 
+    /* HV == 1, bit 512: stage() and distances() fused for the common case (bitmap inserted-set, duplicate-free lists, no
+     * label filter).  The inserted-set atomics and the SBQ code gather of EVERY listed id are issued together, so the
+     * two L2/HBM round trips overlap instead of following each other; rows of ids that turn out to be known are
+     * dropped after the fact (about half of them: that is the price).  `scratch` = the other list page (free during an
+     * expansion: it was consumed by this iteration's prediction) holds the 64 raw slot ids so that each lane group can
+     * pick up the id of its row slots.  Ids in slots past the first RP*RPI (48 for 192-byte codes) are handled by the
+     * ordinary distance round afterwards.  Same list order, same distances, same counters as stage() + distances(). */
+    template <bool EXACT>
+    __device__ __forceinline__ void expand_fused(uint32_t *list, uint32_t *dl, uint32_t *scratch, uint32_t n0, bool v0,
+                                                 uint32_t n1, bool v1) {
+        const unsigned vm0 = __ballot_sync(DANN_FULL, v0), vm1 = __ballot_sync(DANN_FULL, v1);
+        if ((vm0 | vm1) == 0) return;
+        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
+        const uint32_t nchunks = a.ix.cw >> 1;
+        const size_t rowbytes = (size_t)a.ix.cw * 8;
+        const unsigned char *cbase = reinterpret_cast<const unsigned char *>(a.ix.codes) + (size_t)gl * 16;
+        const uint32_t cstep = G * 16;
+        /* inserted-set first (the longer round trip), then the rows */
+        uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+        const uint32_t b0 = 1u << (n0 & 31), b1 = 1u << (n1 & 31);
+        if (v0) o0 = atomicOr(bitmap + (n0 >> 5), b0);
+        if (v1) o1 = atomicOr(bitmap + (n1 >> 5), b1);
+        scratch[lane] = n0;
+        scratch[32 + lane] = n1;
+        __syncwarp();
+        ulonglong2 v[RPI][NCH];
+#pragma unroll
+        for (int u = 0; u < RPI; u++) {
+            const uint32_t slot = u * RP + grp;
+            const bool live = slot < 64u && (((slot < 32u ? vm0 : vm1) >> (slot & 31u)) & 1u);
+            const unsigned char *row = cbase + (size_t)(live ? scratch[slot] : 0u) * rowbytes;
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                const bool ok = live && (EXACT || gl + i * G < nchunks);
+                v[u][i] = ok ? ldg_stream_u128(row + i * cstep) : qc[i];
+            }
+        }
+        /* the atomics' answers: which slots are new, where they go in the page (list order = slot order) */
+        const bool new0 = v0 && !(o0 & b0), new1 = v1 && !(o1 & b1);
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned nm0 = __ballot_sync(DANN_FULL, new0), nm1 = __ballot_sync(DANN_FULL, new1);
+        const uint32_t c0 = __popc(nm0), c1 = __popc(nm1);
+        if (nins + c0 + c1 > a.ins_cap) { /* as in stage(): leave the bitmap as it was and report */
+            if (new0) atomicAnd(bitmap + (n0 >> 5), ~b0);
+            if (new1) atomicAnd(bitmap + (n1 >> 5), ~b1);
+            status |= DANN_ST_HASH;
+            return;
+        }
+        if (new0) ins[nins + __popc(nm0 & lt)] = n0;
+        if (new1) ins[nins + c0 + __popc(nm1 & lt)] = n1;
+        nins += c0 + c1;
+        if (c0 + c1 == 0) return;
+        if (ncand + c0 + c1 + 1 > a.cand_cap) {
+            status |= DANN_ST_HEAP;
+            return;
+        }
+        if (new0) {
+            const uint32_t pos = __popc(nm0 & lt);
+            list[pos] = n0;
+            cnode[ncand + pos] = n0;
+        }
+        if (new1) {
+            const uint32_t pos = c0 + __popc(nm1 & lt);
+            list[pos] = n1;
+            cnode[ncand + pos] = n1;
+        }
+        listn = c0 + c1;
+        /* distances of the new ids among the first RP*RPI slots, straight from the rows already in registers */
+#pragma unroll
+        for (int u = 0; u < RPI; u++) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < NCH; i++) sum += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
+            for (uint32_t o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(DANN_FULL, sum, o);
+            const uint32_t slot = u * RP + grp;
+            if (gl == 0 && slot < 64u) {
+                const bool isnew = ((slot < 32u ? nm0 : nm1) >> (slot & 31u)) & 1u;
+                if (isnew) {
+                    const uint32_t pos = slot < 32u ? __popc(nm0 & ((1u << slot) - 1u))
+                                                    : c0 + __popc(nm1 & ((1u << (slot - 32u)) - 1u));
+                    dl[pos] = sum;
+                }
+            }
+        }
+        __syncwarp();
+        /* new ids in slots RP*RPI .. 63 (lists longer than 48): the ordinary round over the tail of the page */
+        const uint32_t first = RP * RPI;
+        if (first < 64u) {
+            const uint32_t lo = first < 32u ? __popc(nm0 & ((1u << first) - 1u))
+                                            : c0 + __popc(nm1 & ((1u << (first - 32u)) - 1u));
+            for (uint32_t b = lo; b < listn; b += RP * RPI) distances_round<EXACT, RPI>(list, dl, listn, b);
+            __syncwarp();
+        }
+    }
+
     __device__ __forceinline__ void run_memory(uint32_t q) {
         const IndexView &ix = a.ix;
         ncand = nins = status = 0;
@@ -464,13 +559,19 @@ struct PairSearch {
             visits++;
             uint32_t *list = listp + p * DANN_LIST_CAP, *dl = dlp + p * DANN_LIST_CAP;
             listn = 0;
+            bool fused_done = false;
             if (!status) {
                 const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
                 const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
                 const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
                 const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
                 const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-                if (a.lists_unique) {
+                if (HV == 1 && (a.hv_flags & DANN_HV_FUSED) && a.lists_unique && a.bitmap_words && !filter) {
+                    uint32_t *scratch = listp + pp * DANN_LIST_CAP;
+                    if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) expand_fused<true>(list, dl, scratch, n0, v0, n1, v1);
+                    else expand_fused<false>(list, dl, scratch, n0, v0, n1, v1);
+                    fused_done = true;
+                } else if (a.lists_unique) {
                     stage(list, n0, v0, n1, v1, filter, true);
                 } else {
                     stage(list, n0, v0, DANN_INVALID_NODE, false, filter);
@@ -478,7 +579,7 @@ struct PairSearch {
                 }
             }
             if (status) listn = 0;
-            distances(list, dl, listn);
+            if (!fused_done) distances(list, dl, listn);
             if (lane == 0) {
                 ctl->tn[p] = listn;
                 ctl->seq0[p] = ncand;

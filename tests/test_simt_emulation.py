@@ -146,7 +146,7 @@ def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
     assert info["hv"] == 1 and info["bitmap_words"] == 0
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 3, 380, 131, 511])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 3, 892, 131, 511, 1023])
 def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
     """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
     s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
@@ -162,6 +162,17 @@ def test_emulated_hv1_visited_search_list_sizes(emu, L):
     q = fixtures.gen_vectors(2, 32, 29, "normal")
     info = check(emu, s, q, L, 40, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": 32})
     assert info["hv"] == 1
+
+
+@pytest.mark.parametrize("dim,R", [(768, 64), (1536, 40), (384, 64)])
+def test_emulated_hv1_fused_expansion_long_lists(emu, dim, R):
+    """Lists longer than the rows one fused round holds (48 slots at 768-d x 2 bits, 24 at 1536-d): the tail of the
+    page goes through the ordinary distance round."""
+    s = build_case(260, dim, COSINE, seed=3, kind="normal", R=R, L_build=R + 16)
+    q = fixtures.gen_vectors(2, dim, 8, "normal")
+    for flags in (512, 1023):
+        info = check(emu, s, q, 25, 34, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags})
+        assert info["hv"] == 1
 
 
 def test_emulated_heap_engine_v2_reference_shape(emu):

@@ -34,14 +34,16 @@ if not a.no_check:
     from oracle import oracle
     want = oracle.scan_batch(s, q[:32], None, None, a.L, a.rescore, a.k)
 
-VARIANTS = [("default", None, None), ("hv1 all", 1, 511), ("hv1 none (same code paths as default)", 1, 0),
+VARIANTS = [("default", None, None), ("hv1 all", 1, 1023), ("hv1 none (same code paths as default)", 1, 0),
             ("push only", 1, 1), ("pop only", 1, 2), ("push+pop", 1, 3), ("distances only", 1, 4),
             ("code prefetch only", 1, 8), ("nbr prefetch only", 1, 16), ("visited search only", 1, 32),
             ("no intra-list dedupe only", 1, 64),
             ("root node id + prefetch by the heap warp only", 1, 128),
             ("heap v2 + root node (1+2+128)", 1, 131),
             ("TID prefetch only", 1, 256),
-            ("controller all (4+8+16+32+64+256)", 1, 380)]
+            ("fused expansion only", 1, 512),
+            ("all but fused expansion", 1, 511),
+            ("controller all (4+8+16+32+64+256+512)", 1, 892)]
 for name, hv, flags in VARIANTS:
     for k_, v_ in (("DANN_HEAP_V2", hv), ("DANN_HV_FLAGS", flags)):
         if v_ is None:
