@@ -505,8 +505,9 @@ static search_fn pick_search2(uint32_t nch) {
         case 1: return dann_search2_kernel<T, 1, HV>;
         case 2: return dann_search2_kernel<T, 2, HV>;
         case 3: return dann_search2_kernel<T, 3, HV>;
-        case 4: return dann_search2_kernel<T, 4, HV>;
-        default: return dann_search2_kernel<T, 8, HV>;
+        /* codes wider than 96 16-byte chunks (> 12 288 bits): only the measured flavour is instantiated */
+        case 4: return dann_search2_kernel<T, 4, 0>;
+        default: return dann_search2_kernel<T, 8, 0>;
     }
 }
 static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0, bool plain = false) {
