@@ -12,7 +12,7 @@
 
 struct SearchPlan {
     uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
-    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64 */
+    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64, 3 = Ent32n21 (HV = 1 only) */
     bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
     int hv;     /* heap-warp engine of the two-warp kernel (dann_search2.cuh: 0 = round-1 path, 1 = DANN_HEAP_V2) */
 };
@@ -92,10 +92,14 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     /* kernel choice: the two-warp kernel handles neighbour lists of up to 64 ids */
     p->pairs = !force_single && in.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1 && !in.plain_dim;
     p->hv = p->pairs && env_u32("DANN_HEAP_V2", 0) == 1 ? 1 : 0;
+    /* HV = 1 and at most 2M nodes: 4-byte entries that carry the node id (Ent32n21, no seq -> node table) */
+    if (p->hv == 1 && p->entry == 0 && in.n <= (1u << 21) && !getenv("DANN_SEARCH_ENTRY") &&
+        env_u32("DANN_HV_NODE_ENTRIES", 1) == 1)
+        p->entry = 3;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4) +
                          (size_t)((in.plain_dim + 3u) & ~3u) * 4 + /* plain layout: the query's index slice */
-                         (p->hv == 1 ? 16u : 0u);                  /* HV == 1: published root node ids */
+                         (p->hv == 1 ? 16u + 256u : 0u);           /* HV == 1: published root node ids, fused-expansion scratch */
     if (fixed + 1024 > budget) {
         snprintf(err, errlen, "visited list of %u entries does not fit shared memory", p->vcap);
         return DANN_ERR_CAPACITY;

@@ -112,21 +112,36 @@ struct SearchArgs {
  * to 2M candidates per query in 4 bytes; Ent32x16: 16-bit distances, up to 65536 candidates; Ent64: anything. */
 struct Ent32x21 {
     using E = uint32_t;
+    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 21;
     static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 21) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0x1FFFFFu; }
 };
 struct Ent32x16 {
     using E = uint32_t;
+    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 16;
     static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 16) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0xFFFFu; }
 };
 struct Ent64 {
     using E = uint64_t;
+    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 32;
     static __device__ __forceinline__ uint64_t make(uint32_t d, uint32_t seq) { return ((uint64_t)d << 32) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint64_t e) { return (uint32_t)e; }
+};
+/* Ent32x21's layout with the NODE ID as payload instead of the candidate sequence number (indexes of up to 2M nodes,
+ * 11-bit distances): the heap then needs no seq -> node table - no global store per candidate, no global load to learn
+ * which node the root is.  A node enters the heap at most once (inserted-set), so the payload is as unique as a
+ * sequence number, and only the key takes part in comparisons either way.  Used by the HV = 1 flavour of the two-warp
+ * kernel only. */
+struct Ent32n21 {
+    using E = uint32_t;
+    static constexpr bool PAYLOAD_IS_NODE = true;
+    static constexpr int KSHIFT = 21;
+    static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t node) { return (d << 21) | node; }
+    static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0x1FFFFFu; }
 };
 
 /* PLAIN = 1: the plain storage layout.  Keys are total_ukey(f32 distance) (Ent64 entries), every comparison is a

@@ -71,6 +71,7 @@ struct PairSearch {
     PairCtl *ctl;
     E *cqe;         /* [32] compacted active pushes: entry */
     uint32_t *xroot; /* HV == 1: [2] node id of the published root (+2 spare words), behind cqe */
+    uint32_t *fscratch; /* HV == 1: [64] raw slot ids of the list being expanded (fused expansion) */
     uint32_t *cqp;  /* [32]                          : 1-based slot */
     uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
@@ -182,12 +183,12 @@ struct PairSearch {
         if (p0) {
             uint32_t pos = listn + __popc(pm0 & lt);
             list[pos] = n0;
-            cnode[ncand + pos] = n0;
+            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n0;
         }
         if (p1) {
             uint32_t pos = listn + t0 + __popc(pm1 & lt);
             list[pos] = n1;
-            cnode[ncand + pos] = n1;
+            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n1;
         }
         listn += t0 + t1;
         __syncwarp();
@@ -291,9 +292,8 @@ struct PairSearch {
     /* HV == 1, bit 512: stage() and distances() fused for the common case (bitmap inserted-set, duplicate-free lists, no
      * label filter).  The inserted-set atomics and the SBQ code gather of EVERY listed id are issued together, so the
      * two L2/HBM round trips overlap instead of following each other; rows of ids that turn out to be known are
-     * dropped after the fact (about half of them: that is the price).  `scratch` = the other list page (free during an
-     * expansion: it was consumed by this iteration's prediction) holds the 64 raw slot ids so that each lane group can
-     * pick up the id of its row slots.  Ids in slots past the first RP*RPI (48 for 192-byte codes) are handled by the
+     * dropped after the fact (about half of them: that is the price).  `scratch` (64 words of shared memory of its own)
+     * holds the raw slot ids so that each lane group can pick up the id of its row slots.  Ids in slots past the first RP*RPI (48 for 192-byte codes) are handled by the
      * ordinary distance round afterwards.  Same list order, same distances, same counters as stage() + distances(). */
     template <bool EXACT>
     __device__ __forceinline__ void expand_fused(uint32_t *list, uint32_t *dl, uint32_t *scratch, uint32_t n0, bool v0,
@@ -347,12 +347,12 @@ struct PairSearch {
         if (new0) {
             const uint32_t pos = __popc(nm0 & lt);
             list[pos] = n0;
-            cnode[ncand + pos] = n0;
+            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n0;
         }
         if (new1) {
             const uint32_t pos = c0 + __popc(nm1 & lt);
             list[pos] = n1;
-            cnode[ncand + pos] = n1;
+            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n1;
         }
         listn = c0 + c1;
         /* distances of the new ids among the first RP*RPI slots, straight from the rows already in registers */
@@ -483,7 +483,8 @@ struct PairSearch {
                 node = pl[idx];
                 key = m;
             } else if (rv) { /* the root the pop left behind stays on top */
-                if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) node = xroot[pp];
+                if (T::PAYLOAD_IS_NODE) node = ctl->root_seq[pp]; /* the entry carries the node id itself */
+                else if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) node = xroot[pp];
                 else node = cnode[ctl->root_seq[pp]];
                 key = ctl->root_key[pp];
             }
@@ -567,7 +568,7 @@ struct PairSearch {
                 const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
                 const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
                 if (HV == 1 && (a.hv_flags & DANN_HV_FUSED) && a.lists_unique && a.bitmap_words && !filter) {
-                    uint32_t *scratch = listp + pp * DANN_LIST_CAP;
+                    uint32_t *scratch = fscratch; /* not a list page: the heap warp may still read the previous one */
                     if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) expand_fused<true>(list, dl, scratch, n0, v0, n1, v1);
                     else expand_fused<false>(list, dl, scratch, n0, v0, n1, v1);
                     fused_done = true;
@@ -627,14 +628,15 @@ struct PairSearch {
      * the batch do) are written in parallel; the others are compacted into a small queue and
      * replayed in order through the cooperative sift-up, the next one prefetched meanwhile. */
     template <bool PSM, typename Store>
-    __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
+    __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0,
+                                               const uint32_t *lp = nullptr) {
         const unsigned lt = (1u << lane) - 1u;
         for (uint32_t base = 0; base < tn; base += 32) {
             const uint32_t r = base + lane;
             const bool have = r < tn;
             const uint32_t dmine = have ? dl[r] : 0u;
             const uint32_t slot = heap_len + r + 1;
-            const E mine = T::make(dmine, seq0 + r);
+            const E mine = T::make(dmine, T::PAYLOAD_IS_NODE ? (have ? lp[r] : 0u) : seq0 + r);
             bool inert = false;
             if (have && slot > 1) {
                 const uint32_t parent = slot >> 1;
@@ -675,7 +677,8 @@ struct PairSearch {
      * writes back, the warp syncs and reloads.  Requires heap_len >= 64 >= tn: every ancestor of a new slot is then an old
      * slot, never a slot of this batch. */
     template <typename Store>
-    __device__ __forceinline__ void push_batch_v2(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
+    __device__ __forceinline__ void push_batch_v2(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0,
+                                                  const uint32_t *lp) {
         constexpr E KM = (E(1) << T::KSHIFT) - E(1);
         const uint32_t lanebit = 1u << lane, lanebit2 = lanebit << 1;
         uint32_t pos = heap_len + 1;
@@ -688,7 +691,7 @@ struct PairSearch {
         }
         for (uint32_t base = 0; base < tn; base += 32) {
             const uint32_t r = base + lane;
-            const E mine = T::make(r < tn ? dl[r] : 0u, seq0 + r);
+            const E mine = T::make(r < tn ? dl[r] : 0u, T::PAYLOAD_IS_NODE ? (r < tn ? lp[r] : 0u) : seq0 + r);
             const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
             for (uint32_t i = 0; i < cnt; i++) {
                 const E e = __shfl_sync(DANN_FULL, mine, (int)i);
@@ -730,14 +733,15 @@ struct PairSearch {
     __device__ __forceinline__ void push_page(uint32_t p) {
         const uint32_t tn = ctl->tn[p], seq0 = ctl->seq0[p];
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
+        const uint32_t *lp = listp + p * DANN_LIST_CAP; /* the page's node ids (entries that carry them) */
         if (tn == 0) return;
         if constexpr (HV == 1) {
             if (heap_len >= 64 && (a.hv_flags & DANN_HV_PUSH)) {
                 if (heap_len + tn < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
-                    push_batch_v2(sm, dl, tn, seq0);
+                    push_batch_v2(sm, dl, tn, seq0, lp);
                 } else {
-                    push_batch_v2(heap, dl, tn, seq0);
+                    push_batch_v2(heap, dl, tn, seq0, lp);
                 }
                 heap_len += tn;
                 return;
@@ -745,11 +749,11 @@ struct PairSearch {
         }
         if (heap_len + tn < heap.hs) { /* everything in shared memory */
             ArrayStore<E> sm{heap.sm};
-            push_batch<true>(sm, dl, tn, seq0);
+            push_batch<true>(sm, dl, tn, seq0, lp);
         } else if (heap_len + tn < 2 * heap.hs) { /* leaves spill to HBM, every parent still in shared memory */
-            push_batch<true>(heap, dl, tn, seq0);
+            push_batch<true>(heap, dl, tn, seq0, lp);
         } else {
-            push_batch<false>(heap, dl, tn, seq0);
+            push_batch<false>(heap, dl, tn, seq0, lp);
         }
         heap_len += tn;
     }
@@ -817,7 +821,7 @@ struct PairSearch {
              * and start pulling that node's neighbour row into L2 - it is the next visit unless the page being
              * built beats it */
             if (rv) {
-                const uint32_t rn = __ldcg(cnode + T::seq(root));
+                const uint32_t rn = T::PAYLOAD_IS_NODE ? T::seq(root) : __ldcg(cnode + T::seq(root));
                 if (lane == 0) xroot[p] = rn;
                 if ((uint32_t)lane * 128u < a.ix.Rp * 4u)
                     prefetch_l2(reinterpret_cast<const unsigned char *>(a.ix.nbrs + (size_t)rn * a.ix.Rp) + lane * 128);
@@ -875,7 +879,7 @@ struct PairSearch {
                     if (lane == 0) ctl->status_b = DANN_ST_INTERNAL;
                     continue;
                 }
-                node_chk = __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
+                node_chk = T::PAYLOAD_IS_NODE ? T::seq(head) : __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
                     if (HV == 1 && (a.hv_flags & DANN_HV_POP)) H::pop_warp1_la(sm, heap_len, lane);
@@ -907,7 +911,8 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
     w.ctl = reinterpret_cast<PairCtl *>(w.dlp + 2 * DANN_LIST_CAP);
     w.cqp = reinterpret_cast<uint32_t *>(w.ctl + 1);
     w.cqe = reinterpret_cast<E *>(w.cqp + 32);
-    w.xroot = reinterpret_cast<uint32_t *>(w.cqe + 32); /* the plan reserves these 16 bytes only for HV == 1 */
+    w.xroot = reinterpret_cast<uint32_t *>(w.cqe + 32); /* the plan reserves these 16 + 256 bytes only for HV == 1 */
+    w.fscratch = w.xroot + 4;
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.ins = a.ins_list + (size_t)slot * a.ins_cap;

@@ -512,6 +512,9 @@ static search_fn pick_search2(uint32_t nch) {
 }
 static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0, bool plain = false) {
     if (plain) return dann_search_kernel<Ent64, 1, 1>;
+    if (pairs && hv == 1 && entry == 3 && nch <= 3)
+        return nch == 1 ? dann_search2_kernel<Ent32n21, 1, 1> : nch == 2 ? dann_search2_kernel<Ent32n21, 2, 1> : dann_search2_kernel<Ent32n21, 3, 1>;
+    if (entry == 3) entry = 0; /* same 4-byte layout with sequence numbers */
     if (pairs && hv == 1) return entry == 0 ? pick_search2<Ent32x21, 1>(nch) : entry == 1 ? pick_search2<Ent32x16, 1>(nch) : pick_search2<Ent64, 1>(nch);
     if (pairs) return entry == 0 ? pick_search2<Ent32x21, 0>(nch) : entry == 1 ? pick_search2<Ent32x16, 0>(nch) : pick_search2<Ent64, 0>(nch);
     return entry == 0 ? pick_search<Ent32x21>(nch) : entry == 1 ? pick_search<Ent32x16>(nch) : pick_search<Ent64>(nch);

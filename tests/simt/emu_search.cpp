@@ -34,6 +34,8 @@ static emu_kernel pick2(uint32_t nch) {
 }
 static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv, bool plain = false) {
     if (plain) return dann_search_kernel<Ent64, 1, 1>;
+    if (pairs && hv == 1 && entry == 3) return pick2<Ent32n21, 1>(nch);
+    if (entry == 3) entry = 0;
     if (pairs && hv == 1) return entry == 0 ? pick2<Ent32x21, 1>(nch) : entry == 1 ? pick2<Ent32x16, 1>(nch) : pick2<Ent64, 1>(nch);
     if (pairs) return entry == 0 ? pick2<Ent32x21, 0>(nch) : entry == 1 ? pick2<Ent32x16, 0>(nch) : pick2<Ent64, 0>(nch);
     return entry == 0 ? pick1<Ent32x21>(nch) : entry == 1 ? pick1<Ent32x16>(nch) : pick1<Ent64>(nch);

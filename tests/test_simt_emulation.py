@@ -164,6 +164,22 @@ def test_emulated_hv1_visited_search_list_sizes(emu, L):
     assert info["hv"] == 1
 
 
+@pytest.mark.parametrize("hs", [None, 16, 256])
+@pytest.mark.parametrize("flags", [0, 3, 1023])
+def test_emulated_hv1_node_carrying_entries(emu, hs, flags):
+    """Ent32n21: 4-byte heap entries whose payload is the node id (no seq -> node table), chosen for HV = 1 when the
+    index has at most 2M nodes and the entry layout is not forced."""
+    s = build_case(2500, 64, COSINE, seed=71, kind="normal", R=32, L_build=64, deleted_every=17)
+    q = fixtures.gen_vectors(3, 64, 13, "normal")
+    env = {"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags}
+    if hs is not None:
+        env["DANN_SEARCH_HS"] = hs
+    info = check(emu, s, q, 80, 150, env=env)
+    assert info["hv"] == 1 and info["entry"] == 3
+    info = check(emu, s, q[:1], 80, 150, env=dict(env, DANN_HV_NODE_ENTRIES=0))
+    assert info["entry"] == 0
+
+
 @pytest.mark.parametrize("dim,R", [(768, 64), (1536, 40), (384, 64)])
 def test_emulated_hv1_fused_expansion_long_lists(emu, dim, R):
     """Lists longer than the rows one fused round holds (48 slots at 768-d x 2 bits, 24 at 1536-d): the tail of the
