@@ -44,7 +44,10 @@ VARIANTS = [("default", None, None), ("hv1 all", 1, 1023), ("hv1 none (same code
             ("fused expansion only", 1, 512),
             ("all but fused expansion", 1, 511),
             ("controller all (4+8+16+32+64+256+512)", 1, 892)]
+# node-carrying entries are on for every hv1 variant above; one more line with them off
+VARIANTS.append(("hv1 all, sequence-number entries (DANN_HV_NODE_ENTRIES=0)", 1, 1023))
 for name, hv, flags in VARIANTS:
+    os.environ["DANN_HV_NODE_ENTRIES"] = "0" if "DANN_HV_NODE_ENTRIES=0" in name else "1"
     for k_, v_ in (("DANN_HEAP_V2", hv), ("DANN_HV_FLAGS", flags)):
         if v_ is None:
             os.environ.pop(k_, None)
