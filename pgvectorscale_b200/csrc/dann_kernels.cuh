@@ -496,3 +496,92 @@ __global__ void dann_scan_resort_kernel(IndexView ix, ScanWindow *w, uint64_t *w
     w->len = len;
     *out = r;
 }
+
+/* ---- one-synchronisation amgettuple (DANN_SCAN_FUSED=1): the search launch, the exact distances of the rows it
+ * appended and the window step are enqueued back to back; the two kernels below read the search's outcome (rows
+ * produced, overflow bits) from device memory instead of the host doing so in between, and the last one gathers
+ * everything the host needs into one ScanStepOut.  A search that overflowed its workspace leaves the window alone. */
+struct ScanStepOut {
+    uint32_t overflow, slen;
+    dann_query_stats stats;
+    ScanRow row;
+    ScanWindow win;
+};
+
+__global__ void __launch_bounds__(128) dann_scan_distance_kernel(IndexView ix, const float *q_full, const uint32_t *stream,
+                                                                 const uint32_t *slen_p, const uint32_t *overflow_p,
+                                                                 uint32_t skip, float *out) {
+    DANN_DYN_SMEM(dann_smem);
+    float *qs = reinterpret_cast<float *>(dann_smem);
+    DANN_STATIC_SMEM uint64_t bar;
+    if (*overflow_p) return;
+    const uint32_t slen = *slen_p;
+    if (slen <= skip) return;
+    stage_query_row(qs, q_full, ix.dim, &bar);
+    const uint32_t lane = threadIdx.x & 31, mm = lane & 7, gbase = lane & 24;
+    const uint32_t group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+    const bool vec4 = (ix.dim & 3u) == 0;
+    const uint32_t m = slen - skip, rounds = (m + ngroups - 1) / ngroups;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t it = skip + r * ngroups + group;
+        const uint32_t node = it < slen ? stream[it] : 0u;
+        const float *x = ix.vectors + (size_t)node * ix.dim;
+        const float d = vec4 ? full_distance_group8<true>(ix.distance_type, x, qs, ix.dim, mm, gbase)
+                             : full_distance_group8<false>(ix.distance_type, x, qs, ix.dim, mm, gbase);
+        if (mm == 0 && it < slen) out[it] = d;
+    }
+}
+
+__global__ void dann_scan_finish_kernel(IndexView ix, ScanWindow *w, uint64_t *win, uint32_t rescore, const uint32_t *stream,
+                                        const float *dist, uint32_t skip, const uint32_t *slen_p, uint32_t slen_fixed,
+                                        const uint32_t *overflow_p, const dann_query_stats *stats_p, ScanStepOut *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ScanStepOut o;
+    o.overflow = overflow_p ? *overflow_p : 0u;
+    o.slen = slen_p ? *slen_p : slen_fixed; /* no search this call: nothing new beyond `skip` */
+    o.stats = *stats_p;
+    o.row.tid = DANN_INVALID_TID;
+    o.row.node = DANN_INVALID_NODE;
+    o.row.have = 0;
+    o.row.dist = DANN_NAN_F;
+    o.row.pad = 0;
+    if (o.overflow) { /* the host regrows the workspace and replays: the window must not move */
+        o.win = *w;
+        *out = o;
+        return;
+    }
+    const uint32_t nnew = o.slen;
+    if (rescore == 0) {
+        if (nnew > skip) {
+            o.row.node = stream[skip];
+            o.row.tid = ix.tids[o.row.node];
+            o.row.have = 1;
+        }
+        o.win = *w;
+        *out = o;
+        return;
+    }
+    using H = RustHeap<uint64_t, 32>;
+    ArrayStore<uint64_t> store{win};
+    uint32_t len = w->len, dfull = w->d_full;
+    for (uint32_t i = skip; i < nnew; i++) {
+        H::push(store, len, ((uint64_t)total_ukey(dist[i]) << 32) | stream[i]);
+        dfull++;
+    }
+    if (len > 0) {
+        uint64_t e = H::pop(store, len);
+        uint32_t uk = (uint32_t)(e >> 32) ^ 0x80000000u;
+        int32_t b = (int32_t)uk;
+        b ^= (int32_t)(((uint32_t)(b >> 31)) >> 1);
+        o.row.node = (uint32_t)e;
+        o.row.dist = __int_as_float(b);
+        o.row.tid = ix.tids[o.row.node];
+        o.row.have = 1;
+    }
+    w->len = len;
+    w->d_full = dfull;
+    o.win.len = len;
+    o.win.d_full = dfull;
+    *out = o;
+}
+

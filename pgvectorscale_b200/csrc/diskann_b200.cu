@@ -123,6 +123,7 @@ struct dann_scan {
     bool active = false;
     /* suspended search state in HBM (see SavedScan / dann_search.cuh) */
     DevBuf d_qindex; /* plain layout: the prepared index slice */
+    DevBuf d_step;   /* DANN_SCAN_FUSED: one ScanStepOut per amgettuple */
     DevBuf d_query, d_qfull, d_qcodes, d_labels, d_label_off, d_saved, d_heap_sm, d_vis, d_heap_tail, d_cnode, d_set,
         d_ins, d_stream, d_slen, d_stats, d_dist, d_win, d_winst, d_row, d_ctl;
     SearchPlan plan{};
@@ -1020,7 +1021,7 @@ extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) {
 }
 
 static void scan_release(dann_scan *sc) {
-    DevBuf *bufs[] = {&sc->d_qindex, &sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
+    DevBuf *bufs[] = {&sc->d_qindex, &sc->d_step, &sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
                       &sc->d_heap_sm, &sc->d_vis, &sc->d_heap_tail, &sc->d_cnode, &sc->d_set, &sc->d_ins, &sc->d_stream,
                       &sc->d_slen, &sc->d_stats, &sc->d_dist, &sc->d_win, &sc->d_winst, &sc->d_row, &sc->d_ctl};
     for (DevBuf *b : bufs) b->release();
@@ -1118,15 +1119,13 @@ extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t
     return DANN_OK;
 }
 
-/* Pull `need` more rows off the approximate stream into d_stream[skip ..]; returns how many came. */
-static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip_out) {
+/* Enqueue the resumable search for rows [0, want) of this launch (d_ctl[1] receives the overflow bits). */
+static int scan_launch_search(dann_scan *sc, uint32_t want) {
     dann_index *ix = sc->ix;
     const IndexView &v = ix->v;
     cudaStream_t st = ix->stream;
-    uint32_t skip = 0; /* rows that are only re-generated because the workspace had to grow */
-    for (int attempt = 0;; attempt++) {
+    {
         const SearchPlan &p = sc->plan;
-        const uint32_t want = skip + need;
         CK(sc->d_stream.reserve((size_t)want * 4));
         uint32_t *d_ctl = sc->d_ctl.as<uint32_t>();
         CK(cudaMemsetAsync(d_ctl, 0, 8, st));
@@ -1175,6 +1174,20 @@ static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip
         fn<<<1, 32, p.per_warp, st>>>(a);
         ix->launches++;
         CK(cudaGetLastError());
+    }
+    return DANN_OK;
+}
+
+/* Pull `need` more rows off the approximate stream into d_stream[skip ..]; returns how many came. */
+static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip_out) {
+    dann_index *ix = sc->ix;
+    cudaStream_t st = ix->stream;
+    uint32_t skip = 0; /* rows that are only re-generated because the workspace had to grow */
+    for (int attempt = 0;; attempt++) {
+        const uint32_t want = skip + need;
+        int lrc = scan_launch_search(sc, want);
+        if (lrc) return lrc;
+        uint32_t *d_ctl = sc->d_ctl.as<uint32_t>();
         struct {
             uint32_t ctl[2];
         } h;
@@ -1198,6 +1211,75 @@ static int scan_pull(dann_scan *sc, uint32_t need, uint32_t *got, uint32_t *skip
     }
 }
 
+/* DANN_SCAN_FUSED=1: the same amgettuple with ONE host synchronisation: search, exact distances of the new rows and the
+ * window step are enqueued back to back (the kernels read the search's outcome from device memory) and a single
+ * ScanStepOut comes back.  Same rows, same counters after every call; opt-in until it has been timed on hardware. */
+static int gettuple_fused(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) {
+    dann_index *ix = sc->ix;
+    const IndexView &v = ix->v;
+    cudaStream_t st = ix->stream;
+    const uint32_t rescore = (uint32_t)sc->rescore;
+    const uint32_t need = rescore == 0 ? 1u : (sc->win_len < rescore ? rescore - sc->win_len : 0u);
+    const bool searching = need && !sc->exhausted;
+    CK(sc->d_step.reserve(sizeof(ScanStepOut)));
+    ScanStepOut o;
+    uint32_t skip = 0;
+    for (int attempt = 0;; attempt++) {
+        const uint32_t want = skip + need;
+        if (searching) {
+            int lrc = scan_launch_search(sc, want);
+            if (lrc) return lrc;
+            if (rescore > 0) {
+                CK(sc->d_dist.reserve((size_t)want * 4));
+                size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float);
+                if (smem > 48 * 1024)
+                    CK(cudaFuncSetAttribute(dann_scan_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dann_scan_distance_kernel<<<1, 128, smem, st>>>(v, sc->d_qfull.as<float>(), sc->d_stream.as<uint32_t>(),
+                                                               sc->d_slen.as<uint32_t>(), sc->d_ctl.as<uint32_t>() + 1, skip,
+                                                               sc->d_dist.as<float>());
+                ix->launches++;
+                CK(cudaGetLastError());
+            }
+        }
+        dann_scan_finish_kernel<<<1, 32, 0, st>>>(v, sc->d_winst.as<ScanWindow>(), sc->d_win.as<uint64_t>(), rescore,
+                                                 sc->d_stream.as<uint32_t>(), sc->d_dist.as<float>(), skip,
+                                                 searching ? sc->d_slen.as<uint32_t>() : nullptr, skip,
+                                                 searching ? sc->d_ctl.as<uint32_t>() + 1 : nullptr,
+                                                 sc->d_stats.as<dann_query_stats>(), sc->d_step.as<ScanStepOut>());
+        ix->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&o, sc->d_step.p, sizeof o, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!o.overflow) {
+            if (searching) {
+                if (o.slen < want) sc->exhausted = true;
+                sc->streamed += o.slen > skip ? o.slen - skip : 0;
+                sc->stats = o.stats;
+            }
+            break;
+        }
+        /* the scan outgrew its workspace: rebuild it twice as large and replay the stream up to here */
+        if (attempt >= 8) return fail(DANN_ERR_CAPACITY, "scan workspace still too small after %d growth steps", attempt);
+        sc->grow *= 2;
+        int rrc = scan_reset_search(sc);
+        if (rrc) return rrc;
+        skip = sc->streamed;
+    }
+    sc->win_len = o.win.len;
+    sc->stats.d_full = o.win.d_full;
+    if (ix->plain) {
+        sc->stats.d_full += sc->stats.candidates;
+        sc->stats.d_quantized = 0;
+    }
+    sc->stats.stream_len = sc->streamed;
+    if (!o.row.have) return 0;
+    if (block) *block = (uint32_t)(o.row.tid >> 16);
+    if (offset) *offset = (uint16_t)(o.row.tid & 0xFFFFu);
+    if (node_id) *node_id = o.row.node;
+    if (dist) *dist = o.row.dist;
+    return 1;
+}
+
 extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) {
     if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_gettuple: NULL scan");
     if (!sc->active) return fail(DANN_ERR_STATE, "dann_scan_gettuple before dann_scan_rescan");
@@ -1205,6 +1287,7 @@ extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offs
     int rc = check_live(ix);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
+    if (env_u32("DANN_SCAN_FUSED", 0) == 1) return gettuple_fused(sc, block, offset, node_id, dist);
     const IndexView &v = ix->v;
     cudaStream_t st = ix->stream;
     /* next_with_resort (scan.rs:244-305): `while resort_buffer.len() < resort_size { next() ... }` then pop;

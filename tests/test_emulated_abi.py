@@ -55,6 +55,15 @@ def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
     assert passed == 200
 
 
+def test_one_synchronisation_gettuple_passes_under_emulation():
+    """DANN_SCAN_FUSED=1: amgettuple with a single host synchronisation per row (opt-in until timed on hardware)."""
+    passed, _ = _run(["tests/test_gpu_parity.py", "-k", "scan or gettuple or counters or null or empty"],
+                     {"DANN_SCAN_FUSED": "1"})
+    assert passed >= 3
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_SCAN_FUSED": "1", "DANN_DEBUG_SHRINK": "8", "DANN_FUZZ_SEEDS": "120"})
+    assert passed == 120
+
+
 @pytest.mark.parametrize("sched", ["1", "2"])
 def test_parity_under_other_lane_schedules(sched):
     """Descending and shuffled fiber order (exposes missing __syncwarp()s) on a slice of the parity suite."""

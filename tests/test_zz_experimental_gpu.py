@@ -168,3 +168,26 @@ def test_plain_storage_random_small_indexes(lib, monkeypatch, seed):
         for f in ("visits", "d_quantized", "candidates", "d_full"):
             assert st[f] == want["stats"][f], f
         sc.end()
+
+
+def test_one_synchronisation_gettuple_streams_like_the_default(lib, monkeypatch):
+    """DANN_SCAN_FUSED=1 (dann_scan_distance_kernel / dann_scan_finish_kernel): same rows and counters after every call."""
+    from oracle import oracle
+    s = build_case(3000, 128, COSINE, seed=21, kind="normal", labels=True, deleted_every=9)
+    q = _queries(s, 4, 3)
+    monkeypatch.setenv("DANN_SCAN_FUSED", "1")
+    with lib.DiskAnnIndex(s) as idx:
+        sc = idx.begin_scan()
+        for qi, (L, rescore, key) in enumerate(((40, 10, None), (25, 0, None), (60, 50, [3, 9]), (30, 5, None))):
+            sc.rescan(q[qi], labels=key, search_list_size=L, rescore=rescore)
+            for i in range(1, 40):
+                row = sc.gettuple()
+                want = oracle.scan(s, q[qi], key, L, rescore, i)
+                if row is None:
+                    assert len(want["tid"]) < i
+                    break
+                assert ((row[0] << 16) | row[1]) == int(want["tid"][i - 1])
+                st = sc.stats()
+                for f in ("visits", "d_quantized", "candidates", "d_full"):
+                    assert st[f] == want["stats"][f], (qi, i, f)
+        sc.end()

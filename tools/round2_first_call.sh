@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 # 1. regular parity suite must still be green (default kernels are byte-identical, profiles/r01_sass_signature.txt)
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gpu_tests.log 2>&1; tail -2 gpurun_out/r2_gpu_tests.log
 # 2. the opt-in paths: heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout
-DANN_RUN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q > gpurun_out/r2_experimental.log 2>&1
+DANN_RUN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q > gpurun_out/r2_experimental.log 2>&1
 tail -3 gpurun_out/r2_experimental.log
 # 3. A/B timing on the benchmark fixture at the benchmark's operating point, each alternative alone
 python tools/make_snapshot.py --out /tmp/snap --raw > gpurun_out/r2_mk.log 2>&1; tail -1 gpurun_out/r2_mk.log
