@@ -180,6 +180,17 @@ def test_emulated_hv1_node_carrying_entries(emu, hs, flags):
     assert info["entry"] == 0
 
 
+def test_emulated_hv1_at_the_benchmark_operating_point(emu, monkeypatch):
+    """768-d x 2-bit codes, R = 50, L = 150 / 259 rows: ~400 visits and ~10 K candidates per query, several query
+    slots per block, the heap spilling into the global tail - every HV = 1 alternative on, shuffled lane schedule."""
+    s = build_case(6000, 768, COSINE, seed=5, kind="normal", R=50, L_build=100)
+    q = fixtures.gen_vectors(6, 768, 9, "normal")
+    monkeypatch.setenv("SIMT_SCHED", "2")
+    for env in ({"DANN_HEAP_V2": 1}, {"DANN_HEAP_V2": 1, "DANN_HV_NODE_ENTRIES": 0, "DANN_SEARCH_HS": 1024}):
+        info = check(emu, s, q, 150, 259, env=env, sm_count=1)
+        assert info["hv"] == 1 and info["W"] == 6 and info["cand_cap"] >= 20000
+
+
 @pytest.mark.parametrize("dim,R", [(768, 64), (1536, 40), (384, 64)])
 def test_emulated_hv1_fused_expansion_long_lists(emu, dim, R):
     """Lists longer than the rows one fused round holds (48 slots at 768-d x 2 bits, 24 at 1536-d): the tail of the
