@@ -47,6 +47,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS]
+    # experiment knob: extra -D... for this build only, e.g. DANN_NVCC_DEFINES="-DDANN_HV_NO_FUSED" with force=True
+    cmd += [d for d in os.environ.get("DANN_NVCC_DEFINES", "").split() if d.startswith("-D")]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]

@@ -567,7 +567,11 @@ struct PairSearch {
                 const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
                 const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
                 const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
+#ifdef DANN_HV_NO_FUSED /* build-time knob (DANN_NVCC_DEFINES): compile the fused expansion out to see what its registers cost */
+                if (false) {
+#else
                 if (HV == 1 && (a.hv_flags & DANN_HV_FUSED) && a.lists_unique && a.bitmap_words && !filter) {
+#endif
                     uint32_t *scratch = fscratch; /* not a list page: the heap warp may still read the previous one */
                     if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) expand_fused<true>(list, dl, scratch, n0, v0, n1, v1);
                     else expand_fused<false>(list, dl, scratch, n0, v0, n1, v1);

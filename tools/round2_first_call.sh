@@ -28,3 +28,8 @@ for T in 64 256 1024; do
   /tmp/coalescer_load /tmp/snap.raw /tmp/snap_q.f32 $T 64 150 250 10 1024 200 >> gpurun_out/r2_coalescer.jsonl 2>> gpurun_out/r2_coalescer.err
 done
 cat gpurun_out/r2_coalescer.jsonl
+# 7. what the fused expansion's registers cost the rest of the HV=1 kernel: rebuild without it, re-time, restore
+DANN_NVCC_DEFINES="-DDANN_HV_NO_FUSED" python -c "from pgvectorscale_b200.build import build_library as b; b(force=True)"
+timeout 600 python tools/hv_ab.py --snap /tmp/snap --L 150 --rescore 250 --steps 20 --no-check > gpurun_out/r2_hv_ab_nofused_build.jsonl 2>> gpurun_out/r2_hv_ab.err
+python -c "from pgvectorscale_b200.build import build_library as b; b(force=True)"
+cat gpurun_out/r2_hv_ab_nofused_build.jsonl
