@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: hardware verdict on everything that was written after this round's GPU minutes
 # were spent (bit-exact under CPU emulation only so far), then the A/B timing that decides what becomes the default.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'   (about 30 GPU-minutes)
 # Output lands in gpurun_out/ (r2_*.log / .json / .ncu-rep).
 mkdir -p gpurun_out
 # 1. regular parity suite must still be green (default kernels are byte-identical, profiles/r01_sass_signature.txt)
