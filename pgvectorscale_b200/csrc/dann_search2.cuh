@@ -694,18 +694,33 @@ struct PairSearch {
             if (node + 1 <= heap_len) nxt = st.get(node + 1);
         }
         for (uint32_t base = 0; base < tn; base += 32) {
+            /* inert elements (the parent's key is already <= their own: they stay at their leaf whatever the earlier
+             * pushes of the page do) need no ballot and no shuffle, only the path's step to the next leaf.  The test
+             * reads the parent from memory, which may lag behind a register copy - keys in a slot only ever decrease
+             * during pushes, so a stale parent can hide an inert element but never fake one. */
             const uint32_t r = base + lane;
-            const E mine = T::make(r < tn ? dl[r] : 0u, T::PAYLOAD_IS_NODE ? (r < tn ? lp[r] : 0u) : seq0 + r);
+            bool inert = false;
+            if (r < tn) inert = H::key(st.get((heap_len + 1 + r) >> 1)) <= dl[r];
+            const unsigned im = __ballot_sync(DANN_FULL, inert);
             const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
             for (uint32_t i = 0; i < cnt; i++) {
-                const E e = __shfl_sync(DANN_FULL, mine, (int)i);
-                const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
-                const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
-                const unsigned tm1 = x & ~(x + 1u); /* bit 0 (the leaf) and the consecutive ancestors passed: lanes 0..rise */
-                const E up = __shfl_down_sync(DANN_FULL, val, 1);
-                if (tm1 & lanebit2) val = up;     /* lanes below `rise`: the ancestor above moves down into this slot */
-                else if (tm1 & lanebit) val = e;  /* lane `rise`: the element lands */
-                dirty = dirty || (tm1 & lanebit) != 0;
+                /* every lane builds the element itself from the page in shared memory (uniform address: a broadcast
+                 * load, independent of the chain through `val`) */
+                const E e = T::make(dl[base + i], T::PAYLOAD_IS_NODE ? lp[base + i] : seq0 + base + i);
+                if ((im >> i) & 1u) { /* warp-uniform */
+                    if (lane == 0) {
+                        val = e;
+                        dirty = true;
+                    }
+                } else {
+                    const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
+                    const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
+                    const unsigned tm1 = x & ~(x + 1u); /* bit 0 (the leaf) and the consecutive ancestors passed: lanes 0..rise */
+                    const E up = __shfl_down_sync(DANN_FULL, val, 1);
+                    if (tm1 & lanebit2) val = up;     /* lanes below `rise`: the ancestor above moves down into this slot */
+                    else if (tm1 & lanebit) val = e;  /* lane `rise`: the element lands */
+                    dirty = dirty || (tm1 & lanebit) != 0;
+                }
                 if (base + i + 1 < tn) { /* move the path to the next leaf */
                     const uint32_t pos1 = pos + 1;
                     if ((pos1 & pos) == 0) { /* new leaf level: every slot changes owner */
