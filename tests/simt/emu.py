@@ -12,7 +12,8 @@ from pgvectorscale_b200.diskann import _SnapshotDesc, _QueryStats  # noqa: E402 
 
 class EmuInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("retries", "entry", "W", "hs", "pairs", "grid", "cand_cap", "vcap",
-                                          "bitmap_words", "nch", "G", "hv")] + [("switches", C.c_uint64)]
+                                          "bitmap_words", "nch", "G", "hv")] + [("switches", C.c_uint64), ("coll_even", C.c_uint64),
+                                                                              ("coll_odd", C.c_uint64)]
 
 
 _lib = None

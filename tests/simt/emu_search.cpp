@@ -48,6 +48,7 @@ struct emu_info {
     uint32_t retries, entry, W, hs, pairs, grid, cand_cap, vcap, bitmap_words, nch, G;
     uint32_t hv;
     uint64_t switches;
+    uint64_t coll_even, coll_odd; /* warp collectives completed by even / odd warps (controller / heap warp) */
 };
 
 /* One dann_search_batch-style search pass (no rerank): the approximate stream of every query.
@@ -130,6 +131,8 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
     uint32_t ctl[2];
     SearchPlan p{};
     const uint64_t sw0 = simt::total_switches();
+    uint64_t cp0[2];
+    simt::collectives_by_warp_parity(cp0);
     for (int attempt = 0;; attempt++) {
         char err[256];
         int rc = dann_make_plan(in, nq, L, c_target, grow, qoff != nullptr, &p, force_single != 0, err, sizeof err);
@@ -247,6 +250,10 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         info->G = G;
         info->hv = (uint32_t)p.hv;
         info->switches = simt::total_switches() - sw0;
+        uint64_t cp1[2];
+        simt::collectives_by_warp_parity(cp1);
+        info->coll_even = cp1[0] - cp0[0];
+        info->coll_odd = cp1[1] - cp0[1];
     }
     return 0;
 }

@@ -36,9 +36,14 @@ namespace simt {
 Block *g_blk = nullptr;
 Fiber *g_cur = nullptr;
 static uint64_t g_total_switches = 0;
+static uint64_t g_coll_parity[2] = {0, 0}; /* completed warp collectives by warp index parity (two-warp kernel: 0 = controller, 1 = heap) */
 static const size_t kStack = 128 * 1024;
 
 uint64_t total_switches() { return g_total_switches; }
+void collectives_by_warp_parity(uint64_t out[2]) {
+    out[0] = g_coll_parity[0];
+    out[1] = g_coll_parity[1];
+}
 
 void yield() {
     Block *b = g_blk;
@@ -182,6 +187,7 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
         s->gen++;
         b->progress++;
         b->collectives++;
+        g_coll_parity[(f->tid >> 5) & 1u]++;
     } else {
         f->blocked_on = "warp collective";
         while (s->gen == mygen) yield();

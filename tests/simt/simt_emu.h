@@ -77,6 +77,7 @@ void named_barrier(unsigned id, unsigned count);
 /* runs `body` once per thread of every block of the grid, blocks one after the other */
 void launch(unsigned grid, unsigned block, const std::function<void()> &body);
 uint64_t total_switches();
+void collectives_by_warp_parity(uint64_t out[2]);
 
 inline unsigned lane_id() { return g_cur->tid & 31u; }
 
