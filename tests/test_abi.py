@@ -99,6 +99,10 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "oracle.h" not in text, f
+                # ... nor the CPU SIMT emulator / the emulated ABI build (tests/simt): the only trace allowed in the
+                # product sources is the DANN_SIMT_EMU preprocessor guard around PTX and shared-memory declarations
+                assert "simt_emu.h" not in text and "libdiskann_b200_emu" not in text and "fake_cuda" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+(emu|build_emu|cu2cpp)\b", text, flags=re.M), f
 
 
 def test_plain_c_program_links_and_fails_loudly_without_a_device(lib_built, tmp_path):
