@@ -127,7 +127,12 @@ def test_sidecar_process_serves_concurrent_backends(lib, lib_built, tmp_path):
             if os.path.exists(sock) or proc.poll() is not None:
                 break
             time.sleep(0.05)
-        assert proc.poll() is None and os.path.exists(sock), proc.stderr.read() if proc.poll() is not None else "no socket"
+        if proc.poll() is not None:
+            err = proc.stderr.read()
+            if "unavailable" in err or "exclusive" in err.lower():      # GPU in exclusive-process mode: one context only
+                pytest.skip("a second process cannot open the GPU on this box: " + err.strip()[-120:])
+            pytest.fail("sidecar exited: " + err)
+        assert os.path.exists(sock), "no socket"
         q = fixtures.gen_vectors(24, 48, 31, "normal")
         out, errors = {}, []
 
