@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
+#include <time.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -33,6 +34,31 @@
 static dann_coalescer *g_co;
 static uint32_t g_dim, g_n;
 static volatile sig_atomic_t g_stop;
+/* open connections, so that shutdown can wake their threads and wait for them before the coalescer goes away */
+enum { MAX_CONN = 4096 };
+static pthread_mutex_t g_conn_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_conn_fd[MAX_CONN];
+static int g_conn_n;
+
+static int conn_add(int fd) {
+    int ok = 0;
+    pthread_mutex_lock(&g_conn_mu);
+    if (g_conn_n < MAX_CONN) {
+        g_conn_fd[g_conn_n++] = fd;
+        ok = 1;
+    }
+    pthread_mutex_unlock(&g_conn_mu);
+    return ok;
+}
+static void conn_remove(int fd) {
+    pthread_mutex_lock(&g_conn_mu);
+    for (int i = 0; i < g_conn_n; i++)
+        if (g_conn_fd[i] == fd) {
+            g_conn_fd[i] = g_conn_fd[--g_conn_n];
+            break;
+        }
+    pthread_mutex_unlock(&g_conn_mu);
+}
 
 static int read_full(int fd, void *buf, size_t n) {
     unsigned char *p = (unsigned char *)buf;
@@ -107,6 +133,7 @@ static void *serve(void *arg) {
     }
 out:
     free(query);
+    conn_remove(fd);
     close(fd);
     return NULL;
 }
@@ -166,11 +193,30 @@ int main(int argc, char **argv) {
             break;
         }
         pthread_t th;
+        if (!conn_add(fd)) {
+            close(fd);
+            continue;
+        }
         if (pthread_create(&th, NULL, serve, (void *)(intptr_t)fd) == 0) pthread_detach(th);
-        else close(fd);
+        else {
+            conn_remove(fd);
+            close(fd);
+        }
     }
     close(ls);
     unlink(argv[2]);
+    /* wake every connection thread (its read() returns 0) and give them a moment to leave the coalescer */
+    pthread_mutex_lock(&g_conn_mu);
+    for (int i = 0; i < g_conn_n; i++) shutdown(g_conn_fd[i], SHUT_RDWR);
+    pthread_mutex_unlock(&g_conn_mu);
+    for (int spin = 0; spin < 400; spin++) {
+        pthread_mutex_lock(&g_conn_mu);
+        const int left = g_conn_n;
+        pthread_mutex_unlock(&g_conn_mu);
+        if (!left) break;
+        struct timespec ts = {0, 5 * 1000 * 1000};
+        nanosleep(&ts, NULL);
+    }
     uint64_t batches = 0, queries = 0, largest = 0;
     dann_coalescer_stats(g_co, &batches, &queries, &largest);
     fprintf(stderr, "dann_sidecar: %llu queries in %llu batches (largest %llu)\n", (unsigned long long)queries,
