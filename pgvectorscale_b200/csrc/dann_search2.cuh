@@ -222,7 +222,12 @@ struct PairSearch {
 #pragma unroll
             for (int i = 0; i < NCH; i++)
                 s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-            for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+            if (HV == 1 && (a.hv_flags & DANN_HV_REDUX)) {
+                /* one REDUX over the row's lane group instead of log2(G) shuffles (groups meet independently) */
+                if (G > 1) s = __reduce_add_sync(G >= 32u ? DANN_FULL : ((1u << G) - 1u) << (lane & ~(G - 1u)), s);
+            } else {
+                for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+            }
             const uint32_t r = b + u * RP + grp;
             if (gl == 0 && r < tn) dl[r] = s;
         }
@@ -361,7 +366,11 @@ struct PairSearch {
             uint32_t sum = 0;
 #pragma unroll
             for (int i = 0; i < NCH; i++) sum += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-            for (uint32_t o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(DANN_FULL, sum, o);
+            if (a.hv_flags & DANN_HV_REDUX) {
+                if (G > 1) sum = __reduce_add_sync(G >= 32u ? DANN_FULL : ((1u << G) - 1u) << (lane & ~(G - 1u)), sum);
+            } else {
+                for (uint32_t o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(DANN_FULL, sum, o);
+            }
             const uint32_t slot = u * RP + grp;
             if (gl == 0 && slot < 64u) {
                 const bool isnew = ((slot < 32u ? nm0 : nm1) >> (slot & 31u)) & 1u;
@@ -474,7 +483,9 @@ struct PairSearch {
             uint32_t d0 = lane < ptn ? pd[lane] : 0xFFFFFFFFu;
             uint32_t d1 = lane + 32 < ptn ? pd[lane + 32] : 0xFFFFFFFFu;
             uint32_t m = min(d0, d1);
-            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
+            if (HV == 1 && (a.hv_flags & DANN_HV_REDUX)) m = __reduce_min_sync(DANN_FULL, m); /* one REDUX instead of five shuffles */
+            else
+                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
             uint32_t node = DANN_INVALID_NODE, key = 0;
             const bool rv = ctl->root_valid[pp] != 0;
             if (ptn && (!rv || m < ctl->root_key[pp])) { /* first element of the batch attaining a strictly smaller minimum */

@@ -36,13 +36,14 @@ namespace simt {
 Block *g_blk = nullptr;
 Fiber *g_cur = nullptr;
 static uint64_t g_total_switches = 0;
-static uint64_t g_coll_parity[2] = {0, 0}; /* completed warp collectives by warp index parity (two-warp kernel: 0 = controller, 1 = heap) */
+static uint64_t g_coll_parity[2] = {0, 0}; /* lane-participations in completed warp collectives (32 = one full-warp collective)
+                                              by warp index parity (two-warp kernel: 0 = controller, 1 = heap) */
 static const size_t kStack = 128 * 1024;
 
 uint64_t total_switches() { return g_total_switches; }
 void collectives_by_warp_parity(uint64_t out[2]) {
-    out[0] = g_coll_parity[0];
-    out[1] = g_coll_parity[1];
+    out[0] = g_coll_parity[0] / 32;
+    out[1] = g_coll_parity[1] / 32;
 }
 
 void yield() {
@@ -66,6 +67,11 @@ static void trampoline() {
         for (Slot &c : w.slots)
             if (c.arrived && ((c.arrived | w.exited) & c.mask) == c.mask) {
                 complete(c, c.mask);
+                for (int l = 0; l < 32; l++)
+                    if ((c.arrived >> l) & 1u) {
+                        w.result[l] = c.out[c.gen & 1][l];
+                        w.ready[l] = true;
+                    }
                 c.arrived = 0;
                 c.gen++;
                 g_blk->progress++;
@@ -131,6 +137,14 @@ static void complete(Slot &s, unsigned nlanes_mask) {
                 out[l] = ((s.arrived >> src) & 1u) ? s.val[src] : s.val[l];
             }
             break;
+        case K_REDUX_MIN:
+        case K_REDUX_ADD: {
+            uint64_t r = s.kind == K_REDUX_MIN ? ~0ull : 0ull;
+            for (int l = 0; l < 32; l++)
+                if ((s.arrived >> l) & 1u) r = s.kind == K_REDUX_MIN ? (s.val[l] < r ? s.val[l] : r) : (uint64_t)(uint32_t)(r + s.val[l]);
+            for (int l = 0; l < 32; l++) out[l] = r;
+            break;
+        }
         case K_MATCH_ANY:
             for (int l = 0; l < 32; l++) {
                 if (!((s.arrived >> l) & 1u)) continue;
@@ -169,7 +183,7 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
                 break;
             }
     if (!s) {
-        fprintf(stderr, "simt: more than 4 divergent collectives in flight in one warp\n");
+        fprintf(stderr, "simt: more than 32 divergent collectives in flight in one warp\n");
         abort();
     }
     if (s->kind != kind) {
@@ -183,17 +197,23 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
     s->arrived |= 1u << lane;
     if (((s->arrived | w.exited) & mask) == mask) {
         complete(*s, mask);
+        for (int l = 0; l < 32; l++)
+            if ((s->arrived >> l) & 1u) {
+                w.result[l] = s->out[mygen & 1][l];
+                w.ready[l] = true;
+            }
         s->arrived = 0;
         s->gen++;
         b->progress++;
         b->collectives++;
-        g_coll_parity[(f->tid >> 5) & 1u]++;
+        g_coll_parity[(f->tid >> 5) & 1u] += (uint64_t)__builtin_popcount(mask);
     } else {
         f->blocked_on = "warp collective";
-        while (s->gen == mygen) yield();
+        while (!w.ready[lane]) yield(); /* the slot itself may already serve another group's collective by now */
         f->blocked_on = nullptr;
     }
-    return s->out[mygen & 1][lane];
+    w.ready[lane] = false;
+    return w.result[lane];
 }
 
 void named_barrier(unsigned id, unsigned count) {

@@ -26,7 +26,7 @@ struct Dim3 {
     unsigned x = 1, y = 1, z = 1;
 };
 
-enum Kind { K_SYNC = 1, K_BALLOT, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_MATCH_ANY, K_ANY, K_ALL };
+enum Kind { K_SYNC = 1, K_BALLOT, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_MATCH_ANY, K_ANY, K_ALL, K_REDUX_MIN, K_REDUX_ADD };
 
 struct Slot {
     unsigned mask = 0, arrived = 0;
@@ -38,7 +38,9 @@ struct Slot {
 };
 
 struct Warp {
-    Slot slots[4];
+    Slot slots[32]; /* collectives in flight at once (lane groups with disjoint masks meet independently) */
+    uint64_t result[32]; /* per-lane mailbox: a lane is in at most one collective, so its result waits here safely */
+    bool ready[32] = {};
     unsigned exited = 0; /* lanes whose thread has returned: collectives do not wait for them (CUDA: "all NON-EXITED
                             threads named in mask must execute the same intrinsic") */
 };
@@ -198,6 +200,12 @@ template <typename T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
     if (width != 32) abort();
     return ::simt::from_bits<T>(::simt::rendezvous(::simt::K_SHFL_XOR, mask, ::simt::to_bits(v), (uint32_t)lanemask));
+}
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+    return (unsigned)::simt::rendezvous(::simt::K_REDUX_MIN, mask, v, 0);
+}
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    return (unsigned)::simt::rendezvous(::simt::K_REDUX_ADD, mask, v, 0);
 }
 template <typename T>
 inline unsigned __match_any_sync(unsigned mask, T v) {
