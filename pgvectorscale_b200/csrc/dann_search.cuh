@@ -87,7 +87,8 @@ struct SearchArgs {
      * index's lists are known to be duplicate-free, 128 the heap warp resolves (and prefetches the neighbour row of) the
      * root's node id, 256 the TID of the visited list's head is fetched one visit ahead, 512 inserted-set
      * atomics and code gather issued together (fused expansion), 1024 REDUX (one instruction) for the page minimum and
-     * the per-row popcount sums instead of shuffle trees.  Kept last: the offsets of the fields above are unchanged. */
+     * the per-row popcount sums instead of shuffle trees, 2048 the heap warp's root prediction read by every lane
+     * (no broadcast shuffles).  Kept last: the offsets of the fields above are unchanged. */
     uint32_t hv_flags;
     /* plain storage layout (SearchWarp<.., PLAIN=1> only; storage.rs:144-169, plain/storage.rs:223-299): the beam
      * search compares the query's index slice with the f32 vector each node stores.  Kept after everything else. */
@@ -106,6 +107,7 @@ struct SearchArgs {
 #define DANN_HV_TIDPF 256u
 #define DANN_HV_FUSED 512u
 #define DANN_HV_REDUX 1024u
+#define DANN_HV_UNIFORM 2048u
 
 #define DANN_LIST_CAP 64u
 

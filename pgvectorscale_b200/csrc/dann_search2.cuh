@@ -877,7 +877,10 @@ struct PairSearch {
             const uint32_t p = k & 1;
             E head = 0, pub = 0;
             int pv = 0;
-            if (lane == 0 && heap_len > 0) {
+            /* HV == 1: every lane reads the (at most four) slots itself - uniform addresses, one broadcast transaction
+             * each - so the three shuffles that spread lane 0's answer disappear from the path to the hand-off */
+            const bool all_lanes = HV == 1 && (a.hv_flags & DANN_HV_UNIFORM) != 0;
+            if ((lane == 0 || all_lanes) && heap_len > 0) {
                 head = heap.get(1);
                 if (k < nstart_pages) { /* a start page is pushed without a pop: the root is the root */
                     pub = head;
@@ -897,9 +900,11 @@ struct PairSearch {
                     pv = 1;
                 }
             }
-            head = __shfl_sync(DANN_FULL, head, 0);
-            pub = __shfl_sync(DANN_FULL, pub, 0);
-            pv = __shfl_sync(DANN_FULL, pv, 0);
+            if (!all_lanes) {
+                head = __shfl_sync(DANN_FULL, head, 0);
+                pub = __shfl_sync(DANN_FULL, pub, 0);
+                pv = __shfl_sync(DANN_FULL, pv, 0);
+            }
             handoff(pv != 0, pub);
             const uint32_t cmd = ctl->cmd[p];
             if (cmd == 0) break;

@@ -600,7 +600,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.vis_out = vis_out;
         a.vis_out_len = vis_out_len;
         a.vis_out_cap = vis_out_cap;
-        a.hv_flags = env_u32("DANN_HV_FLAGS", 2047);
+        a.hv_flags = env_u32("DANN_HV_FLAGS", 4095);
         a.plain_vectors = ix->index_vectors;
         a.q_index = d_q_index;
         a.plain_dim = ix->plain ? v.dim_index : 0;

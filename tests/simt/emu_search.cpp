@@ -201,7 +201,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.G = G;
         a.Gshift = Gshift;
         a.per_warp_smem = p.per_warp;
-        a.hv_flags = env_u32("DANN_HV_FLAGS", 2047);
+        a.hv_flags = env_u32("DANN_HV_FLAGS", 4095);
         a.plain_vectors = ivp;
         a.q_index = qip;
         a.plain_dim = in.plain_dim;
@@ -345,7 +345,7 @@ extern "C" int emu_heap_script(int entry, int hv, const uint32_t *kinds, const u
         return DANN_ERR_INVALID_ARG;
     }
     SearchArgs a{};
-    a.hv_flags = env_u32("DANN_HV_FLAGS", 2047);
+    a.hv_flags = env_u32("DANN_HV_FLAGS", 4095);
     std::vector<ulonglong2> tail((size_t)cap / 2 + 2);
     auto run = [&](auto tag, auto hvtag) {
         using T = decltype(tag);

@@ -146,7 +146,7 @@ def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
     assert info["hv"] == 1 and info["bitmap_words"] == 0
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 1028, 1536, 3, 892, 131, 511, 2047])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 1028, 1536, 3, 892, 2179, 511, 4095])
 def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
     """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
     s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
@@ -165,7 +165,7 @@ def test_emulated_hv1_visited_search_list_sizes(emu, L):
 
 
 @pytest.mark.parametrize("hs", [None, 16, 256])
-@pytest.mark.parametrize("flags", [0, 3, 2047])
+@pytest.mark.parametrize("flags", [0, 3, 4095])
 def test_emulated_hv1_node_carrying_entries(emu, hs, flags):
     """Ent32n21: 4-byte heap entries whose payload is the node id (no seq -> node table), chosen for HV = 1 when the
     index has at most 2M nodes and the entry layout is not forced."""
@@ -197,7 +197,7 @@ def test_emulated_hv1_fused_expansion_long_lists(emu, dim, R):
     page goes through the ordinary distance round."""
     s = build_case(260, dim, COSINE, seed=3, kind="normal", R=R, L_build=R + 16)
     q = fixtures.gen_vectors(2, dim, 8, "normal")
-    for flags in (512, 1536, 2047):
+    for flags in (512, 1536, 4095):
         info = check(emu, s, q, 25, 34, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags})
         assert info["hv"] == 1
 

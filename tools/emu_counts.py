@@ -20,7 +20,7 @@ rows = [("measured kernel (HV=0)", {}),
         ("HV=1, no alternative", {"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": 0, "DANN_HV_NODE_ENTRIES": 0})]
 names = {1: "register-path pushes", 2: "look-ahead pop", 4: "page-sized distance rounds", 8: "code-row prefetch",
          16: "nbr-row prefetch", 32: "32-ary visited search", 64: "no intra-list dedupe", 128: "root node by heap warp",
-         256: "TID prefetch", 512: "fused expansion", 1024: "REDUX reductions"}
+         256: "TID prefetch", 512: "fused expansion", 1024: "REDUX reductions", 2048: "uniform root prediction"}
 for bit, nm in names.items():
     rows.append((f"HV=1 + {nm} ({bit})", {"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": bit, "DANN_HV_NODE_ENTRIES": 0}))
 rows.append(("HV=1, everything, node-carrying entries", {"DANN_HEAP_V2": 1}))

@@ -34,7 +34,7 @@ if not a.no_check:
     from oracle import oracle
     want = oracle.scan_batch(s, q[:32], None, None, a.L, a.rescore, a.k)
 
-VARIANTS = [("default", None, None), ("hv1 all", 1, 2047), ("hv1 none (same code paths as default)", 1, 0),
+VARIANTS = [("default", None, None), ("hv1 all", 1, 4095), ("hv1 none (same code paths as default)", 1, 0),
             ("push only", 1, 1), ("pop only", 1, 2), ("push+pop", 1, 3), ("distances only", 1, 4),
             ("code prefetch only", 1, 8), ("nbr prefetch only", 1, 16), ("visited search only", 1, 32),
             ("no intra-list dedupe only", 1, 64),
@@ -42,11 +42,13 @@ VARIANTS = [("default", None, None), ("hv1 all", 1, 2047), ("hv1 none (same code
             ("heap v2 + root node (1+2+128)", 1, 131),
             ("TID prefetch only", 1, 256),
             ("fused expansion only", 1, 512),
-            ("all but fused expansion", 1, 2047 - 512),
+            ("all but fused expansion", 1, 4095 - 512),
+            ("uniform root prediction only", 1, 2048),
+            ("heap warp all (1+2+128+2048)", 1, 2179),
             ("REDUX reductions only (with page-sized rounds: 4+1024)", 1, 1028),
             ("controller all (4+8+16+32+64+256+512)", 1, 892)]
 # node-carrying entries are on for every hv1 variant above; one more line with them off
-VARIANTS.append(("hv1 all, sequence-number entries (DANN_HV_NODE_ENTRIES=0)", 1, 2047))
+VARIANTS.append(("hv1 all, sequence-number entries (DANN_HV_NODE_ENTRIES=0)", 1, 4095))
 for name, hv, flags in VARIANTS:
     os.environ["DANN_HV_NODE_ENTRIES"] = "0" if "DANN_HV_NODE_ENTRIES=0" in name else "1"
     for k_, v_ in (("DANN_HEAP_V2", hv), ("DANN_HV_FLAGS", flags)):
