@@ -57,7 +57,7 @@ def lib_built():
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
         import build_emu
         from pgvectorscale_b200 import diskann
-        so = build_emu.build_abi()
+        so = build_emu.build_abi(asan=os.environ.get("DANN_EMULATE_ASAN") == "1")   # ASan build: needs LD_PRELOAD=libasan
         diskann._LIB = None
         diskann._LIB = diskann.load_library(so)      # explicit path: the package itself never looks for this file
         return so

@@ -17,14 +17,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(files, extra_env=None, workers=4, timeout=1500):
+def _run(files, extra_env=None, workers=4, timeout=1500, asan=False):
     env = dict(os.environ)
     env.update({"DANN_EMULATE": "1", "SIMT_SM_COUNT": "8"})
     env.update(extra_env or {})
     # build once here: the xdist workers would otherwise race on the same output file
     sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
     import build_emu
-    build_emu.build_abi()
+    build_emu.build_abi(asan=asan)
+    if asan:    # python itself is not instrumented: the runtime has to come first in the link order
+        env.update({"DANN_EMULATE_ASAN": "1", "LD_PRELOAD": build_emu.libasan(),
+                    "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=1"})
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-n", str(workers)] + files
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     tail = (r.stdout + r.stderr)[-3000:]
@@ -53,6 +56,21 @@ def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_SEARCH_KERNEL": "1",
                                                        "DANN_SEARCH_BITMAP": "0", "SIMT_SCHED": "1"})
     assert passed == 120
+
+
+def test_address_sanitizer_finds_nothing_in_host_code_or_kernels():
+    """The emulated ABI built with -fsanitize=address: every "device" buffer is a red-zoned host allocation, so an
+    out-of-bounds access by a kernel (or by the host code around it) aborts the run.  Edge-case fuzz with the measured
+    kernels and with the alternative flavour on tiny heap tops, forced growth and the one-synchronisation gettuple."""
+    if not os.path.exists(__import__("subprocess").run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
+                                                       text=True).stdout.strip()):
+        pytest.skip("libasan not installed")
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "80"}, asan=True)
+    assert passed == 80
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"],
+                     {"DANN_FUZZ_SEEDS": "80", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16", "DANN_DEBUG_SHRINK": "8",
+                      "DANN_SCAN_FUSED": "1", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"}, asan=True)
+    assert passed == 80
 
 
 def test_one_synchronisation_gettuple_passes_under_emulation():
