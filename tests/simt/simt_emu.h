@@ -116,7 +116,7 @@ inline T from_bits(uint64_t b) {
 #define blockDim (::simt::g_blk->bdim)
 #define gridDim (::simt::g_blk->gdim)
 
-struct uint2 {
+struct __attribute__((aligned(8))) uint2 { /* CUDA's alignment: a misaligned pair load traps on the GPU */
     uint32_t x, y;
 };
 struct __attribute__((aligned(16))) uint4 {
