@@ -34,7 +34,15 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     p->sharedMemPerBlockOptin = 232448;
     return cudaSuccess;
 }
+/* failure injection for the error paths: the k-th cudaMalloc from now on (0-based) reports out of memory */
+inline long g_fake_malloc_countdown = -1;
+/* (set through fake_cuda_fail_malloc_after(), which build_emu.py defines in the emulated ABI) */
+
 inline cudaError_t cudaMalloc(void **p, size_t bytes) {
+    if (g_fake_malloc_countdown >= 0 && g_fake_malloc_countdown-- == 0) {
+        *p = nullptr;
+        return cudaErrorMemoryAllocation;
+    }
     const size_t sz = (bytes + 255) & ~(size_t)255;
     *p = aligned_alloc(256, sz ? sz : 256);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
