@@ -74,7 +74,12 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+/* failure injection: the k-th cudaStreamSynchronize from now on reports a (sticky-style) launch failure */
+inline long g_fake_sync_countdown = -1;
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) {
+    if (g_fake_sync_countdown >= 0 && g_fake_sync_countdown-- == 0) return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
     *e = (void *)1;
     return cudaSuccess;

@@ -53,3 +53,30 @@ def test_every_allocation_site_reports_oom_cleanly(lib):
     else:
         pytest.fail("the sequence never ran out of allocation sites")
     assert failures >= 20, failures
+
+
+def test_a_cuda_error_poisons_the_handle_and_only_the_handle(lib):
+    """A non-OOM CUDA error is sticky for that index (DANN_ERR_CUDA on every later call, include/diskann_b200.h), while a
+    freshly loaded index works."""
+    from oracle import fixtures
+    s = build_case(200, 16, 1, seed=4, kind="normal", R=8, L_build=16)
+    q = fixtures.gen_vectors(2, 16, 5, "normal")
+    inject = lib.load_library().fake_cuda_fail_sync_after
+    inject.argtypes = [C.c_long]
+    inject.restype = None
+    idx = lib.DiskAnnIndex(s)
+    try:
+        idx.search_batch(q, k=3, search_list_size=10, rescore=5)
+        inject(0)
+        with pytest.raises(lib.DiskAnnError) as e:
+            idx.search_batch(q, k=3, search_list_size=10, rescore=5)
+        assert e.value.code == -2
+        inject(-1)
+        with pytest.raises(lib.DiskAnnError, match="poisoned") as e:
+            idx.search_batch(q, k=3, search_list_size=10, rescore=5)
+        assert e.value.code == -2
+    finally:
+        inject(-1)
+        idx.close()
+    with lib.DiskAnnIndex(s) as fresh:
+        assert fresh.search_batch(q, k=3, search_list_size=10, rescore=5)["count"].tolist() == [3, 3]
