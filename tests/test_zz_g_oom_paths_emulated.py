@@ -80,3 +80,33 @@ def test_a_cuda_error_poisons_the_handle_and_only_the_handle(lib):
         idx.close()
     with lib.DiskAnnIndex(s) as fresh:
         assert fresh.search_batch(q, k=3, search_list_size=10, rescore=5)["count"].tolist() == [3, 3]
+
+
+def test_builder_allocation_sites_report_oom_cleanly(lib):
+    from pgvectorscale_b200.snapshot import INVALID_NODE
+    s = build_case(120, 16, 1, seed=6, kind="normal", R=8, L_build=16)
+    s.R = 64
+    s.nbrs = np.full((120, 64), INVALID_NODE, np.uint32)
+    s.start_default = 0
+    inject = lib.load_library().fake_cuda_fail_malloc_after
+    inject.argtypes = [C.c_long]
+    inject.restype = None
+    failures = 0
+    with lib.DiskAnnIndex(s) as idx:
+        for k in range(0, 200):
+            inject(k)
+            try:
+                idx.build_graph(12, 24, 1.2, 64)
+                inject(-1)
+                break
+            except lib.DiskAnnError as e:
+                assert e.code == -4, (k, e)
+                failures += 1
+            finally:
+                inject(-1)
+        else:
+            pytest.fail("the build never ran out of allocation sites")
+        st = idx.build_graph(12, 24, 1.2, 64)          # and a clean build still works on the same handle
+        nb = idx.download_nbrs()
+    assert failures >= 10 and st["batches"] >= 3
+    assert ((nb != 0xFFFFFFFF).sum(1)[1:] >= 1).all()
