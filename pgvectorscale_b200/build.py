@@ -49,6 +49,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc(), *NVCC_FLAGS]
     # experiment knob: extra -D... for this build only, e.g. DANN_NVCC_DEFINES="-DDANN_HV_NO_FUSED" with force=True
     cmd += [d for d in os.environ.get("DANN_NVCC_DEFINES", "").split() if d.startswith("-D")]
+    # development loops only: e.g. DANN_NVCC_EXTRA="-split-compile=8" builds in ~40 s instead of ~90 s, but ptxas then
+    # schedules differently - the result is NOT the measured binary (tools/sass_signature.py shows it)
+    cmd += os.environ.get("DANN_NVCC_EXTRA", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
