@@ -58,3 +58,10 @@ def test_two_ranks_with_real_replicas_equal_the_oracle(lib_built):
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] == 1 and out[1] == 1
+
+
+def test_graft_entry_smoke_under_emulation(lib_built, capsys):
+    """__graft_entry__.smoke() - the driver's first call on the GPU box - against the emulated ABI."""
+    import __graft_entry__ as g
+    g.smoke()
+    assert "smoke ok" in capsys.readouterr().out
