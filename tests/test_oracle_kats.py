@@ -243,6 +243,38 @@ def test_labeled_recall_property():        # labels/filtering_tests.rs:880-1024:
     assert hits / tot >= 0.9
 
 
+def _null_and_empty_labels_index():
+    """labels/filtering_tests.rs:23-110 as data: `CREATE INDEX ... USING diskann (embedding, labels)` on the empty table
+    (zero-mean quantizer), then four rows: {1,2}, NULL, {}, {1,NULL,3} (NULL array = no labels, NULL element dropped,
+    labels/mod.rs:209-238)."""
+    v = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9], [10, 11, 12]], np.float32)
+    sets = [[1, 2], [], [], [1, 3]]
+    off = np.zeros(5, np.uint32)
+    off[1:] = np.cumsum([len(x) for x in sets])
+    lab = np.array([x for st in sets for x in st], np.int16)
+    return fixtures.make_index(v, COSINE, R=10, L_build=10, label_off=off, labels=lab, train_on_data=False)
+
+
+@pytest.mark.parametrize("key,want", [([1], 2), ([], 0), ([3], 1), (None, 4)])
+def test_null_and_empty_labels_kat(key, want):     # labels/filtering_tests.rs:23-110
+    s = _null_and_empty_labels_index()
+    r = oracle.scan(s, np.zeros(3, np.float32), key, 100, 50, 100)
+    assert len(r["tid"]) == want
+    b_rows, _ = pyref.scan(s, np.zeros(3, np.float32), key, 100, 50, 100)
+    assert [x[0] for x in b_rows] == r["tid"].tolist()
+
+
+def test_mixed_filtering_with_null_labels_kat():    # labels/filtering_tests.rs:170-213 (the index part: `labels && '{1}'`)
+    v = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9], [10, 11, 12], [13, 14, 15], [16, 17, 18]], np.float32)
+    sets = [[1, 2], [], [], [1, 3], [2, 3], []]          # NULL, {} and {NULL} all carry no label
+    off = np.zeros(7, np.uint32)
+    off[1:] = np.cumsum([len(x) for x in sets])
+    lab = np.array([x for st in sets for x in st], np.int16)
+    s = fixtures.make_index(v, COSINE, R=10, L_build=10, label_off=off, labels=lab, train_on_data=False)
+    r = oracle.scan(s, np.zeros(3, np.float32), [1], 100, 50, 100)
+    assert sorted(r["node"].tolist()) == [0, 3]      # the executor's `category = 'blog'` then keeps row 3 only: count 1
+
+
 # ---- the two restatements agree on whole scans ---------------------------------------------
 @pytest.mark.parametrize("dist,bits,labels,dim_index", [(COSINE, 2, False, None), (L2, 1, False, None),
                                                         (IP, 2, True, None), (COSINE, 2, True, 40)])

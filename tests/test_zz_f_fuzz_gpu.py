@@ -79,3 +79,21 @@ def test_random_small_index_batch_and_scan_equal_oracle(lib, seed):
         for f in ("visits", "d_quantized", "candidates", "d_full"):
             assert st[f] == want["stats"][f], (c, L, rescore, f)
         sc.end()
+
+
+@pytest.mark.parametrize("key,want", [([1], 2), ([], 0), ([3], 1), (None, 4)])
+def test_reference_null_and_empty_labels_kat_through_the_abi(lib, key, want):
+    """labels/filtering_tests.rs:23-110 (restated in tests/test_oracle_kats.py) through the C ABI: batch call and scan."""
+    from test_oracle_kats import _null_and_empty_labels_index
+    s = _null_and_empty_labels_index()
+    q = np.zeros((1, 3), np.float32)
+    with lib.DiskAnnIndex(s) as idx:
+        g = idx.search_batch(q, labels=None if key is None else [key], k=10, search_list_size=100, rescore=50)
+        assert int(g["count"][0]) == want
+        sc = idx.begin_scan()
+        sc.rescan(q[0], labels=key, search_list_size=100, rescore=50)
+        n = 0
+        while sc.gettuple() is not None:
+            n += 1
+        sc.end()
+        assert n == want
