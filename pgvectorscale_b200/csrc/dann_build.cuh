@@ -144,6 +144,7 @@ struct BuildArgs {
     uint16_t *nbr_dist;   /* [n][SLACK] */
     uint8_t *deg;         /* [n] */
     uint32_t R;           /* num_neighbors */
+    uint32_t limit;       /* max_neighbors_during_build = ceil(1.3 R) (meta_page.rs:24,253-255), at most the 64 slots */
     float max_alpha;
     uint32_t per_warp_smem;
     const uint32_t *label_off; /* NULL: unlabeled index */
@@ -243,7 +244,7 @@ __global__ void dann_build_heads_kernel(const uint64_t *key, size_t total, uint3
 }
 
 /* step 3: back-pointers.  One warp per destination node: append the (closest 64) new sources; a list
- * that would outgrow the slack is pruned back to R (graph/mod.rs:212-266 add_neighbors) */
+ * that would outgrow max_neighbors_during_build is pruned back to R (graph/mod.rs:212-266 add_neighbors) */
 __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, const uint64_t *key, const uint32_t *val,
                                                                   size_t total, const uint32_t *heads, uint32_t nheads) {
     DANN_DYN_SMEM(dann_smem);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, c
         for (uint32_t t = lane; t < deg; t += 32) ck[t] = ((uint64_t)drow[t] << 32) | row[t];
         __syncwarp();
         const uint32_t tot = deg + nadd;
-        if (tot <= DANN_BUILD_SLACK && !a.label_off) { /* room left and no repeats possible: plain append */
+        if (tot <= a.limit && !a.label_off) { /* room left and no repeats possible: plain append */
             uint32_t *wrow = a.nbrs + (size_t)q * DANN_BUILD_SLACK;
             uint16_t *wdrow = a.nbr_dist + (size_t)q * DANN_BUILD_SLACK;
             for (uint32_t t = deg + lane; t < tot; t += 32) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(256) dann_build_backlink_kernel(BuildArgs a, c
                 __syncwarp();
             }
             uint32_t cnt;
-            if (C <= DANN_BUILD_SLACK) {
+            if (C <= a.limit) {
                 for (uint32_t t = lane; t < C; t += 32) {
                     oid[t] = (uint32_t)ck[t];
                     od[t] = (uint16_t)(ck[t] >> 32);

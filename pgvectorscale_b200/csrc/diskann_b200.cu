@@ -904,6 +904,7 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     ba.nbr_dist = b_dist.as<uint16_t>();
     ba.deg = b_deg.as<uint8_t>();
     ba.R = (uint32_t)num_neighbors;
+    ba.limit = std::min<uint32_t>(DANN_BUILD_SLACK, (uint32_t)std::ceil((double)num_neighbors * 1.3));
     ba.max_alpha = max_alpha;
     ba.label_off = v.has_labels ? v.label_off : nullptr;
     ba.labels = v.has_labels ? v.labels : nullptr;

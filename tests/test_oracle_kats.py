@@ -275,6 +275,16 @@ def test_mixed_filtering_with_null_labels_kat():    # labels/filtering_tests.rs:
     assert sorted(r["node"].tolist()) == [0, 3]      # the executor's `category = 'blog'` then keeps row 3 only: count 1
 
 
+@pytest.mark.parametrize("train_on_data", [True, False])
+def test_small_accuracy_connectivity_property(train_on_data):
+    """build.rs:1717-1853 (test_index_small_accuracy / ..._insert_after_index_created): 1000 random 2-d vectors,
+    num_neighbors = 10, search_list_size = 10; with diskann.query_search_list_size = 2 an unbounded scan still returns
+    every row - no node may get disconnected.  (Postgres' random() stream is not reproducible: our RNG, same property.)"""
+    s = build_case(1000, 2, COSINE, seed=5, kind="uniform", R=10, L_build=10, train_on_data=train_on_data)
+    r = oracle.scan(s, np.ones(2, np.float32), None, 2, 50, 5000)
+    assert len(r["tid"]) == 1000 and len(set(r["tid"].tolist())) == 1000
+
+
 # ---- the two restatements agree on whole scans ---------------------------------------------
 @pytest.mark.parametrize("dist,bits,labels,dim_index", [(COSINE, 2, False, None), (L2, 1, False, None),
                                                         (IP, 2, True, None), (COSINE, 2, True, 40)])
