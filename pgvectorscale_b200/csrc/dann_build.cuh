@@ -336,3 +336,66 @@ __global__ void __launch_bounds__(256) dann_build_finalize_kernel(BuildArgs a) {
         __syncwarp();
     }
 }
+
+/* ---- in-edge rescue (DANN_BUILD_RESCUE=1, not part of the reference's algorithm) --------------------------------
+ * Batched insertion can leave a node without any in-edge (every list that pointed at it was pruned while the node's
+ * batch mates - which it never saw - crowded the same destinations; tie-heavy data makes this common).  Such a node is
+ * invisible to every scan.  After finalize, a few rounds of: mark nodes that have an in-edge; every other node asks its
+ * nearest out-neighbour for a slot - a free one if the list is shorter than R, else one of the farthest (at most R/2
+ * per list and round).  A displaced neighbour that loses its last in-edge is picked up by the next round. */
+__global__ void dann_build_mark_indegree_kernel(const uint32_t *nbrs, const uint8_t *deg, uint32_t n, uint32_t *indeg) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * DANN_BUILD_SLACK;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(i / DANN_BUILD_SLACK), t = (uint32_t)(i % DANN_BUILD_SLACK);
+        if (t < deg[p]) {
+            const uint32_t x = nbrs[i];
+            if (x < n && x != p) atomicAdd(indeg + x, 1u);
+        }
+    }
+}
+
+__global__ void dann_build_rescue_kernel(uint32_t *nbrs, const uint8_t *deg, uint32_t n, uint32_t R, uint32_t *indeg,
+                                         uint32_t *claim, uint32_t *rescued) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        if (p == 0 || indeg[p]) continue; /* node 0 is the entry point */
+        const uint32_t *row = nbrs + (size_t)p * DANN_BUILD_SLACK;
+        const uint32_t dp = deg[p];
+        bool done = false;
+        /* pass A: a FREE slot in the list of any out-neighbour (nearest first), the entry point as a last resort */
+        for (uint32_t t = 0; t <= dp && !done; t++) {
+            const uint32_t q = t < dp ? row[t] : 0u;
+            if (q >= n || q == p) continue;
+            const uint32_t dq = deg[q];
+            if (dq >= R) continue;
+            const uint32_t c = atomicAdd(claim + q, 1u);
+            if (dq + c >= R) continue; /* lost the race for the last free slot */
+            nbrs[(size_t)q * DANN_BUILD_SLACK + dq + c] = p;
+            done = true;
+        }
+        /* pass B: take the place of an entry of a full list that has another in-edge to spare (farthest first): the
+         * swap is a compare-and-swap on the slot, the victim's spare in-edge is reserved with an atomic decrement */
+        for (uint32_t t = 0; t < dp && !done; t++) {
+            const uint32_t q = row[t];
+            if (q >= n || q == p || deg[q] < R) continue;
+            uint32_t *qrow = nbrs + (size_t)q * DANN_BUILD_SLACK;
+            for (uint32_t sl = R; sl-- > R / 2 && !done;) {
+                const uint32_t x = qrow[sl];
+                if (x >= n || x == p) continue;
+                const uint32_t had = atomicSub(indeg + x, 1u);
+                if (had >= 2 && atomicCAS(qrow + sl, x, p) == x) done = true;
+                else atomicAdd(indeg + x, 1u); /* not spare after all (or the slot changed): give it back */
+            }
+        }
+        if (done) atomicAdd(rescued, 1u);
+    }
+}
+
+__global__ void dann_build_rescue_degrees_kernel(uint8_t *deg, const uint32_t *claim, uint32_t n, uint32_t R) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t c = claim[q];
+        if (!c) continue;
+        const uint32_t d = deg[q] + c;
+        deg[q] = (uint8_t)(d < R ? d : R);
+    }
+}
+

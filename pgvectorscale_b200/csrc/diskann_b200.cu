@@ -996,6 +996,34 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     ix->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
+    if (env_u32("DANN_BUILD_RESCUE", 0) == 1 && !v.has_labels) { /* opt-in: see dann_build.cuh "in-edge rescue" */
+        DevBuf b_in, b_claim;
+        struct Rel {
+            DevBuf *a, *b;
+            ~Rel() {
+                a->release();
+                b->release();
+            }
+        } rel{&b_in, &b_claim};
+        CK(b_in.reserve((size_t)n * 4));
+        CK(b_claim.reserve((size_t)n * 4 + 4));
+        uint32_t *d_claim = b_claim.as<uint32_t>(), *d_resc = d_claim + n;
+        for (int round = 0; round < 16; round++) {
+            CK(cudaMemsetAsync(b_in.p, 0, (size_t)n * 4, st));
+            CK(cudaMemsetAsync(d_claim, 0, (size_t)n * 4 + 4, st));
+            dann_build_mark_indegree_kernel<<<ix->sm_count * 8, 256, 0, st>>>(nbrs, b_deg.as<uint8_t>(), n, b_in.as<uint32_t>());
+            dann_build_rescue_kernel<<<ix->sm_count * 4, 256, 0, st>>>(nbrs, b_deg.as<uint8_t>(), n, (uint32_t)num_neighbors,
+                                                                      b_in.as<uint32_t>(), d_claim, d_resc);
+            dann_build_rescue_degrees_kernel<<<ix->sm_count * 4, 256, 0, st>>>(b_deg.as<uint8_t>(), d_claim, n, (uint32_t)num_neighbors);
+            ix->launches += 3;
+            CK(cudaGetLastError());
+            uint32_t resc = 0;
+            CK(cudaMemcpyAsync(&resc, d_resc, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (verbose) fprintf(stderr, "[dann_build] rescue round %d: %u nodes had no in-edge\n", round, resc);
+            if (!resc) break;
+        }
+    }
     bs.total_ms = bs.search_ms + bs.prune_ms + bs.sort_ms + bs.backlink_ms;
     /* average degree */
     {

@@ -220,6 +220,12 @@ inline T atomicAdd(T *p, T v) {
     return o;
 }
 template <typename T>
+inline T atomicSub(T *p, T v) {
+    T o = *p;
+    *p = o - v;
+    return o;
+}
+template <typename T>
 inline T atomicOr(T *p, T v) {
     T o = *p;
     *p = o | v;

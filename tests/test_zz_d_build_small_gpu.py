@@ -108,14 +108,18 @@ def test_small_built_labeled_graph_valid_and_parity(lib):
         idx.close()
 
 
-@pytest.mark.parametrize("dim,floor", [(8, 0.99), (2, 0.35)])
-def test_small_accuracy_connectivity_of_the_gpu_builder(lib, dim, floor):
+@pytest.mark.parametrize("dim,R,rescue,floor", [(8, 10, 0, 0.99), (2, 10, 0, 0.35), (8, 10, 1, 1.0), (2, 20, 1, 1.0),
+                                                 (2, 10, 1, 0.65)])
+def test_small_accuracy_connectivity_of_the_gpu_builder(lib, monkeypatch, dim, R, rescue, floor):
     """build.rs:1717-1853 (1000 random low-dimensional vectors, num_neighbors = 10, search_list_size = 10, unbounded scan
     at query_search_list_size = 2 must return every row) applied to dann_build_graph.  The reference's SERIAL build - and
     the oracle's restatement of it, tests/test_oracle_kats.py - keeps every node reachable.  The batch builder matches
     that at 8 dimensions; at 2 dimensions (2-bit SBQ leaves 9 distinct codes for 1000 points, every batch is a crowd of
     zero-distance duplicates that do not see each other) it does NOT: a known limit of batched insertion, recorded
-    here with the floor it currently reaches."""
+    here with the floor it currently reaches.  DANN_BUILD_RESCUE=1 (opt-in, not the reference's
+    algorithm) hands every node without an in-edge a slot in a neighbour's list after the build: everything but the
+    most degenerate case (5 distinct codes, R = 10) then comes back complete."""
+    monkeypatch.setenv("DANN_BUILD_RESCUE", str(rescue))
     from pgvectorscale_b200.snapshot import INVALID_NODE
     n = 1000
     s = build_case(n, dim, 0, seed=5, kind="uniform", R=4, L_build=8)
@@ -123,7 +127,11 @@ def test_small_accuracy_connectivity_of_the_gpu_builder(lib, dim, floor):
     s.nbrs = np.full((n, 64), INVALID_NODE, np.uint32)
     s.start_default = 0
     with lib.DiskAnnIndex(s) as idx:
-        idx.build_graph(10, 10, 1.2, 256)
+        idx.build_graph(R, 10 if R == 10 else 40, 1.2, 256)
+        nb = idx.download_nbrs()
+        valid = nb != INVALID_NODE
+        assert valid.sum(1).max() <= R and (nb[valid] < n).all()
+        assert (valid[:, :-1] >= valid[:, 1:]).all()          # still INVALID-terminated prefixes after the rescue
         sc = idx.begin_scan()
         sc.rescan(np.ones(dim, np.float32), search_list_size=2, rescore=50)
         got = set()
