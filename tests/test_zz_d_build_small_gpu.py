@@ -108,8 +108,10 @@ def test_small_built_labeled_graph_valid_and_parity(lib):
         idx.close()
 
 
-@pytest.mark.parametrize("dim,R,rescue,floor", [(8, 10, 0, 0.99), (2, 10, 0, 0.35), (8, 10, 1, 1.0), (2, 20, 1, 1.0),
-                                                 (2, 10, 1, 0.65)])
+# floors leave room for the builder's run-to-run variation on hardware (atomics order); under emulation the five cases
+# return 997, 446, 1000, 1000 and 750 of 1000 rows
+@pytest.mark.parametrize("dim,R,rescue,floor", [(8, 10, 0, 0.98), (2, 10, 0, 0.3), (8, 10, 1, 0.995), (2, 20, 1, 0.99),
+                                                 (2, 10, 1, 0.6)])
 def test_small_accuracy_connectivity_of_the_gpu_builder(lib, monkeypatch, dim, R, rescue, floor):
     """build.rs:1717-1853 (1000 random low-dimensional vectors, num_neighbors = 10, search_list_size = 10, unbounded scan
     at query_search_list_size = 2 must return every row) applied to dann_build_graph.  The reference's SERIAL build - and
