@@ -119,7 +119,7 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     while (W > 1 && budget / W < fixed + 1024) W--;
     size_t per_warp = (budget / W) & ~(size_t)15;
     uint32_t hs = (uint32_t)std::min<size_t>(p->cand_cap, (per_warp - fixed) / p->esize);
-    hs = env_u32("DANN_SEARCH_HS", hs);
+    hs = std::min<uint32_t>(env_u32("DANN_SEARCH_HS", hs), (uint32_t)((per_warp - fixed) / p->esize)); /* test hook, never past the budget */
     hs = std::min(hs, p->cand_cap) & ~3u;
     p->hs = hs;
     p->W = W;

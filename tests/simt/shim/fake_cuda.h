@@ -91,7 +91,11 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) {
     return cudaSuccess;
 }
 template <typename F>
-inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute attr, int value) {
+    /* like the real runtime: more dynamic shared memory than the device's opt-in limit is an error, not a silent overflow */
+    if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize && value > 232448) return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
 template <typename F>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) {
     *n = 1;

@@ -78,6 +78,14 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux);
 void named_barrier(unsigned id, unsigned count);
 /* runs `body` once per thread of every block of the grid, blocks one after the other */
 void launch(unsigned grid, unsigned block, const std::function<void()> &body);
+/* the same with the launch's dynamic shared memory size checked against the emulator's arena (dann_smem, 256 KB) */
+inline void launch_checked(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body) {
+    if (smem_bytes > 256u * 1024u) {
+        fprintf(stderr, "simt: launch asks for %zu bytes of dynamic shared memory, the arena holds 262144\n", smem_bytes);
+        abort();
+    }
+    launch(grid, block, body);
+}
 uint64_t total_switches();
 void collectives_by_warp_parity(uint64_t out[2]);
 

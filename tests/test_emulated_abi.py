@@ -41,7 +41,7 @@ def test_gpu_parity_suite_passes_under_emulation():
     passed, out = _run(["tests/test_gpu_parity.py", "tests/test_zz_c_harness_gpu.py", "tests/test_zz_d_build_small_gpu.py",
                         "tests/test_zz_e_coalescer_gpu.py", "tests/test_zz_f_fuzz_gpu.py",
                         "tests/test_zz_g_oom_paths_emulated.py", "tests/test_zz_h_two_rank_emulated.py"])
-    assert passed >= 77 and "skipped" not in out.splitlines()[-1], out[-500:]
+    assert passed >= 85 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
 def test_not_yet_on_hardware_paths_pass_under_emulation():
@@ -53,10 +53,10 @@ def test_not_yet_on_hardware_paths_pass_under_emulation():
 def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16",
                                                        "DANN_DEBUG_SHRINK": "8", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"})
-    assert passed == 120 + 4      # the seeds + the four reference-KAT cases in the same file
+    assert passed == 120 + 12     # the seeds + the four reference-KAT cases and the eight medium cases in the same file
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_SEARCH_KERNEL": "1",
                                                        "DANN_SEARCH_BITMAP": "0", "SIMT_SCHED": "1"})
-    assert passed == 120 + 4      # the seeds + the four reference-KAT cases in the same file
+    assert passed == 120 + 12     # the seeds + the four reference-KAT cases and the eight medium cases in the same file
 
 
 def test_address_sanitizer_finds_nothing_in_host_code_or_kernels():
@@ -67,11 +67,11 @@ def test_address_sanitizer_finds_nothing_in_host_code_or_kernels():
                                                        text=True).stdout.strip()):
         pytest.skip("libasan not installed")
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "80"}, asan=True)
-    assert passed == 80 + 4
+    assert passed == 80 + 12
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"],
                      {"DANN_FUZZ_SEEDS": "80", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16", "DANN_DEBUG_SHRINK": "8",
                       "DANN_SCAN_FUSED": "1", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"}, asan=True)
-    assert passed == 80 + 4
+    assert passed == 80 + 12
 
 
 def test_one_synchronisation_gettuple_passes_under_emulation():
@@ -80,7 +80,7 @@ def test_one_synchronisation_gettuple_passes_under_emulation():
                      {"DANN_SCAN_FUSED": "1"})
     assert passed >= 2
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_SCAN_FUSED": "1", "DANN_DEBUG_SHRINK": "8", "DANN_FUZZ_SEEDS": "120"})
-    assert passed == 120 + 4      # the seeds + the four reference-KAT cases in the same file
+    assert passed == 120 + 12     # the seeds + the four reference-KAT cases and the eight medium cases in the same file
 
 
 @pytest.mark.parametrize("sched", ["2"])

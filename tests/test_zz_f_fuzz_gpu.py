@@ -97,3 +97,37 @@ def test_reference_null_and_empty_labels_kat_through_the_abi(lib, key, want):
             n += 1
         sc.end()
         assert n == want
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_medium_index_long_scans_equal_oracle(lib, monkeypatch, seed):
+    """Bigger random cases: up to 5000 nodes x 768 dimensions, lists of up to 64 ids, L up to 300, 300 rerank rows,
+    k = 50, shared-memory heap tops from 64 entries to "as large as fits", optional forced workspace growth - the heap
+    spills, pages straddle leaf levels, several query slots share a block."""
+    from oracle import fixtures, oracle
+    rng = np.random.default_rng(50000 + seed)
+    n = int(rng.choice([700, 2000, 5000]))
+    dim = int(rng.choice([16, 64, 200, 768]))
+    dist = int(rng.integers(0, 3))
+    R = int(rng.choice([16, 32, 50, 64]))
+    labels = bool(rng.random() < 0.3)
+    s = build_case(n, dim, dist, bits=int(rng.choice([1, 2])), seed=seed, kind="normal", R=R, L_build=2 * R, labels=labels,
+                   deleted_every=int(rng.choice([0, 0, 7])))
+    q = fixtures.gen_vectors(4, dim, 100 + seed, "normal")
+    keys = None
+    if labels and rng.random() < 0.6:
+        keys = [[int(x) for x in rng.integers(1, 17, size=int(rng.integers(1, 3)))] for _ in range(4)]
+    monkeypatch.setenv("DANN_SEARCH_HS", str(int(rng.choice([64, 512, 4096, 100000]))))
+    if rng.random() < 0.5:
+        monkeypatch.setenv("DANN_DEBUG_SHRINK", "4")
+    k, L, rescore = int(rng.choice([10, 50])), int(rng.choice([50, 150, 300])), int(rng.choice([0, 50, 300]))
+    with lib.DiskAnnIndex(s) as idx:
+        g = idx.search_batch(q, labels=keys, k=k, search_list_size=L, rescore=rescore)
+    for b in range(4):
+        r = oracle.scan(s, q[b], None if keys is None else keys[b], L, rescore, k)
+        nrow = len(r["tid"])
+        assert int(g["count"][b]) == nrow and g["tid"][b, :nrow].tolist() == r["tid"].tolist(), (seed, b)
+        if rescore:
+            assert g["dist"][b, :nrow].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
+        for f in ("visits", "d_quantized", "candidates", "d_full"):
+            assert int(g["stats"][f][b]) == r["stats"][f], (seed, b, f)
