@@ -41,7 +41,7 @@ def test_gpu_parity_suite_passes_under_emulation():
     passed, out = _run(["tests/test_gpu_parity.py", "tests/test_zz_c_harness_gpu.py", "tests/test_zz_d_build_small_gpu.py",
                         "tests/test_zz_e_coalescer_gpu.py", "tests/test_zz_f_fuzz_gpu.py",
                         "tests/test_zz_g_oom_paths_emulated.py", "tests/test_zz_h_two_rank_emulated.py"])
-    assert passed >= 85 and "skipped" not in out.splitlines()[-1], out[-500:]
+    assert passed >= 97 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
 def test_not_yet_on_hardware_paths_pass_under_emulation():

@@ -144,3 +144,55 @@ def test_small_accuracy_connectivity_of_the_gpu_builder(lib, monkeypatch, dim, R
             got.add((row[0], row[1]))
         sc.end()
     assert len(got) >= floor * n, len(got)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_builds_are_valid_graphs_with_scan_parity(lib, monkeypatch, seed):
+    """Builder fuzz: 1..1200 nodes, num_neighbors 1..64, build search lists 1..100, batch limits 1..unbounded, with and
+    without labels and the in-edge rescue - every result is a structurally valid graph (INVALID-terminated lists of at
+    most R distinct in-range ids, no self loops) and scans over it equal the oracle's on the same snapshot."""
+    from oracle import fixtures, oracle
+    from pgvectorscale_b200.snapshot import INVALID_NODE
+    rng = np.random.default_rng(90000 + seed)
+    n = int(rng.choice([1, 2, 5, 70, 400, 1200]))
+    dim = int(rng.choice([2, 8, 48, 200]))
+    dist = int(rng.integers(0, 3))
+    labels = bool(rng.random() < 0.4)
+    R, Lb, mb = int(rng.choice([1, 4, 12, 32, 50, 64])), int(rng.choice([1, 5, 30, 100])), int(rng.choice([1, 7, 64, 1 << 20]))
+    monkeypatch.setenv("DANN_BUILD_RESCUE", str(int(rng.integers(0, 2))))
+    s = build_case(n, dim, dist, bits=int(rng.choice([1, 2])), seed=seed, kind=str(rng.choice(["normal", "uniform"])), R=4,
+                   L_build=8, labels=labels)
+    s.R = 64
+    s.nbrs = np.full((n, 64), INVALID_NODE, np.uint32)
+    s.start_default = 0
+    if labels:
+        first = {}
+        for i in range(n):
+            for l in s.labels[s.label_off[i]:s.label_off[i + 1]]:
+                first.setdefault(int(l), i)
+        ks = sorted(first)
+        s.start_labels = np.array(ks, np.int16)
+        s.start_label_nodes = np.array([first[k] for k in ks], np.uint32)
+    with lib.DiskAnnIndex(s) as idx:
+        idx.build_graph(R, Lb, 1.2, mb)
+        s.nbrs = idx.download_nbrs()
+        _check_structure_general(s, R)
+        q = fixtures.gen_vectors(2, dim, 3 + seed, "normal")
+        key = [[1], [2, 3]] if labels else None
+        g = idx.search_batch(q, labels=key, k=5, search_list_size=20, rescore=10)
+    for b in range(2):
+        r = oracle.scan(s, q[b], None if key is None else key[b], 20, 10, 5)
+        nrow = len(r["tid"])
+        assert int(g["count"][b]) == nrow and g["tid"][b, :nrow].tolist() == r["tid"].tolist(), (seed, b)
+
+
+def _check_structure_general(s, R):
+    n, nb = s.n, s.nbrs
+    valid = nb != 0xFFFFFFFF
+    assert valid.sum(1).max() <= R
+    assert (valid[:, :-1] >= valid[:, 1:]).all()
+    assert (nb[valid] < n).all()
+    assert not (nb == np.arange(n, dtype=np.uint32)[:, None]).any()
+    for i in range(n):
+        row = nb[i][valid[i]]
+        assert len(set(row.tolist())) == len(row)
