@@ -15,6 +15,7 @@ def _dependencies():
     """Every source the library is compiled from: all of csrc/ plus the public header."""
     import glob
     deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+    deps += glob.glob(os.path.join(CSRC, "*.h"))    # dann_plan.h decides every launch shape, dann_coalescer.h is compiled in
     deps += glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
     deps.append(os.path.abspath(__file__))      # flag changes rebuild too
     return deps
