@@ -1,0 +1,582 @@
+// dann_search3.cuh — "lean" persistent warp-per-query StreamingDiskANN beam search (sm_100a), sized for FULL
+// occupancy: up to 32 resident queries per SM (one warp each, <= 64 registers per thread, a few KB of shared
+// memory per query) instead of the 7 two-warp slots of dann_search2.cuh.  Same algorithm, same results and
+// counters as dann_search.cuh (see that file for the reference map; paths below are relative to
+// /root/reference/pgvectorscale/src/access_method/):
+//   ListSearchResult::{new,prepare_insert,insert_neighbor,visit_closest,consume}   graph/mod.rs:97-185
+//   Graph::greedy_search_iterate                                                   graph/mod.rs:357-385
+//   SbqSpeedupStorage::visit_lsn_internal (Disk arm)                               sbq/storage.rs:125-190
+//   distance_xor_optimized                                                         distance/mod.rs:265-323
+//   TSVResponseIterator::next (deleted-tuple skip)                                 scan.rs:210-242
+//
+// The search of one query is a dependent chain (pop -> neighbour row -> inserted-set -> code rows -> pushes -> pop);
+// one warp cannot make it shorter than its memory round trips, so throughput = resident queries / chain latency.
+// This kernel therefore minimises (a) the per-query footprint and (b) the instructions per visit:
+//   * heap entries carry their own node reference (node id under the bitmap inserted-set, hash slot under the
+//     hash inserted-set): no seq -> node table, no store per candidate, no inserted-id list;
+//   * BinaryHeap::push x page with the root-ward path of the current leaf held in registers (lane j = height j):
+//     a push is ballot + shuffle + select, memory is touched only where the path steps to the next leaf;
+//   * BinaryHeap::pop's sift_down_to_bottom four levels per memory round trip: 30 lanes fetch the hole's
+//     2+4+8+16 descendants at once, one ballot decides every sibling pair ("right child on ties"), the path is
+//     walked on that mask in registers and the winners store themselves into their parents;
+//   * visited list = ring buffer of heap entries (4 bytes each at 768-d), 32-ary partition_point, the shorter
+//     side is shifted; consume() is a head increment;
+//   * the bitmap inserted-set is cleared with one streaming memset per query (n/8 bytes) instead of replaying a list.
+// Everything is an exact restatement of the sequential algorithm: Rust's BinaryHeap decides which of several equal
+// Hamming distances pops first, and that decides returned row ids (dann_heap.cuh).
+//
+// Shared memory per query slot: visited ring [vcap] E, heap slots [hs] E (1-based, slot 0 unused), page of node ids
+// [64] u32 and page of entries [64] E.  HBM per slot: heap tail [cand_cap] E, inserted-set (bitmap n/8 bytes, or
+// hash_cap u32).
+#pragma once
+#include "dann_search.cuh"
+
+template <typename T, int NCH>
+struct LeanWarp {
+    using E = typename T::E;
+    using H = RustHeap<E, T::KSHIFT>;
+    static constexpr E KM = (E(1) << T::KSHIFT) - E(1);
+    /* a 4-byte entry under the hash inserted-set carries the node's hash slot (21 bits) */
+    static constexpr bool SMALL = sizeof(E) == 4;
+
+    const SearchArgs &a;
+    const int lane;
+    E *vis;         /* ring [a.vcap] */
+    uint32_t *list; /* [64] node ids of the page being expanded */
+    E *ent;         /* [64] payload, then (key | payload) of the page */
+    uint32_t *hash, *bitmap;
+    SplitStore<E> heap; /* 1-based: Rust's data[i] is slot i + 1 */
+    ulonglong2 qc[NCH];
+    const int16_t *ql;
+    uint32_t nql;
+    bool filter, slotpay;
+    uint32_t heap_len, vis_head, vis_len, nset, listn, visits, dq, status;
+
+    __device__ __forceinline__ LeanWarp(const SearchArgs &a_, int lane_) : a(a_), lane(lane_) {}
+
+    __device__ __forceinline__ uint32_t node_of(E e) const {
+        const uint32_t p = T::seq(e);
+        return slotpay ? __ldcg(hash + p) : p;
+    }
+
+    /* prepare_insert = HashSet::insert (graph/mod.rs:126-128); returns true when n is new; *slot = where it lives */
+    __device__ __forceinline__ bool hash_insert(uint32_t n, uint32_t *slot) {
+        const uint32_t cap = a.hash_cap; /* any size: multiplicative hash scaled to [0, cap), linear probing */
+        uint32_t h = __umulhi(n * 2654435761u, cap);
+        for (uint32_t probe = 0; probe < cap; probe++) {
+            const uint32_t old = atomicCAS(hash + h, DANN_INVALID_NODE, n);
+            if (old == DANN_INVALID_NODE || old == n) {
+                *slot = h;
+                return old == DANN_INVALID_NODE;
+            }
+            h = h + 1 == cap ? 0u : h + 1;
+        }
+        *slot = 0;
+        return false;
+    }
+
+    __device__ __forceinline__ bool node_passes_filter(uint32_t n) {
+        /* labels.overlaps(node_neighbor.get_labels()), sbq/storage.rs:165-172 */
+        if (!a.ix.has_labels) return false;
+        const uint32_t o0 = __ldg(a.ix.label_off + n), o1 = __ldg(a.ix.label_off + n + 1);
+        return labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
+    }
+
+    /* dedupe (within the list, then against `inserted`) + label filter of up to 64 neighbour ids (list slots `lane`
+     * and `lane + 32`), appended to the page in list order: sbq/storage.rs:149-172 */
+    __device__ __forceinline__ void stage(uint32_t n0, bool v0, uint32_t n1, bool v1, bool apply_filter, bool unique) {
+        if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
+        bool f0 = v0, f1 = v1;
+        if (!unique) { /* a node listed twice within a chunk: only its first occurrence may insert */
+            const unsigned m0 = __match_any_sync(DANN_FULL, n0);
+            const unsigned m1 = __match_any_sync(DANN_FULL, n1);
+            f0 = v0 && ((__ffs(m0) - 1) == lane);
+            f1 = v1 && ((__ffs(m1) - 1) == lane);
+        }
+        bool new0 = false, new1 = false;
+        uint32_t s0 = n0, s1 = n1; /* payload: the node id, or its hash slot */
+        if (a.bitmap_words) {
+            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+            const uint32_t b0 = 1u << (n0 & 31), b1 = 1u << (n1 & 31);
+            if (f0) o0 = atomicOr(bitmap + (n0 >> 5), b0);
+            if (f1) o1 = atomicOr(bitmap + (n1 >> 5), b1);
+            new0 = f0 && !(o0 & b0);
+            new1 = f1 && !(o1 & b1);
+        } else {
+            uint32_t h0 = 0, h1 = 0;
+            if (f0) new0 = hash_insert(n0, &h0);
+            __syncwarp();
+            if (f1) new1 = hash_insert(n1, &h1);
+            if (slotpay) {
+                s0 = h0;
+                s1 = h1;
+            }
+            nset += __popc(__ballot_sync(DANN_FULL, new0)) + __popc(__ballot_sync(DANN_FULL, new1));
+            if ((uint64_t)nset * 3u > (uint64_t)a.hash_cap * 2u) { /* load factor bound 2/3 */
+                status |= DANN_ST_HASH;
+                return;
+            }
+        }
+        bool p0 = new0, p1 = new1;
+        if (apply_filter) {
+            if (new0) p0 = node_passes_filter(n0);
+            if (new1) p1 = node_passes_filter(n1);
+        }
+#ifdef DANN_SIMT_EMU
+        if (getenv("DANN_DBG2")) fprintf(stderr, "  lane %d n0=%u v0=%d f0=%d new0=%d p0=%d | n1=%u v1=%d new1=%d p1=%d\n", lane, n0, v0, f0, new0, p0, n1, v1, new1, p1);
+#endif
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned pm0 = __ballot_sync(DANN_FULL, p0), pm1 = __ballot_sync(DANN_FULL, p1);
+        const uint32_t t0 = __popc(pm0), t1 = __popc(pm1);
+        if (t0 + t1 == 0) return;
+        if (heap_len + listn + t0 + t1 + 1 > a.cand_cap) { /* 1-based heap slots: the last one is cand_cap - 1 */
+            status |= DANN_ST_HEAP;
+            return;
+        }
+        if (p0) {
+            const uint32_t pos = listn + __popc(pm0 & lt);
+            list[pos] = n0;
+            ent[pos] = (E)s0;
+        }
+        if (p1) {
+            const uint32_t pos = listn + t0 + __popc(pm1 & lt);
+            list[pos] = n1;
+            ent[pos] = (E)s1;
+        }
+        listn += t0 + t1;
+        __syncwarp();
+    }
+
+    /* SBQ distance of every node of the page (distance/mod.rs:265-323): G lanes per code row, 128-bit no-allocate
+     * loads, two row slots per lane group in flight, XOR + popcount + shuffle reduction; ent[r] becomes the entry */
+    __device__ __forceinline__ void distances(uint32_t tn) {
+        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
+        const uint32_t nchunks = a.ix.cw >> 1;
+        for (uint32_t b = 0; b < tn; b += 2 * RP) {
+            ulonglong2 v[2][NCH];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t r = b + u * RP + grp;
+                const bool live = r < tn;
+                const ulonglong2 *row =
+                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)(live ? list[r] : 0u) * a.ix.cw);
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    const uint32_t c = gl + i * G;
+                    v[u][i] = (live && c < nchunks) ? ldg_stream_u128(row + c) : qc[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int i = 0; i < NCH; i++) s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
+                for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+                const uint32_t r = b + u * RP + grp;
+                if (gl == 0 && r < tn) ent[r] = T::make(s, T::seq(ent[r]));
+            }
+        }
+        __syncwarp();
+    }
+
+    /* BinaryHeap::push x tn in page order (insert_neighbor, graph/mod.rs:144-147) with the root-ward path of the
+     * current leaf in registers: lane j owns the slot at height j above the leaf (lane 0 = the leaf itself).  A push
+     * is one ballot ("which ancestors does the element pass" - sift_up moves while elem < parent), one shuffle (those
+     * ancestors move one level down) and a select.  When the leaf advances to the next slot only the lanes whose
+     * ancestor changes (heights <= ctz(slot)) write their slot back and take the right-hand neighbour, which they
+     * prefetched when they entered the old one.  Exactness: a slot at height j of the current leaf level is read and
+     * written by lane j only until the leaf level changes at a power-of-two slot, where every lane writes back, the
+     * warp syncs and reloads.  Requires 1 <= tn <= heap_len: every ancestor of a new slot is then an old slot. */
+    __device__ __forceinline__ void push_page_regs(uint32_t tn) {
+        const uint32_t lanebit = 1u << lane, lanebit2 = lanebit << 1;
+        uint32_t pos = heap_len + 1;
+        uint32_t node = pos >> lane;
+        E val = 0, nxt = 0;
+        bool dirty = false;
+        if (lane >= 1 && node != 0) {
+            val = heap.get(node);
+            if (node + 1 <= heap_len) nxt = heap.get(node + 1);
+        }
+        for (uint32_t base = 0; base < tn; base += 32) {
+            /* inert elements (the parent's key is already <= their own: they stay at their leaf whatever the earlier
+             * pushes of the page do) need no ballot and no shuffle.  The test reads the parent from memory, which may
+             * lag behind a register copy - keys in a slot only ever decrease during pushes, so a stale parent can
+             * hide an inert element but never fake one. */
+            const uint32_t r = base + lane;
+            bool inert = false;
+            if (r < tn) inert = heap.get((heap_len + 1 + r) >> 1) <= (ent[r] | KM);
+            const unsigned im = __ballot_sync(DANN_FULL, inert);
+            const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const E e = ent[base + i]; /* uniform address: a broadcast load off the chain through `val` */
+                if ((im >> i) & 1u) {      /* warp-uniform */
+                    if (lane == 0) {
+                        val = e;
+                        dirty = true;
+                    }
+                } else {
+                    const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
+                    const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
+                    const unsigned tm1 = x & ~(x + 1u); /* the leaf and the consecutive ancestors passed: lanes 0..rise */
+                    const E up = __shfl_down_sync(DANN_FULL, val, 1);
+                    if (tm1 & lanebit2) val = up;    /* lanes below `rise`: the ancestor above moves down into this slot */
+                    else if (tm1 & lanebit) val = e; /* lane `rise`: the element lands */
+                    dirty = dirty || (tm1 & lanebit) != 0;
+                }
+                if (base + i + 1 < tn) { /* move the path to the next leaf */
+                    const uint32_t pos1 = pos + 1;
+                    if ((pos1 & pos) == 0) { /* new leaf level: every slot changes owner */
+                        if (dirty) heap.set(node, val);
+                        __syncwarp();
+                        node = pos1 >> lane;
+                        dirty = false;
+                        val = nxt = 0;
+                        if (lane >= 1 && node != 0) {
+                            val = heap.get(node);
+                            if (node + 1 <= heap_len) nxt = heap.get(node + 1);
+                        }
+                    } else { /* heights 0..ctz(pos1) step to the right */
+                        const bool adv = lanebit <= (pos1 & (0u - pos1));
+                        if (adv && dirty) heap.set(node, val);
+                        node += adv ? 1u : 0u;
+                        val = adv ? nxt : val;
+                        dirty = dirty && !adv;
+                        if (adv && lane >= 1 && node + 1 <= heap_len) nxt = heap.get(node + 1);
+                    }
+                    pos = pos1;
+                }
+            }
+        }
+        if (dirty) heap.set(node, val);
+        __syncwarp();
+        heap_len += tn;
+    }
+
+    /* The same pushes without the register-resident path: elements that are inert (parent key <= own key: they stay
+     * at their leaf whatever earlier pushes of the page do, because a slot's key never increases during pushes) are
+     * written by all lanes at once; the others go through the cooperative sift-up one at a time, in page order. */
+    __device__ __forceinline__ void push_page_coop(uint32_t tn) {
+        for (uint32_t base = 0; base < tn; base += 32) {
+            const uint32_t r = base + lane;
+            const bool have = r < tn;
+            const E mine = have ? ent[r] : E(0);
+            const uint32_t slot = heap_len + r + 1;
+            bool inert = false;
+            if (have && slot > 1) {
+                const uint32_t parent = slot >> 1;
+                if (parent <= heap_len + base) { /* parent is settled (old, or from an earlier round) */
+                    inert = heap.get(parent) <= (mine | KM);
+                    if (inert) heap.set(slot, mine);
+                }
+            }
+            unsigned act = __ballot_sync(DANN_FULL, have && !inert);
+            __syncwarp();
+            while (act) { /* warp-uniform loop */
+                const int b = __ffs(act) - 1;
+                act &= act - 1;
+                H::template sift_up_warp1<false>(heap, heap_len + base + (uint32_t)b + 1, ent[base + b], lane);
+            }
+        }
+        heap_len += tn;
+    }
+
+    __device__ __forceinline__ void push_page(uint32_t tn) {
+        if (tn <= heap_len) {
+            if (a.hv_flags & DANN_HV_PUSH) push_page_regs(tn);
+            else push_page_coop(tn);
+            return;
+        }
+        /* the first pages of a scan: ancestors of a new slot may belong to the page itself */
+        for (uint32_t i = 0; i < tn; i++) {
+            heap_len++;
+            H::template sift_up_warp1<false>(heap, heap_len, ent[i], lane);
+        }
+    }
+
+    /* BinaryHeap::pop: the last element replaces the root, sift_down_to_bottom(0) walks the hole to the bottom taking
+     * `child += (data[child] <= data[child+1])` (the right child on ties), then sift_up.  Four levels per round: lane
+     * map 0-1 / 2-5 / 6-13 / 14-29 = the hole's children / grandchildren / ..., one ballot over all sibling pairs.
+     * heap_len > 0; the caller has already read the root. */
+    __device__ __forceinline__ void pop() {
+        __syncwarp(); /* every lane has read the root (the caller's peek) before any lane overwrites slot 1 */
+        if (!(a.hv_flags & DANN_HV_POP)) { /* lane 0 walks the hole down, one level per shared-memory round trip */
+            H::pop_warp1(heap, heap_len, lane);
+            return;
+        }
+        heap_len--;
+        if (heap_len == 0) return;
+        const uint32_t end = heap_len;
+        const E item = heap.get(end + 1);
+        const int lvl = lane < 2 ? 1 : lane < 6 ? 2 : lane < 14 ? 3 : lane < 30 ? 4 : 0;
+        const uint32_t off = (uint32_t)lane - ((1u << lvl) - 2u);
+        uint32_t p = 1;
+        while (2u * p + 1u <= end) {
+            const uint32_t s = (p << lvl) + off;
+            const bool ok = lvl != 0 && s <= end;
+            E v = 0;
+            if (ok) v = heap.get(s);
+            const E vr = __shfl_down_sync(DANN_FULL, v, 1);
+            const unsigned m = __ballot_sync(DANN_FULL, vr <= (v | KM)); /* data[child] <= data[child+1] */
+            unsigned win = 0;
+            uint32_t cur = p, idx = 0;
+#pragma unroll
+            for (int l = 1; l <= 4; l++) {
+                const uint32_t c = 2u * cur;
+                const uint32_t left = (1u << l) - 2u + 2u * idx;
+                if (c + 1u <= end) {
+                    const uint32_t r = (m >> left) & 1u;
+                    win |= 1u << (left + r);
+                    cur = c + r;
+                    idx = 2u * idx + r;
+                } else {
+                    if (c == end) { /* a single child at the bottom is moved up without a comparison */
+                        win |= 1u << left;
+                        cur = c;
+                    }
+                    break;
+                }
+            }
+            if ((win >> lane) & 1u) heap.set(s >> 1, v);
+            p = cur;
+        }
+        if (2u * p == end) { /* round boundary fell on the single-child step */
+            const E c = heap.get(end);
+            if (lane == 0) heap.set(p, c);
+            p = end;
+        }
+        __syncwarp();
+        H::template sift_up_warp1<false>(heap, p, item, lane);
+    }
+
+    __device__ __forceinline__ uint32_t vix(uint32_t i) const {
+        const uint32_t x = vis_head + i;
+        return x >= a.vcap ? x - a.vcap : x;
+    }
+
+    /* visited.insert(partition_point(|x| x < c), c): graph/mod.rs:166-168 */
+    __device__ __forceinline__ void visited_insert(E e) {
+        if (vis_len + 1 > a.vcap) {
+            status |= DANN_ST_VIS;
+            return;
+        }
+        const E eh = e & ~KM; /* x < eh  <=>  key(x) < key(e) */
+        /* 32-ary search: one probe per lane at the end of its stride finds the boundary stride, then count inside it */
+        const uint32_t stride = (vis_len + 31u) >> 5;
+        const uint32_t s0 = (uint32_t)lane * stride;
+        const uint32_t pe = s0 + stride < vis_len ? s0 + stride : vis_len;
+        const bool whole = s0 < vis_len && vis[vix(pe - 1)] < eh;
+        const uint32_t c = __popc(__ballot_sync(DANN_FULL, whole));
+        uint32_t idx = c * stride < vis_len ? c * stride : vis_len;
+        const uint32_t b0 = idx, b1 = b0 + stride < vis_len ? b0 + stride : vis_len;
+        for (uint32_t i0 = b0; i0 < b1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool lt = i < b1 && vis[vix(i)] < eh;
+            idx += __popc(__ballot_sync(DANN_FULL, lt));
+        }
+        if (idx * 2 < vis_len) { /* fewer elements in front: open the gap by moving them one slot towards the head */
+            vis_head = vis_head ? vis_head - 1 : a.vcap - 1;
+            for (uint32_t i0 = 0; i0 < idx; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool act = i < idx;
+                E t = 0;
+                if (act) t = vis[vix(i + 1)];
+                __syncwarp();
+                if (act) vis[vix(i)] = t;
+                __syncwarp();
+            }
+        } else {
+            for (int hi = (int)vis_len; hi > (int)idx; hi -= 32) {
+                const int i = hi - 1 - lane;
+                const bool act = i >= (int)idx;
+                E t = 0;
+                if (act) t = vis[vix((uint32_t)i)];
+                __syncwarp();
+                if (act) vis[vix((uint32_t)i + 1)] = t;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) vis[vix(idx)] = e;
+        vis_len++;
+        __syncwarp();
+    }
+
+    /* expand one visited node: sbq/storage.rs:135-190.  n0/n1 = list slots lane, lane + 32 (loaded by the caller so
+     * that the HBM latency overlaps the pop).  R <= 64. */
+    __device__ __forceinline__ void expand(uint32_t n0, uint32_t n1) {
+        /* iter_neighbors stops at the first InvalidBlockNumber slot (sbq/node.rs:261-285) */
+        const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
+        const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
+        const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
+        const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
+        const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
+        if (a.lists_unique) {
+            stage(n0, v0, n1, v1, filter, true);
+        } else { /* a list may repeat an id: keep strict list order across the two chunks */
+            stage(n0, v0, DANN_INVALID_NODE, false, filter, false);
+            if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter, false);
+        }
+        flush();
+    }
+
+    __device__ __forceinline__ void flush() {
+        const uint32_t tn = listn;
+        listn = 0;
+        if (tn == 0 || status) return;
+        distances(tn);
+#ifdef DANN_SIMT_EMU
+        if (getenv("DANN_DBG") && lane == 0) { fprintf(stderr, " page tn=%u:", tn); for (uint32_t i = 0; i < tn; i++) fprintf(stderr, " %u/%u", list[i], (unsigned)(ent[i] >> T::KSHIFT)); fprintf(stderr, "\n"); }
+#endif
+        push_page(tn);
+        dq += tn;
+    }
+
+    __device__ __forceinline__ void run(uint32_t q) {
+        const IndexView &ix = a.ix;
+        heap_len = vis_head = vis_len = nset = listn = 0;
+        visits = dq = status = 0;
+        uint32_t scount = 0;
+        slotpay = SMALL && a.bitmap_words == 0;
+        { /* query code chunks this lane compares against (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) */
+            const uint32_t gl = lane & (a.G - 1), nchunks = ix.cw >> 1;
+            const ulonglong2 *qrow = reinterpret_cast<const ulonglong2 *>(a.q_codes + (size_t)q * ix.cw);
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                const uint32_t c = gl + i * a.G;
+                qc[i] = c < nchunks ? qrow[c] : make_ulonglong2(0, 0);
+            }
+        }
+        if (!a.bitmap_words) { /* inserted = HashSet::new() (the bitmap flavour is left all zero by the previous query) */
+            const uint4 ff = make_uint4(DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE);
+            uint4 *h4 = reinterpret_cast<uint4 *>(hash);
+            for (uint32_t i = lane; i < a.hash_cap / 4; i += 32) h4[i] = ff;
+            __threadfence_block();
+            __syncwarp();
+        }
+        ql = nullptr;
+        nql = 0;
+        filter = false;
+        if (a.q_label_off) {
+            const int32_t o0 = a.q_label_off[q], o1 = a.q_label_off[q + 1];
+            ql = a.q_labels + o0;
+            nql = (uint32_t)(o1 - o0);
+            filter = nql > 0; /* has_label_filter, scan.rs:189 */
+        }
+        /* greedy_search_streaming_init + ListSearchResult::new (graph/mod.rs:97-124,331-354) */
+        if (ix.start_default != DANN_INVALID_NODE) {
+            if (a.q_label_off) { /* StartNodes::get_for_node(Some(labels)), start_nodes.rs:39-48 */
+                for (uint32_t b = 0; b < nql && !status; b += 32) {
+                    const uint32_t i = b + lane;
+                    uint32_t n = DANN_INVALID_NODE;
+                    bool valid = false;
+                    if (i < nql) {
+                        const int16_t lab = __ldg(ql + i);
+                        uint32_t lo = 0, hi = ix.n_start_labels;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (__ldg(ix.start_labels + mid) < lab) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < ix.n_start_labels && __ldg(ix.start_labels + lo) == lab) {
+                            n = __ldg(ix.start_label_nodes + lo);
+                            valid = true;
+                        }
+                    }
+                    /* start nodes are not label-checked (storage.rs:365-391); two labels may share a start node */
+                    stage(n, valid, DANN_INVALID_NODE, false, false, false);
+                    flush();
+                }
+            } else {
+                stage(lane == 0 ? ix.start_default : DANN_INVALID_NODE, lane == 0, DANN_INVALID_NODE, false, false, true);
+                flush();
+            }
+        }
+
+        bool done = false;
+        while (!done && !status) { /* TSVResponseIterator::next, scan.rs:210-242 */
+            /* greedy_search_iterate: while let Some(idx) = visit_closest(L) */
+            while (heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
+                const E head = heap.get_sm(1);
+                if (vis_len > a.L) {
+                    const E at = vis[vix(a.L - 1)];
+                    if ((head | KM) >= (at | KM)) break; /* key(head) >= key(at) */
+                }
+                /* the popped element IS the current root: fetch its neighbour list first, the pop's descent and
+                 * the visited insert run under that latency */
+                const uint32_t node = node_of(head);
+                const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
+                const uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+                const uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
+#ifdef DANN_SIMT_EMU
+                if (getenv("DANN_DBG3")) fprintf(stderr, "  L%d row[%u]+%d = %u (direct %u)\n", lane, node, lane, n0, row[lane]);
+#endif
+                pop();
+#ifdef DANN_SIMT_EMU
+                if (getenv("DANN_DBG") && lane == 0) fprintf(stderr, "visit node=%u key=%u heap_len=%u vis_len=%u\n", node, (unsigned)(head >> T::KSHIFT), heap_len, vis_len);
+#endif
+                visited_insert(head);
+                if (status) break;
+                visits++;
+                expand(n0, n1);
+                if (status) break;
+            }
+            if (status) break;
+            if (vis_len == 0) break; /* consume() -> None */
+            const E e = vis[vis_head]; /* visited.remove(0), graph/mod.rs:174-184 */
+            __syncwarp();
+            vis_head = vix(1);
+            vis_len--;
+            const uint32_t node = node_of(e);
+            const uint64_t tid = __ldg(ix.tids + node); /* return_lsn, sbq/storage.rs:404-414 */
+            if ((tid & 0xFFFFull) == 0) continue;       /* InvalidOffsetNumber: deleted tuple, scan.rs:231-234 */
+            if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = node;
+            scount++;
+            if (scount == a.c_target) done = true;
+        }
+        if (a.bitmap_words) { /* leave the bitmap all zero for the slot's next query */
+            __syncwarp();
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 *b4 = reinterpret_cast<uint4 *>(bitmap);
+            for (uint32_t i = lane; i < a.bitmap_words / 4; i += 32) b4[i] = z;
+            __threadfence_block();
+        }
+        if (lane == 0) {
+            a.stream_len[q] = scount;
+            dann_query_stats st;
+            st.visits = visits;
+            st.d_quantized = dq;
+            st.candidates = dq;
+            st.d_full = 0u;
+            st.stream_len = scount;
+            st.status = status;
+            a.stats[q] = st;
+            if (status) atomicOr(a.overflow, status);
+        }
+        __syncwarp();
+    }
+};
+
+/* MAXW = resident query slots (warps) per SM this instantiation is compiled for: 32 -> 64 registers per thread. */
+template <typename T, int NCH, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) dann_search3_kernel(const SearchArgs a) {
+    using E = typename T::E;
+    DANN_DYN_SMEM(dann_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t slot = blockIdx.x * W + warp;
+    unsigned char *base = dann_smem + (size_t)warp * a.per_warp_smem;
+    LeanWarp<T, NCH> w(a, lane);
+    w.vis = reinterpret_cast<E *>(base);
+    w.heap.sm = reinterpret_cast<E *>(base + (size_t)a.vcap * sizeof(E));
+    w.ent = w.heap.sm + a.hs;
+    w.list = reinterpret_cast<uint32_t *>(w.ent + DANN_LIST_CAP);
+    w.hash = a.hash + (size_t)slot * a.hash_cap;
+    w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
+    w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;
+    w.heap.hs = a.hs;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(a.counter, 1u);
+        qi = __shfl_sync(DANN_FULL, qi, 0);
+        if (qi >= a.nq) break;
+        w.run(a.qlist ? a.qlist[qi] : qi);
+    }
+}

@@ -21,6 +21,7 @@
 #include "dann_kernels.cuh"
 #include "dann_search.cuh"
 #include "dann_search2.cuh"
+#include "dann_search3.cuh"
 #include "dann_build.cuh"
 #include "dann_plan.h"
 
@@ -523,8 +524,22 @@ static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0, bo
 
 
 
+template <typename T, int MAXW>
+static search_fn pick_lean_t(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search3_kernel<T, 1, MAXW>;
+        case 2: return dann_search3_kernel<T, 2, MAXW>;
+        default: return dann_search3_kernel<T, 3, MAXW>; /* the plan offers the lean kernel up to 96 16-byte chunks */
+    }
+}
+/* dann_search3.cuh: 4-byte (key11 | node-or-hash-slot21) or 8-byte (key32 | node32) entries; 32 or 16 resident warps */
+static search_fn pick_lean(int entry, uint32_t nch, int maxw) {
+    if (maxw <= 16) return entry == 0 ? pick_lean_t<Ent32x21, 16>(nch) : pick_lean_t<Ent64, 16>(nch);
+    return entry == 0 ? pick_lean_t<Ent32x21, 32>(nch) : pick_lean_t<Ent64, 32>(nch);
+}
+
 static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target, uint32_t grow, bool keyed,
-                     SearchPlan *p, bool force_single = false) {
+                     SearchPlan *p, bool force_single = false, bool allow_lean = false) {
     PlanInputs in;
     in.n = ix->v.n;
     in.R = ix->v.R;
@@ -532,6 +547,19 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     in.smem_optin = ix->smem_optin;
     in.sm_count = ix->sm_count;
     in.plain_dim = ix->plain ? ix->v.dim_index : 0;
+    in.allow_lean = allow_lean;
+    in.ws_budget = 0;
+    if (allow_lean) {
+        /* what the per-slot workspaces may take: free HBM now plus what they already hold, less a reserve for the
+         * batch scratch that is sized after the plan */
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+            const uint64_t held = (uint64_t)ix->ws_hash.cap + ix->ws_heap.cap + ix->ws_bitmap.cap + ix->ws_cand.cap + ix->ws_ins.cap;
+            const uint64_t reserve = 768ull << 20;
+            const uint64_t avail = (uint64_t)fr + held;
+            in.ws_budget = avail > reserve ? avail - reserve : 1;
+        }
+    }
     char err[256];
     int rc = dann_make_plan(in, nq, L, c_target, grow, keyed, p, force_single, err, sizeof err);
     if (rc) return fail(rc, "%s", err);
@@ -552,16 +580,16 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
     uint32_t nq = (uint32_t)B;
     for (int attempt = 0;; attempt++) {
         SearchPlan p;
-        rc = make_plan(ix, nq, L, c_target, grow, d_label_off != nullptr, &p);
+        rc = make_plan(ix, nq, L, c_target, grow, d_label_off != nullptr, &p, false, vis_out == nullptr);
         if (rc) return rc;
         const size_t slots = (size_t)p.grid * p.W;
         if (!p.bitmap_words) CK(ix->ws_hash.reserve(slots * p.hash_cap * sizeof(uint32_t)));
-        CK(ix->ws_cand.reserve(slots * p.cand_cap * sizeof(uint32_t)));
+        if (!p.lean) CK(ix->ws_cand.reserve(slots * p.cand_cap * sizeof(uint32_t))); /* lean entries carry their node */
         CK(ix->ws_heap.reserve(slots * p.cand_cap * (size_t)p.esize));
         if (p.bitmap_words) {
             CK(ix->ws_bitmap.reserve(slots * (size_t)p.bitmap_words * 4));
             if (ix->ws_bitmap.fresh) CK(cudaMemsetAsync(ix->ws_bitmap.p, 0, ix->ws_bitmap.cap, st));
-            CK(ix->ws_ins.reserve(slots * (size_t)p.ins_cap * 4));
+            if (!p.lean) CK(ix->ws_ins.reserve(slots * (size_t)p.ins_cap * 4));
         }
         CK(cudaMemsetAsync(d_ctl, 0, 8, st));
         SearchArgs a;
@@ -604,7 +632,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.plain_vectors = ix->index_vectors;
         a.q_index = d_q_index;
         a.plain_dim = ix->plain ? v.dim_index : 0;
-        search_fn fn = pick_kernel(p.pairs, p.entry, ix->NCH, p.hv, ix->plain);
+        search_fn fn = p.lean ? pick_lean(p.entry, ix->NCH, p.maxw) : pick_kernel(p.pairs, p.entry, ix->NCH, p.hv, ix->plain);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);

@@ -12,8 +12,8 @@ from pgvectorscale_b200.diskann import _SnapshotDesc, _QueryStats  # noqa: E402 
 
 class EmuInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("retries", "entry", "W", "hs", "pairs", "grid", "cand_cap", "vcap",
-                                          "bitmap_words", "nch", "G", "hv")] + [("switches", C.c_uint64), ("coll_even", C.c_uint64),
-                                                                              ("coll_odd", C.c_uint64)]
+                                          "bitmap_words", "nch", "G", "hv", "lean", "maxw", "hash_cap")] + \
+        [("switches", C.c_uint64), ("coll_even", C.c_uint64), ("coll_odd", C.c_uint64)]
 
 
 _lib = None
@@ -22,7 +22,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build_emu.build())
+        _lib = C.CDLL(os.environ.get("DANN_EMU_LIB") or build_emu.build())
         _lib.emu_last_error.restype = C.c_char_p
         _lib.emu_search.restype = C.c_int
     return _lib
@@ -59,7 +59,7 @@ def _desc(s):
 
 
 def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148, smem_optin=232448, env=None,
-           q_index=None):
+           q_index=None, kernel=None):
     """Approximate streams of B prepared queries through the emulated search kernel.
     labels: None, or a list (one entry per query) of sorted, de-duplicated label lists.
     env: DANN_* test knobs applied around the call (the plan reads them with getenv).
@@ -88,7 +88,11 @@ def search(s, q_codes, L, c_target, labels=None, single_warp=False, sm_count=148
     stats = (_QueryStats * B)()
     info = EmuInfo()
     old = {}
-    for k, v in (env or {}).items():
+    env = dict(env or {})
+    # kernel: "lean" = dann_search3.cuh (the product's default for batch searches), None/"pairs" = the two-warp kernel
+    # (or the single-warp one with single_warp=True)
+    env.setdefault("DANN_SEARCH_KERNEL", 3 if kernel == "lean" else 2)
+    for k, v in env.items():
         old[k] = os.environ.get(k)
         os.environ[k] = str(v)
     try:

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "dann_search2.cuh"
+#include "dann_search3.cuh"
 #include "dann_plan.h"
 
 alignas(128) unsigned char dann_smem[256 * 1024];
@@ -32,6 +33,19 @@ static emu_kernel pick2(uint32_t nch) {
         default: return nullptr;
     }
 }
+template <typename T, int MAXW>
+static emu_kernel pick3(uint32_t nch) {
+    switch (nch) {
+        case 1: return dann_search3_kernel<T, 1, MAXW>;
+        case 2: return dann_search3_kernel<T, 2, MAXW>;
+        case 3: return dann_search3_kernel<T, 3, MAXW>;
+        default: return nullptr;
+    }
+}
+static emu_kernel pick_lean(int entry, uint32_t nch, int maxw) {
+    if (maxw <= 16) return entry == 0 ? pick3<Ent32x21, 16>(nch) : pick3<Ent64, 16>(nch);
+    return entry == 0 ? pick3<Ent32x21, 32>(nch) : pick3<Ent64, 32>(nch);
+}
 static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv, bool plain = false) {
     if (plain) return dann_search_kernel<Ent64, 1, 1>;
     if (pairs && hv == 1 && entry == 3) return pick2<Ent32n21, 1>(nch);
@@ -46,7 +60,7 @@ extern "C" const char *emu_last_error(void) { return g_emu_err.c_str(); }
 
 struct emu_info {
     uint32_t retries, entry, W, hs, pairs, grid, cand_cap, vcap, bitmap_words, nch, G;
-    uint32_t hv;
+    uint32_t hv, lean, maxw, hash_cap;
     uint64_t switches;
     uint64_t coll_even, coll_odd; /* warp collectives completed by even / odd warps (controller / heap warp) */
 };
@@ -114,6 +128,8 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
     in.smem_optin = smem_optin;
     in.sm_count = (int)sm_count;
     in.plain_dim = plain ? s->dim_index : 0;
+    in.allow_lean = true;
+    in.ws_budget = 0;
     /* 16-byte aligned copies of the f32 rows, like cudaMalloc'ed memory */
     std::vector<float4> iv_store, qi_store;
     const float *ivp = nullptr, *qip = nullptr;
@@ -167,9 +183,9 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         } g_hash, g_cand, g_bitmap, g_ins, g_heap;
         (void)GUARD;
         g_hash.init(p.bitmap_words ? 16 : slots * (size_t)p.hash_cap * 4, 0);
-        g_cand.init(slots * (size_t)p.cand_cap * 4, 0);
+        g_cand.init(p.lean ? 16 : slots * (size_t)p.cand_cap * 4, 0);
         g_bitmap.init(slots * (size_t)p.bitmap_words * 4 + 16, 0);
-        g_ins.init(p.bitmap_words ? slots * (size_t)p.ins_cap * 4 : 16, 0);
+        g_ins.init(p.bitmap_words && !p.lean ? slots * (size_t)p.ins_cap * 4 : 16, 0);
         g_heap.init(slots * (size_t)p.cand_cap * p.esize, 0);
         ctl[0] = ctl[1] = 0;
         SearchArgs a{};
@@ -205,7 +221,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.plain_vectors = ivp;
         a.q_index = qip;
         a.plain_dim = in.plain_dim;
-        emu_kernel fn = pick(p.pairs, p.entry, NCH, p.hv, plain);
+        emu_kernel fn = p.lean ? pick_lean(p.entry, NCH, p.maxw) : pick(p.pairs, p.entry, NCH, p.hv, plain);
         if (!fn) {
             g_emu_err = "this code width is not instantiated in the emulator build";
             return DANN_ERR_INVALID_ARG;
@@ -249,6 +265,9 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         info->nch = NCH;
         info->G = G;
         info->hv = (uint32_t)p.hv;
+        info->lean = p.lean ? 1u : 0u;
+        info->maxw = (uint32_t)p.maxw;
+        info->hash_cap = p.hash_cap;
         info->switches = simt::total_switches() - sw0;
         uint64_t cp1[2];
         simt::collectives_by_warp_parity(cp1);
@@ -269,6 +288,8 @@ extern "C" int emu_plan(uint32_t n, uint32_t R, uint32_t words, uint32_t nq, uin
     in.smem_optin = smem_optin;
     in.sm_count = (int)sm_count;
     in.plain_dim = 0;
+    in.allow_lean = getenv("DANN_EMU_PLAN_LEAN") != nullptr;
+    in.ws_budget = 0;
     SearchPlan p{};
     char err[256];
     int rc = dann_make_plan(in, nq, L, c_target, grow, keyed != 0, &p, force_single != 0, err, sizeof err);

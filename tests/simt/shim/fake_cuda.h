@@ -64,6 +64,13 @@ inline cudaError_t cudaMemcpy2D(void *d, size_t dpitch, const void *s, size_t sp
     for (size_t r = 0; r < height; r++) memcpy((char *)d + r * dpitch, (const char *)s + r * spitch, width);
     return cudaSuccess;
 }
+/* "free HBM": plenty unless DANN_FAKE_FREE_MB says otherwise (lets a test see the plan shrink its slot count) */
+inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) {
+    const char *e = getenv("DANN_FAKE_FREE_MB");
+    *tot = (size_t)180 << 30;
+    *fr = e && *e ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)160 << 30;
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemset(void *p, int v, size_t n) {
     if (n) memset(p, v, n);
     return cudaSuccess;

@@ -1,4 +1,5 @@
 // simt_emu.cpp — fibers, scheduler and warp collectives of the SIMT emulator (see simt_emu.h).  Test infrastructure.
+#include <execinfo.h>
 #include "simt_emu.h"
 
 #include <algorithm>
@@ -189,6 +190,11 @@ uint64_t rendezvous(int kind, unsigned mask, uint64_t val, uint32_t aux) {
     if (s->kind != kind) {
         fprintf(stderr, "simt: lanes of warp %u meet in different collectives (%d vs %d, mask %08x)\n", f->tid >> 5, s->kind,
                 kind, mask);
+        {   /* where this lane is (resolve with addr2line -e <the emulator .so> -f -C -i <offsets>) */
+            void *bt[24];
+            const int nbt = backtrace(bt, 24);
+            backtrace_symbols_fd(bt, nbt, 2);
+        }
         abort();
     }
     const uint64_t mygen = s->gen;

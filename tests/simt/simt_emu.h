@@ -153,6 +153,7 @@ inline T max(T a, T b) {
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline unsigned __brev(unsigned v) {
     unsigned r = 0;

@@ -431,3 +431,76 @@ def test_plan_scales_with_growth_and_keys(emu):
     assert c["pairs"] == 0
     with pytest.raises(RuntimeError, match="2\\^30"):
         emu.plan(n=1000, R=64, words=24, nq=1, L=10000, c_target=1009, grow=1 << 12)
+
+
+# ---- lean warp-per-query kernel (dann_search3.cuh): the product's default for batch searches ---------------------
+@pytest.mark.parametrize("dist,bits,dim", [(COSINE, 2, 96), (L2, 1, 200), (IP, 2, 40)])
+def test_emulated_lean_kernel_equals_oracle(emu, dist, bits, dim):
+    s = build_case(500, dim, dist, bits=bits, seed=11 + dim, kind="normal", R=20, L_build=40, deleted_every=9)
+    q = fixtures.gen_vectors(4, dim, 5, "normal")
+    info = check(emu, s, q, 25, 30, kernel="lean")
+    assert info["lean"] == 1 and info["pairs"] == 0
+
+
+def test_emulated_lean_reference_shape_768d_2bit(emu):
+    s = build_case(300, 768, COSINE, seed=2, kind="normal", R=32, L_build=48)
+    q = fixtures.gen_vectors(2, 768, 8, "normal")
+    info = check(emu, s, q, 20, 29, kernel="lean")
+    assert (info["nch"], info["G"], info["lean"], info["entry"]) == (3, 4, 1, 0)
+
+
+@pytest.mark.parametrize("flags", [3, 0, 1, 2])
+@pytest.mark.parametrize("entry", [0, 2])
+@pytest.mark.parametrize("bitmap", [0, 1])
+@pytest.mark.parametrize("hs", [None, 4, 16, 128, 1024])
+def test_emulated_lean_long_scans_entries_sets_and_tails(emu, entry, bitmap, hs, flags):
+    """Long scans: the heap crosses several leaf levels, the pop's four-level rounds straddle the shared/global split,
+    the visited ring wraps; both inserted-set flavours (node-carrying vs hash-slot-carrying 4-byte entries)."""
+    s = build_case(2500, 64, COSINE, seed=71, kind="normal", R=32, L_build=64, deleted_every=17)
+    q = fixtures.gen_vectors(3, 64, 13, "normal")
+    # flags: bit 1 = register-path pushes, bit 2 = four-level pop rounds (the alternatives are the cooperative forms)
+    env = {"DANN_SEARCH_ENTRY": entry, "DANN_SEARCH_BITMAP": bitmap, "DANN_HV_FLAGS": flags}
+    if hs is not None:
+        env["DANN_SEARCH_HS"] = hs
+    info = check(emu, s, q, 80, 150, env=env, kernel="lean")
+    assert info["lean"] == 1 and info["entry"] == entry and (info["bitmap_words"] != 0) == bool(bitmap)
+
+
+@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 64, 200, 1100])
+def test_emulated_lean_visited_ring_list_sizes(emu, L):
+    s = build_case(1500, 48, L2, seed=91, kind="normal", R=24, L_build=48, deleted_every=11)
+    q = fixtures.gen_vectors(2, 48, 17, "normal")
+    check(emu, s, q, L, 40, kernel="lean")
+    check(emu, s, q, L, 40, kernel="lean", env={"DANN_SEARCH_BITMAP": 0, "DANN_SEARCH_HS": 32})
+
+
+def test_emulated_lean_labels_retries_and_packed_block(emu):
+    s = build_case(800, 48, L2, seed=81, kind="normal", R=24, L_build=48, labels=True, deleted_every=13)
+    q = fixtures.gen_vectors(6, 48, 3, "normal")
+    labs = [[3], [7, 1, 7], [], [16, 2, 9, 4], [5, 5], [12]]
+    check(emu, s, q, 30, 25, labels=labs, kernel="lean")
+    check(emu, s, q, 100, 59, labels=labs, kernel="lean", env={"DANN_HV_FLAGS": 0})   # heap runs empty: pop with 1-3 entries
+    info = check(emu, s, q, 30, 25, labels=labs, kernel="lean", env={"DANN_SEARCH_BITMAP": 0})
+    assert info["bitmap_words"] == 0
+    info = check(emu, s, q, 40, 60, labels=labs, kernel="lean", env={"DANN_DEBUG_SHRINK": 16}, sm_count=1)
+    assert info["retries"] >= 1 and info["grid"] == 1 and info["lean"] == 1
+
+
+def test_emulated_lean_repeated_ids_and_stream_exhaustion(emu):
+    s = build_case(300, 32, L2, seed=61, kind="normal", R=16, L_build=32, deleted_every=5)
+    nb = s.nbrs.copy()
+    nb[:, 5] = nb[:, 1]
+    nb[::3, 9] = nb[::3, 0]
+    s.nbrs = nb
+    q = fixtures.gen_vectors(3, 32, 12, "normal")
+    check(emu, s, q, 20, 30, kernel="lean")
+    check(emu, s, q, 10, 400, kernel="lean", env={"DANN_SEARCH_BITMAP": 0})
+
+
+def test_emulated_lean_at_the_benchmark_operating_point(emu):
+    s = build_case(6000, 768, COSINE, seed=3, kind="normal", R=50, L_build=100)
+    q = fixtures.gen_vectors(2, 768, 9, "normal")
+    info = check(emu, s, q, 150, 259, kernel="lean", sm_count=1)
+    assert info["lean"] == 1
+    info = check(emu, s, q, 150, 259, kernel="lean", env={"DANN_SEARCH_BITMAP": 0, "DANN_SEARCH_HS": 256})
+    assert info["bitmap_words"] == 0

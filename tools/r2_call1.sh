@@ -13,7 +13,6 @@ except Exception as e: print("cpu.max n/a", e)
 import shutil; print("disk /tmp", shutil.disk_usage("/tmp")); print("memtotal", open("/proc/meminfo").readline().strip())
 PY
 cat gpurun_out/r2a_mem.txt
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_gpu_tests.log 2>&1; tail -2 gpurun_out/r2a_gpu_tests.log
 DANN_RUN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q > gpurun_out/r2a_experimental.log 2>&1
 tail -5 gpurun_out/r2a_experimental.log
 python tools/make_snapshot.py --out /tmp/snap > gpurun_out/r2a_mk.log 2>&1; tail -1 gpurun_out/r2a_mk.log
