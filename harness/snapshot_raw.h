@@ -42,21 +42,55 @@ static void *dann_snapshot_raw_read(const char *path, dann_snapshot_desc *s, con
     s->start_default = (uint32_t)h[9];
     s->n_start_labels = (uint32_t)h[10];
     const void *arr[11];
+    uint64_t alen[11];
     size_t off = 8 + 16 * 8;
     for (int i = 0; i < 11; i++) {
         uint64_t len;
-        if (off + 8 > (size_t)size) {
+        if ((size_t)size - off < 8) { /* off <= size always holds here */
             free(buf);
             return NULL;
         }
         memcpy(&len, buf + off, 8);
         off += 8;
-        if (off + len > (size_t)size) {
+        if (len > (uint64_t)((size_t)size - off)) { /* untrusted length: compare without adding to it */
             free(buf);
             return NULL;
         }
         arr[i] = len ? (const void *)(buf + off) : NULL;
-        off += (size_t)len + (size_t)((64 - len % 64) % 64);
+        alen[i] = len;
+        uint64_t adv = len + (64 - len % 64) % 64;
+        if (adv > (uint64_t)((size_t)size - off)) adv = (uint64_t)((size_t)size - off); /* padding of the last array may be cut */
+        off += (size_t)adv;
+    }
+    /* every array's byte length must match the header geometry (64-bit products: n, dim, words, R are 32-bit) - a
+     * truncated or inconsistent file must not hand dann_index_load pointers it would read past */
+    {
+        const uint64_t n = s->n, plain = h[11];
+        const uint64_t nlab = (s->has_labels && alen[8] >= (n + 1) * 4) ? ((const uint32_t *)arr[8])[n] : 0;
+        const uint64_t want[11] = {
+            (uint64_t)s->dim_index * 4,                 /* mean */
+            (uint64_t)s->dim_index * 4,                 /* m2 (may be absent for 1-bit codes) */
+            n * s->words * 8,                           /* codes */
+            n * s->R * 4,                               /* nbrs */
+            n * 8,                                      /* heap_tid */
+            n * s->dim * 4,                             /* vectors (optional: dann_index_set_vectors) */
+            (uint64_t)s->n_start_labels * 2,            /* start_labels */
+            (uint64_t)s->n_start_labels * 4,            /* start_label_nodes */
+            s->has_labels ? (n + 1) * 4 : 0,            /* label_off */
+            nlab * 2,                                   /* labels */
+            plain ? n * s->dim_index * 4 : 0,           /* index_vectors (plain layout only) */
+        };
+        const int optional[11] = {plain ? 1 : 0, 1, plain ? 1 : 0, 0, 0, 1, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 11; i++) {
+            if (alen[i] == want[i]) continue;
+            if (alen[i] == 0 && optional[i]) continue;
+            free(buf);
+            return NULL;
+        }
+        if (plain > 1 || (plain && !arr[10] && n)) { /* storage_type must agree with the presence of index_vectors */
+            free(buf);
+            return NULL;
+        }
     }
     s->mean = (const float *)arr[0];
     s->m2 = (const float *)arr[1];

@@ -190,6 +190,41 @@ int dann_build_graph(dann_index *ix, int num_neighbors, int search_list_size, fl
 int dann_index_download_nbrs(dann_index *ix, uint32_t *out);
 /* Supply (or replace) the heap vectors of an index loaded with vectors == NULL; [n][dim] host floats. */
 int dann_index_set_vectors(dann_index *ix, const float *vectors);
+/* The same with the rows already in HBM on the index's device: d_vectors [n][dim] is BORROWED - the index reads it in
+ * place (no second copy: 50M x 768-d rows are 153.6 GB of the 180) and, for cosine, normalises it in place once like
+ * dann_index_load does; the caller keeps it allocated until dann_index_free. */
+int dann_index_set_vectors_device(dann_index *ix, float *d_vectors);
+
+/* ---- query-batch data parallelism over replicated indexes ------------------------------
+ * One host process, one full replica of the index per GPU.  dann_group_search_batch cuts the batch into contiguous
+ * slices (the first devices take the remainder), every device runs the whole hot path on its slice concurrently,
+ * and each device's result copy lands directly in the caller's arrays at its slice's offset: rows come back in
+ * query order, identical to a single-device dann_search_batch.  The graph is never sharded (every hop would cross
+ * NVLink).  Separate PROCESSES per GPU (torchrun) gather with one NCCL collective instead: pgvectorscale_b200/group.py.
+ * devices == NULL means devices 0..ndev-1.  Host pointers, borrowed for the call. */
+typedef struct dann_group dann_group;
+int dann_group_create(const dann_snapshot_desc *snap, int ndev, const int *devices, dann_group **out);
+int dann_group_size(const dann_group *g);
+dann_index *dann_group_replica(dann_group *g, int i); /* replica i (e.g. to attach vectors or read timings); NULL if out of range */
+int dann_group_search_batch(dann_group *g, const float *queries, const int16_t *labels, const int32_t *label_offsets,
+                            int B, int k, int search_list_size, int rescore, uint64_t *out_tid, float *out_dist,
+                            uint32_t *out_count, dann_query_stats *out_stats);
+void dann_group_free(dann_group *g);
+
+/* How the last batch search of this index was planned (diagnostics for benchmarks and profiles). */
+typedef struct {
+    uint32_t kernel;         /* 1 = single-warp, 2 = two-warp (round 1), 3 = lean warp-per-query (dann_search3.cuh) */
+    uint32_t slots_per_sm;   /* resident queries per SM */
+    uint32_t grid;           /* CTAs (one per SM) */
+    uint32_t heap_smem;      /* heap entries kept in shared memory per query */
+    uint32_t visited_cap, cand_cap;
+    uint32_t entry_bytes;    /* 4 or 8 */
+    uint32_t bitmap;         /* 1 = bitmap inserted-set, 0 = hash set */
+    uint64_t slot_hbm_bytes; /* per-slot HBM workspace (heap tail + inserted-set [+ side tables]) */
+    uint32_t smem_per_slot;
+    uint32_t retries;        /* workspace-growth reruns of the last call */
+} dann_search_plan_info;
+int dann_last_search_plan(dann_index *ix, dann_search_plan_info *out);
 
 /* ---- query coalescing (multi-process serving, the in-process half) ----------------------
  * Postgres is process-per-connection with amcanparallel = false (mod.rs:63): one scan per backend at a time, while

@@ -53,21 +53,49 @@ struct dann_coalescer {
             cv_work.wait_until(lk, deadline, [&] { return stop || (int)queue.size() >= max_batch; });
             std::vector<CoalescedRequest *> batch;
             CoalescedRequest *head = queue.front();
+            try {
+                batch.reserve(std::min<size_t>(queue.size(), (size_t)max_batch));
+            } catch (...) { /* no memory for the batch list: fail the oldest request, keep serving */
+                queue.pop_front();
+                head->rc = DANN_ERR_OOM;
+                head->err = "host allocation failed";
+                head->done = true;
+                cv_done.notify_all();
+                continue;
+            }
             for (auto it = queue.begin(); it != queue.end() && (int)batch.size() < max_batch;) {
                 if (compatible(head, *it)) {
-                    batch.push_back(*it);
+                    batch.push_back(*it); /* reserved above: does not allocate */
                     it = queue.erase(it);
                 } else {
                     ++it; /* different scan parameters: next window */
                 }
             }
             lk.unlock();
-            execute(batch);
+            /* the dispatcher is a std::thread: an exception escaping it would std::terminate the host process (the
+             * sidecar and every backend behind it), so whatever execute() throws becomes the batch's status */
+            int xrc = 0;
+            try {
+                execute(batch);
+            } catch (const std::bad_alloc &) {
+                xrc = DANN_ERR_OOM;
+            } catch (...) {
+                xrc = DANN_ERR_STATE;
+            }
             lk.lock();
             n_batches++;
             n_queries += batch.size();
             max_seen = std::max<uint64_t>(max_seen, batch.size());
-            for (CoalescedRequest *r : batch) r->done = true;
+            for (CoalescedRequest *r : batch) {
+                if (xrc) {
+                    r->rc = xrc;
+                    try {
+                        r->err = xrc == DANN_ERR_OOM ? "host allocation failed" : "unexpected C++ exception in the coalescer";
+                    } catch (...) {
+                    }
+                }
+                r->done = true;
+            }
             cv_done.notify_all();
         }
     }
@@ -110,7 +138,7 @@ struct dann_coalescer {
     }
 };
 
-extern "C" int dann_coalescer_create(dann_index *ix, int max_batch, int max_wait_us, dann_coalescer **out) {
+extern "C" int dann_coalescer_create(dann_index *ix, int max_batch, int max_wait_us, dann_coalescer **out) try {
     if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "dann_coalescer_create: NULL argument");
     if (max_batch < 1 || max_batch > 65536 || max_wait_us < 0) return fail(DANN_ERR_INVALID_ARG, "dann_coalescer_create: bad limits");
     dann_coalescer *c = new (std::nothrow) dann_coalescer();
@@ -121,11 +149,11 @@ extern "C" int dann_coalescer_create(dann_index *ix, int max_batch, int max_wait
     c->worker = std::thread([c] { c->run(); });
     *out = c;
     return DANN_OK;
-}
+} DANN_CATCH
 
 extern "C" int dann_coalescer_search(dann_coalescer *c, const float *query, const int16_t *labels, int nlabels, int k,
                                      int search_list_size, int rescore, uint64_t *out_tid, float *out_dist,
-                                     uint32_t *out_count, dann_query_stats *out_stats) {
+                                     uint32_t *out_count, dann_query_stats *out_stats) try {
     if (!c || !query || !out_tid || k <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_coalescer_search: bad argument");
     if (nlabels > 0 && !labels) return fail(DANN_ERR_INVALID_ARG, "labels is NULL but nlabels > 0");
     CoalescedRequest r;
@@ -146,16 +174,16 @@ extern "C" int dann_coalescer_search(dann_coalescer *c, const float *query, cons
     c->cv_done.wait(lk, [&] { return r.done; });
     if (r.rc) return fail(r.rc, "%s", r.err.c_str());
     return DANN_OK;
-}
+} DANN_CATCH
 
-extern "C" int dann_coalescer_stats(dann_coalescer *c, uint64_t *batches, uint64_t *queries, uint64_t *largest_batch) {
+extern "C" int dann_coalescer_stats(dann_coalescer *c, uint64_t *batches, uint64_t *queries, uint64_t *largest_batch) try {
     if (!c) return fail(DANN_ERR_INVALID_ARG, "NULL coalescer");
     std::lock_guard<std::mutex> lk(c->mu);
     if (batches) *batches = c->n_batches;
     if (queries) *queries = c->n_queries;
     if (largest_batch) *largest_batch = c->max_seen;
     return DANN_OK;
-}
+} DANN_CATCH
 
 extern "C" void dann_coalescer_destroy(dann_coalescer *c) {
     if (!c) return;

@@ -97,43 +97,49 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     p->maxw = 0;
     /* kernel choice, batch searches: the lean warp-per-query kernel (dann_search3.cuh) - up to 32 resident queries
      * per SM - whenever neighbour lists fit one 64-id page; DANN_SEARCH_KERNEL=1/2 select the round-1 kernels */
+    uint32_t wneed3 = (nq + in.sm_count - 1) / in.sm_count;
+    wneed3 = std::min<uint32_t>(std::max<uint32_t>(wneed3, 1), 32u);
+    /* batches that fit the 7 two-warp slots per SM of dann_search2.cuh in one wave stay there: with so few resident
+     * queries the chain latency of a query is the step time, and two warps per query shorten it (measured at
+     * 1M x 768, batch 1024: 3.5 ms vs 3.9 ms); DANN_SEARCH_KERNEL=3 forces the lean kernel */
+    const bool small_batch = wneed3 <= 7u && !getenv("DANN_SEARCH_KERNEL") && !getenv("DANN_SEARCH_WARPS");
     if (in.allow_lean && !force_single && in.R <= 64 && !in.plain_dim && ((in.words + 1u) & ~1u) <= 192u &&
-        env_u32("DANN_SEARCH_KERNEL", 3) == 3) {
+        env_u32("DANN_SEARCH_KERNEL", 3) == 3 && !small_batch) {
         /* inserted-set: bitmap over node ids while a node id fits the 21-bit payload of a 4-byte entry and the
          * bitmap is not larger than the hash set; else an open-addressing set of 1.5 x the candidate bound
          * (3 x under a label key: rejected ids are recorded too), any multiple of 4 slots */
-        uint64_t hcap = ((uint64_t)p->cand_cap * (keyed ? 3u : 1u) * 3u / 2u + 3u) & ~3ull;
+        const uint64_t hcap = ((uint64_t)p->cand_cap * (keyed ? 3u : 1u) * 3u / 2u + 3u) & ~3ull;
         const uint64_t bm_bytes = (uint64_t)((in.n + 127u) / 128u) * 16u;
         bool bm = in.n <= (1u << 21) && bm_bytes <= hcap * 4u;
         if (getenv("DANN_SEARCH_BITMAP")) bm = env_u32("DANN_SEARCH_BITMAP", 0) != 0 && in.n <= (16u << 20);
-        p->bitmap_words = bm ? ((in.n + 127u) / 128u) * 4u : 0u;
-        p->hash_cap = bm ? 4u : (uint32_t)hcap;
-        p->ins_cap = 0;
         const bool small = maxdist < 2048 && (bm ? in.n <= (1u << 21) : hcap <= (1u << 21)) && p->cand_cap <= (1u << 21);
-        p->entry = small ? 0 : 2;
-        if (getenv("DANN_SEARCH_ENTRY") && env_u32("DANN_SEARCH_ENTRY", 0) == 2) p->entry = 2; /* test hook */
-        p->esize = p->entry == 2 ? 8 : 4;
-        const size_t fixed3 = (size_t)p->vcap * p->esize + (size_t)DANN_LIST_CAP * (p->esize + 4u);
+        int entry3 = small ? 0 : 2;
+        if (getenv("DANN_SEARCH_ENTRY") && env_u32("DANN_SEARCH_ENTRY", 0) == 2) entry3 = 2; /* test hook */
+        const uint32_t esize3 = entry3 == 2 ? 8 : 4;
+        const size_t fixed3 = (size_t)p->vcap * esize3 + (size_t)DANN_LIST_CAP * (esize3 + 4u) + (size_t)DANN_STG_CAP * esize3;
         const uint32_t hs_floor = (uint32_t)std::min<uint64_t>((uint64_t)p->cand_cap, 256);
-        if (fixed3 + (size_t)hs_floor * p->esize + 64 <= budget) {
-            uint32_t wneed3 = (nq + in.sm_count - 1) / in.sm_count;
-            wneed3 = std::min<uint32_t>(std::max<uint32_t>(wneed3, 1), 32u);
+        if (fixed3 + (size_t)hs_floor * esize3 + 64 <= budget && hcap <= 0xFFFFFFFCull) {
             uint32_t W3 = env_u32("DANN_SEARCH_WARPS", wneed3);
             W3 = std::min<uint32_t>(std::max<uint32_t>(W3, 1), 32u);
-            const uint64_t per_slot_hbm = (uint64_t)p->cand_cap * p->esize + (bm ? bm_bytes : hcap * 4u);
+            const uint64_t per_slot_hbm = (uint64_t)p->cand_cap * esize3 + (bm ? bm_bytes : hcap * 4u);
             for (;; W3--) {
                 const uint64_t slots = (uint64_t)std::min<uint32_t>((uint32_t)in.sm_count, (nq + W3 - 1) / W3) * W3;
-                const bool smem_ok = (budget / W3 & ~(size_t)15) >= fixed3 + (size_t)hs_floor * p->esize;
+                const bool smem_ok = (budget / W3 & ~(size_t)15) >= fixed3 + (size_t)hs_floor * esize3;
                 const bool hbm_ok = !in.ws_budget || slots * per_slot_hbm <= in.ws_budget;
                 if ((smem_ok && hbm_ok) || W3 == 1) break;
             }
             const size_t per_warp3 = (budget / W3) & ~(size_t)15;
-            uint32_t hs3 = (uint32_t)std::min<size_t>((size_t)p->cand_cap, (per_warp3 - fixed3) / p->esize);
-            hs3 = std::min<uint32_t>(env_u32("DANN_SEARCH_HS", hs3), (uint32_t)((per_warp3 - fixed3) / p->esize));
+            uint32_t hs3 = (uint32_t)std::min<size_t>((size_t)p->cand_cap, (per_warp3 - fixed3) / esize3);
+            hs3 = std::min<uint32_t>(env_u32("DANN_SEARCH_HS", hs3), (uint32_t)((per_warp3 - fixed3) / esize3));
             hs3 = std::max<uint32_t>(hs3 & ~3u, 4u);
+            p->bitmap_words = bm ? ((in.n + 127u) / 128u) * 4u : 0u;
+            p->hash_cap = bm ? 4u : (uint32_t)hcap;
+            p->ins_cap = 0;
+            p->entry = entry3;
+            p->esize = esize3;
             p->hs = hs3;
             p->W = W3;
-            p->per_warp = (uint32_t)((fixed3 + (size_t)hs3 * p->esize + 15) & ~(size_t)15);
+            p->per_warp = (uint32_t)((fixed3 + (size_t)hs3 * esize3 + 15) & ~(size_t)15);
             p->grid = std::min<uint32_t>((uint32_t)in.sm_count, (nq + W3 - 1) / W3);
             p->pairs = false;
             p->hv = 0;

@@ -14,8 +14,8 @@
 // This kernel therefore minimises (a) the per-query footprint and (b) the instructions per visit:
 //   * heap entries carry their own node reference (node id under the bitmap inserted-set, hash slot under the
 //     hash inserted-set): no seq -> node table, no store per candidate, no inserted-id list;
-//   * BinaryHeap::push x page with the root-ward path of the current leaf held in registers (lane j = height j):
-//     a push is ballot + shuffle + select, memory is touched only where the path steps to the next leaf;
+//   * BinaryHeap::push x page: inert elements written by all lanes at once, the rest through a warp-cooperative
+//     sift-up (one load, one ballot, one store whatever the rise height);
 //   * BinaryHeap::pop's sift_down_to_bottom four levels per memory round trip: 30 lanes fetch the hole's
 //     2+4+8+16 descendants at once, one ballot decides every sibling pair ("right child on ties"), the path is
 //     walked on that mask in registers and the winners store themselves into their parents;
@@ -26,10 +26,13 @@
 // Hamming distances pops first, and that decides returned row ids (dann_heap.cuh).
 //
 // Shared memory per query slot: visited ring [vcap] E, heap slots [hs] E (1-based, slot 0 unused), page of node ids
-// [64] u32 and page of entries [64] E.  HBM per slot: heap tail [cand_cap] E, inserted-set (bitmap n/8 bytes, or
+// [64] u32, page of entries [64] E, staging area of the pushes [160] E.  HBM per slot: heap tail [cand_cap] E, inserted-set (bitmap n/8 bytes, or
 // hash_cap u32).
 #pragma once
 #include "dann_search.cuh"
+
+/* staged slots of one page of pushes: tn leaves + (tn/2 + 1) + (tn/4 + 1) + ... <= 2 tn + 32 */
+#define DANN_STG_CAP (2u * DANN_LIST_CAP + 32u)
 
 template <typename T, int NCH>
 struct LeanWarp {
@@ -44,6 +47,7 @@ struct LeanWarp {
     E *vis;         /* ring [a.vcap] */
     uint32_t *list; /* [64] node ids of the page being expanded */
     E *ent;         /* [64] payload, then (key | payload) of the page */
+    E *stg;         /* [DANN_STG_CAP] heap slots staged for the pushes of one page */
     uint32_t *hash, *bitmap;
     SplitStore<E> heap; /* 1-based: Rust's data[i] is slot i + 1 */
     ulonglong2 qc[NCH];
@@ -82,35 +86,50 @@ struct LeanWarp {
         return labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
     }
 
-    /* dedupe (within the list, then against `inserted`) + label filter of up to 64 neighbour ids (list slots `lane`
-     * and `lane + 32`), appended to the page in list order: sbq/storage.rs:149-172 */
-    __device__ __forceinline__ void stage(uint32_t n0, bool v0, uint32_t n1, bool v1, bool apply_filter, bool unique) {
-        if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
-        bool f0 = v0, f1 = v1;
+    /* prepare_insert of up to 64 neighbour ids (list slots `lane` and `lane + 32`): dedupe within the list, then
+     * against `inserted` (sbq/storage.rs:149-163).  Bitmap flavour: the two atomics are only ISSUED here - o0/o1 are
+     * first read in stage_tail, so whatever the caller runs in between overlaps their L2/HBM round trip. */
+    struct Probe {
+        uint32_t o0, o1, s0, s1; /* bitmap: old words; hash: 1 = new / 0 = known.  s = payload (node id or hash slot) */
+        bool f0, f1;
+    };
+    __device__ __forceinline__ Probe stage_probe(uint32_t n0, bool v0, uint32_t n1, bool v1, bool unique) {
+        Probe pr;
+        pr.f0 = v0;
+        pr.f1 = v1;
         if (!unique) { /* a node listed twice within a chunk: only its first occurrence may insert */
             const unsigned m0 = __match_any_sync(DANN_FULL, n0);
             const unsigned m1 = __match_any_sync(DANN_FULL, n1);
-            f0 = v0 && ((__ffs(m0) - 1) == lane);
-            f1 = v1 && ((__ffs(m1) - 1) == lane);
+            pr.f0 = v0 && ((__ffs(m0) - 1) == lane);
+            pr.f1 = v1 && ((__ffs(m1) - 1) == lane);
         }
-        bool new0 = false, new1 = false;
-        uint32_t s0 = n0, s1 = n1; /* payload: the node id, or its hash slot */
+        pr.s0 = n0;
+        pr.s1 = n1;
+        pr.o0 = pr.o1 = 0xFFFFFFFFu;
         if (a.bitmap_words) {
-            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
-            const uint32_t b0 = 1u << (n0 & 31), b1 = 1u << (n1 & 31);
-            if (f0) o0 = atomicOr(bitmap + (n0 >> 5), b0);
-            if (f1) o1 = atomicOr(bitmap + (n1 >> 5), b1);
-            new0 = f0 && !(o0 & b0);
-            new1 = f1 && !(o1 & b1);
+            if (pr.f0) pr.o0 = atomicOr(bitmap + (n0 >> 5), 1u << (n0 & 31));
+            if (pr.f1) pr.o1 = atomicOr(bitmap + (n1 >> 5), 1u << (n1 & 31));
         } else {
             uint32_t h0 = 0, h1 = 0;
-            if (f0) new0 = hash_insert(n0, &h0);
+            bool new0 = false, new1 = false;
+            if (pr.f0) new0 = hash_insert(n0, &h0);
             __syncwarp();
-            if (f1) new1 = hash_insert(n1, &h1);
+            if (pr.f1) new1 = hash_insert(n1, &h1);
             if (slotpay) {
-                s0 = h0;
-                s1 = h1;
+                pr.s0 = h0;
+                pr.s1 = h1;
             }
+            pr.o0 = new0 ? 0u : 0xFFFFFFFFu;
+            pr.o1 = new1 ? 0u : 0xFFFFFFFFu;
+        }
+        return pr;
+    }
+
+    /* label filter of the new ids (sbq/storage.rs:165-172) and their compaction into the page, in list order */
+    __device__ __forceinline__ void stage_tail(const Probe &pr, uint32_t n0, uint32_t n1, bool apply_filter) {
+        const bool new0 = pr.f0 && !(pr.o0 & (a.bitmap_words ? 1u << (n0 & 31) : 1u));
+        const bool new1 = pr.f1 && !(pr.o1 & (a.bitmap_words ? 1u << (n1 & 31) : 1u));
+        if (!a.bitmap_words) {
             nset += __popc(__ballot_sync(DANN_FULL, new0)) + __popc(__ballot_sync(DANN_FULL, new1));
             if ((uint64_t)nset * 3u > (uint64_t)a.hash_cap * 2u) { /* load factor bound 2/3 */
                 status |= DANN_ST_HASH;
@@ -122,9 +141,6 @@ struct LeanWarp {
             if (new0) p0 = node_passes_filter(n0);
             if (new1) p1 = node_passes_filter(n1);
         }
-#ifdef DANN_SIMT_EMU
-        if (getenv("DANN_DBG2")) fprintf(stderr, "  lane %d n0=%u v0=%d f0=%d new0=%d p0=%d | n1=%u v1=%d new1=%d p1=%d\n", lane, n0, v0, f0, new0, p0, n1, v1, new1, p1);
-#endif
         const unsigned lt = (1u << lane) - 1u;
         const unsigned pm0 = __ballot_sync(DANN_FULL, p0), pm1 = __ballot_sync(DANN_FULL, p1);
         const uint32_t t0 = __popc(pm0), t1 = __popc(pm1);
@@ -136,22 +152,40 @@ struct LeanWarp {
         if (p0) {
             const uint32_t pos = listn + __popc(pm0 & lt);
             list[pos] = n0;
-            ent[pos] = (E)s0;
+            ent[pos] = (E)pr.s0;
         }
         if (p1) {
             const uint32_t pos = listn + t0 + __popc(pm1 & lt);
             list[pos] = n1;
-            ent[pos] = (E)s1;
+            ent[pos] = (E)pr.s1;
         }
         listn += t0 + t1;
         __syncwarp();
     }
 
+    __device__ __forceinline__ void stage(uint32_t n0, bool v0, uint32_t n1, bool v1, bool apply_filter, bool unique) {
+        if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
+        const Probe pr = stage_probe(n0, v0, n1, v1, unique);
+        stage_tail(pr, n0, n1, apply_filter);
+    }
+
     /* SBQ distance of every node of the page (distance/mod.rs:265-323): G lanes per code row, 128-bit no-allocate
-     * loads, two row slots per lane group in flight, XOR + popcount + shuffle reduction; ent[r] becomes the entry */
-    __device__ __forceinline__ void distances(uint32_t tn) {
+     * loads, two row slots per lane group in flight, XOR + popcount + shuffle reduction; ent[r] becomes the entry.
+     * EXACT: every lane's NCH chunk slots exist (cw / 2 == NCH * G, e.g. 768-d x 2 bits with G = 4), so the loads
+     * need no bounds test and row slots past the end of the page simply read row 0. */
+    template <bool EXACT>
+    __device__ __forceinline__ void distances_t(uint32_t tn) {
         const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
         const uint32_t nchunks = a.ix.cw >> 1;
+        if (tn > 2 * RP) { /* rows of the later rounds: pull them into L2 now, their loads then cost an L2 hit */
+            const size_t rowbytes = (size_t)a.ix.cw * 8;
+            const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
+            for (uint32_t r = 2 * RP + lane; r < tn; r += 32) {
+                const unsigned char *rowp = cb + (size_t)list[r] * rowbytes;
+                prefetch_l2(rowp);
+                if (rowbytes > 128) prefetch_l2(rowp + 128);
+            }
+        }
         for (uint32_t b = 0; b < tn; b += 2 * RP) {
             ulonglong2 v[2][NCH];
 #pragma unroll
@@ -159,11 +193,11 @@ struct LeanWarp {
                 const uint32_t r = b + u * RP + grp;
                 const bool live = r < tn;
                 const ulonglong2 *row =
-                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)(live ? list[r] : 0u) * a.ix.cw);
+                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)(live ? list[r] : 0u) * a.ix.cw) + gl;
 #pragma unroll
                 for (int i = 0; i < NCH; i++) {
-                    const uint32_t c = gl + i * G;
-                    v[u][i] = (live && c < nchunks) ? ldg_stream_u128(row + c) : qc[i];
+                    if (EXACT) v[u][i] = ldg_stream_u128(row + i * G);
+                    else v[u][i] = (live && gl + i * G < nchunks) ? ldg_stream_u128(row + i * G) : qc[i];
                 }
             }
 #pragma unroll
@@ -171,119 +205,107 @@ struct LeanWarp {
                 uint32_t s = 0;
 #pragma unroll
                 for (int i = 0; i < NCH; i++) s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-                for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    if ((uint32_t)o < G) s += __shfl_xor_sync(DANN_FULL, s, o); /* warp-uniform */
                 const uint32_t r = b + u * RP + grp;
                 if (gl == 0 && r < tn) ent[r] = T::make(s, T::seq(ent[r]));
             }
         }
         __syncwarp();
     }
-
-    /* BinaryHeap::push x tn in page order (insert_neighbor, graph/mod.rs:144-147) with the root-ward path of the
-     * current leaf in registers: lane j owns the slot at height j above the leaf (lane 0 = the leaf itself).  A push
-     * is one ballot ("which ancestors does the element pass" - sift_up moves while elem < parent), one shuffle (those
-     * ancestors move one level down) and a select.  When the leaf advances to the next slot only the lanes whose
-     * ancestor changes (heights <= ctz(slot)) write their slot back and take the right-hand neighbour, which they
-     * prefetched when they entered the old one.  Exactness: a slot at height j of the current leaf level is read and
-     * written by lane j only until the leaf level changes at a power-of-two slot, where every lane writes back, the
-     * warp syncs and reloads.  Requires 1 <= tn <= heap_len: every ancestor of a new slot is then an old slot. */
-    __device__ __forceinline__ void push_page_regs(uint32_t tn) {
-        const uint32_t lanebit = 1u << lane, lanebit2 = lanebit << 1;
-        uint32_t pos = heap_len + 1;
-        uint32_t node = pos >> lane;
-        E val = 0, nxt = 0;
-        bool dirty = false;
-        if (lane >= 1 && node != 0) {
-            val = heap.get(node);
-            if (node + 1 <= heap_len) nxt = heap.get(node + 1);
-        }
-        for (uint32_t base = 0; base < tn; base += 32) {
-            /* inert elements (the parent's key is already <= their own: they stay at their leaf whatever the earlier
-             * pushes of the page do) need no ballot and no shuffle.  The test reads the parent from memory, which may
-             * lag behind a register copy - keys in a slot only ever decrease during pushes, so a stale parent can
-             * hide an inert element but never fake one. */
-            const uint32_t r = base + lane;
-            bool inert = false;
-            if (r < tn) inert = heap.get((heap_len + 1 + r) >> 1) <= (ent[r] | KM);
-            const unsigned im = __ballot_sync(DANN_FULL, inert);
-            const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const E e = ent[base + i]; /* uniform address: a broadcast load off the chain through `val` */
-                if ((im >> i) & 1u) {      /* warp-uniform */
-                    if (lane == 0) {
-                        val = e;
-                        dirty = true;
-                    }
-                } else {
-                    const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
-                    const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
-                    const unsigned tm1 = x & ~(x + 1u); /* the leaf and the consecutive ancestors passed: lanes 0..rise */
-                    const E up = __shfl_down_sync(DANN_FULL, val, 1);
-                    if (tm1 & lanebit2) val = up;    /* lanes below `rise`: the ancestor above moves down into this slot */
-                    else if (tm1 & lanebit) val = e; /* lane `rise`: the element lands */
-                    dirty = dirty || (tm1 & lanebit) != 0;
-                }
-                if (base + i + 1 < tn) { /* move the path to the next leaf */
-                    const uint32_t pos1 = pos + 1;
-                    if ((pos1 & pos) == 0) { /* new leaf level: every slot changes owner */
-                        if (dirty) heap.set(node, val);
-                        __syncwarp();
-                        node = pos1 >> lane;
-                        dirty = false;
-                        val = nxt = 0;
-                        if (lane >= 1 && node != 0) {
-                            val = heap.get(node);
-                            if (node + 1 <= heap_len) nxt = heap.get(node + 1);
-                        }
-                    } else { /* heights 0..ctz(pos1) step to the right */
-                        const bool adv = lanebit <= (pos1 & (0u - pos1));
-                        if (adv && dirty) heap.set(node, val);
-                        node += adv ? 1u : 0u;
-                        val = adv ? nxt : val;
-                        dirty = dirty && !adv;
-                        if (adv && lane >= 1 && node + 1 <= heap_len) nxt = heap.get(node + 1);
-                    }
-                    pos = pos1;
-                }
-            }
-        }
-        if (dirty) heap.set(node, val);
-        __syncwarp();
-        heap_len += tn;
+    __device__ __forceinline__ void distances(uint32_t tn) {
+        if (a.ix.cw == 2u * NCH * a.G) distances_t<true>(tn);
+        else distances_t<false>(tn);
     }
 
-    /* The same pushes without the register-resident path: elements that are inert (parent key <= own key: they stay
-     * at their leaf whatever earlier pushes of the page do, because a slot's key never increases during pushes) are
-     * written by all lanes at once; the others go through the cooperative sift-up one at a time, in page order. */
-    __device__ __forceinline__ void push_page_coop(uint32_t tn) {
+    /* Σ_{t<h} (x >> t) */
+    static __device__ __forceinline__ uint32_t shift_sum(uint32_t x, uint32_t h) {
+        return 2u * x - (uint32_t)__popc(x) - 2u * (x >> h) + (uint32_t)__popc(x >> h);
+    }
+
+    /* BinaryHeap::push x tn in page order (insert_neighbor, graph/mod.rs:144-147) for a page whose leaves s0..s1 lie on
+     * ONE heap level.  Elements that are inert (parent key <= own key: they stay at their leaf whatever earlier pushes
+     * of the page do, because a slot's key never increases during pushes) are written by all lanes at once; the others
+     * go through a warp-cooperative sift-up one at a time, in page order: lane j owns the path slot at height j, loads
+     * its parent, one ballot finds where std's loop would break, the passed ancestors move one level down and the
+     * element lands - one load, one ballot, one store whatever the rise height.  (A register-resident root-ward path -
+     * ballot + shuffle per push, no memory on the chain - was measured slower on B200 at 7 and at 28 resident warps
+     * per SM, round-2 profiles, and is gone.)
+     * Slots in the HBM tail: every slot the pushes can touch - the leaves and, per height h, the ancestors
+     * (s0 >> h)..(s1 >> h), about 2 tn + log n slots - is staged in shared memory with ONE round trip (all loads
+     * issued together), the sift-ups run at shared-memory latency, and the staged slots go back in one pass; without
+     * this every non-inert push of a deep heap waits for its own L2/HBM round trip (measured: 9 of the 30 us per visit
+     * at 28 resident warps per SM).  Heights >= hcut have all their slots below hs, i.e. in the shared-memory top
+     * already; the staging area sits in the same shared-memory array (behind the page), so a lane addresses its slot
+     * as sm[B + slot] with a per-lane base B chosen once per page - no branch in the loop.
+     * Requires tn <= heap_len (every ancestor is an old slot) and tn <= DANN_LIST_CAP.  eoff: where the (sub-)page
+     * starts in ent[]. */
+    __device__ __forceinline__ void push_page_staged(uint32_t tn, uint32_t eoff) {
+        const E *pg = ent + eoff; /* this (sub-)page's entries */
+        E *const sm = heap.sm;
+        const uint32_t s0 = heap_len + 1, s1 = heap_len + tn;
+        uint32_t hcut = 0;
+        while ((s1 >> hcut) >= heap.hs) hcut++;
+        /* staged index of slot x at height h: off(h) + x - (s0 >> h), off(h) = sum over t < h of the per-height counts */
+        const uint32_t SB = (uint32_t)(stg - sm);
+        const uint32_t hj = (uint32_t)lane, hp = lane < 31 ? (uint32_t)lane + 1u : 31u; /* lane 31 has no slot */
+        const uint32_t B0 = hj < hcut ? SB + shift_sum(s1, hj) - shift_sum(s0, hj) + hj - (s0 >> hj) : 0u;
+        const uint32_t B1 = hp < hcut ? SB + shift_sum(s1, hp) - shift_sum(s0, hp) + hp - (s0 >> hp) : 0u;
+        const uint32_t Bpar = hcut > 1 ? SB + tn - (s0 >> 1) : 0u; /* height 1 (off(1) = tn), the same for every lane */
+        const uint32_t Bleaf = hcut > 0 ? SB - s0 : 0u;
+        for (uint32_t h = 1; h < hcut; h++) { /* stage the ancestors: independent loads, one round trip */
+            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+            for (uint32_t i = lane; i < cnt; i += 32) stg[off + i] = heap.get(lo + i);
+        }
+        __syncwarp();
         for (uint32_t base = 0; base < tn; base += 32) {
             const uint32_t r = base + lane;
             const bool have = r < tn;
-            const E mine = have ? ent[r] : E(0);
-            const uint32_t slot = heap_len + r + 1;
+            const E mine = have ? pg[r] : E(0);
+            const uint32_t slot = s0 + r;
             bool inert = false;
-            if (have && slot > 1) {
-                const uint32_t parent = slot >> 1;
-                if (parent <= heap_len + base) { /* parent is settled (old, or from an earlier round) */
-                    inert = heap.get(parent) <= (mine | KM);
-                    if (inert) heap.set(slot, mine);
-                }
+            if (have) {
+                inert = sm[Bpar + (slot >> 1)] <= (mine | KM);
+                if (inert) sm[Bleaf + slot] = mine;
             }
             unsigned act = __ballot_sync(DANN_FULL, have && !inert);
             __syncwarp();
-            while (act) { /* warp-uniform loop */
+            while (act) { /* warp-uniform: one cooperative sift-up per remaining element, in page order */
                 const int b = __ffs(act) - 1;
                 act &= act - 1;
-                H::template sift_up_warp1<false>(heap, heap_len + base + (uint32_t)b + 1, ent[base + b], lane);
+                const E elem = pg[base + b];
+                const uint32_t pp = s0 + base + (uint32_t)b;
+                const uint32_t ast = pp >> lane, ald = ast >> 1;
+                E av = 0;
+                if (ald) av = sm[B1 + ald];
+                const unsigned above = __ballot_sync(DANN_FULL, av > (elem | KM)); /* av = 0 above the root */
+                const unsigned tm = above & ~(above + 1u); /* trailing ones: the ancestors the element passes */
+                const unsigned wm = tm | (tm + 1u);        /* lanes 0..rise write */
+                if ((wm >> lane) & 1u) sm[B0 + ast] = ((tm >> lane) & 1u) ? av : elem;
+                __syncwarp();
             }
         }
+        for (uint32_t h = 0; h < hcut; h++) { /* staged slots back to the heap */
+            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+            for (uint32_t i = lane; i < cnt; i += 32) heap.set(lo + i, stg[off + i]);
+        }
+        __syncwarp();
         heap_len += tn;
     }
 
     __device__ __forceinline__ void push_page(uint32_t tn) {
         if (tn <= heap_len) {
-            if (a.hv_flags & DANN_HV_PUSH) push_page_regs(tn);
-            else push_page_coop(tn);
+            const uint32_t s0 = heap_len + 1, s1 = heap_len + tn;
+            /* leaves on two heap levels (the page crosses a power of two): one sub-page per level */
+            const uint32_t top = 0x80000000u >> __clz(s1); /* first slot of s1's level */
+            if (s0 < top) {
+                const uint32_t first = top - s0;
+                push_page_staged(first, 0);
+                push_page_staged(tn - first, first);
+            } else {
+                push_page_staged(tn, 0);
+            }
             return;
         }
         /* the first pages of a scan: ancestors of a new slot may belong to the page itself */
@@ -400,34 +422,89 @@ struct LeanWarp {
         __syncwarp();
     }
 
-    /* expand one visited node: sbq/storage.rs:135-190.  n0/n1 = list slots lane, lane + 32 (loaded by the caller so
-     * that the HBM latency overlaps the pop).  R <= 64. */
-    __device__ __forceinline__ void expand(uint32_t n0, uint32_t n1) {
+    /* One visit (graph/mod.rs:166-168,370-383 + sbq/storage.rs:135-190): pop the root `head`, insert it into the
+     * visited list, expand its neighbour list n0/n1 (list slots lane, lane + 32; R <= 64; loaded by the caller one
+     * phase ahead).  The inserted-set atomics are issued first and the heap / visited-list work - which does not
+     * depend on them - runs under their round trip.  Leaves the page (ids + entries with distances) staged: the
+     * caller pushes it.  Returns the page length. */
+    __device__ __forceinline__ uint32_t visit(E head, uint32_t n0, uint32_t n1) {
         /* iter_neighbors stops at the first InvalidBlockNumber slot (sbq/node.rs:261-285) */
         const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
         const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
         const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
         const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
         const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-        if (a.lists_unique) {
-            stage(n0, v0, n1, v1, filter, true);
-        } else { /* a list may repeat an id: keep strict list order across the two chunks */
-            stage(n0, v0, DANN_INVALID_NODE, false, filter, false);
-            if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter, false);
+        if (a.lists_unique && a.bitmap_words) {
+            const Probe pr = stage_probe(n0, v0, n1, v1, true);
+            pop();
+            visited_insert(head);
+            if (status) return 0;
+            stage_tail(pr, n0, n1, filter);
+        } else {
+            pop();
+            visited_insert(head);
+            if (status) return 0;
+            if (a.lists_unique) {
+                stage(n0, v0, n1, v1, filter, true);
+            } else { /* a list may repeat an id: keep strict list order across the two chunks */
+                stage(n0, v0, DANN_INVALID_NODE, false, filter, false);
+                if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter, false);
+            }
         }
-        flush();
+        const uint32_t tn = listn;
+        listn = 0;
+        if (tn == 0 || status) return 0;
+        distances(tn);
+        dq += tn;
+        return tn;
     }
 
+    /* start nodes: page -> distances -> pushes at once */
     __device__ __forceinline__ void flush() {
         const uint32_t tn = listn;
         listn = 0;
         if (tn == 0 || status) return;
         distances(tn);
-#ifdef DANN_SIMT_EMU
-        if (getenv("DANN_DBG") && lane == 0) { fprintf(stderr, " page tn=%u:", tn); for (uint32_t i = 0; i < tn; i++) fprintf(stderr, " %u/%u", list[i], (unsigned)(ent[i] >> T::KSHIFT)); fprintf(stderr, "\n"); }
-#endif
         push_page(tn);
         dq += tn;
+    }
+
+    /* visit_closest's test (graph/mod.rs:153-170) for a candidate root */
+    __device__ __forceinline__ bool may_visit(E head) const {
+        if (vis_len > a.L) {
+            const E at = vis[vix(a.L - 1)];
+            if ((head | KM) >= (at | KM)) return false; /* head >= node_at_pos */
+        }
+        return true;
+    }
+
+    /* The entry the heap's root will hold once the staged page (tn entries in ent[]) has been pushed.  A pushed
+     * element reaches the root iff its key is STRICTLY below the root's at that moment (sift_up moves only while
+     * elem < parent), so the root after the page is the FIRST entry attaining the page minimum if that minimum is
+     * strictly below the current root's key (or the heap is empty), else the current root.  Exact, not speculative:
+     * it lets the next visit's neighbour row be fetched while the pushes run.  false = the heap stays empty. */
+    __device__ __forceinline__ bool root_after_page(uint32_t tn, E *out) const {
+        E best = ~E(0);
+        for (uint32_t r = lane; r < tn; r += 32) {
+            const E c = (ent[r] & ~KM) | (E)r; /* key, then page position: the minimum is the first of the ties */
+            best = c < best ? c : best;
+        }
+        if constexpr (SMALL) {
+            best = __reduce_min_sync(DANN_FULL, best);
+        } else {
+            for (int o = 16; o > 0; o >>= 1) {
+                const E t = __shfl_xor_sync(DANN_FULL, best, o);
+                best = t < best ? t : best;
+            }
+        }
+        if (heap_len == 0) {
+            if (tn == 0) return false;
+            *out = ent[(uint32_t)(best & E(63))];
+            return true;
+        }
+        const E root = heap.get_sm(1);
+        *out = (tn != 0 && (best | KM) < (root & ~KM)) ? ent[(uint32_t)(best & E(63))] : root;
+        return true;
     }
 
     __device__ __forceinline__ void run(uint32_t q) {
@@ -494,30 +571,32 @@ struct LeanWarp {
         bool done = false;
         while (!done && !status) { /* TSVResponseIterator::next, scan.rs:210-242 */
             /* greedy_search_iterate: while let Some(idx) = visit_closest(L) */
-            while (heap_len > 0) { /* visit_closest, graph/mod.rs:153-170 */
-                const E head = heap.get_sm(1);
-                if (vis_len > a.L) {
-                    const E at = vis[vix(a.L - 1)];
-                    if ((head | KM) >= (at | KM)) break; /* key(head) >= key(at) */
+            if (heap_len > 0) {
+                E head = heap.get_sm(1);
+                bool go = may_visit(head);
+                uint32_t n0 = DANN_INVALID_NODE, n1 = DANN_INVALID_NODE;
+                if (go) { /* the popped element IS the current root: fetch its neighbour list */
+                    const uint32_t *row = ix.nbrs + (size_t)node_of(head) * ix.Rp;
+                    if ((uint32_t)lane < ix.R) n0 = ldg_stream_u32(row + lane);
+                    if ((uint32_t)lane + 32 < ix.R) n1 = ldg_stream_u32(row + 32 + lane);
                 }
-                /* the popped element IS the current root: fetch its neighbour list first, the pop's descent and
-                 * the visited insert run under that latency */
-                const uint32_t node = node_of(head);
-                const uint32_t *row = ix.nbrs + (size_t)node * ix.Rp;
-                const uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
-                const uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
-#ifdef DANN_SIMT_EMU
-                if (getenv("DANN_DBG3")) fprintf(stderr, "  L%d row[%u]+%d = %u (direct %u)\n", lane, node, lane, n0, row[lane]);
-#endif
-                pop();
-#ifdef DANN_SIMT_EMU
-                if (getenv("DANN_DBG") && lane == 0) fprintf(stderr, "visit node=%u key=%u heap_len=%u vis_len=%u\n", node, (unsigned)(head >> T::KSHIFT), heap_len, vis_len);
-#endif
-                visited_insert(head);
-                if (status) break;
-                visits++;
-                expand(n0, n1);
-                if (status) break;
+                while (go) {
+                    visits++;
+                    const uint32_t tn = visit(head, n0, n1);
+                    if (status) break;
+                    /* the next visit is decided before this page is pushed, and its neighbour row is in flight
+                     * while the pushes run */
+                    E next;
+                    go = root_after_page(tn, &next) && may_visit(next);
+                    n0 = n1 = DANN_INVALID_NODE;
+                    if (go) {
+                        const uint32_t *row = ix.nbrs + (size_t)node_of(next) * ix.Rp;
+                        if ((uint32_t)lane < ix.R) n0 = ldg_stream_u32(row + lane);
+                        if ((uint32_t)lane + 32 < ix.R) n1 = ldg_stream_u32(row + 32 + lane);
+                    }
+                    if (tn) push_page(tn);
+                    head = next;
+                }
             }
             if (status) break;
             if (vis_len == 0) break; /* consume() -> None */
@@ -567,7 +646,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) dann_search3_kernel(const Search
     w.vis = reinterpret_cast<E *>(base);
     w.heap.sm = reinterpret_cast<E *>(base + (size_t)a.vcap * sizeof(E));
     w.ent = w.heap.sm + a.hs;
-    w.list = reinterpret_cast<uint32_t *>(w.ent + DANN_LIST_CAP);
+    w.stg = w.ent + DANN_LIST_CAP;
+    w.list = reinterpret_cast<uint32_t *>(w.stg + DANN_STG_CAP);
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;

@@ -36,20 +36,29 @@ static int fail(int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    g_err = buf;
+    try {
+        g_err = buf;
+    } catch (...) { /* out of memory while recording the message: the code still goes back */
+    }
     return code;
 }
 
 extern "C" const char *dann_last_error(void) { return g_err.c_str(); }
 
-extern "C" int dann_device_count(void) {
+/* Nothing may propagate out of an extern "C" entry point into the Rust / pgrx caller: every int-returning entry
+ * point is a function-try-block that ends with this handler (std::bad_alloc from a host-side vector -> DANN_ERR_OOM). */
+#define DANN_CATCH                                                                               \
+    catch (const std::bad_alloc &) { return fail(DANN_ERR_OOM, "host allocation failed"); }      \
+    catch (...) { return fail(DANN_ERR_STATE, "unexpected C++ exception in the host code"); }
+
+extern "C" int dann_device_count(void) try {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     return n;
-}
+} DANN_CATCH
 
 #define CK(call)                                                                               \
     do {                                                                                       \
@@ -105,6 +114,7 @@ struct dann_index {
     /* staging for the host-buffer entry point */
     DevBuf st_queries, st_labels, st_label_off, st_tid, st_dist, st_count, st_stats;
     dann_batch_timing timing{};
+    dann_search_plan_info last_plan{};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t G = 1, Gshift = 0, NCH = 1;
     uint32_t lists_unique = 0;
@@ -360,28 +370,35 @@ static int index_load_impl(const dann_snapshot_desc *s, const float *index_vecto
     return DANN_OK;
 }
 
-extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) {
+extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_index **out) try {
     return index_load_impl(s, nullptr, device, out);
-}
+} DANN_CATCH
 
-extern "C" int dann_index_load_plain(const dann_snapshot_desc *s, const float *index_vectors, int device, dann_index **out) {
+extern "C" int dann_index_load_plain(const dann_snapshot_desc *s, const float *index_vectors, int device, dann_index **out) try {
     if (!index_vectors && s && s->n) return fail(DANN_ERR_INVALID_ARG, "dann_index_load_plain: NULL index_vectors");
     /* Bit-exact against the oracle under the CPU SIMT emulator, not yet run on hardware: opt-in until it has been. */
     if (env_u32("DANN_EXPERIMENTAL_PLAIN", 0) != 1)
         return fail(DANN_ERR_INVALID_ARG, "storage_layout=plain scans are experimental: set DANN_EXPERIMENTAL_PLAIN=1");
     static const float dummy = 0.0f;
     return index_load_impl(s, index_vectors ? index_vectors : &dummy, device, out);
-}
+} DANN_CATCH
 
 extern "C" uint64_t dann_index_hbm_bytes(const dann_index *ix) { return ix ? ix->hbm_bytes : 0; }
 extern "C" uint64_t dann_kernel_launches(const dann_index *ix) { return ix ? ix->launches.load() : 0; }
 extern "C" uint32_t dann_code_stride(const dann_index *ix) { return ix ? ix->v.cw : 0; }
 
-extern "C" int dann_last_batch_timing(dann_index *ix, dann_batch_timing *out) {
+extern "C" int dann_last_search_plan(dann_index *ix, dann_search_plan_info *out) try {
+    if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "dann_last_search_plan: NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = ix->last_plan;
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" int dann_last_batch_timing(dann_index *ix, dann_batch_timing *out) try {
     if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "NULL argument");
     *out = ix->timing;
     return DANN_OK;
-}
+} DANN_CATCH
 
 /* ------------------------------------------------------------------------------------ */
 static int check_live(dann_index *ix) {
@@ -407,7 +424,7 @@ static int launch_prepare(dann_index *ix, const float *d_queries, int B, float *
 }
 
 extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int B, float *d_q_full,
-                                    uint64_t *d_q_codes, void *stream) {
+                                    uint64_t *d_q_codes, void *stream) try {
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_queries || !d_q_codes || B <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_prepare_queries: bad argument");
@@ -418,7 +435,7 @@ extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int 
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
     return DANN_OK;
-}
+} DANN_CATCH
 
 template <int NCH, int UNR>
 static void launch_sbq_u(dann_index *ix, const uint64_t *q, const uint32_t *pq, const uint32_t *pn, size_t np,
@@ -452,7 +469,7 @@ static void launch_sbq(dann_index *ix, const uint64_t *q, const uint32_t *pq, co
 }
 
 extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const uint32_t *d_pair_q,
-                                 const uint32_t *d_pair_node, size_t npairs, uint32_t *d_out, void *stream) {
+                                 const uint32_t *d_pair_node, size_t npairs, uint32_t *d_out, void *stream) try {
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_qcodes || !d_pair_q || !d_pair_node || !d_out) return fail(DANN_ERR_INVALID_ARG, "dann_sbq_distance: NULL buffer");
@@ -470,10 +487,10 @@ extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const
     CK(cudaGetLastError());
     if (!stream) CK(cudaStreamSynchronize(st));
     return DANN_OK;
-}
+} DANN_CATCH
 
 extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const uint32_t *d_nodes, int B, int m,
-                                  float *d_out, void *stream) {
+                                  float *d_out, void *stream) try {
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_q_full || !d_nodes || !d_out || B <= 0 || m <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_full_distance: bad argument");
@@ -486,7 +503,7 @@ extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const u
     CK(cudaGetLastError());
     if (!stream) CK(cudaStreamSynchronize(st));
     return DANN_OK;
-}
+} DANN_CATCH
 
 /* ------------------------------------------------------------------------------------ */
 /* search kernel dispatch                                                                */
@@ -632,6 +649,23 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         a.plain_vectors = ix->index_vectors;
         a.q_index = d_q_index;
         a.plain_dim = ix->plain ? v.dim_index : 0;
+        if (attempt == 0) {
+            dann_search_plan_info &pi = ix->last_plan;
+            pi.kernel = p.lean ? 3u : p.pairs ? 2u : 1u;
+            pi.slots_per_sm = p.W;
+            pi.grid = p.grid;
+            pi.heap_smem = p.hs;
+            pi.visited_cap = p.vcap;
+            pi.cand_cap = p.cand_cap;
+            pi.entry_bytes = p.esize;
+            pi.bitmap = p.bitmap_words ? 1u : 0u;
+            pi.slot_hbm_bytes = (uint64_t)p.cand_cap * p.esize + (p.bitmap_words ? (uint64_t)p.bitmap_words * 4u : (uint64_t)p.hash_cap * 4u) +
+                                (p.lean ? 0u : (uint64_t)p.cand_cap * 4u + (p.bitmap_words ? (uint64_t)p.ins_cap * 4u : 0u));
+            pi.smem_per_slot = p.per_warp;
+            pi.retries = 0;
+        } else {
+            ix->last_plan.retries = (uint32_t)attempt;
+        }
         search_fn fn = p.lean ? pick_lean(p.entry, ix->NCH, p.maxw) : pick_kernel(p.pairs, p.entry, ix->NCH, p.hv, ix->plain);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -755,14 +789,14 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
 extern "C" int dann_search_batch_device(dann_index *ix, const float *d_queries, const int16_t *d_labels,
                                         const int32_t *d_label_off, int B, int k, int search_list_size,
                                         int rescore, uint64_t *d_out_tid, float *d_out_dist,
-                                        uint32_t *d_out_count, dann_query_stats *d_out_stats, void *stream) {
+                                        uint32_t *d_out_count, dann_query_stats *d_out_stats, void *stream) try {
     int rc = check_live(ix);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     return search_batch_device_locked(ix, d_queries, d_labels, d_label_off, B, k, search_list_size, rescore,
                                       d_out_tid, d_out_dist, nullptr, d_out_count, d_out_stats, st);
-}
+} DANN_CATCH
 
 /* host-buffer batch with optional node ids (used by the scan operator too) */
 static int search_batch_host(dann_index *ix, const float *queries, const int16_t *labels,
@@ -825,15 +859,15 @@ static int search_batch_host(dann_index *ix, const float *queries, const int16_t
 extern "C" int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
                                  const int32_t *label_off, int B, int k, int search_list_size, int rescore,
                                  uint64_t *out_tid, float *out_dist, uint32_t *out_count,
-                                 dann_query_stats *out_stats) {
+                                 dann_query_stats *out_stats) try {
     return search_batch_host(ix, queries, labels, label_off, B, k, search_list_size, rescore, out_tid, out_dist,
                              nullptr, out_count, out_stats);
-}
+} DANN_CATCH
 
 /* ------------------------------------------------------------------------------------ */
 /* index construction — see dann_build.cuh                            */
 
-extern "C" int dann_index_set_vectors(dann_index *ix, const float *vectors) {
+extern "C" int dann_index_set_vectors(dann_index *ix, const float *vectors) try {
     int rc = check_live(ix);
     if (rc) return rc;
     if (!vectors) return fail(DANN_ERR_INVALID_ARG, "dann_index_set_vectors: NULL vectors");
@@ -859,9 +893,34 @@ extern "C" int dann_index_set_vectors(dann_index *ix, const float *vectors) {
         CK(cudaStreamSynchronize(ix->stream));
     }
     return DANN_OK;
-}
+} DANN_CATCH
 
-extern "C" int dann_index_download_nbrs(dann_index *ix, uint32_t *out) {
+extern "C" int dann_index_set_vectors_device(dann_index *ix, float *d_vectors) try {
+    int rc = check_live(ix);
+    if (rc) return rc;
+    if (!d_vectors) return fail(DANN_ERR_INVALID_ARG, "dann_index_set_vectors_device: NULL vectors");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    IndexView &v = ix->v;
+    if (!v.n) return DANN_OK;
+    if (v.vectors) return fail(DANN_ERR_STATE, "dann_index_set_vectors_device: the index already owns a vector array");
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, d_vectors) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != ix->device) {
+        cudaGetLastError();
+        return fail(DANN_ERR_INVALID_ARG, "dann_index_set_vectors_device: not a device pointer on device %d", ix->device);
+    }
+    v.vectors = d_vectors; /* borrowed: not in ix->owned */
+    ix->hbm_bytes += (uint64_t)v.n * v.dim * sizeof(float);
+    if (v.distance_type == DANN_COSINE) {
+        int blocks = std::min<long long>((v.n + 255) / 256, (long long)ix->sm_count * 8);
+        dann_normalize_rows_kernel<<<std::max(blocks, 1), 256, 0, ix->stream>>>(d_vectors, v.n, v.dim);
+        ix->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ix->stream));
+    }
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" int dann_index_download_nbrs(dann_index *ix, uint32_t *out) try {
     int rc = check_live(ix);
     if (rc) return rc;
     if (!out) return fail(DANN_ERR_INVALID_ARG, "dann_index_download_nbrs: NULL buffer");
@@ -870,10 +929,10 @@ extern "C" int dann_index_download_nbrs(dann_index *ix, uint32_t *out) {
     if (!v.n) return DANN_OK;
     CK(cudaMemcpy2D(out, (size_t)v.R * 4, v.nbrs, (size_t)v.Rp * 4, (size_t)v.R * 4, v.n, cudaMemcpyDeviceToHost));
     return DANN_OK;
-}
+} DANN_CATCH
 
 extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_list_size, float max_alpha,
-                                uint32_t max_batch, dann_build_stats *out) {
+                                uint32_t max_batch, dann_build_stats *out) try {
     int rc = check_live(ix);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1063,19 +1122,19 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     }
     if (out) *out = bs;
     return DANN_OK;
-}
+} DANN_CATCH
 
 /* ------------------------------------------------------------------------------------ */
 /* scan operator: ambeginscan / amrescan / amgettuple / amendscan (scan.rs:309-476)       */
 
-extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) {
+extern "C" int dann_scan_begin(dann_index *ix, dann_scan **out) try {
     if (!ix || !out) return fail(DANN_ERR_INVALID_ARG, "dann_scan_begin: NULL argument");
     dann_scan *sc = new (std::nothrow) dann_scan();
     if (!sc) return fail(DANN_ERR_OOM, "host allocation failed");
     sc->ix = ix;
     *out = sc;
     return DANN_OK;
-}
+} DANN_CATCH
 
 static void scan_release(dann_scan *sc) {
     DevBuf *bufs[] = {&sc->d_qindex, &sc->d_step, &sc->d_query, &sc->d_qfull, &sc->d_qcodes, &sc->d_labels, &sc->d_label_off, &sc->d_saved,
@@ -1108,7 +1167,7 @@ static int scan_reset_search(dann_scan *sc) {
 }
 
 extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
-                                int search_list_size, int rescore) {
+                                int search_list_size, int rescore) try {
     if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_rescan: NULL scan");
     if (search_list_size < 1 || search_list_size > 10000) return fail(DANN_ERR_INVALID_ARG, "search_list_size %d outside 1..10000", search_list_size);
     if (rescore < 0 || rescore > 1000) return fail(DANN_ERR_INVALID_ARG, "rescore %d outside 0..1000", rescore);
@@ -1174,7 +1233,7 @@ extern "C" int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t
     CK(cudaStreamSynchronize(st));
     sc->active = true;
     return DANN_OK;
-}
+} DANN_CATCH
 
 /* Enqueue the resumable search for rows [0, want) of this launch (d_ctl[1] receives the overflow bits). */
 static int scan_launch_search(dann_scan *sc, uint32_t want) {
@@ -1337,7 +1396,7 @@ static int gettuple_fused(dann_scan *sc, uint32_t *block, uint16_t *offset, uint
     return 1;
 }
 
-extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) {
+extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_t *node_id, float *dist) try {
     if (!sc) return fail(DANN_ERR_INVALID_ARG, "dann_scan_gettuple: NULL scan");
     if (!sc->active) return fail(DANN_ERR_STATE, "dann_scan_gettuple before dann_scan_rescan");
     dann_index *ix = sc->ix;
@@ -1390,13 +1449,13 @@ extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offs
     if (node_id) *node_id = row.node;
     if (dist) *dist = row.dist;
     return 1;
-}
+} DANN_CATCH
 
-extern "C" int dann_scan_stats(dann_scan *sc, dann_query_stats *out) {
+extern "C" int dann_scan_stats(dann_scan *sc, dann_query_stats *out) try {
     if (!sc || !out) return fail(DANN_ERR_INVALID_ARG, "dann_scan_stats: NULL argument");
     *out = sc->stats;
     return DANN_OK;
-}
+} DANN_CATCH
 
 extern "C" void dann_scan_end(dann_scan *sc) {
     if (!sc) return;
@@ -1409,3 +1468,4 @@ extern "C" void dann_scan_end(dann_scan *sc) {
 /* ------------------------------------------------------------------------------------ */
 /* query coalescing for process-per-connection hosts                */
 #include "dann_coalescer.h"
+#include "dann_group.h"

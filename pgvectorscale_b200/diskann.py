@@ -49,6 +49,12 @@ class _BatchTiming(C.Structure):
                 ("resort_ms", C.c_float), ("total_ms", C.c_float), ("retries", C.c_uint32)]
 
 
+class _SearchPlanInfo(C.Structure):
+    _fields_ = [("kernel", C.c_uint32), ("slots_per_sm", C.c_uint32), ("grid", C.c_uint32), ("heap_smem", C.c_uint32),
+                ("visited_cap", C.c_uint32), ("cand_cap", C.c_uint32), ("entry_bytes", C.c_uint32), ("bitmap", C.c_uint32),
+                ("slot_hbm_bytes", C.c_uint64), ("smem_per_slot", C.c_uint32), ("retries", C.c_uint32)]
+
+
 class _BuildStats(C.Structure):
     _fields_ = [("batches", C.c_uint32), ("search_ms", C.c_float), ("prune_ms", C.c_float), ("sort_ms", C.c_float),
                 ("backlink_ms", C.c_float), ("total_ms", C.c_float), ("avg_degree", C.c_double)]
@@ -70,7 +76,9 @@ EXPORTS = [
     "dann_scan_stats", "dann_scan_end", "dann_search_batch", "dann_search_batch_device",
     "dann_prepare_queries", "dann_code_stride", "dann_sbq_distance", "dann_full_distance",
     "dann_kernel_launches", "dann_last_batch_timing",
-    "dann_build_graph", "dann_index_download_nbrs", "dann_index_set_vectors",
+    "dann_build_graph", "dann_index_download_nbrs", "dann_index_set_vectors", "dann_index_set_vectors_device",
+    "dann_last_search_plan",
+    "dann_group_create", "dann_group_size", "dann_group_replica", "dann_group_search_batch", "dann_group_free",
 ]
 
 _LIB = None
@@ -115,6 +123,15 @@ def load_library(path: Optional[str] = None):
     lib.dann_build_graph.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(_BuildStats)]
     lib.dann_index_download_nbrs.argtypes = [vp, vp]
     lib.dann_index_set_vectors.argtypes = [vp, vp]
+    lib.dann_index_set_vectors_device.argtypes = [vp, vp]
+    lib.dann_last_search_plan.argtypes = [vp, C.POINTER(_SearchPlanInfo)]
+    lib.dann_group_create.argtypes = [C.POINTER(_SnapshotDesc), C.c_int, vp, C.POINTER(vp)]
+    lib.dann_group_size.argtypes = [vp]
+    lib.dann_group_replica.argtypes = [vp, C.c_int]
+    lib.dann_group_replica.restype = vp
+    lib.dann_group_search_batch.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.dann_group_free.argtypes = [vp]
+    lib.dann_group_free.restype = None
     lib.dann_coalescer_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.dann_coalescer_search.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.dann_coalescer_stats.argtypes = [vp, vp, vp, vp]
@@ -149,6 +166,37 @@ def device_count() -> int:
     return int(load_library().dann_device_count())
 
 
+def _make_desc(s: Snapshot):
+    """dann_snapshot_desc over the snapshot's (contiguous) arrays; `keep` holds them alive for the call."""
+    keep = []
+
+    def arr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return C.c_void_p(a.ctypes.data)
+
+    d = _SnapshotDesc()
+    d.n, d.dim, d.dim_index, d.bits, d.words, d.R = s.n, s.dim, s.dim_index, s.bits, s.words, s.R
+    d.distance_type = int(s.distance_type)
+    d.has_labels = int(bool(s.has_labels))
+    d.count = int(s.count)
+    d.mean = arr(s.mean, np.float32)
+    d.m2 = arr(s.m2, np.float32)
+    d.codes = arr(s.codes, np.uint64)
+    d.nbrs = arr(s.nbrs, np.uint32)
+    d.heap_tid = arr(s.heap_tid, np.uint64)
+    d.vectors = arr(s.vectors, np.float32)
+    d.start_default = int(s.start_default)
+    d.n_start_labels = 0 if s.start_labels is None else len(s.start_labels)
+    d.start_labels = arr(s.start_labels, np.int16)
+    d.start_label_nodes = arr(s.start_label_nodes, np.uint32)
+    d.label_off = arr(s.label_off, np.uint32)
+    d.labels = arr(s.labels, np.int16)
+    return d, keep
+
+
 class DiskAnnIndex:
     """One diskann index resident in the HBM of one B200 (dann_index_load)."""
 
@@ -162,32 +210,7 @@ class DiskAnnIndex:
             # been checked under CPU emulation so far; it is refused unless explicitly enabled.  No CPU fallback either way.
             raise DiskAnnError(-1, "storage_layout=plain snapshots are not supported by the CUDA scan path "
                                    "(experimental: set DANN_EXPERIMENTAL_PLAIN=1)")
-        keep = []
-
-        def arr(a, dt):
-            if a is None:
-                return None
-            a = np.ascontiguousarray(a, dtype=dt)
-            keep.append(a)
-            return C.c_void_p(a.ctypes.data)
-
-        d = _SnapshotDesc()
-        d.n, d.dim, d.dim_index, d.bits, d.words, d.R = s.n, s.dim, s.dim_index, s.bits, s.words, s.R
-        d.distance_type = int(s.distance_type)
-        d.has_labels = int(bool(s.has_labels))
-        d.count = int(s.count)
-        d.mean = arr(s.mean, np.float32)
-        d.m2 = arr(s.m2, np.float32)
-        d.codes = arr(s.codes, np.uint64)
-        d.nbrs = arr(s.nbrs, np.uint32)
-        d.heap_tid = arr(s.heap_tid, np.uint64)
-        d.vectors = arr(s.vectors, np.float32)
-        d.start_default = int(s.start_default)
-        d.n_start_labels = 0 if s.start_labels is None else len(s.start_labels)
-        d.start_labels = arr(s.start_labels, np.int16)
-        d.start_label_nodes = arr(s.start_label_nodes, np.uint32)
-        d.label_off = arr(s.label_off, np.uint32)
-        d.labels = arr(s.labels, np.int16)
+        d, keep = _make_desc(s)
         h = C.c_void_p()
         if plain:
             iv = np.ascontiguousarray(s.index_vectors, dtype=np.float32)
@@ -234,6 +257,11 @@ class DiskAnnIndex:
     def code_stride(self) -> int:
         return int(self._lib.dann_code_stride(self._h))
 
+    def last_search_plan(self) -> dict:
+        t = _SearchPlanInfo()
+        _check(self._lib, self._lib.dann_last_search_plan(self._h, C.byref(t)))
+        return {k: int(getattr(t, k)) for k, _ in _SearchPlanInfo._fields_}
+
     def last_batch_timing(self) -> dict:
         t = _BatchTiming()
         _check(self._lib, self._lib.dann_last_batch_timing(self._h, C.byref(t)))
@@ -257,6 +285,10 @@ class DiskAnnIndex:
         v = np.ascontiguousarray(vectors, dtype=np.float32)
         assert v.shape == (self.n, self.dim)
         _check(self._lib, self._lib.dann_index_set_vectors(self._h, _np_ptr(v)))
+
+    def set_vectors_device(self, device_ptr: int):
+        """Borrow [n][dim] f32 rows that already sit in this device's HBM (kept alive by the caller)."""
+        _check(self._lib, self._lib.dann_index_set_vectors_device(self._h, C.c_void_p(int(device_ptr))))
 
     # -- scan operator ----------------------------------------------------------------
     def begin_scan(self) -> "IndexScan":
@@ -387,6 +419,54 @@ class IndexScan:
     def __del__(self):
         try:
             self.end()
+        except Exception:
+            pass
+
+
+class IndexGroup:
+    """dann_group: one replica of the index per GPU inside this process; a batch is split into contiguous slices, every
+    device runs the whole hot path on its slice, rows come back in query order."""
+
+    def __init__(self, snapshot: Snapshot, devices: Optional[Sequence[int]] = None, ndev: Optional[int] = None):
+        self._lib = load_library()
+        snapshot.validate()
+        d, keep = _make_desc(snapshot)
+        devs = None if devices is None else np.ascontiguousarray(list(devices), dtype=np.int32)
+        n = len(devs) if devs is not None else int(ndev if ndev is not None else device_count())
+        h = C.c_void_p()
+        _check(self._lib, self._lib.dann_group_create(C.byref(d), n, _np_ptr(devs), C.byref(h)))
+        self._h = h
+        self.dim = snapshot.dim
+        self.size = int(self._lib.dann_group_size(h))
+        del keep
+
+    def search_batch(self, queries, labels=None, k: int = 10, search_list_size: int = QUERY_SEARCH_LIST_SIZE_DEFAULT,
+                     rescore: int = QUERY_RESCORE_DEFAULT) -> dict:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        B = q.shape[0]
+        lab, off = DiskAnnIndex._labels_csr(labels, B)
+        out = dict(tid=np.empty((B, k), np.uint64), dist=np.empty((B, k), np.float32),
+                   count=np.empty(B, np.uint32), stats=np.empty(B, STATS_DTYPE))
+        _check(self._lib, self._lib.dann_group_search_batch(
+            self._h, _np_ptr(q), _np_ptr(lab) if lab is not None and lab.size else None, _np_ptr(off), B, int(k),
+            int(search_list_size), int(rescore), _np_ptr(out["tid"]), _np_ptr(out["dist"]), _np_ptr(out["count"]),
+            _np_ptr(out["stats"])))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dann_group_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

@@ -33,15 +33,20 @@ class QueryShardGroup:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
-    def gather_rows(self, tid: torch.Tensor, dst_dist: torch.Tensor, per_rank: int):
-        """all_gather of equally sized [per_rank,k] blocks (ranks pad their slice to per_rank rows)."""
+    def gather_packed(self, tid: torch.Tensor, dst_dist: torch.Tensor, per_rank: int):
+        """ONE collective per step: (tid, dist bits) packed into a single int64 block per rank and all_gathered on the
+        CURRENT stream's order (torch makes the collective wait for the current stream and the current stream wait
+        for the collective), so a search launched on that stream afterwards cannot overwrite `tid` under it.
+        Returns (tids [world*per_rank, k] int64, dists [world*per_rank, k] float32)."""
         if self.world == 1:
             return tid, dst_dist
-        tids = torch.empty((self.world * per_rank, self.k), dtype=tid.dtype, device=self.device)
-        dists = torch.empty((self.world * per_rank, self.k), dtype=dst_dist.dtype, device=self.device)
-        dist.all_gather_into_tensor(tids, tid.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(dists, dst_dist.contiguous(), group=self.group)
-        return tids, dists
+        k = self.k
+        pack = torch.empty((per_rank, 2 * k), dtype=torch.int64, device=self.device)
+        pack[:, :k] = tid
+        pack[:, k:] = dst_dist.contiguous().view(torch.int32).to(torch.int64)
+        out = torch.empty((self.world * per_rank, 2 * k), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, pack, group=self.group)
+        return out[:, :k].contiguous(), out[:, k:].to(torch.int32).view(torch.float32)
 
     def search(self, queries: torch.Tensor):
         """queries: the GLOBAL batch [B, dim] (same tensor on every rank). Returns the global
@@ -55,7 +60,7 @@ class QueryShardGroup:
             t, d = self.search_fn(queries[lo:hi])
             tid[: hi - lo] = t
             dst[: hi - lo] = d
-        tids, dists = self.gather_rows(tid, dst, per_rank)
+        tids, dists = self.gather_packed(tid, dst, per_rank)
         if self.world == 1:
             return tids[:B], dists[:B]
         rows = []

@@ -23,8 +23,9 @@ struct cudaDeviceProp {
 
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int *n) {
-    *n = 1;
+inline cudaError_t cudaGetDeviceCount(int *n) { /* SIMT_FAKE_DEVICES=2: a two-GPU box for the dann_group tests */
+    const char *s = getenv("SIMT_FAKE_DEVICES");
+    *n = s && *s ? atoi(s) : 1;
     return cudaSuccess;
 }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -62,6 +63,17 @@ inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) 
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
 inline cudaError_t cudaMemcpy2D(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind) {
     for (size_t r = 0; r < height; r++) memcpy((char *)d + r * dpitch, (const char *)s + r * spitch, width);
+    return cudaSuccess;
+}
+/* every pointer of the fake runtime is "device memory" of device 0 */
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes {
+    cudaMemoryType type;
+    int device;
+};
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) {
+    a->type = cudaMemoryTypeDevice;
+    a->device = 0;
     return cudaSuccess;
 }
 /* "free HBM": plenty unless DANN_FAKE_FREE_MB says otherwise (lets a test see the plan shrink its slot count) */

@@ -1,5 +1,6 @@
 // simt_emu.cpp — fibers, scheduler and warp collectives of the SIMT emulator (see simt_emu.h).  Test infrastructure.
 #include <execinfo.h>
+#include <mutex>
 #include "simt_emu.h"
 
 #include <algorithm>
@@ -246,6 +247,10 @@ void named_barrier(unsigned id, unsigned count) {
 }
 
 void launch(unsigned grid, unsigned block, const std::function<void()> &body) {
+    /* the emulator's state (current block, fiber switcher) is global: launches from several host threads - the
+     * replicas of a dann_group, one worker thread each - run one after the other */
+    static std::mutex launch_mu;
+    std::lock_guard<std::mutex> launch_lock(launch_mu);
     /* one set of fiber stacks per launch, reused by every block (blocks run one after the other) */
     char *stacks = (char *)aligned_alloc(64, (size_t)block * kStack);
     if (!stacks) abort();

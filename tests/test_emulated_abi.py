@@ -44,6 +44,12 @@ def test_gpu_parity_suite_passes_under_emulation():
     assert passed >= 97 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
+def test_two_replica_group_under_emulation():
+    """dann_group with two (fake) devices: slices, worker threads, rows in query order, label keys, error path."""
+    passed, out = _run(["tests/test_zz_i_group_gpu.py"], {"SIMT_FAKE_DEVICES": "2"}, workers=1)
+    assert passed == 3 and "skipped" not in out.splitlines()[-1], out[-500:]
+
+
 def test_not_yet_on_hardware_paths_pass_under_emulation():
     """Heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout, through the real host code."""
     passed, out = _run(["tests/test_zz_experimental_gpu.py"], {"DANN_RUN_EXPERIMENTAL": "1"})

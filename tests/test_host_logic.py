@@ -107,3 +107,22 @@ int main(int argc, char **argv) {
     want = [s.n, s.dim, s.dim_index, s.bits, s.words, s.R, int(s.distance_type), 1, int(s.count), int(s.start_default),
             len(s.start_labels), 0, h]
     assert [int(x) for x in out] == want
+    # a truncated file, an array whose length disagrees with the header geometry, and a length that would wrap the
+    # bounds check are all refused (exit status 1 = NULL), never read past the buffer
+    raw = (tmp_path / "s.raw").read_bytes()
+    hdr_end = 8 + 16 * 8
+    bad = {}
+    bad["truncated"] = raw[: len(raw) // 2]
+    n_up = bytearray(raw)
+    n_up[8:16] = np.uint64(s.n + 1).tobytes()              # header says one more node than the arrays hold
+    bad["geometry"] = bytes(n_up)
+    wrap = bytearray(raw)
+    wrap[hdr_end:hdr_end + 8] = np.uint64(2 ** 64 - 8).tobytes()   # off + len wraps around
+    bad["wrap"] = bytes(wrap)
+    plain_flag = bytearray(raw)
+    plain_flag[8 + 11 * 8:8 + 12 * 8] = np.uint64(1).tobytes()     # storage_type = plain without index_vectors
+    bad["storage_type"] = bytes(plain_flag)
+    for name, blob in bad.items():
+        (tmp_path / "bad.raw").write_bytes(blob)
+        r = subprocess.run([exe, str(tmp_path / "bad.raw")], capture_output=True, text=True)
+        assert r.returncode == 1, (name, r.returncode, r.stdout, r.stderr)

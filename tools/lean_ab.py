@@ -35,15 +35,13 @@ if not a.no_check:
 
 # (name, DANN_SEARCH_KERNEL, DANN_HV_FLAGS, DANN_SEARCH_WARPS, extra env)
 VARIANTS = [("pairs (round 1)", 2, None, None, {}),
-            ("lean regs-push + 4-level pop", 3, 3, None, {}),
-            ("lean coop-push + 4-level pop", 3, 2, None, {}),
-            ("lean regs-push + lane-0 pop", 3, 1, None, {}),
-            ("lean coop-push + lane-0 pop", 3, 0, None, {}),
-            ("lean (3) 16 warps/SM", 3, 3, 16, {}),
-            ("lean (3) 24 warps/SM", 3, 3, 24, {}),
-            ("lean (3) 32 warps/SM", 3, 3, 32, {}),
-            ("lean (3) hash set", 3, 3, None, {"DANN_SEARCH_BITMAP": "0"}),
-            ("lean (3) 8-byte entries", 3, 3, None, {"DANN_SEARCH_ENTRY": "2"})]
+            ("lean, 4-level pop", 3, 2, None, {}),
+            ("lean, lane-0 pop", 3, 0, None, {}),
+            ("lean, staged pushes always", 3, 3, None, {}),
+            ("lean (2) 20 warps/SM", 3, 2, 20, {}),
+            ("lean (2) 24 warps/SM", 3, 2, 24, {}),
+            ("lean (2) 32 warps/SM", 3, 2, 32, {}),
+            ("lean (2) hash set", 3, 2, None, {"DANN_SEARCH_BITMAP": "0"})]
 KEYS = ("DANN_SEARCH_KERNEL", "DANN_HV_FLAGS", "DANN_SEARCH_WARPS", "DANN_SEARCH_BITMAP", "DANN_SEARCH_ENTRY")
 for B in [int(x) for x in a.batches.split(",")]:
     for name, kern, flags, warps, extra in VARIANTS:
@@ -55,6 +53,8 @@ for B in [int(x) for x in a.batches.split(",")]:
         if warps is not None:
             os.environ["DANN_SEARCH_WARPS"] = str(warps)
         os.environ.update(extra)
+        if warps is not None and B < 148 * warps // 2:
+            continue    # forcing more slots per SM than the batch fills only idles SMs
         ms, tot = [], []
         for i in range(a.steps + 2):
             qb = q[(i * B) % (len(q) - B + 1):][:B]

@@ -57,5 +57,5 @@ for r in rows:
 ti = sum(v[0] for v in out.values()) or 1
 ts = sum(v[1] for v in out.values()) or 1
 print(f"\n# hottest source lines ({ti / 1e6:.1f}M warp instructions, {int(ts)} stall samples)")
-for k, v in sorted(out.items(), key=lambda kv: -kv[1][1])[:30]:
+for k, v in sorted(out.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 30]:
     print(f"{k[0][:18]:18s}:{k[1]:4d} inst {v[0] / ti * 100:5.1f}%  samples {v[1] / ts * 100:5.1f}%  | {k[2]}")
