@@ -91,6 +91,30 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 #endif
 }
 
+// Asynchronous global -> shared copy of one 4- or 8-byte word (LDGSTS: no register, the issuing thread does not wait);
+// dann_cp_async_wait_all() makes this thread's copies visible to it, a __syncwarp() after it to the rest of the warp.
+template <typename W>
+__device__ __forceinline__ void dann_cp_async(W *smem_dst, const W *gmem_src) {
+    static_assert(sizeof(W) == 4 || sizeof(W) == 8, "cp.async word size");
+#ifdef DANN_SIMT_EMU
+    *smem_dst = *gmem_src;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if constexpr (sizeof(W) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void dann_cp_async_commit() {
+#ifndef DANN_SIMT_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void dann_cp_async_wait_all() {
+#ifndef DANN_SIMT_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // f32::total_cmp key (core::f32::total_cmp): monotone signed-int image of the float.
 __device__ __forceinline__ int32_t total_key(float f) {
     int32_t b = __float_as_int(f);

@@ -116,7 +116,11 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
         int entry3 = small ? 0 : 2;
         if (getenv("DANN_SEARCH_ENTRY") && env_u32("DANN_SEARCH_ENTRY", 0) == 2) entry3 = 2; /* test hook */
         const uint32_t esize3 = entry3 == 2 ? 8 : 4;
-        const size_t fixed3 = (size_t)p->vcap * esize3 + (size_t)DANN_LIST_CAP * (esize3 + 4u) + (size_t)DANN_STG_CAP * esize3;
+        uint32_t G3 = 1, Gs3 = 0, NCH3 = 1;
+        pick_code_mapping((in.words + 1u) & ~1u, &G3, &Gs3, &NCH3);
+        /* visited ring + page (entries, ids) + push staging area + the query's SBQ code (NCH x G 16-byte chunks) */
+        const size_t fixed3 = (size_t)p->vcap * esize3 + (size_t)DANN_LIST_CAP * (esize3 + 4u) + (size_t)DANN_STG_CAP * esize3 +
+                              (size_t)NCH3 * G3 * 16u + 16u;
         const uint32_t hs_floor = (uint32_t)std::min<uint64_t>((uint64_t)p->cand_cap, 256);
         if (fixed3 + (size_t)hs_floor * esize3 + 64 <= budget && hcap <= 0xFFFFFFFCull) {
             uint32_t W3 = env_u32("DANN_SEARCH_WARPS", wneed3);

@@ -48,9 +48,10 @@ struct LeanWarp {
     uint32_t *list; /* [64] node ids of the page being expanded */
     E *ent;         /* [64] payload, then (key | payload) of the page */
     E *stg;         /* [DANN_STG_CAP] heap slots staged for the pushes of one page */
+    bool stg_async; /* the ancestors of the page about to be pushed are already on their way into stg (cp.async) */
     uint32_t *hash, *bitmap;
     SplitStore<E> heap; /* 1-based: Rust's data[i] is slot i + 1 */
-    ulonglong2 qc[NCH];
+    ulonglong2 *qcode; /* [NCH * G] 16-byte chunks of the query's SBQ code, zero past the code's end */
     const int16_t *ql;
     uint32_t nql;
     bool filter, slotpay;
@@ -63,20 +64,39 @@ struct LeanWarp {
         return slotpay ? __ldcg(hash + p) : p;
     }
 
-    /* prepare_insert = HashSet::insert (graph/mod.rs:126-128); returns true when n is new; *slot = where it lives */
-    __device__ __forceinline__ bool hash_insert(uint32_t n, uint32_t *slot) {
-        const uint32_t cap = a.hash_cap; /* any size: multiplicative hash scaled to [0, cap), linear probing */
-        uint32_t h = __umulhi(n * 2654435761u, cap);
-        for (uint32_t probe = 0; probe < cap; probe++) {
-            const uint32_t old = atomicCAS(hash + h, DANN_INVALID_NODE, n);
-            if (old == DANN_INVALID_NODE || old == n) {
-                *slot = h;
-                return old == DANN_INVALID_NODE;
+    /* prepare_insert = HashSet::insert (graph/mod.rs:126-128) for this lane's two ids at once: the first probes of both
+     * are in flight together, later probes only for the lanes that collided (open addressing, linear probing, any
+     * table size: multiplicative hash scaled to [0, cap)).  new* = the id was not in the set; h* = the slot it lives in. */
+    __device__ __forceinline__ void hash_insert2(uint32_t n0, bool f0, uint32_t n1, bool f1, bool *new0, bool *new1,
+                                                 uint32_t *s0, uint32_t *s1) {
+        const uint32_t cap = a.hash_cap;
+        uint32_t h0 = __umulhi(n0 * 2654435761u, cap), h1 = __umulhi(n1 * 2654435761u, cap);
+        bool p0 = f0, p1 = f1, w0 = false, w1 = false;
+        for (uint32_t probe = 0; probe < cap && (p0 || p1); probe++) {
+            uint32_t o0 = 0, o1 = 0;
+            if (p0) o0 = atomicCAS(hash + h0, DANN_INVALID_NODE, n0);
+            if (p1) o1 = atomicCAS(hash + h1, DANN_INVALID_NODE, n1);
+            if (p0) {
+                if (o0 == DANN_INVALID_NODE || o0 == n0) {
+                    w0 = o0 == DANN_INVALID_NODE;
+                    p0 = false;
+                } else {
+                    h0 = h0 + 1 == cap ? 0u : h0 + 1;
+                }
             }
-            h = h + 1 == cap ? 0u : h + 1;
+            if (p1) {
+                if (o1 == DANN_INVALID_NODE || o1 == n1) {
+                    w1 = o1 == DANN_INVALID_NODE;
+                    p1 = false;
+                } else {
+                    h1 = h1 + 1 == cap ? 0u : h1 + 1;
+                }
+            }
         }
-        *slot = 0;
-        return false;
+        *new0 = w0;
+        *new1 = w1;
+        *s0 = h0;
+        *s1 = h1;
     }
 
     __device__ __forceinline__ bool node_passes_filter(uint32_t n) {
@@ -112,9 +132,8 @@ struct LeanWarp {
         } else {
             uint32_t h0 = 0, h1 = 0;
             bool new0 = false, new1 = false;
-            if (pr.f0) new0 = hash_insert(n0, &h0);
+            hash_insert2(n0, pr.f0, n1, pr.f1, &new0, &new1, &h0, &h1);
             __syncwarp();
-            if (pr.f1) new1 = hash_insert(n1, &h1);
             if (slotpay) {
                 pr.s0 = h0;
                 pr.s1 = h1;
@@ -174,10 +193,36 @@ struct LeanWarp {
      * EXACT: every lane's NCH chunk slots exist (cw / 2 == NCH * G, e.g. 768-d x 2 bits with G = 4), so the loads
      * need no bounds test and row slots past the end of the page simply read row 0. */
     template <bool EXACT>
+    __device__ __forceinline__ void load_slot(ulonglong2 (&v)[NCH], uint32_t r, uint32_t tn, const ulonglong2 *qs) const {
+        const bool live = r < tn;
+        const ulonglong2 *row =
+            reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)(live ? list[r] : 0u) * a.ix.cw) + (lane & (a.G - 1));
+#pragma unroll
+        for (int i = 0; i < NCH; i++) {
+            if (EXACT) v[i] = ldg_stream_u128(row + i * a.G);
+            else v[i] = (live && (lane & (a.G - 1)) + i * a.G < (a.ix.cw >> 1)) ? ldg_stream_u128(row + i * a.G) : qs[i * a.G];
+        }
+    }
+    __device__ __forceinline__ void eat_slot(const ulonglong2 (&v)[NCH], uint32_t r, uint32_t tn, const ulonglong2 *qs) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < NCH; i++) {
+            const ulonglong2 qv = qs[i * a.G];
+            s += __popcll(v[i].x ^ qv.x) + __popcll(v[i].y ^ qv.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if ((uint32_t)o < a.G) s += __shfl_xor_sync(DANN_FULL, s, o); /* warp-uniform */
+        if ((lane & (a.G - 1)) == 0 && r < tn) ent[r] = T::make(s, T::seq(ent[r]));
+    }
+    /* A rolling pipeline of depth two over the page's row slots (one slot = one row per lane group, 32 / G rows per
+     * warp): slot s + 2 is requested as soon as slot s has been reduced, so after the first (HBM) wait every later
+     * slot - already on its way into L2 by the prefetch - arrives under the reduction of the slot before it. */
+    template <bool EXACT>
     __device__ __forceinline__ void distances_t(uint32_t tn) {
-        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
-        const uint32_t nchunks = a.ix.cw >> 1;
-        if (tn > 2 * RP) { /* rows of the later rounds: pull them into L2 now, their loads then cost an L2 hit */
+        const uint32_t G = a.G, grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
+        const ulonglong2 *qs = qcode + (lane & (G - 1)); /* this lane's chunks of the query code: qs[i * G] */
+        if (tn > 2 * RP) { /* rows of the later slots: pull them into L2 now, their loads then cost an L2 hit */
             const size_t rowbytes = (size_t)a.ix.cw * 8;
             const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
             for (uint32_t r = 2 * RP + lane; r < tn; r += 32) {
@@ -186,31 +231,15 @@ struct LeanWarp {
                 if (rowbytes > 128) prefetch_l2(rowp + 128);
             }
         }
+        ulonglong2 va[NCH], vb[NCH];
+        load_slot<EXACT>(va, grp, tn, qs);
+        load_slot<EXACT>(vb, RP + grp, tn, qs);
+#pragma unroll 1
         for (uint32_t b = 0; b < tn; b += 2 * RP) {
-            ulonglong2 v[2][NCH];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const uint32_t r = b + u * RP + grp;
-                const bool live = r < tn;
-                const ulonglong2 *row =
-                    reinterpret_cast<const ulonglong2 *>(a.ix.codes + (size_t)(live ? list[r] : 0u) * a.ix.cw) + gl;
-#pragma unroll
-                for (int i = 0; i < NCH; i++) {
-                    if (EXACT) v[u][i] = ldg_stream_u128(row + i * G);
-                    else v[u][i] = (live && gl + i * G < nchunks) ? ldg_stream_u128(row + i * G) : qc[i];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                uint32_t s = 0;
-#pragma unroll
-                for (int i = 0; i < NCH; i++) s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    if ((uint32_t)o < G) s += __shfl_xor_sync(DANN_FULL, s, o); /* warp-uniform */
-                const uint32_t r = b + u * RP + grp;
-                if (gl == 0 && r < tn) ent[r] = T::make(s, T::seq(ent[r]));
-            }
+            eat_slot(va, b + grp, tn, qs);
+            load_slot<EXACT>(va, b + 2 * RP + grp, tn, qs);
+            eat_slot(vb, b + RP + grp, tn, qs);
+            load_slot<EXACT>(vb, b + 3 * RP + grp, tn, qs);
         }
         __syncwarp();
     }
@@ -241,6 +270,29 @@ struct LeanWarp {
      * as sm[B + slot] with a per-lane base B chosen once per page - no branch in the loop.
      * Requires tn <= heap_len (every ancestor is an old slot) and tn <= DANN_LIST_CAP.  eoff: where the (sub-)page
      * starts in ent[]. */
+    /* Called as soon as the page length is known (before the distance stage): starts the copy of the page's ancestor
+     * slots from the HBM tail into the staging area with cp.async - no registers, nothing waits - so that the round
+     * trip runs under the code-row gather instead of in front of the pushes.  Single-level pages only (a page that
+     * crosses a power of two is staged synchronously by its two sub-pages).  heap_len must not change until the push. */
+    __device__ __forceinline__ void stage_ancestors_async(uint32_t tn) {
+        stg_async = false;
+        if (tn == 0 || tn > heap_len) return;
+        const uint32_t s0 = heap_len + 1, s1 = heap_len + tn;
+        if (s0 < (0x80000000u >> __clz(s1))) return;
+        uint32_t hcut = 0;
+        while ((s1 >> hcut) >= heap.hs) hcut++;
+        for (uint32_t h = 1; h < hcut; h++) {
+            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+            for (uint32_t i = lane; i < cnt; i += 32) {
+                const uint32_t slot = lo + i;
+                if (slot < heap.hs) stg[off + i] = heap.sm[slot];
+                else dann_cp_async(stg + off + i, heap.gl + slot);
+            }
+        }
+        dann_cp_async_commit();
+        stg_async = true;
+    }
+
     __device__ __forceinline__ void push_page_staged(uint32_t tn, uint32_t eoff) {
         const E *pg = ent + eoff; /* this (sub-)page's entries */
         E *const sm = heap.sm;
@@ -254,9 +306,14 @@ struct LeanWarp {
         const uint32_t B1 = hp < hcut ? SB + shift_sum(s1, hp) - shift_sum(s0, hp) + hp - (s0 >> hp) : 0u;
         const uint32_t Bpar = hcut > 1 ? SB + tn - (s0 >> 1) : 0u; /* height 1 (off(1) = tn), the same for every lane */
         const uint32_t Bleaf = hcut > 0 ? SB - s0 : 0u;
-        for (uint32_t h = 1; h < hcut; h++) { /* stage the ancestors: independent loads, one round trip */
-            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
-            for (uint32_t i = lane; i < cnt; i += 32) stg[off + i] = heap.get(lo + i);
+        if (stg_async) { /* started by stage_ancestors_async for exactly this page */
+            dann_cp_async_wait_all();
+            stg_async = false;
+        } else {
+            for (uint32_t h = 1; h < hcut; h++) { /* stage the ancestors: independent loads, one round trip */
+                const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+                for (uint32_t i = lane; i < cnt; i += 32) stg[off + i] = heap.get(lo + i);
+            }
         }
         __syncwarp();
         for (uint32_t base = 0; base < tn; base += 32) {
@@ -454,6 +511,7 @@ struct LeanWarp {
         const uint32_t tn = listn;
         listn = 0;
         if (tn == 0 || status) return 0;
+        stage_ancestors_async(tn); /* the pushes' ancestor slots travel while the code rows are gathered */
         distances(tn);
         dq += tn;
         return tn;
@@ -510,17 +568,16 @@ struct LeanWarp {
     __device__ __forceinline__ void run(uint32_t q) {
         const IndexView &ix = a.ix;
         heap_len = vis_head = vis_len = nset = listn = 0;
+        stg_async = false;
         visits = dq = status = 0;
         uint32_t scount = 0;
         slotpay = SMALL && a.bitmap_words == 0;
-        { /* query code chunks this lane compares against (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) */
-            const uint32_t gl = lane & (a.G - 1), nchunks = ix.cw >> 1;
+        { /* the query's SBQ code (SbqSearchDistanceMeasure, sbq/mod.rs:139-159) into shared memory: lane group member gl
+           * compares chunks gl, gl + G, ... of every row against the same chunks of the query */
+            const uint32_t nchunks = ix.cw >> 1, padded = (uint32_t)NCH * a.G;
             const ulonglong2 *qrow = reinterpret_cast<const ulonglong2 *>(a.q_codes + (size_t)q * ix.cw);
-#pragma unroll
-            for (int i = 0; i < NCH; i++) {
-                const uint32_t c = gl + i * a.G;
-                qc[i] = c < nchunks ? qrow[c] : make_ulonglong2(0, 0);
-            }
+            for (uint32_t c = lane; c < padded; c += 32) qcode[c] = c < nchunks ? qrow[c] : make_ulonglong2(0, 0);
+            __syncwarp();
         }
         if (!a.bitmap_words) { /* inserted = HashSet::new() (the bitmap flavour is left all zero by the previous query) */
             const uint4 ff = make_uint4(DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE, DANN_INVALID_NODE);
@@ -648,6 +705,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) dann_search3_kernel(const Search
     w.ent = w.heap.sm + a.hs;
     w.stg = w.ent + DANN_LIST_CAP;
     w.list = reinterpret_cast<uint32_t *>(w.stg + DANN_STG_CAP);
+    w.qcode = reinterpret_cast<ulonglong2 *>(base + a.per_warp_smem - (size_t)NCH * a.G * 16u); /* 16-byte aligned tail */
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;

@@ -5,8 +5,8 @@ Shared by bench.py's two arms.  Only `codes_and_graph` touches the product libra
 Vamana builder); everything else is torch / numpy, so the `--impl reference` arm can call it from a child process
 (tools/make_fixture.py) and never map libdiskann_b200.so itself.
 
-Determinism: chunk c of the dataset is gen_dataset(seed = DATA_SEED + c) - independent of n, so the 1M index is the
-first chunk of the 50M one and every process / rank regenerates identical rows.
+Determinism: chunk c (CHUNK rows) of the dataset is gen_dataset(seed = DATA_SEED + c) - independent of n, so the 1M
+index is a prefix of the 50M one and every process / rank regenerates identical rows.
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ import torch
 
 from tools import synth_index as si
 
-CHUNK = 1 << 20
+CHUNK = 1 << 18            # rows per generator call: 0.75 GiB per temporary, 50M rows leave ~3 GiB of HBM free
 DATA_SEED = 0x5EED0030
 QUERY_SEED0 = 0x5EED0031     # first batch of rank 0 (recall, operating point, parity)
 QUERY_SEED = 0x5EED0033      # later batches
@@ -50,8 +50,8 @@ class RunningTopK:
         self.best_i = torch.full((q.shape[0], k), -1, device=q.device, dtype=torch.int64)
         torch.backends.cuda.matmul.allow_tf32 = False
 
-    def add(self, x: torch.Tensor, start: int, sub: int = 1 << 18):
-        for s in range(0, x.shape[0], sub):          # [B, sub] scores at a time: 4096 x 256K x 4 B = 4 GB
+    def add(self, x: torch.Tensor, start: int, sub: int = 1 << 16):
+        for s in range(0, x.shape[0], sub):          # [B, sub] scores at a time: 4096 x 64K x 4 B = 1 GiB
             e = min(x.shape[0], s + sub)
             sc = self.q @ x[s:e].T
             v, i = torch.topk(sc, min(self.k, e - s), dim=1)
