@@ -20,7 +20,7 @@
  *     get_full_distance_for_resort  sbq/storage.rs:304-328
  *   amendscan              scan.rs:439-476           dann_scan_end (+ dann_scan_stats)
  *   MetaPage::fetch / SbqMeans::load (index -> RAM)  dann_index_load (index -> HBM)
- *   PlainStorage::load_for_search plain/storage.rs   dann_index_load_plain (experimental)
+ *   PlainStorage::load_for_search plain/storage.rs   dann_index_load_plain
  *   distance_xor_optimized distance/mod.rs:265-323   dann_sbq_distance (micro-kernel)
  *   distance_l2 / _cosine / _inner_product :88-209   dann_full_distance (micro-kernel)
  *   SbqQuantizer::quantize sbq/quantize.rs:52-102    dann_prepare_queries
@@ -109,8 +109,7 @@ int dann_index_load(const dann_snapshot_desc *snap, int device, dann_index **out
  * snapshot's SBQ fields (bits, words, count, mean, m2, codes) are ignored.  As in the reference (build.rs:264-290)
  * inner product, label filters and more than 2000 indexed dimensions are rejected.  Scans rerank from `vectors` only
  * when dim_index < dim (scan.rs:392-403), otherwise rows come back in beam-search order with dist = NaN.
- * EXPERIMENTAL: bit-exact against the oracle under CPU emulation of the kernel, not yet run on hardware; refused
- * unless DANN_EXPERIMENTAL_PLAIN=1 is set in the environment. */
+ * Verified bit-exact against the oracle on B200 (tests/test_zz_plain_gpu.py) and under CPU emulation of the kernel. */
 int dann_index_load_plain(const dann_snapshot_desc *snap, const float *index_vectors, int device, dann_index **out);
 void dann_index_free(dann_index *ix);
 /* `vectors` may be NULL in the snapshot (see dann_index_set_vectors); scans then need rescore == 0.

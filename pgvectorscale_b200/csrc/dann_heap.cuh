@@ -157,58 +157,6 @@ struct RustHeap {
         sift_up_warp1<false>(s, p, item, lane);
     }
 
-    /* pop_warp1 with a two-level look-ahead in the descent: the four grandchildren of the hole are one aligned
-     * 16-byte (4-byte entries) or 32-byte load next to the children pair, both issued before either compare, so
-     * two levels cost one shared-memory round trip instead of two.  `a <= (b | payload)` is key(a) <= key(b) on
-     * packed entries.  Rounds run while all four grandchildren exist (4p+3 <= end: both levels are then
-     * two-children steps of std's loop); the remaining levels use the one-level loop.  Same array as pop_warp1. */
-    template <typename Store>
-    static __device__ __forceinline__ void pop_warp1_la(Store &s, uint32_t &len, int lane) {
-        len--;
-        if (len == 0) return;
-        uint32_t p = 1;
-        E item = 0;
-        if (lane == 0) {
-            constexpr E KM = (E(1) << KSHIFT) - E(1);
-            item = s.get(len + 1);
-            const uint32_t end = len;
-            while (4u * p + 3u <= end) {
-                E c0, c1, g0, g1, g2, g3;
-                s.get2(2u * p, c0, c1);
-                s.get4(4u * p, g0, g1, g2, g3);
-                const bool r1 = c1 <= (c0 | KM); /* data[child] <= data[child+1]: right child on ties */
-                const E cs = r1 ? c1 : c0;
-                const E ga = r1 ? g2 : g0, gb = r1 ? g3 : g1;
-                const bool r2 = gb <= (ga | KM);
-                const E gs = r2 ? gb : ga;
-                const uint32_t c = 2u * p + (r1 ? 1u : 0u);
-                s.set(p, cs);
-                s.set(c, gs);
-                p = 2u * c + (r2 ? 1u : 0u);
-            }
-            uint32_t c = 2u * p;
-            while (c + 1 <= end) {
-                E cl, cr;
-                s.get2(c, cl, cr);
-                if (key(cr) <= key(cl)) {
-                    c++;
-                    cl = cr;
-                }
-                s.set(p, cl);
-                p = c;
-                c = 2 * p;
-            }
-            if (c == end) {
-                s.set(p, s.get(c));
-                p = c;
-            }
-        }
-        p = __shfl_sync(0xFFFFFFFFu, p, 0);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        __syncwarp();
-        sift_up_warp1<false>(s, p, item, lane);
-    }
-
     /* len must be > 0 */
     template <typename Store>
     static __device__ __forceinline__ E pop(Store &s, uint32_t &len) {

@@ -12,9 +12,8 @@
 
 struct SearchPlan {
     uint32_t need, cand_cap, hash_cap, vcap, hs, W, grid, per_warp, esize, bitmap_words, ins_cap;
-    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64, 3 = Ent32n21 (HV = 1 only) */
+    int entry; /* 0 = Ent32x21, 1 = Ent32x16, 2 = Ent64 */
     bool pairs; /* two-warp kernel (memory warp + heap warp per query) */
-    int hv;     /* heap-warp engine of the two-warp kernel (dann_search2.cuh: 0 = round-1 path, 1 = DANN_HEAP_V2) */
     bool lean;  /* dann_search3.cuh: one warp and a few KB of shared memory per query, up to 32 queries per SM */
     int maxw;   /* lean: the instantiation's resident-warp bound (32 -> 64 registers per thread, 16 -> 128) */
 };
@@ -146,7 +145,6 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
             p->per_warp = (uint32_t)((fixed3 + (size_t)hs3 * esize3 + 15) & ~(size_t)15);
             p->grid = std::min<uint32_t>((uint32_t)in.sm_count, (nq + W3 - 1) / W3);
             p->pairs = false;
-            p->hv = 0;
             p->lean = true;
             p->maxw = W3 <= 16 ? 16 : 32;
             return DANN_OK;
@@ -154,15 +152,9 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
     }
     /* the two-warp kernel handles neighbour lists of up to 64 ids */
     p->pairs = !force_single && in.R <= 64 && env_u32("DANN_SEARCH_KERNEL", 2) != 1 && !in.plain_dim;
-    p->hv = p->pairs && env_u32("DANN_HEAP_V2", 0) == 1 ? 1 : 0;
-    /* HV = 1 and at most 2M nodes: 4-byte entries that carry the node id (Ent32n21, no seq -> node table) */
-    if (p->hv == 1 && p->entry == 0 && in.n <= (1u << 21) && !getenv("DANN_SEARCH_ENTRY") &&
-        env_u32("DANN_HV_NODE_ENTRIES", 1) == 1)
-        p->entry = 3;
     const uint32_t wmax = p->pairs ? 7u : 12u; /* __launch_bounds__ of the two kernels */
     const size_t fixed = (size_t)p->vcap * 8 + (p->pairs ? 4 * DANN_LIST_CAP * 4 + sizeof(PairCtl) + 32 * 4 + 32 * 8 : 2 * DANN_LIST_CAP * 4) +
-                         (size_t)((in.plain_dim + 3u) & ~3u) * 4 + /* plain layout: the query's index slice */
-                         (p->hv == 1 ? 16u + 256u : 0u);           /* HV == 1: published root node ids, fused-expansion scratch */
+                         (size_t)((in.plain_dim + 3u) & ~3u) * 4; /* plain layout: the query's index slice */
     if (fixed + 1024 > budget) {
         snprintf(err, errlen, "visited list of %u entries does not fit shared memory", p->vcap);
         return DANN_ERR_CAPACITY;

@@ -81,14 +81,9 @@ struct SearchArgs {
     uint64_t *vis_out;      /* [B][vis_out_cap] (dist << 32) | node, ascending */
     uint32_t *vis_out_len;  /* [B] */
     uint32_t vis_out_cap;
-    /* dann_search2_kernel<.., HV=1> only: which of its alternatives run (DANN_HV_FLAGS, default all), so that each can
-     * be timed alone: 1 register-path pushes, 2 look-ahead pop, 4 page-sized distance rounds, 8 code-row L2
-     * prefetch, 16 neighbour-row L2 prefetch, 32 32-ary visited-list search, 64 no intra-list dedupe when the
-     * index's lists are known to be duplicate-free, 128 the heap warp resolves (and prefetches the neighbour row of) the
-     * root's node id, 256 the TID of the visited list's head is fetched one visit ahead, 512 inserted-set
-     * atomics and code gather issued together (fused expansion), 1024 REDUX (one instruction) for the page minimum and
-     * the per-row popcount sums instead of shuffle trees, 2048 the heap warp's root prediction read by every lane
-     * (no broadcast shuffles).  Kept last: the offsets of the fields above are unchanged. */
+    /* engine switches read from DANN_HV_FLAGS (default: all on).  Bit 2 (DANN_HV_POP): the lean kernel's pop walks
+     * the hole down four heap levels per memory round trip (off: lane 0 walks it level by level).  Kept last: the
+     * offsets of the fields above are unchanged. */
     uint32_t hv_flags;
     /* plain storage layout (SearchWarp<.., PLAIN=1> only; storage.rs:144-169, plain/storage.rs:223-299): the beam
      * search compares the query's index slice with the f32 vector each node stores.  Kept after everything else. */
@@ -96,18 +91,7 @@ struct SearchArgs {
     const float *q_index;       /* [B][plain_dim] prepared (truncated, cosine-normalised) queries */
     uint32_t plain_dim;         /* num_dimensions_to_index */
 };
-#define DANN_HV_PUSH 1u
 #define DANN_HV_POP 2u
-#define DANN_HV_DIST 4u
-#define DANN_HV_PF_CODES 8u
-#define DANN_HV_PF_NBRS 16u
-#define DANN_HV_VIS 32u
-#define DANN_HV_NOMATCH 64u
-#define DANN_HV_ROOTNODE 128u
-#define DANN_HV_TIDPF 256u
-#define DANN_HV_FUSED 512u
-#define DANN_HV_REDUX 1024u
-#define DANN_HV_UNIFORM 2048u
 
 #define DANN_LIST_CAP 64u
 
@@ -116,38 +100,22 @@ struct SearchArgs {
  * to 2M candidates per query in 4 bytes; Ent32x16: 16-bit distances, up to 65536 candidates; Ent64: anything. */
 struct Ent32x21 {
     using E = uint32_t;
-    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 21;
     static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 21) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0x1FFFFFu; }
 };
 struct Ent32x16 {
     using E = uint32_t;
-    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 16;
     static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t seq) { return (d << 16) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0xFFFFu; }
 };
 struct Ent64 {
     using E = uint64_t;
-    static constexpr bool PAYLOAD_IS_NODE = false;
     static constexpr int KSHIFT = 32;
     static __device__ __forceinline__ uint64_t make(uint32_t d, uint32_t seq) { return ((uint64_t)d << 32) | seq; }
     static __device__ __forceinline__ uint32_t seq(uint64_t e) { return (uint32_t)e; }
 };
-/* Ent32x21's layout with the NODE ID as payload instead of the candidate sequence number (indexes of up to 2M nodes,
- * 11-bit distances): the heap then needs no seq -> node table - no global store per candidate, no global load to learn
- * which node the root is.  A node enters the heap at most once (inserted-set), so the payload is as unique as a
- * sequence number, and only the key takes part in comparisons either way.  Used by the HV = 1 flavour of the two-warp
- * kernel only. */
-struct Ent32n21 {
-    using E = uint32_t;
-    static constexpr bool PAYLOAD_IS_NODE = true;
-    static constexpr int KSHIFT = 21;
-    static __device__ __forceinline__ uint32_t make(uint32_t d, uint32_t node) { return (d << 21) | node; }
-    static __device__ __forceinline__ uint32_t seq(uint32_t e) { return e & 0x1FFFFFu; }
-};
-
 /* PLAIN = 1: the plain storage layout.  Keys are total_ukey(f32 distance) (Ent64 entries), every comparison is a
  * full-distance comparison (counted as d_full), there is no label filter (plain/storage.rs:260). */
 template <typename T, int NCH, int PLAIN = 0>

@@ -52,11 +52,7 @@ __device__ __forceinline__ void pair_sync(uint32_t id) {
 #endif
 }
 
-/* HV selects the heap warp's engine: 0 = cooperative sift-up per active push + one-level pop descent (the measured
- * round-1 path), 1 = register-resident push path + look-ahead pop (push_batch_v2 / pop_warp1_la below: same heap
- * array after every page, checked under the CPU SIMT emulator in tests/test_simt_emulation.py; selected with
- * DANN_HEAP_V2=1 until it has been timed on hardware). */
-template <typename T, int NCH, int HV = 0>
+template <typename T, int NCH>
 struct PairSearch {
     using E = typename T::E;
     using H = RustHeap<E, T::KSHIFT>;
@@ -70,8 +66,6 @@ struct PairSearch {
     uint32_t *listp, *dlp; /* [2][64] */
     PairCtl *ctl;
     E *cqe;         /* [32] compacted active pushes: entry */
-    uint32_t *xroot; /* HV == 1: [2] node id of the published root (+2 spare words), behind cqe */
-    uint32_t *fscratch; /* HV == 1: [64] raw slot ids of the list being expanded (fused expansion) */
     uint32_t *cqp;  /* [32]                          : 1-based slot */
     uint32_t *hash, *bitmap, *ins, *cnode;
     SplitStore<E> heap;
@@ -109,7 +103,7 @@ struct PairSearch {
                                           bool apply_filter, bool known_unique = false) {
         if (__ballot_sync(DANN_FULL, v0 || v1) == 0) return;
         bool f0, f1;
-        if (HV == 1 && known_unique && (a.hv_flags & DANN_HV_NOMATCH)) {
+        if (known_unique) {
             /* the index was checked at load to have no repeated id within a neighbour list (lists_unique): the
              * intra-list dedupe - two MATCH.ANY on the path between the list's arrival and the inserted-set
              * atomics - has nothing to find */
@@ -121,9 +115,10 @@ struct PairSearch {
             f0 = v0 && ((__ffs(m0) - 1) == lane);
             f1 = v1 && ((__ffs(m1) - 1) == lane);
         }
-        if (HV == 1 && (a.hv_flags & DANN_HV_PF_CODES)) {
+        if (known_unique) {
             /* the SBQ code rows are needed one L2 round trip from now (after the inserted-set answers): start pulling
-             * them into L2 already; rows of ids that turn out to be known are the only wasted traffic */
+             * them into L2 already; rows of ids that turn out to be known are the only wasted traffic (measured on
+             * B200, round 2: 3.27 ms vs 3.45 ms per 1024-query batch at 1M x 768) */
             const size_t rowbytes = (size_t)a.ix.cw * 8;
             const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
             if (f0) {
@@ -183,12 +178,12 @@ struct PairSearch {
         if (p0) {
             uint32_t pos = listn + __popc(pm0 & lt);
             list[pos] = n0;
-            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n0;
+            cnode[ncand + pos] = n0;
         }
         if (p1) {
             uint32_t pos = listn + t0 + __popc(pm1 & lt);
             list[pos] = n1;
-            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n1;
+            cnode[ncand + pos] = n1;
         }
         listn += t0 + t1;
         __syncwarp();
@@ -196,42 +191,7 @@ struct PairSearch {
 
     /* SBQ distances of page `list` -> `dl` (distance/mod.rs:265-323).  EXACT: every lane's NCH
      * chunk slots exist (cw/2 == NCH*G), so the per-chunk bounds test disappears.
-     * One round = NU row slots per lane group: all 16-byte loads first, then XOR + popcount + group reduction. */
-    template <bool EXACT, int NU>
-    __device__ __forceinline__ void distances_round(const uint32_t *list, uint32_t *dl, uint32_t tn, uint32_t b) {
-        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
-        const uint32_t nchunks = a.ix.cw >> 1;
-        const size_t rowbytes = (size_t)a.ix.cw * 8;
-        const unsigned char *cbase = reinterpret_cast<const unsigned char *>(a.ix.codes) + (size_t)gl * 16;
-        const uint32_t cstep = G * 16;
-        ulonglong2 v[NU][NCH];
-#pragma unroll
-        for (int u = 0; u < NU; u++) {
-            const uint32_t r = b + u * RP + grp;
-            const bool live = r < tn;
-            const unsigned char *row = cbase + (size_t)(live ? list[r] : 0u) * rowbytes;
-#pragma unroll
-            for (int i = 0; i < NCH; i++) {
-                const bool ok = live && (EXACT || gl + i * G < nchunks);
-                v[u][i] = ok ? ldg_stream_u128(row + i * cstep) : qc[i];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NU; u++) {
-            uint32_t s = 0;
-#pragma unroll
-            for (int i = 0; i < NCH; i++)
-                s += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-            if (HV == 1 && (a.hv_flags & DANN_HV_REDUX)) {
-                /* one REDUX over the row's lane group instead of log2(G) shuffles (groups meet independently) */
-                if (G > 1) s = __reduce_add_sync(G >= 32u ? DANN_FULL : ((1u << G) - 1u) << (lane & ~(G - 1u)), s);
-            } else {
-                for (uint32_t o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(DANN_FULL, s, o);
-            }
-            const uint32_t r = b + u * RP + grp;
-            if (gl == 0 && r < tn) dl[r] = s;
-        }
-    }
+     * One round = RPI row slots per lane group: all 16-byte loads first, then XOR + popcount + group reduction. */
     template <bool EXACT>
     __device__ __forceinline__ void distances_impl(const uint32_t *list, uint32_t *dl, uint32_t tn) {
         const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
@@ -265,131 +225,9 @@ struct PairSearch {
         }
         __syncwarp();
     }
-    /* HV == 1: row slots past the end of the page are not computed at all (a 50-id page is 7 of the 12 slots of its
-     * two rounds).  Three round sizes keep every v[][] index a compile-time constant (registers, no local memory). */
-    template <bool EXACT>
-    __device__ __forceinline__ void distances_impl2(const uint32_t *list, uint32_t *dl, uint32_t tn) {
-        const uint32_t RP = 32u >> a.Gshift;
-        for (uint32_t b = 0; b < tn; b += RP * RPI) {
-            if constexpr (RPI >= 4) {
-                const uint32_t nu = (tn - b + RP - 1) / RP;
-                if (nu > (uint32_t)RPI * 2 / 3) distances_round<EXACT, RPI>(list, dl, tn, b);
-                else if (nu > (uint32_t)RPI / 3) distances_round<EXACT, RPI * 2 / 3>(list, dl, tn, b);
-                else distances_round<EXACT, RPI / 3>(list, dl, tn, b);
-            } else {
-                distances_round<EXACT, RPI>(list, dl, tn, b);
-            }
-        }
-        __syncwarp();
-    }
     __device__ __forceinline__ void distances(const uint32_t *list, uint32_t *dl, uint32_t tn) {
-        if constexpr (HV == 1) {
-            if (a.hv_flags & DANN_HV_DIST) {
-                if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl2<true>(list, dl, tn);
-                else distances_impl2<false>(list, dl, tn);
-                return;
-            }
-        }
         if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) distances_impl<true>(list, dl, tn);
         else distances_impl<false>(list, dl, tn);
-    }
-
-    /* HV == 1, bit 512: stage() and distances() fused for the common case (bitmap inserted-set, duplicate-free lists, no
-     * label filter).  The inserted-set atomics and the SBQ code gather of EVERY listed id are issued together, so the
-     * two L2/HBM round trips overlap instead of following each other; rows of ids that turn out to be known are
-     * dropped after the fact (about half of them: that is the price).  `scratch` (64 words of shared memory of its own)
-     * holds the raw slot ids so that each lane group can pick up the id of its row slots.  Ids in slots past the first RP*RPI (48 for 192-byte codes) are handled by the
-     * ordinary distance round afterwards.  Same list order, same distances, same counters as stage() + distances(). */
-    template <bool EXACT>
-    __device__ __forceinline__ void expand_fused(uint32_t *list, uint32_t *dl, uint32_t *scratch, uint32_t n0, bool v0,
-                                                 uint32_t n1, bool v1) {
-        const unsigned vm0 = __ballot_sync(DANN_FULL, v0), vm1 = __ballot_sync(DANN_FULL, v1);
-        if ((vm0 | vm1) == 0) return;
-        const uint32_t G = a.G, gl = lane & (G - 1), grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
-        const uint32_t nchunks = a.ix.cw >> 1;
-        const size_t rowbytes = (size_t)a.ix.cw * 8;
-        const unsigned char *cbase = reinterpret_cast<const unsigned char *>(a.ix.codes) + (size_t)gl * 16;
-        const uint32_t cstep = G * 16;
-        /* inserted-set first (the longer round trip), then the rows */
-        uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
-        const uint32_t b0 = 1u << (n0 & 31), b1 = 1u << (n1 & 31);
-        if (v0) o0 = atomicOr(bitmap + (n0 >> 5), b0);
-        if (v1) o1 = atomicOr(bitmap + (n1 >> 5), b1);
-        scratch[lane] = n0;
-        scratch[32 + lane] = n1;
-        __syncwarp();
-        ulonglong2 v[RPI][NCH];
-#pragma unroll
-        for (int u = 0; u < RPI; u++) {
-            const uint32_t slot = u * RP + grp;
-            const bool live = slot < 64u && (((slot < 32u ? vm0 : vm1) >> (slot & 31u)) & 1u);
-            const unsigned char *row = cbase + (size_t)(live ? scratch[slot] : 0u) * rowbytes;
-#pragma unroll
-            for (int i = 0; i < NCH; i++) {
-                const bool ok = live && (EXACT || gl + i * G < nchunks);
-                v[u][i] = ok ? ldg_stream_u128(row + i * cstep) : qc[i];
-            }
-        }
-        /* the atomics' answers: which slots are new, where they go in the page (list order = slot order) */
-        const bool new0 = v0 && !(o0 & b0), new1 = v1 && !(o1 & b1);
-        const unsigned lt = (1u << lane) - 1u;
-        const unsigned nm0 = __ballot_sync(DANN_FULL, new0), nm1 = __ballot_sync(DANN_FULL, new1);
-        const uint32_t c0 = __popc(nm0), c1 = __popc(nm1);
-        if (nins + c0 + c1 > a.ins_cap) { /* as in stage(): leave the bitmap as it was and report */
-            if (new0) atomicAnd(bitmap + (n0 >> 5), ~b0);
-            if (new1) atomicAnd(bitmap + (n1 >> 5), ~b1);
-            status |= DANN_ST_HASH;
-            return;
-        }
-        if (new0) ins[nins + __popc(nm0 & lt)] = n0;
-        if (new1) ins[nins + c0 + __popc(nm1 & lt)] = n1;
-        nins += c0 + c1;
-        if (c0 + c1 == 0) return;
-        if (ncand + c0 + c1 + 1 > a.cand_cap) {
-            status |= DANN_ST_HEAP;
-            return;
-        }
-        if (new0) {
-            const uint32_t pos = __popc(nm0 & lt);
-            list[pos] = n0;
-            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n0;
-        }
-        if (new1) {
-            const uint32_t pos = c0 + __popc(nm1 & lt);
-            list[pos] = n1;
-            if (!T::PAYLOAD_IS_NODE) cnode[ncand + pos] = n1;
-        }
-        listn = c0 + c1;
-        /* distances of the new ids among the first RP*RPI slots, straight from the rows already in registers */
-#pragma unroll
-        for (int u = 0; u < RPI; u++) {
-            uint32_t sum = 0;
-#pragma unroll
-            for (int i = 0; i < NCH; i++) sum += __popcll(v[u][i].x ^ qc[i].x) + __popcll(v[u][i].y ^ qc[i].y);
-            if (a.hv_flags & DANN_HV_REDUX) {
-                if (G > 1) sum = __reduce_add_sync(G >= 32u ? DANN_FULL : ((1u << G) - 1u) << (lane & ~(G - 1u)), sum);
-            } else {
-                for (uint32_t o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(DANN_FULL, sum, o);
-            }
-            const uint32_t slot = u * RP + grp;
-            if (gl == 0 && slot < 64u) {
-                const bool isnew = ((slot < 32u ? nm0 : nm1) >> (slot & 31u)) & 1u;
-                if (isnew) {
-                    const uint32_t pos = slot < 32u ? __popc(nm0 & ((1u << slot) - 1u))
-                                                    : c0 + __popc(nm1 & ((1u << (slot - 32u)) - 1u));
-                    dl[pos] = sum;
-                }
-            }
-        }
-        __syncwarp();
-        /* new ids in slots RP*RPI .. 63 (lists longer than 48): the ordinary round over the tail of the page */
-        const uint32_t first = RP * RPI;
-        if (first < 64u) {
-            const uint32_t lo = first < 32u ? __popc(nm0 & ((1u << first) - 1u))
-                                            : c0 + __popc(nm1 & ((1u << (first - 32u)) - 1u));
-            for (uint32_t b = lo; b < listn; b += RP * RPI) distances_round<EXACT, RPI>(list, dl, listn, b);
-            __syncwarp();
-        }
     }
 
     __device__ __forceinline__ void run_memory(uint32_t q) {
@@ -425,8 +263,6 @@ struct PairSearch {
         }
         vis_head = vis_len = 0;
         uint32_t visits = 0, scount = 0, k = 0;
-        uint32_t pf_node = DANN_INVALID_NODE; /* HV == 1: node whose TID offset is already in pf_off */
-        uint32_t pf_off = 0;                  /* its heap offset number (0 = deleted tuple) */
         /* ---- start nodes (graph/mod.rs:97-124, start_nodes.rs:39-48): 64 per page, never label-checked */
         for (; k < nstart_pages; k++) {
             const uint32_t p = k & 1;
@@ -483,9 +319,7 @@ struct PairSearch {
             uint32_t d0 = lane < ptn ? pd[lane] : 0xFFFFFFFFu;
             uint32_t d1 = lane + 32 < ptn ? pd[lane + 32] : 0xFFFFFFFFu;
             uint32_t m = min(d0, d1);
-            if (HV == 1 && (a.hv_flags & DANN_HV_REDUX)) m = __reduce_min_sync(DANN_FULL, m); /* one REDUX instead of five shuffles */
-            else
-                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(DANN_FULL, m, o));
             uint32_t node = DANN_INVALID_NODE, key = 0;
             const bool rv = ctl->root_valid[pp] != 0;
             if (ptn && (!rv || m < ctl->root_key[pp])) { /* first element of the batch attaining a strictly smaller minimum */
@@ -494,21 +328,8 @@ struct PairSearch {
                 node = pl[idx];
                 key = m;
             } else if (rv) { /* the root the pop left behind stays on top */
-                if (T::PAYLOAD_IS_NODE) node = ctl->root_seq[pp]; /* the entry carries the node id itself */
-                else if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) node = xroot[pp];
-                else node = cnode[ctl->root_seq[pp]];
+                node = cnode[ctl->root_seq[pp]];
                 key = ctl->root_key[pp];
-            }
-            if constexpr (HV == 1) {
-                /* the best new candidate of the page is not visited now (the old root wins) but very likely soon:
-                 * pull its neighbour row into L2 (lanes 0..: one 128-byte line each) */
-                if ((a.hv_flags & DANN_HV_PF_NBRS) && ptn && rv && !(m < ctl->root_key[pp])) {
-                    unsigned e0 = __ballot_sync(DANN_FULL, d0 == m), e1 = __ballot_sync(DANN_FULL, d1 == m);
-                    const uint32_t idx = e0 ? (uint32_t)(__ffs(e0) - 1) : 32u + (uint32_t)(__ffs(e1) - 1);
-                    const uint32_t rb = ix.Rp * 4u;
-                    if ((uint32_t)lane * 128u < rb)
-                        prefetch_l2(reinterpret_cast<const unsigned char *>(ix.nbrs + (size_t)pl[idx] * ix.Rp) + lane * 128);
-                }
             }
             const bool have = node != DANN_INVALID_NODE;
             bool visit = false;
@@ -531,20 +352,7 @@ struct PairSearch {
                 vis_head++;
                 vis_len--;
                 const uint32_t cn = (uint32_t)e;
-                uint64_t tid;
-                if (HV == 1 && (a.hv_flags & DANN_HV_TIDPF)) {
-                    /* the head of the visited list is known a whole visit before it is consumed: the offset half of
-                     * its TID (all that the deleted-tuple test needs; little-endian low 16 bits) was asked for then
-                     * (below), so this dependent HBM load is off the consume -> visit path */
-                    const unsigned short *off16 = reinterpret_cast<const unsigned short *>(ix.tids);
-                    tid = cn == pf_node ? pf_off : __ldg(off16 + (size_t)cn * 4);
-                    if (vis_len) { /* the next head, for a burst of consumes */
-                        pf_node = (uint32_t)vis[vis_head];
-                        pf_off = __ldg(off16 + (size_t)pf_node * 4);
-                    }
-                } else {
-                    tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
-                }
+                const uint64_t tid = __ldg(ix.tids + cn); /* return_lsn, sbq/storage.rs:404-414 */
                 if ((tid & 0xFFFFull) == 0) continue;     /* InvalidOffsetNumber: deleted tuple, scan.rs:231-234 */
                 if (lane == 0) a.stream[(size_t)q * a.c_target + scount] = cn;
                 scount++;
@@ -561,33 +369,16 @@ struct PairSearch {
             uint32_t n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
             uint32_t n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
             visited_insert(key, node);
-            if (HV == 1 && (a.hv_flags & DANN_HV_TIDPF) && !status) {
-                const uint32_t hn = (uint32_t)vis[vis_head]; /* vis_len >= 1 after the insert */
-                if (hn != pf_node) {
-                    pf_node = hn;
-                    pf_off = __ldg(reinterpret_cast<const unsigned short *>(ix.tids) + (size_t)hn * 4);
-                }
-            }
             visits++;
             uint32_t *list = listp + p * DANN_LIST_CAP, *dl = dlp + p * DANN_LIST_CAP;
             listn = 0;
-            bool fused_done = false;
             if (!status) {
                 const unsigned i0 = __ballot_sync(DANN_FULL, n0 == DANN_INVALID_NODE);
                 const unsigned i1 = __ballot_sync(DANN_FULL, n1 == DANN_INVALID_NODE);
                 const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
                 const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
                 const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-#ifdef DANN_HV_NO_FUSED /* build-time knob (DANN_NVCC_DEFINES): compile the fused expansion out to see what its registers cost */
-                if (false) {
-#else
-                if (HV == 1 && (a.hv_flags & DANN_HV_FUSED) && a.lists_unique && a.bitmap_words && !filter) {
-#endif
-                    uint32_t *scratch = fscratch; /* not a list page: the heap warp may still read the previous one */
-                    if ((a.ix.cw >> 1) == (uint32_t)NCH * a.G) expand_fused<true>(list, dl, scratch, n0, v0, n1, v1);
-                    else expand_fused<false>(list, dl, scratch, n0, v0, n1, v1);
-                    fused_done = true;
-                } else if (a.lists_unique) {
+                if (a.lists_unique) {
                     stage(list, n0, v0, n1, v1, filter, true);
                 } else {
                     stage(list, n0, v0, DANN_INVALID_NODE, false, filter);
@@ -595,7 +386,7 @@ struct PairSearch {
                 }
             }
             if (status) listn = 0;
-            if (!fused_done) distances(list, dl, listn);
+            distances(list, dl, listn);
             if (lane == 0) {
                 ctl->tn[p] = listn;
                 ctl->seq0[p] = ncand;
@@ -643,15 +434,14 @@ struct PairSearch {
      * the batch do) are written in parallel; the others are compacted into a small queue and
      * replayed in order through the cooperative sift-up, the next one prefetched meanwhile. */
     template <bool PSM, typename Store>
-    __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0,
-                                               const uint32_t *lp = nullptr) {
+    __device__ __forceinline__ void push_batch(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0) {
         const unsigned lt = (1u << lane) - 1u;
         for (uint32_t base = 0; base < tn; base += 32) {
             const uint32_t r = base + lane;
             const bool have = r < tn;
             const uint32_t dmine = have ? dl[r] : 0u;
             const uint32_t slot = heap_len + r + 1;
-            const E mine = T::make(dmine, T::PAYLOAD_IS_NODE ? (have ? lp[r] : 0u) : seq0 + r);
+            const E mine = T::make(dmine, seq0 + r);
             bool inert = false;
             if (have && slot > 1) {
                 const uint32_t parent = slot >> 1;
@@ -682,108 +472,17 @@ struct PairSearch {
         }
     }
 
-    /* The same pushes with the root-ward path of the current leaf held in registers: lane j owns the slot at height
-     * j above the leaf (lane 0 = the leaf itself), so a push is one ballot ("which ancestors does the element
-     * pass"), one shuffle (those ancestors move one level down) and a select - no memory access on the dependent
-     * chain.  When the leaf advances to the next slot only the lanes whose ancestor changes (heights <= ctz(slot))
-     * write their slot back and take the right-hand neighbour, which they prefetched when they entered the old one.
-     * Exactness: a slot at height j of the current leaf level is read and written by lane j only (so program
-     * order is the only ordering needed) until the leaf level changes at a power-of-two slot, where every lane
-     * writes back, the warp syncs and reloads.  Requires heap_len >= 64 >= tn: every ancestor of a new slot is then an old
-     * slot, never a slot of this batch. */
-    template <typename Store>
-    __device__ __forceinline__ void push_batch_v2(Store &st, const uint32_t *dl, uint32_t tn, uint32_t seq0,
-                                                  const uint32_t *lp) {
-        constexpr E KM = (E(1) << T::KSHIFT) - E(1);
-        const uint32_t lanebit = 1u << lane, lanebit2 = lanebit << 1;
-        uint32_t pos = heap_len + 1;
-        uint32_t node = pos >> lane;
-        E val = 0, nxt = 0;
-        bool dirty = false;
-        if (lane >= 1 && node != 0) {
-            val = st.get(node);
-            if (node + 1 <= heap_len) nxt = st.get(node + 1);
-        }
-        for (uint32_t base = 0; base < tn; base += 32) {
-            /* inert elements (the parent's key is already <= their own: they stay at their leaf whatever the earlier
-             * pushes of the page do) need no ballot and no shuffle, only the path's step to the next leaf.  The test
-             * reads the parent from memory, which may lag behind a register copy - keys in a slot only ever decrease
-             * during pushes, so a stale parent can hide an inert element but never fake one. */
-            const uint32_t r = base + lane;
-            bool inert = false;
-            if (r < tn) inert = H::key(st.get((heap_len + 1 + r) >> 1)) <= dl[r];
-            const unsigned im = __ballot_sync(DANN_FULL, inert);
-            const uint32_t cnt = tn - base < 32u ? tn - base : 32u;
-            for (uint32_t i = 0; i < cnt; i++) {
-                /* every lane builds the element itself from the page in shared memory (uniform address: a broadcast
-                 * load, independent of the chain through `val`) */
-                const E e = T::make(dl[base + i], T::PAYLOAD_IS_NODE ? lp[base + i] : seq0 + base + i);
-                if ((im >> i) & 1u) { /* warp-uniform */
-                    if (lane == 0) {
-                        val = e;
-                        dirty = true;
-                    }
-                } else {
-                    const E eh = e | KM; /* val > eh  <=>  key(val) > key(e): the element passes this ancestor */
-                    const unsigned x = __ballot_sync(DANN_FULL, lane == 0 || (node != 0 && val > eh));
-                    const unsigned tm1 = x & ~(x + 1u); /* bit 0 (the leaf) and the consecutive ancestors passed: lanes 0..rise */
-                    const E up = __shfl_down_sync(DANN_FULL, val, 1);
-                    if (tm1 & lanebit2) val = up;     /* lanes below `rise`: the ancestor above moves down into this slot */
-                    else if (tm1 & lanebit) val = e;  /* lane `rise`: the element lands */
-                    dirty = dirty || (tm1 & lanebit) != 0;
-                }
-                if (base + i + 1 < tn) { /* move the path to the next leaf */
-                    const uint32_t pos1 = pos + 1;
-                    if ((pos1 & pos) == 0) { /* new leaf level: every slot changes owner */
-                        if (dirty) st.set(node, val);
-                        __syncwarp();
-                        node = pos1 >> lane;
-                        dirty = false;
-                        val = nxt = 0;
-                        if (lane >= 1 && node != 0) {
-                            val = st.get(node);
-                            if (node + 1 <= heap_len) nxt = st.get(node + 1);
-                        }
-                    } else { /* heights 0..ctz(pos1) step to the right (written for predication, not branches) */
-                        const bool adv = lanebit <= (pos1 & (0u - pos1));
-                        if (adv && dirty) st.set(node, val);
-                        node += adv ? 1u : 0u;
-                        val = adv ? nxt : val;
-                        dirty = dirty && !adv;
-                        if (adv && lane >= 1 && node + 1 <= heap_len) nxt = st.get(node + 1);
-                    }
-                    pos = pos1;
-                }
-            }
-        }
-        if (dirty) st.set(node, val);
-        __syncwarp();
-    }
-
     __device__ __forceinline__ void push_page(uint32_t p) {
         const uint32_t tn = ctl->tn[p], seq0 = ctl->seq0[p];
         const uint32_t *dl = dlp + p * DANN_LIST_CAP;
-        const uint32_t *lp = listp + p * DANN_LIST_CAP; /* the page's node ids (entries that carry them) */
         if (tn == 0) return;
-        if constexpr (HV == 1) {
-            if (heap_len >= 64 && (a.hv_flags & DANN_HV_PUSH)) {
-                if (heap_len + tn < heap.hs) {
-                    ArrayStore<E> sm{heap.sm};
-                    push_batch_v2(sm, dl, tn, seq0, lp);
-                } else {
-                    push_batch_v2(heap, dl, tn, seq0, lp);
-                }
-                heap_len += tn;
-                return;
-            }
-        }
         if (heap_len + tn < heap.hs) { /* everything in shared memory */
             ArrayStore<E> sm{heap.sm};
-            push_batch<true>(sm, dl, tn, seq0, lp);
+            push_batch<true>(sm, dl, tn, seq0);
         } else if (heap_len + tn < 2 * heap.hs) { /* leaves spill to HBM, every parent still in shared memory */
-            push_batch<true>(heap, dl, tn, seq0, lp);
+            push_batch<true>(heap, dl, tn, seq0);
         } else {
-            push_batch<false>(heap, dl, tn, seq0, lp);
+            push_batch<false>(heap, dl, tn, seq0);
         }
         heap_len += tn;
     }
@@ -806,27 +505,10 @@ struct PairSearch {
         }
         uint64_t *w = vis + vis_head;
         uint32_t idx = 0;
-        if (HV == 1 && (a.hv_flags & DANN_HV_VIS)) {
-            /* partition_point(x < d) on the sorted list with a 32-ary search: one probe per lane at the end of its
-             * stride finds the boundary stride, a second ballot counts inside it - 2 ballots instead of len/32 */
-            const uint32_t stride = (vis_len + 31u) >> 5;
-            const uint32_t s0 = (uint32_t)lane * stride;
-            uint32_t pe = s0 + stride < vis_len ? s0 + stride : vis_len; /* end of this lane's stride */
-            const bool whole = s0 < vis_len && (uint32_t)(w[pe - 1] >> 32) < d;
-            const uint32_t c = __popc(__ballot_sync(DANN_FULL, whole));
-            idx = c * stride < vis_len ? c * stride : vis_len; /* the last stride may be short */
-            const uint32_t b0 = idx, b1 = b0 + stride < vis_len ? b0 + stride : vis_len;
-            for (uint32_t i0 = b0; i0 < b1; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const bool lt = i < b1 && (uint32_t)(w[i] >> 32) < d;
-                idx += __popc(__ballot_sync(DANN_FULL, lt));
-            }
-        } else {
-            for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
-                uint32_t i = i0 + lane;
-                bool lt = i < vis_len && (uint32_t)(w[i] >> 32) < d;
-                idx += __popc(__ballot_sync(DANN_FULL, lt));
-            }
+        for (uint32_t i0 = 0; i0 < vis_len; i0 += 32) {
+            uint32_t i = i0 + lane;
+            bool lt = i < vis_len && (uint32_t)(w[i] >> 32) < d;
+            idx += __popc(__ballot_sync(DANN_FULL, lt));
         }
         for (int hi = (int)vis_len; hi > (int)idx; hi -= 32) {
             int i = hi - 1 - lane;
@@ -845,18 +527,6 @@ struct PairSearch {
     /* publish the heap root as it stands before page k is pushed, and meet the memory warp */
     __device__ __forceinline__ void handoff(bool rv, E root) {
         const uint32_t p = hk & 1;
-        if (HV == 1 && (a.hv_flags & DANN_HV_ROOTNODE)) {
-            /* the heap warp is ahead of the controller here: translate the root's sequence number into its node id
-             * (a global load the controller would otherwise wait for before it can even ask for the neighbour list)
-             * and start pulling that node's neighbour row into L2 - it is the next visit unless the page being
-             * built beats it */
-            if (rv) {
-                const uint32_t rn = T::PAYLOAD_IS_NODE ? T::seq(root) : __ldcg(cnode + T::seq(root));
-                if (lane == 0) xroot[p] = rn;
-                if ((uint32_t)lane * 128u < a.ix.Rp * 4u)
-                    prefetch_l2(reinterpret_cast<const unsigned char *>(a.ix.nbrs + (size_t)rn * a.ix.Rp) + lane * 128);
-            }
-        }
         if (lane == 0) {
             ctl->root_valid[p] = rv ? 1u : 0u;
             ctl->root_key[p] = H::key(root);
@@ -877,10 +547,7 @@ struct PairSearch {
             const uint32_t p = k & 1;
             E head = 0, pub = 0;
             int pv = 0;
-            /* HV == 1: every lane reads the (at most four) slots itself - uniform addresses, one broadcast transaction
-             * each - so the three shuffles that spread lane 0's answer disappear from the path to the hand-off */
-            const bool all_lanes = HV == 1 && (a.hv_flags & DANN_HV_UNIFORM) != 0;
-            if ((lane == 0 || all_lanes) && heap_len > 0) {
+            if (lane == 0 && heap_len > 0) {
                 head = heap.get(1);
                 if (k < nstart_pages) { /* a start page is pushed without a pop: the root is the root */
                     pub = head;
@@ -900,11 +567,9 @@ struct PairSearch {
                     pv = 1;
                 }
             }
-            if (!all_lanes) {
-                head = __shfl_sync(DANN_FULL, head, 0);
-                pub = __shfl_sync(DANN_FULL, pub, 0);
-                pv = __shfl_sync(DANN_FULL, pv, 0);
-            }
+            head = __shfl_sync(DANN_FULL, head, 0);
+            pub = __shfl_sync(DANN_FULL, pub, 0);
+            pv = __shfl_sync(DANN_FULL, pv, 0);
             handoff(pv != 0, pub);
             const uint32_t cmd = ctl->cmd[p];
             if (cmd == 0) break;
@@ -914,14 +579,12 @@ struct PairSearch {
                     if (lane == 0) ctl->status_b = DANN_ST_INTERNAL;
                     continue;
                 }
-                node_chk = T::PAYLOAD_IS_NODE ? T::seq(head) : __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
+                node_chk = __ldcg(cnode + T::seq(head)); /* cross-check, read under the pop */
                 if (heap_len < heap.hs) {
                     ArrayStore<E> sm{heap.sm};
-                    if (HV == 1 && (a.hv_flags & DANN_HV_POP)) H::pop_warp1_la(sm, heap_len, lane);
-                    else H::pop_warp1(sm, heap_len, lane);
+                    H::pop_warp1(sm, heap_len, lane);
                 } else {
-                    if (HV == 1 && (a.hv_flags & DANN_HV_POP)) H::pop_warp1_la(heap, heap_len, lane);
-                    else H::pop_warp1(heap, heap_len, lane);
+                    H::pop_warp1(heap, heap_len, lane);
                 }
             }
             push_page(p);
@@ -930,7 +593,7 @@ struct PairSearch {
     }
 };
 
-template <typename T, int NCH, int HV = 0>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a) {
     using E = typename T::E;
     DANN_DYN_SMEM(dann_smem);
@@ -938,7 +601,7 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
     const int P = blockDim.x >> 6;
     const uint32_t slot = blockIdx.x * P + pair;
     unsigned char *base = dann_smem + (size_t)pair * a.per_warp_smem;
-    PairSearch<T, NCH, HV> w(a, lane, 1u + (uint32_t)pair);
+    PairSearch<T, NCH> w(a, lane, 1u + (uint32_t)pair);
     w.vis = reinterpret_cast<uint64_t *>(base);
     E *hsm = reinterpret_cast<E *>(base + (size_t)a.vcap * 8);
     w.listp = reinterpret_cast<uint32_t *>(base + (size_t)a.vcap * 8 + (size_t)a.hs * sizeof(E));
@@ -946,8 +609,6 @@ __global__ void __launch_bounds__(448, 1) dann_search2_kernel(const SearchArgs a
     w.ctl = reinterpret_cast<PairCtl *>(w.dlp + 2 * DANN_LIST_CAP);
     w.cqp = reinterpret_cast<uint32_t *>(w.ctl + 1);
     w.cqe = reinterpret_cast<E *>(w.cqp + 32);
-    w.xroot = reinterpret_cast<uint32_t *>(w.cqe + 32); /* the plan reserves these 16 + 256 bytes only for HV == 1 */
-    w.fscratch = w.xroot + 4;
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.ins = a.ins_list + (size_t)slot * a.ins_cap;

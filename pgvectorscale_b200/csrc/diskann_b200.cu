@@ -377,8 +377,6 @@ extern "C" int dann_index_load(const dann_snapshot_desc *s, int device, dann_ind
 extern "C" int dann_index_load_plain(const dann_snapshot_desc *s, const float *index_vectors, int device, dann_index **out) try {
     if (!index_vectors && s && s->n) return fail(DANN_ERR_INVALID_ARG, "dann_index_load_plain: NULL index_vectors");
     /* Bit-exact against the oracle under the CPU SIMT emulator, not yet run on hardware: opt-in until it has been. */
-    if (env_u32("DANN_EXPERIMENTAL_PLAIN", 0) != 1)
-        return fail(DANN_ERR_INVALID_ARG, "storage_layout=plain scans are experimental: set DANN_EXPERIMENTAL_PLAIN=1");
     static const float dummy = 0.0f;
     return index_load_impl(s, index_vectors ? index_vectors : &dummy, device, out);
 } DANN_CATCH
@@ -518,28 +516,21 @@ static search_fn pick_search(uint32_t nch) {
         default: return dann_search_kernel<T, 8>;
     }
 }
-template <typename T, int HV>
+template <typename T>
 static search_fn pick_search2(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search2_kernel<T, 1, HV>;
-        case 2: return dann_search2_kernel<T, 2, HV>;
-        case 3: return dann_search2_kernel<T, 3, HV>;
-        /* codes wider than 96 16-byte chunks (> 12 288 bits): only the measured flavour is instantiated */
-        case 4: return dann_search2_kernel<T, 4, 0>;
-        default: return dann_search2_kernel<T, 8, 0>;
+        case 1: return dann_search2_kernel<T, 1>;
+        case 2: return dann_search2_kernel<T, 2>;
+        case 3: return dann_search2_kernel<T, 3>;
+        case 4: return dann_search2_kernel<T, 4>;
+        default: return dann_search2_kernel<T, 8>;
     }
 }
-static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, int hv = 0, bool plain = false) {
+static search_fn pick_kernel(bool pairs, int entry, uint32_t nch, bool plain = false) {
     if (plain) return dann_search_kernel<Ent64, 1, 1>;
-    if (pairs && hv == 1 && entry == 3 && nch <= 3)
-        return nch == 1 ? dann_search2_kernel<Ent32n21, 1, 1> : nch == 2 ? dann_search2_kernel<Ent32n21, 2, 1> : dann_search2_kernel<Ent32n21, 3, 1>;
-    if (entry == 3) entry = 0; /* same 4-byte layout with sequence numbers */
-    if (pairs && hv == 1) return entry == 0 ? pick_search2<Ent32x21, 1>(nch) : entry == 1 ? pick_search2<Ent32x16, 1>(nch) : pick_search2<Ent64, 1>(nch);
-    if (pairs) return entry == 0 ? pick_search2<Ent32x21, 0>(nch) : entry == 1 ? pick_search2<Ent32x16, 0>(nch) : pick_search2<Ent64, 0>(nch);
+    if (pairs) return entry == 0 ? pick_search2<Ent32x21>(nch) : entry == 1 ? pick_search2<Ent32x16>(nch) : pick_search2<Ent64>(nch);
     return entry == 0 ? pick_search<Ent32x21>(nch) : entry == 1 ? pick_search<Ent32x16>(nch) : pick_search<Ent64>(nch);
 }
-
-
 
 template <typename T, int MAXW>
 static search_fn pick_lean_t(uint32_t nch) {
@@ -666,7 +657,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         } else {
             ix->last_plan.retries = (uint32_t)attempt;
         }
-        search_fn fn = p.lean ? pick_lean(p.entry, ix->NCH, p.maxw) : pick_kernel(p.pairs, p.entry, ix->NCH, p.hv, ix->plain);
+        search_fn fn = p.lean ? pick_lean(p.entry, ix->NCH, p.maxw) : pick_kernel(p.pairs, p.entry, ix->NCH, ix->plain);
         size_t smem = (size_t)p.per_warp * p.W;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);
@@ -1285,7 +1276,7 @@ static int scan_launch_search(dann_scan *sc, uint32_t want) {
         a.plain_vectors = ix->index_vectors;
         a.q_index = sc->d_qindex.as<float>();
         a.plain_dim = ix->plain ? v.dim_index : 0;
-        search_fn fn = pick_kernel(false, p.entry, ix->NCH, 0, ix->plain);
+        search_fn fn = pick_kernel(false, p.entry, ix->NCH, ix->plain);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
         fn<<<1, 32, p.per_warp, st>>>(a);
         ix->launches++;

@@ -205,11 +205,6 @@ class DiskAnnIndex:
         snapshot.validate()
         s = snapshot
         plain = int(getattr(s, "storage_type", 0) or 0) != 0
-        if plain and os.environ.get("DANN_EXPERIMENTAL_PLAIN") != "1":
-            # storage_layout = plain (storage.rs:144-169): the kernel flavour exists (dann_index_load_plain) but has only
-            # been checked under CPU emulation so far; it is refused unless explicitly enabled.  No CPU fallback either way.
-            raise DiskAnnError(-1, "storage_layout=plain snapshots are not supported by the CUDA scan path "
-                                   "(experimental: set DANN_EXPERIMENTAL_PLAIN=1)")
         d, keep = _make_desc(s)
         h = C.c_void_p()
         if plain:

@@ -150,7 +150,7 @@ def heap_script(ops, entry=0, hv=0, hs=64, cap=1 << 16):
                                C.c_void_p(out.ctypes.data), C.c_void_p(olen.ctypes.data), C.c_void_p(pops.ctypes.data))
     if rc != 0:
         raise RuntimeError(f"emu_heap_script failed ({rc}): {lib().emu_last_error().decode()}")
-    sh = KSHIFT[entry]
+    sh = KSHIFT[entry] if (hv == 0 or entry != 1) else 32     # the lean kernel has no 16-bit-key layout: Ent64 there
     heap = [(int(e) >> sh, int(e) & ((1 << sh) - 1)) for e in out[:int(olen[0])]]
     return heap, pops
 

@@ -24,12 +24,12 @@ static emu_kernel pick1(uint32_t nch) {
         default: return nullptr;
     }
 }
-template <typename T, int HV>
+template <typename T>
 static emu_kernel pick2(uint32_t nch) {
     switch (nch) {
-        case 1: return dann_search2_kernel<T, 1, HV>;
-        case 2: return dann_search2_kernel<T, 2, HV>;
-        case 3: return dann_search2_kernel<T, 3, HV>;
+        case 1: return dann_search2_kernel<T, 1>;
+        case 2: return dann_search2_kernel<T, 2>;
+        case 3: return dann_search2_kernel<T, 3>;
         default: return nullptr;
     }
 }
@@ -46,12 +46,9 @@ static emu_kernel pick_lean(int entry, uint32_t nch, int maxw) {
     if (maxw <= 16) return entry == 0 ? pick3<Ent32x21, 16>(nch) : pick3<Ent64, 16>(nch);
     return entry == 0 ? pick3<Ent32x21, 32>(nch) : pick3<Ent64, 32>(nch);
 }
-static emu_kernel pick(bool pairs, int entry, uint32_t nch, int hv, bool plain = false) {
+static emu_kernel pick(bool pairs, int entry, uint32_t nch, bool plain = false) {
     if (plain) return dann_search_kernel<Ent64, 1, 1>;
-    if (pairs && hv == 1 && entry == 3) return pick2<Ent32n21, 1>(nch);
-    if (entry == 3) entry = 0;
-    if (pairs && hv == 1) return entry == 0 ? pick2<Ent32x21, 1>(nch) : entry == 1 ? pick2<Ent32x16, 1>(nch) : pick2<Ent64, 1>(nch);
-    if (pairs) return entry == 0 ? pick2<Ent32x21, 0>(nch) : entry == 1 ? pick2<Ent32x16, 0>(nch) : pick2<Ent64, 0>(nch);
+    if (pairs) return entry == 0 ? pick2<Ent32x21>(nch) : entry == 1 ? pick2<Ent32x16>(nch) : pick2<Ent64>(nch);
     return entry == 0 ? pick1<Ent32x21>(nch) : entry == 1 ? pick1<Ent32x16>(nch) : pick1<Ent64>(nch);
 }
 
@@ -221,7 +218,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         a.plain_vectors = ivp;
         a.q_index = qip;
         a.plain_dim = in.plain_dim;
-        emu_kernel fn = p.lean ? pick_lean(p.entry, NCH, p.maxw) : pick(p.pairs, p.entry, NCH, p.hv, plain);
+        emu_kernel fn = p.lean ? pick_lean(p.entry, NCH, p.maxw) : pick(p.pairs, p.entry, NCH, plain);
         if (!fn) {
             g_emu_err = "this code width is not instantiated in the emulator build";
             return DANN_ERR_INVALID_ARG;
@@ -264,7 +261,7 @@ extern "C" int emu_search(const dann_snapshot_desc *s, const uint64_t *q_codes, 
         info->bitmap_words = p.bitmap_words;
         info->nch = NCH;
         info->G = G;
-        info->hv = (uint32_t)p.hv;
+        info->hv = 0;
         info->lean = p.lean ? 1u : 0u;
         info->maxw = (uint32_t)p.maxw;
         info->hash_cap = p.hash_cap;
@@ -307,7 +304,7 @@ extern "C" int emu_plan(uint32_t n, uint32_t R, uint32_t words, uint32_t nq, uin
  * run_heap, one warp, dumped after the last operation.  kinds[i]: 0 = push page of n[i] keys (taken from keys[] in
  * order), 1 = pop.  out_heap[len] receives the packed entries of slots 1..len, pops_seq[] the sequence number of
  * every popped root.  hs = entries kept in "shared memory", the rest in the tail. */
-template <typename T, int HV>
+template <typename T>
 static void heap_script_warp(const uint32_t *kinds, const uint32_t *n, uint32_t nops, const uint32_t *keys, uint32_t hs,
                              uint32_t cap, uint64_t *out_heap, uint32_t *out_len, uint32_t *pops_seq, SearchArgs &a,
                              typename T::E *tail) {
@@ -315,7 +312,7 @@ static void heap_script_warp(const uint32_t *kinds, const uint32_t *n, uint32_t 
     using H = RustHeap<E, T::KSHIFT>;
     const int lane = threadIdx.x & 31;
     unsigned char *base = dann_smem;
-    PairSearch<T, 1, HV> w(a, lane, 1u);
+    PairSearch<T, 1> w(a, lane, 1u);
     E *hsm = reinterpret_cast<E *>(base);
     w.listp = reinterpret_cast<uint32_t *>(base + (size_t)hs * sizeof(E));
     w.dlp = w.listp + 2 * DANN_LIST_CAP;
@@ -345,11 +342,9 @@ static void heap_script_warp(const uint32_t *kinds, const uint32_t *n, uint32_t 
             __syncwarp();
             if (w.heap_len < w.heap.hs) {
                 ArrayStore<E> sm{w.heap.sm};
-                if constexpr (HV == 1) H::pop_warp1_la(sm, w.heap_len, lane);
-                else H::pop_warp1(sm, w.heap_len, lane);
+                H::pop_warp1(sm, w.heap_len, lane);
             } else {
-                if constexpr (HV == 1) H::pop_warp1_la(w.heap, w.heap_len, lane);
-                else H::pop_warp1(w.heap, w.heap_len, lane);
+                H::pop_warp1(w.heap, w.heap_len, lane);
             }
             __syncwarp();
         }
@@ -357,6 +352,43 @@ static void heap_script_warp(const uint32_t *kinds, const uint32_t *n, uint32_t 
     for (uint32_t s = 1 + lane; s <= w.heap_len; s += 32) out_heap[s - 1] = (uint64_t)w.heap.get(s);
     if (lane == 0) *out_len = w.heap_len;
     (void)cap;
+}
+
+/* the same script through the lean kernel's heap code (LeanWarp::push_page - staged, cooperative - and ::pop) */
+template <typename T>
+static void heap_script_lean(const uint32_t *kinds, const uint32_t *n, uint32_t nops, const uint32_t *keys, uint32_t hs,
+                             uint64_t *out_heap, uint32_t *out_len, uint32_t *pops_seq, SearchArgs &a, typename T::E *tail) {
+    using E = typename T::E;
+    const int lane = threadIdx.x & 31;
+    unsigned char *base = dann_smem;
+    LeanWarp<T, 1> w(a, lane);
+    w.heap.sm = reinterpret_cast<E *>(base);
+    w.ent = w.heap.sm + hs;
+    w.stg = w.ent + DANN_LIST_CAP;
+    w.list = reinterpret_cast<uint32_t *>(w.stg + DANN_STG_CAP);
+    w.heap.gl = tail;
+    w.heap.hs = hs;
+    w.heap_len = 0;
+    w.stg_async = false;
+    uint32_t seq = 0, kpos = 0, npop = 0;
+    for (uint32_t i = 0; i < nops; i++) {
+        if (kinds[i] == 0) {
+            for (uint32_t r = lane; r < n[i]; r += 32) w.ent[r] = T::make(keys[kpos + r], seq + r);
+            __syncwarp();
+            if (n[i] && (i & 1)) w.stage_ancestors_async(n[i]); /* every other page through the early-staging path */
+            if (n[i]) w.push_page(n[i]);
+            __syncwarp();
+            seq += n[i];
+            kpos += n[i];
+        } else if (w.heap_len > 0) {
+            if (lane == 0) pops_seq[npop] = T::seq(w.heap.get(1));
+            npop++;
+            w.pop();
+            __syncwarp();
+        }
+    }
+    for (uint32_t s = 1 + lane; s <= w.heap_len; s += 32) out_heap[s - 1] = (uint64_t)w.heap.get(s);
+    if (lane == 0) *out_len = w.heap_len;
 }
 
 extern "C" int emu_heap_script(int entry, int hv, const uint32_t *kinds, const uint32_t *n, uint32_t nops, const uint32_t *keys,
@@ -368,20 +400,22 @@ extern "C" int emu_heap_script(int entry, int hv, const uint32_t *kinds, const u
     SearchArgs a{};
     a.hv_flags = env_u32("DANN_HV_FLAGS", 4095);
     std::vector<ulonglong2> tail((size_t)cap / 2 + 2);
-    auto run = [&](auto tag, auto hvtag) {
+    /* hv: 0 = the two-warp kernel's heap warp; 1 = the lean kernel's heap code with four-level pop rounds; 2 = the same
+     * with lane 0 walking the pop's hole down */
+    if (hv == 2) a.hv_flags &= ~DANN_HV_POP;
+    auto run = [&](auto tag) {
         using T = decltype(tag);
-        constexpr int HV = decltype(hvtag)::value;
         simt::launch(1, 32, [&] {
-            heap_script_warp<T, HV>(kinds, n, nops, keys, hs, cap, out_heap, out_len, pops_seq, a,
+            if (hv == 0)
+                heap_script_warp<T>(kinds, n, nops, keys, hs, cap, out_heap, out_len, pops_seq, a,
+                                    reinterpret_cast<typename T::E *>(tail.data()));
+            else
+                heap_script_lean<T>(kinds, n, nops, keys, hs, out_heap, out_len, pops_seq, a,
                                     reinterpret_cast<typename T::E *>(tail.data()));
         });
     };
-    auto by_hv = [&](auto tag) {
-        if (hv == 1) run(tag, std::integral_constant<int, 1>{});
-        else run(tag, std::integral_constant<int, 0>{});
-    };
-    if (entry == 0) by_hv(Ent32x21{});
-    else if (entry == 1) by_hv(Ent32x16{});
-    else by_hv(Ent64{});
+    if (entry == 0) run(Ent32x21{});
+    else if (entry == 1 && hv == 0) run(Ent32x16{});
+    else run(Ent64{});
     return 0;
 }

@@ -50,14 +50,15 @@ def test_two_replica_group_under_emulation():
     assert passed == 3 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
-def test_not_yet_on_hardware_paths_pass_under_emulation():
-    """Heap engine v2 / controller alternatives (DANN_HEAP_V2=1) and the plain storage layout, through the real host code."""
-    passed, out = _run(["tests/test_zz_experimental_gpu.py"], {"DANN_RUN_EXPERIMENTAL": "1"})
-    assert passed >= 43 and "skipped" not in out.splitlines()[-1], out[-500:]
+def test_plain_storage_and_one_sync_gettuple_pass_under_emulation():
+    """The plain storage layout and the one-synchronisation amgettuple, through the real host code."""
+    passed, out = _run(["tests/test_zz_plain_gpu.py"])
+    assert passed >= 38 and "skipped" not in out.splitlines()[-1], out[-500:]
 
 
-def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
-    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16",
+def test_edge_case_fuzz_with_the_lean_kernel_tiny_heaps_and_retries():
+    """DANN_SEARCH_KERNEL=3 forces the lean warp-per-query kernel (small batches default to the two-warp one)."""
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_SEARCH_KERNEL": "3", "DANN_SEARCH_HS": "16",
                                                        "DANN_DEBUG_SHRINK": "8", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"})
     assert passed == 120 + 12     # the seeds + the four reference-KAT cases and the eight medium cases in the same file
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "120", "DANN_SEARCH_KERNEL": "1",
@@ -68,14 +69,14 @@ def test_edge_case_fuzz_with_the_alternative_engine_tiny_heaps_and_retries():
 def test_address_sanitizer_finds_nothing_in_host_code_or_kernels():
     """The emulated ABI built with -fsanitize=address: every "device" buffer is a red-zoned host allocation, so an
     out-of-bounds access by a kernel (or by the host code around it) aborts the run.  Edge-case fuzz with the measured
-    kernels and with the alternative flavour on tiny heap tops, forced growth and the one-synchronisation gettuple."""
+    kernels and with the lean kernel forced on tiny heap tops, forced growth and the one-synchronisation gettuple."""
     if not os.path.exists(__import__("subprocess").run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
                                                        text=True).stdout.strip()):
         pytest.skip("libasan not installed")
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_FUZZ_SEEDS": "80"}, asan=True)
     assert passed == 80 + 12
     passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"],
-                     {"DANN_FUZZ_SEEDS": "80", "DANN_HEAP_V2": "1", "DANN_SEARCH_HS": "16", "DANN_DEBUG_SHRINK": "8",
+                     {"DANN_FUZZ_SEEDS": "80", "DANN_SEARCH_KERNEL": "3", "DANN_SEARCH_HS": "16", "DANN_DEBUG_SHRINK": "8",
                       "DANN_SCAN_FUSED": "1", "SIMT_SCHED": "2", "SIMT_SM_COUNT": "2"}, asan=True)
     assert passed == 80 + 12
 

@@ -52,16 +52,19 @@ def test_shard_bounds_and_recall_helper_shapes():
     assert shard_bounds(10, 4, 1) == (3, 6)
 
 
-def test_plain_storage_snapshot_is_refused_not_emulated():
-    """The plain layout exists in the oracle only: the product path must refuse it rather
-    than route anywhere else."""
+def test_plain_storage_snapshot_has_no_cpu_route_either():
+    """The plain layout is served by the CUDA path only: without a device the load fails with
+    DANN_ERR_NO_DEVICE like any other snapshot - it is never routed to the oracle."""
     import pytest
     from conftest import build_case
     from oracle import fixtures
-    from pgvectorscale_b200.diskann import DiskAnnError, DiskAnnIndex
+    from pgvectorscale_b200 import diskann
+    if diskann.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
     s = fixtures.to_plain(build_case(64, 16, 1, seed=2, R=8, L_build=16))
-    with pytest.raises(DiskAnnError, match="plain"):
-        DiskAnnIndex(s)
+    with pytest.raises(diskann.DiskAnnError) as e:
+        diskann.DiskAnnIndex(s)
+    assert e.value.code == -3
 
 
 def test_raw_snapshot_file_round_trips_through_the_c_reader(tmp_path):

@@ -121,94 +121,6 @@ def test_emulated_lists_with_repeated_ids(emu):
     check(emu, s, q, 20, 30, single_warp=True)
 
 
-# ---- heap-warp engine v2 (DANN_HEAP_V2=1: register-resident push path + look-ahead pop) ----------------------
-@pytest.mark.parametrize("entry", [0, 1, 2])
-@pytest.mark.parametrize("hs", [None, 16, 128, 1024])
-def test_emulated_heap_engine_v2_equals_oracle(emu, entry, hs):
-    """Long scans so that the heap crosses several leaf levels (power-of-two slots) and, with a small shared-memory
-    top, runs its leaves / parents / pop descent out of the global tail."""
-    s = build_case(2500, 64, COSINE, seed=71, kind="normal", R=32, L_build=64, deleted_every=17)
-    q = fixtures.gen_vectors(3, 64, 13, "normal")
-    env = {"DANN_HEAP_V2": 1, "DANN_SEARCH_ENTRY": entry}
-    if hs is not None:
-        env["DANN_SEARCH_HS"] = hs
-    info = check(emu, s, q, 80, 150, env=env)
-    assert info["hv"] == 1 and info["entry"] == entry and info["cand_cap"] >= 4096
-
-
-def test_emulated_heap_engine_v2_labels_retries_and_packed_block(emu):
-    s = build_case(800, 48, L2, seed=81, kind="normal", R=24, L_build=48, labels=True, deleted_every=13)
-    q = fixtures.gen_vectors(8, 48, 3, "normal")
-    labs = [[3], [7, 1, 7], [], [16, 2, 9, 4], [5], [1, 2], [11], [8, 3]]
-    info = check(emu, s, q, 40, 60, labels=labs, sm_count=1, env={"DANN_HEAP_V2": 1, "DANN_DEBUG_SHRINK": 8})
-    assert info["hv"] == 1 and info["W"] == 7 and info["retries"] >= 1
-    info = check(emu, s, q, 40, 60, labels=labs, sm_count=1, env={"DANN_HEAP_V2": 1, "DANN_SEARCH_BITMAP": 0})
-    assert info["hv"] == 1 and info["bitmap_words"] == 0
-
-
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 1028, 1536, 3, 892, 2179, 511, 4095])
-def test_emulated_hv1_kernel_each_alternative_alone(emu, flags):
-    """DANN_HV_FLAGS switches the HV=1 kernel's alternatives one by one (for A/B timing); every subset is exact."""
-    s = build_case(1200, 96, COSINE, seed=91, kind="normal", R=32, L_build=64, deleted_every=19)
-    q = fixtures.gen_vectors(3, 96, 17, "normal")
-    info = check(emu, s, q, 60, 90, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags, "DANN_SEARCH_HS": 512})
-    assert info["hv"] == 1
-
-
-@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 64, 200, 1100])
-def test_emulated_hv1_visited_search_list_sizes(emu, L):
-    """The 32-ary visited-list search at list lengths around its stride boundaries (and > 1024 entries)."""
-    s = build_case(1500, 32, L2, seed=23, kind="normal", R=16, L_build=32)
-    q = fixtures.gen_vectors(2, 32, 29, "normal")
-    info = check(emu, s, q, L, 40, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": 32})
-    assert info["hv"] == 1
-
-
-@pytest.mark.parametrize("hs", [None, 16, 256])
-@pytest.mark.parametrize("flags", [0, 3, 4095])
-def test_emulated_hv1_node_carrying_entries(emu, hs, flags):
-    """Ent32n21: 4-byte heap entries whose payload is the node id (no seq -> node table), chosen for HV = 1 when the
-    index has at most 2M nodes and the entry layout is not forced."""
-    s = build_case(2500, 64, COSINE, seed=71, kind="normal", R=32, L_build=64, deleted_every=17)
-    q = fixtures.gen_vectors(3, 64, 13, "normal")
-    env = {"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags}
-    if hs is not None:
-        env["DANN_SEARCH_HS"] = hs
-    info = check(emu, s, q, 80, 150, env=env)
-    assert info["hv"] == 1 and info["entry"] == 3
-    info = check(emu, s, q[:1], 80, 150, env=dict(env, DANN_HV_NODE_ENTRIES=0))
-    assert info["entry"] == 0
-
-
-def test_emulated_hv1_at_the_benchmark_operating_point(emu, monkeypatch):
-    """768-d x 2-bit codes, R = 50, L = 150 / 259 rows: ~400 visits and ~10 K candidates per query, several query
-    slots per block, the heap spilling into the global tail - every HV = 1 alternative on, shuffled lane schedule."""
-    s = build_case(6000, 768, COSINE, seed=5, kind="normal", R=50, L_build=100)
-    q = fixtures.gen_vectors(6, 768, 9, "normal")
-    monkeypatch.setenv("SIMT_SCHED", "2")
-    for env in ({"DANN_HEAP_V2": 1}, {"DANN_HEAP_V2": 1, "DANN_HV_NODE_ENTRIES": 0, "DANN_SEARCH_HS": 1024}):
-        info = check(emu, s, q, 150, 259, env=env, sm_count=1)
-        assert info["hv"] == 1 and info["W"] == 6 and info["cand_cap"] >= 20000
-
-
-@pytest.mark.parametrize("dim,R", [(768, 64), (1536, 40), (384, 64)])
-def test_emulated_hv1_fused_expansion_long_lists(emu, dim, R):
-    """Lists longer than the rows one fused round holds (48 slots at 768-d x 2 bits, 24 at 1536-d): the tail of the
-    page goes through the ordinary distance round."""
-    s = build_case(260, dim, COSINE, seed=3, kind="normal", R=R, L_build=R + 16)
-    q = fixtures.gen_vectors(2, dim, 8, "normal")
-    for flags in (512, 1536, 4095):
-        info = check(emu, s, q, 25, 34, env={"DANN_HEAP_V2": 1, "DANN_HV_FLAGS": flags})
-        assert info["hv"] == 1
-
-
-def test_emulated_heap_engine_v2_reference_shape(emu):
-    s = build_case(400, 768, COSINE, seed=2, kind="normal", R=48, L_build=64)
-    q = fixtures.gen_vectors(2, 768, 8, "normal")
-    info = check(emu, s, q, 50, 59, env={"DANN_HEAP_V2": 1})
-    assert (info["nch"], info["G"], info["hv"]) == (3, 4, 1)
-
-
 # ---- the heap warp's engine alone, differential against the Python clone of Rust's BinaryHeap -----------------
 def _model(ops):
     import pyref
@@ -234,7 +146,7 @@ def _random_script(rng, nops, key_range, pop_share, first=None):
     return ops
 
 
-@pytest.mark.parametrize("hv", [0, 1])
+@pytest.mark.parametrize("hv", [0, 1, 2])
 @pytest.mark.parametrize("entry,key_range", [(0, 4), (0, 1500), (1, 40), (2, 3)])
 @pytest.mark.parametrize("hs", [8, 256, 16384])
 def test_emulated_heap_engine_equals_rust_heap_model(emu, monkeypatch, hv, entry, key_range, hs):

@@ -1,10 +1,7 @@
-"""GPU parity of code paths that exist but have NOT been run on hardware yet (this round's GPU minutes were spent
-before they were written).  They are bit-exact under the CPU SIMT emulator (tests/test_simt_emulation.py); these
-tests are the hardware check and only run when DANN_RUN_EXPERIMENTAL=1 is set, so that an unverified path can never
-turn the regular `-m gpu` run red.  First thing to run next round:
-
-    DANN_RUN_EXPERIMENTAL=1 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q
-"""
+"""GPU parity of the plain (uncompressed) storage layout - SURVEY.md §8f row 3: plain/storage.rs:223-307,
+scan.rs:392-403 - and of the one-synchronisation amgettuple (DANN_SCAN_FUSED=1), through the C ABI: batch calls, the
+streaming scan operator with counters after every row, golden vectors, edge-case fuzz.  First run on B200 in round 2
+(44 passed); part of the regular `-m gpu` run since."""
 import os
 
 import numpy as np
@@ -13,9 +10,7 @@ import pytest
 from conftest import build_case
 from test_gpu_parity import _compare_batch, _queries
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DANN_RUN_EXPERIMENTAL") != "1",
-                                 reason="opt-in: set DANN_RUN_EXPERIMENTAL=1 (paths not yet verified on hardware)")]
+pytestmark = pytest.mark.gpu
 
 COSINE, L2, IP = 0, 1, 2
 
@@ -28,40 +23,7 @@ def lib(lib_built):
     return diskann
 
 
-@pytest.fixture()
-def heap_v2(monkeypatch):
-    monkeypatch.setenv("DANN_HEAP_V2", "1")
-
-
-@pytest.mark.parametrize("dist,bits", [(COSINE, 2), (L2, 1)])
-def test_heap_engine_v2_batch_matches_oracle(lib, heap_v2, dist, bits):
-    s = build_case(3000, 768, dist, bits=bits, seed=11 + dist + bits, kind="normal")
-    with lib.DiskAnnIndex(s) as idx:
-        q = _queries(s, 64, 77)
-        _compare_batch(s, idx, q, k=10, L=100, rescore=50)
-        _compare_batch(s, idx, q[:16], k=10, L=25, rescore=0)
-        _compare_batch(s, idx, q[:32], k=20, L=300, rescore=200)
-
-
-@pytest.mark.parametrize("entry", [1, 2])
-def test_heap_engine_v2_entry_layouts_and_tail(lib, heap_v2, monkeypatch, entry):
-    monkeypatch.setenv("DANN_SEARCH_ENTRY", str(entry))
-    monkeypatch.setenv("DANN_SEARCH_HS", "256")       # most of the heap in the HBM tail
-    s = build_case(3000, 256, COSINE, seed=5, kind="normal")
-    with lib.DiskAnnIndex(s) as idx:
-        _compare_batch(s, idx, _queries(s, 48, 3), k=10, L=150, rescore=100)
-
-
-def test_heap_engine_v2_labels(lib, heap_v2):
-    s = build_case(3000, 128, L2, seed=6, kind="uniform", labels=True)
-    rng = np.random.default_rng(4)
-    with lib.DiskAnnIndex(s) as idx:
-        q = _queries(s, 64, 9, "uniform")
-        labels = [[int(x) for x in rng.integers(1, 17, size=int(rng.integers(1, 4)))] for _ in range(64)]
-        _compare_batch(s, idx, q, k=10, L=100, rescore=50, labels=labels)
-
-
-# ---- plain storage layout (dann_index_load_plain, DANN_EXPERIMENTAL_PLAIN=1) ------------------------------------
+# ---- plain storage layout (dann_index_load_plain) ---------------------------------------------------------------
 def _compare_plain(s, idx, q, k, L, rescore):
     from oracle import oracle
     g = idx.search_batch(q, k=k, search_list_size=L, rescore=rescore)
@@ -79,7 +41,6 @@ def _compare_plain(s, idx, q, k, L, rescore):
 @pytest.mark.parametrize("dist,dim,dim_index", [(COSINE, 768, None), (L2, 256, None), (COSINE, 256, 100), (L2, 70, 38)])
 def test_plain_storage_batch_and_scan_match_oracle(lib, monkeypatch, dist, dim, dim_index):
     from oracle import fixtures, oracle
-    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
     s = fixtures.to_plain(build_case(2000, dim, dist, seed=8, kind="normal", R=32, L_build=64, deleted_every=13,
                                      dim_index=dim_index))
     q = _queries(s, 24, 5)
@@ -104,19 +65,10 @@ def test_plain_storage_batch_and_scan_match_oracle(lib, monkeypatch, dist, dim, 
             idx.search_batch(q[:2], labels=[[1], [2]], k=5)
 
 
-def test_plain_storage_is_refused_without_the_opt_in(lib, monkeypatch):
-    from oracle import fixtures
-    monkeypatch.delenv("DANN_EXPERIMENTAL_PLAIN", raising=False)
-    s = fixtures.to_plain(build_case(64, 16, L2, seed=2, R=8, L_build=16))
-    with pytest.raises(lib.DiskAnnError, match="plain"):
-        lib.DiskAnnIndex(s)
-
-
 @pytest.mark.parametrize("name", ["plain_cos128", "plain_l2_96x40", "plain_cos70x38"])
 def test_plain_storage_golden_vectors(lib, monkeypatch, name):
     import os as _os
     from golden.make_plain_golden import make_case
-    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
     z = np.load(_os.path.join(_os.path.dirname(__file__), "golden", "plain_golden.npz"))
     s, q, L, rescore, k = make_case(name)
     with lib.DiskAnnIndex(s) as idx:
@@ -135,7 +87,6 @@ def test_plain_storage_golden_vectors(lib, monkeypatch, name):
 def test_plain_storage_random_small_indexes(lib, monkeypatch, seed):
     """Edge-case fuzz of the plain layout: tiny graphs, 1..100 dimensions, truncated slices, deleted tuples."""
     from oracle import fixtures, oracle
-    monkeypatch.setenv("DANN_EXPERIMENTAL_PLAIN", "1")
     rng = np.random.default_rng(7000 + seed)
     n = int(rng.choice([1, 2, 5, 33, 200]))
     dim = int(rng.choice([1, 2, 3, 8, 31, 33, 64, 100]))
