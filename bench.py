@@ -348,9 +348,14 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
     fx.fill_rows(X, n, dim, args.data, device, topk)
     truth = topk.result()
     del topk
-    chk0 = int(X.view(torch.int32).sum(dtype=torch.int64).item())
+    def checksum():        # bit patterns, 256K rows at a time (the int64 upcast of the whole table would be 286 GiB)
+        acc = 0
+        for _, s_, e_ in fx.chunks(n):
+            acc = (acc + int(X[s_:e_].view(torch.int32).sum(dtype=torch.int64).item())) & 0xFFFFFFFFFFFFFFFF
+        return acc
+    chk0 = checksum()
     idx.set_vectors_device(X.data_ptr())
-    rows_unchanged = chk0 == int(X.view(torch.int32).sum(dtype=torch.int64).item())
+    rows_unchanged = chk0 == checksum()
     torch.cuda.empty_cache()
     t_fixture = time.time() - t0
     log(f"[bench] rank {rank}: n={n} fixture {t_fixture:.1f}s (build {bst['total_ms'] / 1e3:.1f}s), index in HBM "
@@ -433,6 +438,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
             shard.gather_packed(d_tid, d_dist, B)
         launches0 = idx.kernel_launches
         search_ms = rerank_ms = prepare_ms = 0.0
+        step_search_ms, step_retries = [], 0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         clocks = ClockSampler(local_rank)
@@ -444,6 +450,8 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
                 gathered = shard.gather_packed(d_tid, d_dist, B)
                 t = idx.last_batch_timing()
                 search_ms += t["search_ms"]
+                step_search_ms.append(round(t["search_ms"], 3))
+                step_retries += int(t["retries"])
                 rerank_ms += t["rerank_ms"]
                 prepare_ms += t["prepare_ms"]
             ev1.record(stream)
@@ -518,6 +526,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg_bytes_launch), "avg_launch_ms": round(search_avg_ms, 4),
                 "timing": "CUDA events around the kernel on its launch stream (dann_last_batch_timing.search_ms), averaged over the timed steps",
+                "launch_ms_per_step": step_search_ms, "growth_retries_in_timed_steps": step_retries,
                 "per_query": {"visits": round(visits_q, 1), "d_quantized": round(dq_q, 1), "code_bytes": code_bytes,
                               "nbr_bytes_per_visit": nbr_bytes}}
     others = {"dann_rerank_kernel": {"alg_bytes_per_launch": int(rerank_bytes_launch),

@@ -557,20 +557,32 @@ static int make_plan(dann_index *ix, uint32_t nq, uint32_t L, uint32_t c_target,
     in.plain_dim = ix->plain ? ix->v.dim_index : 0;
     in.allow_lean = allow_lean;
     in.ws_budget = 0;
-    if (allow_lean) {
-        /* what the per-slot workspaces may take: free HBM now plus what they already hold, less a reserve for the
-         * batch scratch that is sized after the plan */
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-            const uint64_t held = (uint64_t)ix->ws_hash.cap + ix->ws_heap.cap + ix->ws_bitmap.cap + ix->ws_cand.cap + ix->ws_ins.cap;
-            const uint64_t reserve = 768ull << 20;
-            const uint64_t avail = (uint64_t)fr + held;
-            in.ws_budget = avail > reserve ? avail - reserve : 1;
-        }
-    }
     char err[256];
     int rc = dann_make_plan(in, nq, L, c_target, grow, keyed, p, force_single, err, sizeof err);
     if (rc) return fail(rc, "%s", err);
+    if (p->lean) {
+        /* the lean plan takes as many query slots as the batch fills; only when that needs more HBM than the
+         * workspaces already hold is free memory looked at (cudaMemGetInfo costs about half a millisecond - more than
+         * a small batch's other host work) and the slot count cut to what fits: free HBM now plus what the
+         * workspaces hold, less a reserve for the batch scratch that is sized after the plan */
+        const uint64_t slots = (uint64_t)p->grid * p->W;
+        const uint64_t need_heap = slots * p->cand_cap * (uint64_t)p->esize;
+        const uint64_t need_set = slots * (p->bitmap_words ? (uint64_t)p->bitmap_words * 4u : (uint64_t)p->hash_cap * 4u);
+        const uint64_t held_set = p->bitmap_words ? ix->ws_bitmap.cap : ix->ws_hash.cap;
+        if (need_heap > ix->ws_heap.cap || need_set > held_set) {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+                const uint64_t held = (uint64_t)ix->ws_hash.cap + ix->ws_heap.cap + ix->ws_bitmap.cap + ix->ws_cand.cap + ix->ws_ins.cap;
+                const uint64_t reserve = 768ull << 20;
+                const uint64_t avail = (uint64_t)fr + held;
+                in.ws_budget = avail > reserve ? avail - reserve : 1;
+                /* DevBuf::reserve over-allocates by a quarter: plan against 4/5 of the budget */
+                in.ws_budget = in.ws_budget / 5 * 4;
+                rc = dann_make_plan(in, nq, L, c_target, grow, keyed, p, force_single, err, sizeof err);
+                if (rc) return fail(rc, "%s", err);
+            }
+        }
+    }
     return DANN_OK;
 }
 
