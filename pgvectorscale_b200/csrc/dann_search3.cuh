@@ -64,41 +64,6 @@ struct LeanWarp {
         return slotpay ? __ldcg(hash + p) : p;
     }
 
-    /* prepare_insert = HashSet::insert (graph/mod.rs:126-128) for this lane's two ids at once: the first probes of both
-     * are in flight together, later probes only for the lanes that collided (open addressing, linear probing, any
-     * table size: multiplicative hash scaled to [0, cap)).  new* = the id was not in the set; h* = the slot it lives in. */
-    __device__ __forceinline__ void hash_insert2(uint32_t n0, bool f0, uint32_t n1, bool f1, bool *new0, bool *new1,
-                                                 uint32_t *s0, uint32_t *s1) {
-        const uint32_t cap = a.hash_cap;
-        uint32_t h0 = __umulhi(n0 * 2654435761u, cap), h1 = __umulhi(n1 * 2654435761u, cap);
-        bool p0 = f0, p1 = f1, w0 = false, w1 = false;
-        for (uint32_t probe = 0; probe < cap && (p0 || p1); probe++) {
-            uint32_t o0 = 0, o1 = 0;
-            if (p0) o0 = atomicCAS(hash + h0, DANN_INVALID_NODE, n0);
-            if (p1) o1 = atomicCAS(hash + h1, DANN_INVALID_NODE, n1);
-            if (p0) {
-                if (o0 == DANN_INVALID_NODE || o0 == n0) {
-                    w0 = o0 == DANN_INVALID_NODE;
-                    p0 = false;
-                } else {
-                    h0 = h0 + 1 == cap ? 0u : h0 + 1;
-                }
-            }
-            if (p1) {
-                if (o1 == DANN_INVALID_NODE || o1 == n1) {
-                    w1 = o1 == DANN_INVALID_NODE;
-                    p1 = false;
-                } else {
-                    h1 = h1 + 1 == cap ? 0u : h1 + 1;
-                }
-            }
-        }
-        *new0 = w0;
-        *new1 = w1;
-        *s0 = h0;
-        *s1 = h1;
-    }
-
     __device__ __forceinline__ bool node_passes_filter(uint32_t n) {
         /* labels.overlaps(node_neighbor.get_labels()), sbq/storage.rs:165-172 */
         if (!a.ix.has_labels) return false;
@@ -106,12 +71,16 @@ struct LeanWarp {
         return labels_overlap(ql, nql, a.ix.labels + o0, o1 - o0);
     }
 
-    /* prepare_insert of up to 64 neighbour ids (list slots `lane` and `lane + 32`): dedupe within the list, then
-     * against `inserted` (sbq/storage.rs:149-163).  Bitmap flavour: the two atomics are only ISSUED here - o0/o1 are
-     * first read in stage_tail, so whatever the caller runs in between overlaps their L2/HBM round trip. */
+    /* prepare_insert = HashSet::insert (graph/mod.rs:126-128) of up to 64 neighbour ids (list slots `lane` and
+     * `lane + 32`): dedupe within the list, then against `inserted` (sbq/storage.rs:149-163).  The atomics are only
+     * ISSUED here - one atomicOr per id under the bitmap flavour, the first compare-and-swap probe of each id under
+     * the hash flavour (open addressing, linear probing, any table size: multiplicative hash scaled to [0, cap)) -
+     * and their answers are first read in stage_tail, so whatever the caller runs in between overlaps the L2/HBM
+     * round trip. */
     struct Probe {
-        uint32_t o0, o1, s0, s1; /* bitmap: old words; hash: 1 = new / 0 = known.  s = payload (node id or hash slot) */
-        bool f0, f1;
+        uint32_t o0, o1; /* what the atomics returned */
+        uint32_t h0, h1; /* hash flavour: the slots probed */
+        bool f0, f1;     /* this lane's id takes part (valid and first occurrence) */
     };
     __device__ __forceinline__ Probe stage_probe(uint32_t n0, bool v0, uint32_t n1, bool v1, bool unique) {
         Probe pr;
@@ -123,32 +92,59 @@ struct LeanWarp {
             pr.f0 = v0 && ((__ffs(m0) - 1) == lane);
             pr.f1 = v1 && ((__ffs(m1) - 1) == lane);
         }
-        pr.s0 = n0;
-        pr.s1 = n1;
         pr.o0 = pr.o1 = 0xFFFFFFFFu;
+        pr.h0 = pr.h1 = 0;
         if (a.bitmap_words) {
             if (pr.f0) pr.o0 = atomicOr(bitmap + (n0 >> 5), 1u << (n0 & 31));
             if (pr.f1) pr.o1 = atomicOr(bitmap + (n1 >> 5), 1u << (n1 & 31));
         } else {
-            uint32_t h0 = 0, h1 = 0;
-            bool new0 = false, new1 = false;
-            hash_insert2(n0, pr.f0, n1, pr.f1, &new0, &new1, &h0, &h1);
-            __syncwarp();
-            if (slotpay) {
-                pr.s0 = h0;
-                pr.s1 = h1;
-            }
-            pr.o0 = new0 ? 0u : 0xFFFFFFFFu;
-            pr.o1 = new1 ? 0u : 0xFFFFFFFFu;
+            pr.h0 = __umulhi(n0 * 2654435761u, a.hash_cap);
+            pr.h1 = __umulhi(n1 * 2654435761u, a.hash_cap);
+            if (pr.f0) pr.o0 = atomicCAS(hash + pr.h0, DANN_INVALID_NODE, n0);
+            if (pr.f1) pr.o1 = atomicCAS(hash + pr.h1, DANN_INVALID_NODE, n1);
         }
         return pr;
     }
 
-    /* label filter of the new ids (sbq/storage.rs:165-172) and their compaction into the page, in list order */
+    /* the atomics' answers (hash flavour: further probes for the ids that collided), then the label filter of the new
+     * ids (sbq/storage.rs:165-172) and their compaction into the page, in list order */
     __device__ __forceinline__ void stage_tail(const Probe &pr, uint32_t n0, uint32_t n1, bool apply_filter) {
-        const bool new0 = pr.f0 && !(pr.o0 & (a.bitmap_words ? 1u << (n0 & 31) : 1u));
-        const bool new1 = pr.f1 && !(pr.o1 & (a.bitmap_words ? 1u << (n1 & 31) : 1u));
-        if (!a.bitmap_words) {
+        bool new0, new1;
+        uint32_t s0 = n0, s1 = n1; /* payload: the node id, or its hash slot */
+        if (a.bitmap_words) {
+            new0 = pr.f0 && !(pr.o0 & (1u << (n0 & 31)));
+            new1 = pr.f1 && !(pr.o1 & (1u << (n1 & 31)));
+        } else {
+            const uint32_t cap = a.hash_cap;
+            uint32_t h0 = pr.h0, h1 = pr.h1, o0 = pr.o0, o1 = pr.o1;
+            bool p0 = pr.f0, p1 = pr.f1;
+            new0 = new1 = false;
+            for (uint32_t probe = 0; probe < cap; probe++) {
+                if (p0) {
+                    if (o0 == DANN_INVALID_NODE || o0 == n0) {
+                        new0 = o0 == DANN_INVALID_NODE;
+                        p0 = false;
+                    } else {
+                        h0 = h0 + 1 == cap ? 0u : h0 + 1;
+                    }
+                }
+                if (p1) {
+                    if (o1 == DANN_INVALID_NODE || o1 == n1) {
+                        new1 = o1 == DANN_INVALID_NODE;
+                        p1 = false;
+                    } else {
+                        h1 = h1 + 1 == cap ? 0u : h1 + 1;
+                    }
+                }
+                if (!(p0 || p1)) break;
+                if (p0) o0 = atomicCAS(hash + h0, DANN_INVALID_NODE, n0);
+                if (p1) o1 = atomicCAS(hash + h1, DANN_INVALID_NODE, n1);
+            }
+            __syncwarp();
+            if (slotpay) {
+                s0 = h0;
+                s1 = h1;
+            }
             nset += __popc(__ballot_sync(DANN_FULL, new0)) + __popc(__ballot_sync(DANN_FULL, new1));
             if ((uint64_t)nset * 3u > (uint64_t)a.hash_cap * 2u) { /* load factor bound 2/3 */
                 status |= DANN_ST_HASH;
@@ -171,12 +167,12 @@ struct LeanWarp {
         if (p0) {
             const uint32_t pos = listn + __popc(pm0 & lt);
             list[pos] = n0;
-            ent[pos] = (E)pr.s0;
+            ent[pos] = (E)s0;
         }
         if (p1) {
             const uint32_t pos = listn + t0 + __popc(pm1 & lt);
             list[pos] = n1;
-            ent[pos] = (E)pr.s1;
+            ent[pos] = (E)s1;
         }
         listn += t0 + t1;
         __syncwarp();
@@ -491,7 +487,7 @@ struct LeanWarp {
         const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
         const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
         const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-        if (a.lists_unique && a.bitmap_words) {
+        if (a.lists_unique) {
             const Probe pr = stage_probe(n0, v0, n1, v1, true);
             pop();
             visited_insert(head);
@@ -501,12 +497,9 @@ struct LeanWarp {
             pop();
             visited_insert(head);
             if (status) return 0;
-            if (a.lists_unique) {
-                stage(n0, v0, n1, v1, filter, true);
-            } else { /* a list may repeat an id: keep strict list order across the two chunks */
-                stage(n0, v0, DANN_INVALID_NODE, false, filter, false);
-                if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter, false);
-            }
+            /* a list may repeat an id: keep strict list order across the two chunks */
+            stage(n0, v0, DANN_INVALID_NODE, false, filter, false);
+            if (!status) stage(n1, v1, DANN_INVALID_NODE, false, filter, false);
         }
         const uint32_t tn = listn;
         listn = 0;
