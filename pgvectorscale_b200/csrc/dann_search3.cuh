@@ -277,13 +277,14 @@ struct LeanWarp {
         if (s0 < (0x80000000u >> __clz(s1))) return;
         uint32_t hcut = 0;
         while ((s1 >> hcut) >= heap.hs) hcut++;
-        for (uint32_t h = 1; h < hcut; h++) {
-            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+        for (uint32_t h = 1, off = tn; h < hcut; h++) { /* off(h) = sum of the counts of the heights below */
+            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u;
             for (uint32_t i = lane; i < cnt; i += 32) {
                 const uint32_t slot = lo + i;
                 if (slot < heap.hs) stg[off + i] = heap.sm[slot];
                 else dann_cp_async(stg + off + i, heap.gl + slot);
             }
+            off += cnt;
         }
         dann_cp_async_commit();
         stg_async = true;
@@ -306,9 +307,10 @@ struct LeanWarp {
             dann_cp_async_wait_all();
             stg_async = false;
         } else {
-            for (uint32_t h = 1; h < hcut; h++) { /* stage the ancestors: independent loads, one round trip */
-                const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+            for (uint32_t h = 1, off = tn; h < hcut; h++) { /* stage the ancestors: independent loads, one round trip */
+                const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u;
                 for (uint32_t i = lane; i < cnt; i += 32) stg[off + i] = heap.get(lo + i);
+                off += cnt;
             }
         }
         __syncwarp();
@@ -339,9 +341,10 @@ struct LeanWarp {
                 __syncwarp();
             }
         }
-        for (uint32_t h = 0; h < hcut; h++) { /* staged slots back to the heap */
-            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u, off = shift_sum(s1, h) - shift_sum(s0, h) + h;
+        for (uint32_t h = 0, off = 0; h < hcut; h++) { /* staged slots back to the heap */
+            const uint32_t lo = s0 >> h, cnt = (s1 >> h) - lo + 1u;
             for (uint32_t i = lane; i < cnt; i += 32) heap.set(lo + i, stg[off + i]);
+            off += cnt;
         }
         __syncwarp();
         heap_len += tn;

@@ -28,6 +28,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 /* ------------------------------------------------------------------------------------ */
+#define DANN_SMEM_SLACK 128u /* bytes behind every dynamic shared-memory window (see launch_prepare) */
+
 static thread_local std::string g_err;
 
 static int fail(int code, const char *fmt, ...) {
@@ -412,7 +414,10 @@ static int check_live(dann_index *ix) {
 
 static int launch_prepare(dann_index *ix, const float *d_queries, int B, float *d_q_full, uint64_t *d_q_codes,
                           cudaStream_t st) {
-    size_t smem = (size_t)ix->v.dim_index * sizeof(float);
+    /* DANN_SMEM_SLACK: ptxas may turn neighbouring shared-memory loads of a loop into one 16-byte load issued BEFORE the
+     * loop's bounds test (compute-sanitizer caught dann_prepare_kernel reading 16 bytes past a 28-byte window; on
+     * hardware that is a fault whenever it crosses the CTA's allocation), so no dynamic window ends where its data ends */
+    size_t smem = (size_t)((ix->v.dim_index + 3u) & ~3u) * sizeof(float) + DANN_SMEM_SLACK;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(dann_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dann_prepare_kernel<<<B, 128, smem, st>>>(ix->v, d_queries, B, d_q_full, d_q_codes);
@@ -493,7 +498,7 @@ extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const u
     if (rc) return rc;
     if (!d_q_full || !d_nodes || !d_out || B <= 0 || m <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_full_distance: bad argument");
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
-    size_t smem = (size_t)((ix->v.dim + 3u) & ~3u) * sizeof(float);
+    size_t smem = (size_t)((ix->v.dim + 3u) & ~3u) * sizeof(float) + DANN_SMEM_SLACK;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(dann_full_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dann_full_distance_kernel<<<B, 128, smem, st>>>(ix->v, d_q_full, d_nodes, m, d_out);
@@ -670,7 +675,7 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
             ix->last_plan.retries = (uint32_t)attempt;
         }
         search_fn fn = p.lean ? pick_lean(p.entry, ix->NCH, p.maxw) : pick_kernel(p.pairs, p.entry, ix->NCH, ix->plain);
-        size_t smem = (size_t)p.per_warp * p.W;
+        size_t smem = (size_t)p.per_warp * p.W + DANN_SMEM_SLACK;
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<p.grid, p.W * (p.pairs ? 64 : 32), smem, st>>>(a);
         ix->launches++;
@@ -763,7 +768,7 @@ static int search_batch_device_locked(dann_index *ix, const float *d_queries, co
     r.out_node = d_out_node;
     r.out_count = d_out_count;
     r.stats = d_stats;
-    size_t smem = (size_t)((v.dim + 3u) & ~3u) * 4 + (size_t)((c_target + 1u) & ~1u) * 4 + (size_t)rescore * 8 + 16;
+    size_t smem = (size_t)((v.dim + 3u) & ~3u) * 4 + (size_t)((c_target + 1u) & ~1u) * 4 + (size_t)rescore * 8 + 16 + DANN_SMEM_SLACK;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(dann_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dann_rerank_kernel<<<B, 128, smem, st>>>(r);
@@ -1004,7 +1009,7 @@ extern "C" int dann_build_graph(dann_index *ix, int num_neighbors, int search_li
     const size_t budget = ix->smem_optin > 1024 ? ix->smem_optin - 1024 : ix->smem_optin;
     int bw = (int)std::min<size_t>(8, budget / pw);
     if (bw < 1) return fail(DANN_ERR_CAPACITY, "SBQ code of %u words is too wide for the prune kernel's shared memory", v.words);
-    const size_t bsmem = pw * bw;
+    const size_t bsmem = pw * bw + DANN_SMEM_SLACK;
     CK(cudaFuncSetAttribute(dann_build_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
     CK(cudaFuncSetAttribute(dann_build_backlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
     CK(cudaFuncSetAttribute(dann_build_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
@@ -1289,8 +1294,8 @@ static int scan_launch_search(dann_scan *sc, uint32_t want) {
         a.q_index = sc->d_qindex.as<float>();
         a.plain_dim = ix->plain ? v.dim_index : 0;
         search_fn fn = pick_kernel(false, p.entry, ix->NCH, ix->plain);
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.per_warp));
-        fn<<<1, 32, p.per_warp, st>>>(a);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.per_warp + DANN_SMEM_SLACK)));
+        fn<<<1, 32, p.per_warp + DANN_SMEM_SLACK, st>>>(a);
         ix->launches++;
         CK(cudaGetLastError());
     }
@@ -1350,7 +1355,7 @@ static int gettuple_fused(dann_scan *sc, uint32_t *block, uint16_t *offset, uint
             if (lrc) return lrc;
             if (rescore > 0) {
                 CK(sc->d_dist.reserve((size_t)want * 4));
-                size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float);
+                size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float) + DANN_SMEM_SLACK;
                 if (smem > 48 * 1024)
                     CK(cudaFuncSetAttribute(dann_scan_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 dann_scan_distance_kernel<<<1, 128, smem, st>>>(v, sc->d_qfull.as<float>(), sc->d_stream.as<uint32_t>(),
@@ -1421,7 +1426,7 @@ extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offs
     }
     if (rescore > 0 && got > 0) { /* get_full_distance_for_resort for the rows that just arrived */
         CK(sc->d_dist.reserve((size_t)(skip + got) * 4));
-        size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float);
+        size_t smem = (size_t)((v.dim + 3u) & ~3u) * sizeof(float) + DANN_SMEM_SLACK;
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(dann_full_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dann_full_distance_kernel<<<1, 128, smem, st>>>(v, sc->d_qfull.as<float>(), sc->d_stream.as<uint32_t>(),
