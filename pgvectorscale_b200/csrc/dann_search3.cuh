@@ -52,6 +52,7 @@ struct LeanWarp {
     uint32_t *hash, *bitmap;
     SplitStore<E> heap; /* 1-based: Rust's data[i] is slot i + 1 */
     ulonglong2 *qcode; /* [NCH * G] 16-byte chunks of the query's SBQ code, zero past the code's end */
+    uint32_t *rootnode; /* hash flavour: node id of the heap's root as the last pop left it (filled by cp.async) */
     const int16_t *ql;
     uint32_t nql;
     bool filter, slotpay;
@@ -493,11 +494,13 @@ struct LeanWarp {
         if (a.lists_unique) {
             const Probe pr = stage_probe(n0, v0, n1, v1, true);
             pop();
+            root_node_async();
             visited_insert(head);
             if (status) return 0;
             stage_tail(pr, n0, n1, filter);
         } else {
             pop();
+            root_node_async();
             visited_insert(head);
             if (status) return 0;
             /* a list may repeat an id: keep strict list order across the two chunks */
@@ -532,12 +535,22 @@ struct LeanWarp {
         return true;
     }
 
-    /* The entry the heap's root will hold once the staged page (tn entries in ent[]) has been pushed.  A pushed
-     * element reaches the root iff its key is STRICTLY below the root's at that moment (sift_up moves only while
+    /* Hash flavour: a 4-byte entry names its node through its hash slot.  The root the pop leaves behind is the likeliest
+     * next visit (about two visits in three), so its node id is fetched right after the pop, asynchronously into shared
+     * memory, and root_after_page finds it there instead of paying a dependent HBM load in front of the neighbour row. */
+    __device__ __forceinline__ void root_node_async() {
+        if (slotpay && heap_len > 0) {
+            if (lane == 0) dann_cp_async(rootnode, hash + T::seq(heap.get_sm(1)));
+            dann_cp_async_commit();
+        }
+    }
+
+    /* The entry the heap's root will hold once the staged page (tn entries in ent[]) has been pushed, and its node.  A
+     * pushed element reaches the root iff its key is STRICTLY below the root's at that moment (sift_up moves only while
      * elem < parent), so the root after the page is the FIRST entry attaining the page minimum if that minimum is
      * strictly below the current root's key (or the heap is empty), else the current root.  Exact, not speculative:
      * it lets the next visit's neighbour row be fetched while the pushes run.  false = the heap stays empty. */
-    __device__ __forceinline__ bool root_after_page(uint32_t tn, E *out) const {
+    __device__ __forceinline__ bool root_after_page(uint32_t tn, E *out, uint32_t *node) {
         E best = ~E(0);
         for (uint32_t r = lane; r < tn; r += 32) {
             const E c = (ent[r] & ~KM) | (E)r; /* key, then page position: the minimum is the first of the ties */
@@ -551,13 +564,27 @@ struct LeanWarp {
                 best = t < best ? t : best;
             }
         }
+        const uint32_t idx = (uint32_t)(best & E(63));
         if (heap_len == 0) {
             if (tn == 0) return false;
-            *out = ent[(uint32_t)(best & E(63))];
+            *out = ent[idx];
+            *node = list[idx];
             return true;
         }
         const E root = heap.get_sm(1);
-        *out = (tn != 0 && (best | KM) < (root & ~KM)) ? ent[(uint32_t)(best & E(63))] : root;
+        if (tn != 0 && (best | KM) < (root & ~KM)) {
+            *out = ent[idx];
+            *node = list[idx];
+        } else {
+            *out = root;
+            if (slotpay) {
+                dann_cp_async_wait_all(); /* lane 0's copy of the root's node id (root_node_async) */
+                __syncwarp();
+                *node = *rootnode;
+            } else {
+                *node = T::seq(root);
+            }
+        }
         return true;
     }
 
@@ -622,34 +649,33 @@ struct LeanWarp {
         }
 
         bool done = false;
+        bool pend = false; /* n0 / n1 = the neighbour row of the current root `head`, requested ahead of its visit */
+        uint32_t n0 = DANN_INVALID_NODE, n1 = DANN_INVALID_NODE;
+        E head = 0;
         while (!done && !status) { /* TSVResponseIterator::next, scan.rs:210-242 */
             /* greedy_search_iterate: while let Some(idx) = visit_closest(L) */
-            if (heap_len > 0) {
-                E head = heap.get_sm(1);
-                bool go = may_visit(head);
-                uint32_t n0 = DANN_INVALID_NODE, n1 = DANN_INVALID_NODE;
-                if (go) { /* the popped element IS the current root: fetch its neighbour list */
+            while (heap_len > 0) {
+                if (!pend) head = heap.get_sm(1);
+                if (!may_visit(head)) break; /* a requested row stays valid: nothing touches the heap until the visit */
+                if (!pend) { /* the popped element IS the current root: fetch its neighbour list */
                     const uint32_t *row = ix.nbrs + (size_t)node_of(head) * ix.Rp;
-                    if ((uint32_t)lane < ix.R) n0 = ldg_stream_u32(row + lane);
-                    if ((uint32_t)lane + 32 < ix.R) n1 = ldg_stream_u32(row + 32 + lane);
+                    n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+                    n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
                 }
-                while (go) {
-                    visits++;
-                    const uint32_t tn = visit(head, n0, n1);
-                    if (status) break;
-                    /* the next visit is decided before this page is pushed, and its neighbour row is in flight
-                     * while the pushes run */
-                    E next;
-                    go = root_after_page(tn, &next) && may_visit(next);
-                    n0 = n1 = DANN_INVALID_NODE;
-                    if (go) {
-                        const uint32_t *row = ix.nbrs + (size_t)node_of(next) * ix.Rp;
-                        if ((uint32_t)lane < ix.R) n0 = ldg_stream_u32(row + lane);
-                        if ((uint32_t)lane + 32 < ix.R) n1 = ldg_stream_u32(row + 32 + lane);
-                    }
-                    if (tn) push_page(tn);
-                    head = next;
+                pend = false;
+                visits++;
+                const uint32_t tn = visit(head, n0, n1);
+                if (status) break;
+                /* the next visit is decided before this page is pushed - now, or after the consume()s that make
+                 * room in the visited list - and its neighbour row is in flight while the pushes run */
+                uint32_t nnode = 0;
+                pend = root_after_page(tn, &head, &nnode);
+                if (pend) {
+                    const uint32_t *row = ix.nbrs + (size_t)nnode * ix.Rp;
+                    n0 = (uint32_t)lane < ix.R ? ldg_stream_u32(row + lane) : DANN_INVALID_NODE;
+                    n1 = (uint32_t)lane + 32 < ix.R ? ldg_stream_u32(row + 32 + lane) : DANN_INVALID_NODE;
                 }
+                if (tn) push_page(tn);
             }
             if (status) break;
             if (vis_len == 0) break; /* consume() -> None */
@@ -702,6 +728,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) dann_search3_kernel(const Search
     w.stg = w.ent + DANN_LIST_CAP;
     w.list = reinterpret_cast<uint32_t *>(w.stg + DANN_STG_CAP);
     w.qcode = reinterpret_cast<ulonglong2 *>(base + a.per_warp_smem - (size_t)NCH * a.G * 16u); /* 16-byte aligned tail */
+    w.rootnode = reinterpret_cast<uint32_t *>(w.qcode) - 4; /* the plan leaves 16 bytes in front of the query code */
     w.hash = a.hash + (size_t)slot * a.hash_cap;
     w.bitmap = a.bitmap + (size_t)slot * a.bitmap_words;
     w.heap.gl = reinterpret_cast<E *>(a.heap_tail) + (size_t)slot * a.cand_cap;
