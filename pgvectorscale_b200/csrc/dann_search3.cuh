@@ -389,6 +389,8 @@ struct LeanWarp {
         const int lvl = lane < 2 ? 1 : lane < 6 ? 2 : lane < 14 ? 3 : lane < 30 ? 4 : 0;
         const uint32_t off = (uint32_t)lane - ((1u << lvl) - 2u);
         uint32_t p = 1;
+        E lastv = 0;      /* what the walk moved into the final hole's parent */
+        bool moved = false;
         while (2u * p + 1u <= end) {
             const uint32_t s = (p << lvl) + off;
             const bool ok = lvl != 0 && s <= end;
@@ -397,18 +399,20 @@ struct LeanWarp {
             const E vr = __shfl_down_sync(DANN_FULL, v, 1);
             const unsigned m = __ballot_sync(DANN_FULL, vr <= (v | KM)); /* data[child] <= data[child+1] */
             unsigned win = 0;
-            uint32_t cur = p, idx = 0;
+            uint32_t cur = p, idx = 0, lastlane = 0;
 #pragma unroll
             for (int l = 1; l <= 4; l++) {
                 const uint32_t c = 2u * cur;
                 const uint32_t left = (1u << l) - 2u + 2u * idx;
                 if (c + 1u <= end) {
                     const uint32_t r = (m >> left) & 1u;
-                    win |= 1u << (left + r);
+                    lastlane = left + r;
+                    win |= 1u << lastlane;
                     cur = c + r;
                     idx = 2u * idx + r;
                 } else {
                     if (c == end) { /* a single child at the bottom is moved up without a comparison */
+                        lastlane = left;
                         win |= 1u << left;
                         cur = c;
                     }
@@ -416,12 +420,24 @@ struct LeanWarp {
                 }
             }
             if ((win >> lane) & 1u) heap.set(s >> 1, v);
+            lastv = __shfl_sync(DANN_FULL, v, (int)lastlane); /* the deepest winner of this round */
+            moved = true;
             p = cur;
         }
         if (2u * p == end) { /* round boundary fell on the single-child step */
             const E c = heap.get(end);
             if (lane == 0) heap.set(p, c);
+            lastv = c;
+            moved = true;
             p = end;
+        }
+        /* sift_up(0, p) of the displaced element: it moves only while it is STRICTLY below its parent, and the parent of
+         * the hole is the entry the walk just moved up - known without a load.  A former leaf is rarely smaller than
+         * that, so the ancestor fetch of the generic sift-up (an L2/HBM round trip for a deep heap) is usually saved. */
+        if (moved && !((item | KM) < (lastv & ~KM))) {
+            if (lane == 0) heap.set(p, item);
+            __syncwarp();
+            return;
         }
         __syncwarp();
         H::template sift_up_warp1<false>(heap, p, item, lane);
