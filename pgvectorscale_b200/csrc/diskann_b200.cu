@@ -156,8 +156,14 @@ static cudaError_t upload(dann_index *ix, const Tp *host, size_t count, Tp **out
     if (e != cudaSuccess) return e;
     ix->owned.push_back(p);
     ix->hbm_bytes += bytes;
-    if (host && count) e = cudaMemcpy(p, host, count * sizeof(Tp), cudaMemcpyHostToDevice);
-    else e = cudaMemset(p, 0, bytes);
+    /* Every copy of the index goes through ix->stream, the cudaStreamNonBlocking stream its kernels run on.  A plain
+     * cudaMemcpy from pageable memory runs on the legacy stream and may return once the data is STAGED, before the DMA
+     * has landed; a kernel on a non-blocking stream is not ordered behind it and can read the stale destination
+     * (found in round 2: dann_pad_rows_kernel padded rows of whatever the buffer held before - garbage neighbour ids,
+     * wrong rows or an illegal access, depending on the process's allocation history). */
+    if (host && count) e = cudaMemcpyAsync(p, host, count * sizeof(Tp), cudaMemcpyHostToDevice, ix->stream);
+    else e = cudaMemsetAsync(p, 0, bytes, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream); /* the caller's buffer is borrowed for the call only */
     *out = reinterpret_cast<Tp *>(p);
     return e;
 }
@@ -175,15 +181,18 @@ static cudaError_t upload_padded(dann_index *ix, const Tp *host, size_t n, uint3
     ix->hbm_bytes += bytes;
     *out = reinterpret_cast<Tp *>(p);
     if (n == 0) return cudaSuccess;
-    if (src_w == dst_w) return cudaMemcpy(p, host, n * src_w * sizeof(Tp), cudaMemcpyHostToDevice);
+    if (src_w == dst_w) {
+        e = cudaMemcpyAsync(p, host, n * src_w * sizeof(Tp), cudaMemcpyHostToDevice, ix->stream);
+        return e == cudaSuccess ? cudaStreamSynchronize(ix->stream) : e;
+    }
     size_t chunk = std::max<size_t>(1, (256ull << 20) / (src_w * sizeof(Tp)));
     void *tmp = nullptr;
     e = cudaMalloc(&tmp, std::min(chunk, n) * src_w * sizeof(Tp));
     if (e != cudaSuccess) return e;
     for (size_t r0 = 0; r0 < n && e == cudaSuccess; r0 += chunk) {
         size_t rows = std::min(chunk, n - r0);
-        e = cudaMemcpy(tmp, host + r0 * src_w, rows * src_w * sizeof(Tp), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) break;
+        e = cudaMemcpyAsync(tmp, host + r0 * src_w, rows * src_w * sizeof(Tp), cudaMemcpyHostToDevice, ix->stream);
+        if (e != cudaSuccess) break; /* same stream as the kernel below: ordered */
         dann_pad_rows_kernel<Tp><<<1024, 256, 0, ix->stream>>>(reinterpret_cast<Tp *>(p) + r0 * dst_w,
                                                              reinterpret_cast<Tp *>(tmp), rows, src_w,
                                                              dst_w, fill);
@@ -681,8 +690,18 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         ix->launches++;
         CK(cudaGetLastError());
         uint32_t ctl[2] = {0, 0};
-        CK(cudaMemcpyAsync(ctl, d_ctl, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        {
+            cudaError_t e_ = cudaMemcpyAsync(ctl, d_ctl, 8, cudaMemcpyDeviceToHost, st);
+            if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(st);
+            if (e_ != cudaSuccess) { /* a faulting search kernel: say which one and how it was planned */
+                ix->poisoned = true;
+                return fail(DANN_ERR_CUDA, "search kernel %s failed: %s [attempt %d nq %u L %u c_target %u | n %u R %u Rp %u cw %u "
+                            "keyed %d | grid %u W %u smem %zu per_warp %u hs %u vcap %u cand_cap %u hash_cap %u bitmap_words %u ins_cap %u entry %d]",
+                            p.lean ? "lean" : p.pairs ? "two-warp" : "single-warp", cudaGetErrorString(e_), attempt, nq, L, c_target,
+                            v.n, v.R, v.Rp, v.cw, d_label_off != nullptr, p.grid, p.W, smem, p.per_warp, p.hs, p.vcap, p.cand_cap,
+                            p.hash_cap, p.bitmap_words, p.ins_cap, p.entry);
+            }
+        }
         if (ctl[1] == 0) break;
         if (getenv("DANN_DEBUG_STATUS")) fprintf(stderr, "[diskann_b200] search overflow bits 0x%x (attempt %d, plan need=%u vcap=%u)\n", ctl[1], attempt, p.need, p.vcap);
         if (ctl[1] & DANN_ST_INTERNAL) return fail(DANN_ERR_STATE, "internal error: next-node prediction mismatch in the two-warp search kernel");
@@ -694,7 +713,8 @@ static int run_search(dann_index *ix, const uint64_t *d_q_codes, const int16_t *
         for (int b = 0; b < B; b++)
             if (hstats[b].status) qlist.push_back((uint32_t)b);
         nq = (uint32_t)qlist.size();
-        CK(cudaMemcpy(ix->sc_qlist.p, qlist.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(ix->sc_qlist.p, qlist.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st)); /* ordered before the rerun on st */
+        CK(cudaStreamSynchronize(st));
         grow *= 2;
         ix->timing.retries++;
     }
@@ -892,7 +912,8 @@ extern "C" int dann_index_set_vectors(dann_index *ix, const float *vectors) try 
         d = reinterpret_cast<float *>(p);
         v.vectors = d;
     }
-    CK(cudaMemcpy(d, vectors, (size_t)v.n * v.dim * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(d, vectors, (size_t)v.n * v.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream)); /* ordered before the normalisation */
+    CK(cudaStreamSynchronize(ix->stream));
     if (v.distance_type == DANN_COSINE) {
         int blocks = std::min<long long>((v.n + 255) / 256, (long long)ix->sm_count * 8);
         dann_normalize_rows_kernel<<<std::max(blocks, 1), 256, 0, ix->stream>>>(d, v.n, v.dim);
