@@ -1432,7 +1432,9 @@ extern "C" int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offs
     int rc = check_live(ix);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
-    if (env_u32("DANN_SCAN_FUSED", 0) == 1) return gettuple_fused(sc, block, offset, node_id, dist);
+    /* one host synchronisation per row is the default since it was timed on B200 (4.1 vs 4.6 ms per 10-row scan at
+     * 1M x 768, bench.py --mode scan); DANN_SCAN_FUSED=0 selects the step-by-step path below */
+    if (env_u32("DANN_SCAN_FUSED", 1) == 1) return gettuple_fused(sc, block, offset, node_id, dist);
     const IndexView &v = ix->v;
     cudaStream_t st = ix->stream;
     /* next_with_resort (scan.rs:244-305): `while resort_buffer.len() < resort_size { next() ... }` then pop;

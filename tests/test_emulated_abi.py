@@ -82,11 +82,12 @@ def test_address_sanitizer_finds_nothing_in_host_code_or_kernels():
 
 
 def test_one_synchronisation_gettuple_passes_under_emulation():
-    """DANN_SCAN_FUSED=1: amgettuple with a single host synchronisation per row (opt-in until timed on hardware)."""
+    """amgettuple with a single host synchronisation per row is the default (DANN_SCAN_FUSED=1); the step-by-step path
+    (DANN_SCAN_FUSED=0) stays covered here."""
     passed, _ = _run(["tests/test_gpu_parity.py", "-k", "scan or gettuple or counters or null or empty"],
-                     {"DANN_SCAN_FUSED": "1"})
+                     {"DANN_SCAN_FUSED": "0"})
     assert passed >= 2
-    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_SCAN_FUSED": "1", "DANN_DEBUG_SHRINK": "8", "DANN_FUZZ_SEEDS": "120"})
+    passed, _ = _run(["tests/test_zz_f_fuzz_gpu.py"], {"DANN_SCAN_FUSED": "0", "DANN_DEBUG_SHRINK": "8", "DANN_FUZZ_SEEDS": "120"})
     assert passed == 120 + 12     # the seeds + the four reference-KAT cases and the eight medium cases in the same file
 
 

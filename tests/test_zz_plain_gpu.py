@@ -121,12 +121,14 @@ def test_plain_storage_random_small_indexes(lib, monkeypatch, seed):
         sc.end()
 
 
-def test_one_synchronisation_gettuple_streams_like_the_default(lib, monkeypatch):
-    """DANN_SCAN_FUSED=1 (dann_scan_distance_kernel / dann_scan_finish_kernel): same rows and counters after every call."""
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_one_synchronisation_gettuple_and_the_step_by_step_path_stream_alike(lib, monkeypatch, fused):
+    """DANN_SCAN_FUSED=1 (default: dann_scan_distance_kernel / dann_scan_finish_kernel, one synchronisation per row) and
+    DANN_SCAN_FUSED=0 (step by step): same rows and counters after every call."""
     from oracle import oracle
     s = build_case(3000, 128, COSINE, seed=21, kind="normal", labels=True, deleted_every=9)
     q = _queries(s, 4, 3)
-    monkeypatch.setenv("DANN_SCAN_FUSED", "1")
+    monkeypatch.setenv("DANN_SCAN_FUSED", fused)
     with lib.DiskAnnIndex(s) as idx:
         sc = idx.begin_scan()
         for qi, (L, rescore, key) in enumerate(((40, 10, None), (25, 0, None), (60, 50, [3, 9]), (30, 5, None))):
