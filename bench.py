@@ -590,6 +590,20 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
                "sample": f"{reps} x {sample} queries of the same workload, {threads} host threads "
                          f"(oracle/oracle.cpp, -O2 -mavx2 -mfma -mpopcnt)"}
 
+    # ---- the operator surface north_star keeps (scan.rs:336-405): amrescan + k x amgettuple, one scan at a time -----
+    operator = None
+    if need_oracle and world == 1:
+        try:
+            from oracle import oracle
+            from tools import scan_latency
+            nsc = min(40 if full else 24, ns)       # the parity sample's queries: their rerank rows are resident
+            operator = scan_latency.measure(idx, snap, oracle, q_all[:nsc].cpu().numpy(), L, rescore, k, warm=8, both=False)
+            log(f"[bench] operator surface: scan of {k} rows p50 {operator['gettuple']['scan_of_k_rows_ms']['p50']} ms "
+                f"(CPU oracle, one thread: {operator['cpu_oracle_single_thread_ms']['p50']} ms), rows identical: "
+                f"{operator['parity']['rows_identical']}")
+        except Exception as e:  # the headline must not die on the side measurement
+            operator = {"error": repr(e)}
+
     plan = idx.last_search_plan() if hasattr(idx, "last_search_plan") else None
     line = {
         "metric": metric_name(n, dim),
@@ -616,6 +630,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
         "roofline": roofline,
         "kernels": others,
         "cpu_baseline": cpu,
+        "operator": operator,
         "clocks": clocks.summary(),
     }
     idx.close()
@@ -653,7 +668,7 @@ def main():
         # configs[1] (1M x 768-d, batch 1024) first, while HBM is empty; a shorter run, attached as a secondary key
         try:
             s = run_ours(args, 1_000_000, 1024, min(args.steps, 10), min(args.warmup, 3), device, rank, world, full=False)
-            secondary = {kk: s[kk] for kk in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "parity", "cpu_baseline")}
+            secondary = {kk: s[kk] for kk in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "parity", "cpu_baseline", "operator")}
             secondary["config"] = {kk: s["config"][kk] for kk in ("workload", "search_list_size", "rescore", "recall_at_10")}
         except SystemExit:
             raise
