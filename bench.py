@@ -192,10 +192,10 @@ SWEEP_LARGE = [(200, 300), (300, 400), (400, 600), (600, 600), (600, 800), (800,
 SEL = 512
 
 
-def sweep_points(args):
+def sweep_points(args, n=None):
     if args.L:
         return [(args.L, args.rescore or 50)]
-    return SWEEP_LARGE if args.n >= 10_000_000 else SWEEP_SMALL
+    return SWEEP_LARGE if (n or args.n) >= 10_000_000 else SWEEP_SMALL
 
 
 def recall_at_k(tid, truth_nodes, k):
@@ -374,7 +374,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
     sel = min(SEL, B)
     chosen = None
     sweep_log = []
-    for (L, rescore) in sweep_points(args):
+    for (L, rescore) in sweep_points(args, n):
         run_device(q_all[:B], L, rescore)          # first run of a plan pays for workspace (re)allocation
         run_device(q_all[:B], L, rescore)
         torch.cuda.synchronize(device)
@@ -391,7 +391,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
             if not args.sweep:
                 break
     if chosen is None:
-        L, rescore = sweep_points(args)[-1]
+        L, rescore = sweep_points(args, n)[-1]
         chosen = (L, rescore, sweep_log[-1]["recall"], sweep_log[-1]["recall_selection_sample"])
         log(f"[bench] WARNING: target recall {args.target_recall} not reached; reporting at L={L}")
     L, rescore, recall, recall_sel = chosen

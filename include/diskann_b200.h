@@ -52,7 +52,8 @@ typedef enum {
     DANN_ERR_NO_DEVICE = -3, /* no CUDA device / driver: there is NO CPU fallback */
     DANN_ERR_OOM = -4,
     DANN_ERR_CAPACITY = -5,  /* per-query state outgrew the largest workspace we may allocate */
-    DANN_ERR_STATE = -6
+    DANN_ERR_STATE = -6,
+    DANN_ERR_FORMAT = -7     /* dann_pg_*: the relation file is not what the reader can vouch for; nothing is guessed */
 } dann_status;
 
 typedef enum { DANN_COSINE = 0, DANN_L2 = 1, DANN_IP = 2 } dann_distance; /* distance/mod.rs:11-15 */
@@ -124,7 +125,12 @@ int dann_scan_begin(dann_index *ix, dann_scan **out);
  * GUCs diskann.query_search_list_size / diskann.query_rescore (guc.rs:3-4). */
 int dann_scan_rescan(dann_scan *sc, const float *query, const int16_t *labels, int nlabels,
                      int search_list_size, int rescore);
-/* One amgettuple: resumes the scan's suspended search (its state lives in HBM between calls), pulls
+/* How far a scan may stream: the suspended search's workspace is planned for rescore + 64 streamed rows; a scan that
+ * runs past it (a selective post-filter without LIMIT) has its workspace rebuilt twice as large and the stream
+ * replayed from row 0 - invisible to the caller except in time (the k-th doubling replays 2^k x the first plan) - up
+ * to eight doublings or 2^30 candidates per query, then DANN_ERR_CAPACITY.  The reference can stream the whole index
+ * through amgettuple; this operator is built for top-k scans (k ~ rescore) and says so.
+ * One amgettuple: resumes the scan's suspended search (its state lives in HBM between calls), pulls
  * exactly the rows TSVResponseIterator::next_with_resort would (scan.rs:244-305), pops one.
  * Returns 1 and fills the outputs for the next row, 0 at end of scan, <0 on error.
  * dist is the exact rerank distance (NaN when rescore == 0). Any output may be NULL. */
@@ -133,20 +139,27 @@ int dann_scan_gettuple(dann_scan *sc, uint32_t *block, uint16_t *offset, uint32_
 int dann_scan_stats(dann_scan *sc, dann_query_stats *out);
 void dann_scan_end(dann_scan *sc);
 
+/* ---- entry points that take DEVICE buffers (dann_search_batch_device, dann_prepare_queries, dann_sbq_distance,
+ * dann_full_distance, dann_index_set_vectors_device): `stream` is the CUDA stream the call runs on and the order in
+ * which the caller's buffers must be ready.  stream == NULL: the call runs on the index's own non-blocking stream,
+ * after everything the caller has already submitted to the legacy default stream (the order a default-stream kernel
+ * or a plain cudaMemcpy would have had); buffers produced on OTHER non-blocking streams need that stream passed here,
+ * or a synchronisation by the caller.  Outputs are complete when the call returns. */
+
 /* ---- batch: B independent scans, first k rows of each ---------------------------- */
 /* Host buffers; H2D/D2H copies are part of the call (this is the end-to-end path).
  * labels/label_off: CSR of each query's scan-key labels, label_off == NULL = no key.
  * out_tid [B*k] (block<<16|offset, DANN_INVALID_TID past out_count[b]), out_dist [B*k],
  * out_count [B] rows produced, out_stats [B] (each may be NULL except out_tid).
  * rescore + k is bounded by the rerank kernel's shared memory (about 45 000 rows at 768 dimensions):
- * larger requests return DANN_ERR_INVALID_ARG (the streaming scan operator has no such bound). */
+ * larger requests return DANN_ERR_INVALID_ARG (the streaming scan operator is not bound by the rerank window). */
 int dann_search_batch(dann_index *ix, const float *queries, const int16_t *labels,
                       const int32_t *label_off, int B, int k, int search_list_size,
                       int rescore, uint64_t *out_tid, float *out_dist, uint32_t *out_count,
                       dann_query_stats *out_stats);
 /* Same with every buffer already resident in HBM of the index's device; work is
- * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns
- * after the stream has drained (it must read back a 4-byte overflow flag). Query labels
+ * enqueued on `stream` (a cudaStream_t; NULL = the index's own stream, see the note on device buffers above) and
+ * the call returns after the stream has drained (it must read back a 4-byte overflow flag). Query labels
  * must already be sorted+dedup per query. */
 int dann_search_batch_device(dann_index *ix, const float *d_queries, const int16_t *d_labels,
                              const int32_t *d_label_off, int B, int k, int search_list_size,
@@ -209,6 +222,64 @@ int dann_group_search_batch(dann_group *g, const float *queries, const int16_t *
                             int B, int k, int search_list_size, int rescore, uint64_t *out_tid, float *out_dist,
                             uint32_t *out_count, dann_query_stats *out_stats);
 void dann_group_free(dann_group *g);
+
+/* ---- reading an index RELATION FILE (pgvectorscale_b200/csrc/dann_pgreader.h) -------------------
+ * Host-only, no GPU involved.  Replaces, for an external loader (the sidecar after a CHECKPOINT, an offline exporter):
+ *   ReadablePage::read / get_type / get_item_unchecked   util/page.rs:254-290   dann_pg_relation_open / _info
+ *   TsvPageOpaqueData::read_from_page / verify            util/page.rs:59-97     (every page is checked the same way)
+ *   ChainItemReader::read                                 util/chain.rs:125-183  dann_pg_read_chain
+ *   MetaPage::fetch: magic + version of MetaPageHeader    meta_page.rs:386-419   dann_pg_relation_info.meta_*
+ *   ArchivedSbqNode accessors + SbqMeans::load            sbq/node.rs:236-330, sbq/mod.rs:88-122   dann_pg_extract_sbq
+ * The MetaPage BODY is an rkyv archive of a repr(Rust) struct whose field order cannot be pinned offline: the caller
+ * supplies its scalars (dann_pg_meta; a Rust host fills them from MetaPage's getters) and the reader cross-checks them
+ * against the node items; the node items' own field order is inferred and verified, never assumed (see the header of
+ * dann_pgreader.h).  Anything unexpected is DANN_ERR_FORMAT with a message, not a best effort.
+ * Staleness: a snapshot is valid for exactly the `fingerprint` it was extracted under - a hash over every page's
+ * (block, pd_lsn, pd_checksum, pd_lower, pd_upper); every WAL-logged change of a page moves its pd_lsn. */
+typedef struct dann_pg_relation dann_pg_relation;
+typedef struct {
+    uint32_t nblocks;
+    uint32_t pages_by_type[9]; /* PageType histogram, util/page.rs:28-38 (5 = SbqNode, 7 = SbqMeans, 8 = Meta) */
+    uint32_t new_pages;        /* all-zero pages (PageIsNew) */
+    uint32_t foreign_pages;    /* pages that fail the extension's page checks */
+    uint32_t meta_magic;       /* 768756476 when block 0 is a Meta page whose header item parses, else 0 */
+    uint32_t meta_version;     /* TSV_VERSION (3 in the reference at hand) */
+    uint64_t node_items;       /* LP_NORMAL line pointers on SbqNode pages */
+    uint64_t max_lsn;
+    uint64_t fingerprint;
+} dann_pg_relation_info;
+/* path = the relation's first segment file (base/<db>/<relfilenode>); "<path>.1", ".2", ... are picked up */
+int dann_pg_relation_open(const char *path, dann_pg_relation **out);
+void dann_pg_relation_close(dann_pg_relation *rel);
+int dann_pg_relation_stat(const dann_pg_relation *rel, dann_pg_relation_info *out);
+/* Reassembles the chained item that starts at (block, offset): *len = its size; copies min(*len, cap) bytes into buf
+ * (buf may be NULL with cap == 0 to ask for the size).  page_type < 0 = do not check the pages' PageType. */
+int dann_pg_read_chain(const dann_pg_relation *rel, uint32_t block, uint16_t offset, int page_type, void *buf, size_t cap,
+                       size_t *len);
+typedef struct { /* MetaPage scalars (meta_page.rs:212-282) and the pointers it holds */
+    uint32_t num_dimensions, num_dimensions_to_index, bq_bits, num_neighbors;
+    int32_t distance_type; /* dann_distance */
+    int32_t has_labels;
+    uint32_t start_block;  /* start_nodes.default_node; DANN_INVALID_NODE (InvalidBlockNumber) = empty graph */
+    uint16_t start_offset;
+    uint32_t n_start_labels; /* start_nodes.labeled_nodes */
+    const int16_t *start_labels;
+    const uint32_t *start_label_block;
+    const uint16_t *start_label_offset;
+    uint32_t means_block;  /* quantizer_metadata; DANN_INVALID_NODE = the quantizer uses no means */
+    uint16_t means_offset;
+} dann_pg_meta;
+typedef struct { /* owned by the library until dann_pg_sbq_free */
+    dann_snapshot_desc snap;   /* ready for dann_index_load except vectors == NULL: heap rows live in the TABLE; fetch
+                                  heap_tid[i] in order and attach them with dann_index_set_vectors */
+    const uint64_t *index_tid; /* [n] (block<<16)|offset of node i inside the index relation, ascending: the
+                                  IndexPointer -> dense node id map */
+    uint64_t fingerprint;      /* of the relation as extracted */
+    uint32_t layout[4];        /* which 8-byte cell of the archived root held: heap pointer, code vector, neighbour
+                                  vector, fourth vector (declaration order = 0,1,2,3) */
+} dann_pg_sbq;
+int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_sbq **out);
+void dann_pg_sbq_free(dann_pg_sbq *s);
 
 /* How the last batch search of this index was planned (diagnostics for benchmarks and profiles). */
 typedef struct {

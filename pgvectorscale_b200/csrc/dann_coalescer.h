@@ -32,7 +32,8 @@ struct dann_coalescer {
     int max_batch = 256;
     int max_wait_us = 200;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work, cv_done, cv_idle;
+    int callers = 0; /* threads inside dann_coalescer_search (guarded by mu) */
     std::deque<CoalescedRequest *> queue;
     bool stop = false;
     std::thread worker;
@@ -169,6 +170,16 @@ extern "C" int dann_coalescer_search(dann_coalescer *c, const float *query, cons
     r.out_stats = out_stats;
     std::unique_lock<std::mutex> lk(c->mu);
     if (c->stop) return fail(DANN_ERR_STATE, "coalescer is shutting down");
+    /* `callers` keeps dann_coalescer_destroy from deleting the object while this thread still holds (or is about to
+     * re-acquire, inside cv_done.wait) its mutex */
+    struct Leave {
+        dann_coalescer *c;
+        ~Leave() {
+            if (--c->callers == 0) c->cv_idle.notify_all();
+        }
+    };
+    c->callers++;
+    Leave leave{c}; /* destroyed before lk: runs under the lock */
     c->queue.push_back(&r);
     c->cv_work.notify_one();
     c->cv_done.wait(lk, [&] { return r.done; });
@@ -192,6 +203,10 @@ extern "C" void dann_coalescer_destroy(dann_coalescer *c) {
         c->stop = true;
     }
     c->cv_work.notify_all();
-    if (c->worker.joinable()) c->worker.join();
+    if (c->worker.joinable()) c->worker.join(); /* drains the queue: every queued request is answered */
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        c->cv_idle.wait(lk, [&] { return c->callers == 0; }); /* the answered callers have let go of the mutex */
+    }
     delete c;
 }

@@ -106,8 +106,8 @@ static int dann_make_plan(const PlanInputs &in, uint32_t nq, uint32_t L, uint32_
         env_u32("DANN_SEARCH_KERNEL", 3) == 3 && !small_batch) {
         /* inserted-set: bitmap over node ids while a node id fits the 21-bit payload of a 4-byte entry and the
          * bitmap is not larger than the hash set; else an open-addressing set of 1.5 x the candidate bound
-         * (3 x under a label key: rejected ids are recorded too), any multiple of 8 slots (whole 32-byte buckets) */
-        const uint64_t hcap = ((uint64_t)p->cand_cap * (keyed ? 3u : 1u) * 3u / 2u + 7u) & ~7ull;
+         * (3 x under a label key: rejected ids are recorded too), any multiple of 4 slots */
+        const uint64_t hcap = ((uint64_t)p->cand_cap * (keyed ? 3u : 1u) * 3u / 2u + 3u) & ~3ull;
         const uint64_t bm_bytes = (uint64_t)((in.n + 127u) / 128u) * 16u;
         bool bm = in.n <= (1u << 21) && bm_bytes <= hcap * 4u;
         if (getenv("DANN_SEARCH_BITMAP")) bm = env_u32("DANN_SEARCH_BITMAP", 0) != 0 && in.n <= (16u << 20);

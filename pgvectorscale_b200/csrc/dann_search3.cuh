@@ -73,12 +73,14 @@ struct LeanWarp {
     }
 
     /* prepare_insert = HashSet::insert (graph/mod.rs:126-128) of up to 64 neighbour ids (list slots `lane` and
-     * `lane + 32`): dedupe within the list, then against `inserted` (sbq/storage.rs:149-163).  The memory traffic is only
-     * STARTED here - one atomicOr per id under the bitmap flavour, an L2 prefetch of each id's home bucket under the
-     * hash flavour (8-slot buckets, any table size: multiplicative hash scaled to [0, cap / 8)) - and the answers are
-     * first read in stage_tail, so whatever the caller runs in between overlaps the L2/HBM round trip. */
+     * `lane + 32`): dedupe within the list, then against `inserted` (sbq/storage.rs:149-163).  The atomics are only
+     * ISSUED here - one atomicOr per id under the bitmap flavour, the first compare-and-swap probe of each id under
+     * the hash flavour (open addressing, linear probing, any table size: multiplicative hash scaled to [0, cap)) -
+     * and their answers are first read in stage_tail, so whatever the caller runs in between overlaps the L2/HBM
+     * round trip. */
     struct Probe {
-        uint32_t o0, o1; /* bitmap flavour: what the atomics returned; hash flavour: the ids' home buckets */
+        uint32_t o0, o1; /* what the atomics returned */
+        uint32_t h0, h1; /* hash flavour: the slots probed */
         bool f0, f1;     /* this lane's id takes part (valid and first occurrence) */
     };
     __device__ __forceinline__ Probe stage_probe(uint32_t n0, bool v0, uint32_t n1, bool v1, bool unique) {
@@ -92,60 +94,20 @@ struct LeanWarp {
             pr.f1 = v1 && ((__ffs(m1) - 1) == lane);
         }
         pr.o0 = pr.o1 = 0xFFFFFFFFu;
+        pr.h0 = pr.h1 = 0;
         if (a.bitmap_words) {
             if (pr.f0) pr.o0 = atomicOr(bitmap + (n0 >> 5), 1u << (n0 & 31));
             if (pr.f1) pr.o1 = atomicOr(bitmap + (n1 >> 5), 1u << (n1 & 31));
         } else {
-            /* bucketed hash set: only the home buckets' sectors are requested here (into L2, no register);
-             * bucket_insert reads them after the pop */
-            const uint32_t nb = a.hash_cap >> 3;
-            pr.o0 = __umulhi(n0 * 2654435761u, nb);
-            pr.o1 = __umulhi(n1 * 2654435761u, nb);
-            if (pr.f0) prefetch_l2(hash + 8u * pr.o0);
-            if (pr.f1) prefetch_l2(hash + 8u * pr.o1);
+            pr.h0 = __umulhi(n0 * 2654435761u, a.hash_cap);
+            pr.h1 = __umulhi(n1 * 2654435761u, a.hash_cap);
+            if (pr.f0) pr.o0 = atomicCAS(hash + pr.h0, DANN_INVALID_NODE, n0);
+            if (pr.f1) pr.o1 = atomicCAS(hash + pr.h1, DANN_INVALID_NODE, n1);
         }
         return pr;
     }
 
-    /* One chunk (<= 32 ids, one per lane) of the bucketed inserted-set.  The table is hash_cap / 8 buckets of 8 slots
-     * (one 32-byte sector each), filled from slot 0 upwards and never emptied during a query, so a bucket's content is
-     * the prefix of its slots that is not DANN_INVALID_NODE; an id lives in the first bucket, counted from its home
-     * bucket, that had a free slot when it was inserted.  The table belongs to this warp alone, so nothing here is
-     * atomic: a lane reads its bucket (two 16-byte L2 loads - the sector was requested before the pop), the lanes that
-     * want to insert into the same bucket rank themselves with one match, and rank r takes slot fill + r with a plain
-     * store.  A lane whose bucket is - or has just become - full moves on to the next bucket and stays pending for the
-     * caller's next round.  The caller's __syncwarp() after every chunk orders these stores before the loads of the
-     * chunk behind it (ld.cg reads L2, past any stale L1 line).  With the CAS set every collision was a further
-     * dependent atomic round trip: 4.1 rounds per visit on average at the 50M operating point (load factor up to
-     * 0.38) against 1.06 here.
-     * pend: in = this lane still has an id to place, out = it must look at the next bucket.  Returns "inserted". */
-    __device__ __forceinline__ bool bucket_insert(uint32_t n, uint32_t &b, bool &pend, uint32_t nb, uint32_t *slot) {
-        uint4 x = make_uint4(0, 0, 0, 0), y = x;
-        if (pend) {
-            const uint4 *bp = reinterpret_cast<const uint4 *>(hash + 8u * b);
-            x = __ldcg(bp);
-            y = __ldcg(bp + 1);
-        }
-        const uint32_t I = DANN_INVALID_NODE;
-        const bool found = (x.x == n) | (x.y == n) | (x.z == n) | (x.w == n) | (y.x == n) | (y.y == n) | (y.z == n) | (y.w == n);
-        const uint32_t fill = (uint32_t)(x.x != I) + (x.y != I) + (x.z != I) + (x.w != I) + (y.x != I) + (y.y != I) + (y.z != I) + (y.w != I);
-        const bool want = pend && !found && fill < 8u;
-        /* lanes that do not insert match on a value no bucket index can take (nb <= 2^29) */
-        const unsigned peers = __match_any_sync(DANN_FULL, want ? b : (0x80000000u | (uint32_t)lane));
-        const uint32_t pos = fill + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        const bool st = want && pos < 8u;
-        if (st) {
-            hash[8u * b + pos] = n;
-            *slot = 8u * b + pos;
-        }
-        if (pend) {
-            if (found || st) pend = false;
-            else b = b + 1u == nb ? 0u : b + 1u;
-        }
-        return st;
-    }
-
-    /* the atomics' answers (hash flavour: the bucket reads and inserts), then the label filter of the new
+    /* the atomics' answers (hash flavour: further probes for the ids that collided), then the label filter of the new
      * ids (sbq/storage.rs:165-172) and their compaction into the page, in list order */
     __device__ __forceinline__ void stage_tail(const Probe &pr, uint32_t n0, uint32_t n1, bool apply_filter) {
         bool new0, new1;
@@ -154,24 +116,35 @@ struct LeanWarp {
             new0 = pr.f0 && !(pr.o0 & (1u << (n0 & 31)));
             new1 = pr.f1 && !(pr.o1 & (1u << (n1 & 31)));
         } else {
-            const uint32_t nb = a.hash_cap >> 3;
-            uint32_t b0 = pr.o0, b1 = pr.o1;
+            const uint32_t cap = a.hash_cap;
+            uint32_t h0 = pr.h0, h1 = pr.h1, o0 = pr.o0, o1 = pr.o1;
             bool p0 = pr.f0, p1 = pr.f1;
             new0 = new1 = false;
-            for (uint32_t round = 0; round < nb; round++) { /* one round unless a bucket was (or became) full */
-                if (__ballot_sync(DANN_FULL, p0)) {
-                    if (bucket_insert(n0, b0, p0, nb, &s0)) new0 = true;
-                    __syncwarp();
+            for (uint32_t probe = 0; probe < cap; probe++) {
+                if (p0) {
+                    if (o0 == DANN_INVALID_NODE || o0 == n0) {
+                        new0 = o0 == DANN_INVALID_NODE;
+                        p0 = false;
+                    } else {
+                        h0 = h0 + 1 == cap ? 0u : h0 + 1;
+                    }
                 }
-                if (__ballot_sync(DANN_FULL, p1)) {
-                    if (bucket_insert(n1, b1, p1, nb, &s1)) new1 = true;
-                    __syncwarp();
+                if (p1) {
+                    if (o1 == DANN_INVALID_NODE || o1 == n1) {
+                        new1 = o1 == DANN_INVALID_NODE;
+                        p1 = false;
+                    } else {
+                        h1 = h1 + 1 == cap ? 0u : h1 + 1;
+                    }
                 }
-                if (!__ballot_sync(DANN_FULL, p0 || p1)) break;
+                if (!(p0 || p1)) break;
+                if (p0) o0 = atomicCAS(hash + h0, DANN_INVALID_NODE, n0);
+                if (p1) o1 = atomicCAS(hash + h1, DANN_INVALID_NODE, n1);
             }
-            if (!slotpay) {
-                s0 = n0;
-                s1 = n1;
+            __syncwarp();
+            if (slotpay) {
+                s0 = h0;
+                s1 = h1;
             }
             nset += __popc(__ballot_sync(DANN_FULL, new0)) + __popc(__ballot_sync(DANN_FULL, new1));
             if ((uint64_t)nset * 3u > (uint64_t)a.hash_cap * 2u) { /* load factor bound 2/3 */
@@ -243,10 +216,10 @@ struct LeanWarp {
      * warp): slot s + 2 is requested as soon as slot s has been reduced, so after the first (HBM) wait every later
      * slot - already on its way into L2 by the prefetch - arrives under the reduction of the slot before it. */
     template <bool EXACT>
-    __device__ __forceinline__ void distances_t(uint32_t tn, bool requested) {
+    __device__ __forceinline__ void distances_t(uint32_t tn) {
         const uint32_t G = a.G, grp = lane >> a.Gshift, RP = 32u >> a.Gshift;
         const ulonglong2 *qs = qcode + (lane & (G - 1)); /* this lane's chunks of the query code: qs[i * G] */
-        if (!requested && tn > 2 * RP) { /* rows of the later slots: pull them into L2 now, their loads then cost an L2 hit */
+        if (tn > 2 * RP) { /* rows of the later slots: pull them into L2 now, their loads then cost an L2 hit */
             const size_t rowbytes = (size_t)a.ix.cw * 8;
             const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
             for (uint32_t r = 2 * RP + lane; r < tn; r += 32) {
@@ -267,27 +240,9 @@ struct LeanWarp {
         }
         __syncwarp();
     }
-    /* requested: the page's rows are already on their way into L2 (request_code_rows) */
-    __device__ __forceinline__ void distances(uint32_t tn, bool requested) {
-        if (a.ix.cw == 2u * NCH * a.G) distances_t<true>(tn, requested);
-        else distances_t<false>(tn, requested);
-    }
-
-    /* The SBQ code rows of a neighbour list are needed three round trips from now (after the pop and the inserted-set
-     * answers): start pulling them into L2 as soon as the list is known, so that the distance stage's first loads are L2
-     * hits instead of an exposed HBM round trip.  Rows of ids that turn out to be known already (about one in seven)
-     * are the only wasted traffic; no register, no dependency, results unaffected. */
-    __device__ __forceinline__ void request_code_rows(uint32_t n0, bool v0, uint32_t n1, bool v1) const {
-        const size_t rowbytes = (size_t)a.ix.cw * 8;
-        const unsigned char *cb = reinterpret_cast<const unsigned char *>(a.ix.codes);
-        if (v0) {
-            prefetch_l2(cb + (size_t)n0 * rowbytes);
-            if (rowbytes > 128) prefetch_l2(cb + (size_t)n0 * rowbytes + 128);
-        }
-        if (v1) {
-            prefetch_l2(cb + (size_t)n1 * rowbytes);
-            if (rowbytes > 128) prefetch_l2(cb + (size_t)n1 * rowbytes + 128);
-        }
+    __device__ __forceinline__ void distances(uint32_t tn) {
+        if (a.ix.cw == 2u * NCH * a.G) distances_t<true>(tn);
+        else distances_t<false>(tn);
     }
 
     /* Σ_{t<h} (x >> t) */
@@ -552,7 +507,6 @@ struct LeanWarp {
         const uint32_t cut0 = i0 ? (uint32_t)(__ffs(i0) - 1) : 32u;
         const uint32_t cut1 = i0 ? 0u : (i1 ? (uint32_t)(__ffs(i1) - 1) : 32u);
         const bool v0 = (uint32_t)lane < cut0, v1 = (uint32_t)lane < cut1;
-        request_code_rows(n0, v0, n1, v1);
         if (a.lists_unique) {
             const Probe pr = stage_probe(n0, v0, n1, v1, true);
             pop();
@@ -573,7 +527,7 @@ struct LeanWarp {
         listn = 0;
         if (tn == 0 || status) return 0;
         stage_ancestors_async(tn); /* the pushes' ancestor slots travel while the code rows are gathered */
-        distances(tn, true);
+        distances(tn);
         dq += tn;
         return tn;
     }
@@ -583,7 +537,7 @@ struct LeanWarp {
         const uint32_t tn = listn;
         listn = 0;
         if (tn == 0 || status) return;
-        distances(tn, false);
+        distances(tn);
         push_page(tn);
         dq += tn;
     }

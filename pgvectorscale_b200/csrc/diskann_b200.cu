@@ -73,6 +73,15 @@ extern "C" int dann_device_count(void) try {
         }                                                                                      \
     } while (0)
 
+/* The stream a call that takes DEVICE buffers from its caller runs on.  A caller that names a stream gets exactly that
+ * (its buffers must be ready in that stream's order).  A caller that passes NULL gets the index's own
+ * cudaStreamNonBlocking stream - which is ordered behind NOTHING the caller did, so the library first makes it wait for
+ * everything already submitted to the legacy default stream: what a default-stream kernel or a plain cudaMemcpy of the
+ * caller's would have been ordered after.  (Found on B200 in round 2: the fixture quantized rows that torch was still
+ * generating on its default stream; until e0113f2 the index load's blocking cudaMemcpy calls had been the accidental
+ * barrier.  Work a caller runs on other non-blocking streams needs that stream passed in, or a synchronisation.) */
+struct dann_index;
+static cudaError_t order_after_default_stream(dann_index *ix, cudaStream_t st);
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -118,6 +127,7 @@ struct dann_index {
     dann_batch_timing timing{};
     dann_search_plan_info last_plan{};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_order = nullptr; /* see DANN_DEVICE_INPUT_STREAM */
     uint32_t G = 1, Gshift = 0, NCH = 1;
     uint32_t lists_unique = 0;
     /* plain storage layout (experimental): nodes carry their f32 index vector, no SBQ codes */
@@ -126,6 +136,15 @@ struct dann_index {
     DevBuf sc_qindex;
 };
 
+
+static cudaError_t order_after_default_stream(dann_index *ix, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(ix->ev_order, cudaStreamLegacy);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ix->ev_order, 0);
+    return e;
+}
+#define DANN_DEVICE_INPUT_STREAM(st, stream)                         \
+    cudaStream_t st = (stream) ? (cudaStream_t)(stream) : ix->stream; \
+    if (!(stream)) CK(order_after_default_stream(ix, st))
 
 struct dann_scan {
     dann_index *ix = nullptr;
@@ -214,6 +233,7 @@ extern "C" void dann_index_free(dann_index *ix) {
     for (DevBuf *b : bufs) b->release();
     for (auto &e : ix->ev)
         if (e) cudaEventDestroy(e);
+    if (ix->ev_order) cudaEventDestroy(ix->ev_order);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     cudaGetLastError();
     delete ix;
@@ -301,6 +321,7 @@ static int index_load_impl(const dann_snapshot_desc *s, const float *index_vecto
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto &e : ix->ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&ix->ev_order, cudaEventDisableTiming));
 
     IndexView &v = ix->v;
     v.n = s->n;
@@ -442,7 +463,7 @@ extern "C" int dann_prepare_queries(dann_index *ix, const float *d_queries, int 
     if (!d_queries || !d_q_codes || B <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_prepare_queries: bad argument");
     if (ix->plain) return fail(DANN_ERR_STATE, "dann_prepare_queries: a plain-storage index has no quantizer");
     std::lock_guard<std::mutex> lk(ix->mu);
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    DANN_DEVICE_INPUT_STREAM(st, stream);
     rc = launch_prepare(ix, d_queries, B, d_q_full, d_q_codes, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
@@ -487,7 +508,7 @@ extern "C" int dann_sbq_distance(dann_index *ix, const uint64_t *d_qcodes, const
     if (!d_qcodes || !d_pair_q || !d_pair_node || !d_out) return fail(DANN_ERR_INVALID_ARG, "dann_sbq_distance: NULL buffer");
     if (ix->plain) return fail(DANN_ERR_STATE, "dann_sbq_distance: a plain-storage index has no SBQ codes");
     if (npairs == 0) return DANN_OK;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    DANN_DEVICE_INPUT_STREAM(st, stream);
     switch (ix->NCH) {
         case 1: launch_sbq<1>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
         case 2: launch_sbq<2>(ix, d_qcodes, d_pair_q, d_pair_node, npairs, d_out, st); break;
@@ -506,7 +527,7 @@ extern "C" int dann_full_distance(dann_index *ix, const float *d_q_full, const u
     int rc = check_live(ix);
     if (rc) return rc;
     if (!d_q_full || !d_nodes || !d_out || B <= 0 || m <= 0) return fail(DANN_ERR_INVALID_ARG, "dann_full_distance: bad argument");
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    DANN_DEVICE_INPUT_STREAM(st, stream);
     size_t smem = (size_t)((ix->v.dim + 3u) & ~3u) * sizeof(float) + DANN_SMEM_SLACK;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(dann_full_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -821,7 +842,7 @@ extern "C" int dann_search_batch_device(dann_index *ix, const float *d_queries, 
     int rc = check_live(ix);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ix->mu);
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    DANN_DEVICE_INPUT_STREAM(st, stream);
     return search_batch_device_locked(ix, d_queries, d_labels, d_label_off, B, k, search_list_size, rescore,
                                       d_out_tid, d_out_dist, nullptr, d_out_count, d_out_stats, st);
 } DANN_CATCH
@@ -939,6 +960,7 @@ extern "C" int dann_index_set_vectors_device(dann_index *ix, float *d_vectors) t
     }
     v.vectors = d_vectors; /* borrowed: not in ix->owned */
     ix->hbm_bytes += (uint64_t)v.n * v.dim * sizeof(float);
+    CK(order_after_default_stream(ix, ix->stream)); /* the caller's rows: see DANN_DEVICE_INPUT_STREAM */
     if (v.distance_type == DANN_COSINE) {
         int blocks = std::min<long long>((v.n + 255) / 256, (long long)ix->sm_count * 8);
         dann_normalize_rows_kernel<<<std::max(blocks, 1), 256, 0, ix->stream>>>(d_vectors, v.n, v.dim);
@@ -1500,3 +1522,70 @@ extern "C" void dann_scan_end(dann_scan *sc) {
 /* query coalescing for process-per-connection hosts                */
 #include "dann_coalescer.h"
 #include "dann_group.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* reading an index relation file: host only                       */
+#include "dann_pgreader.h"
+
+struct dann_pg_relation {
+    dannpg::Relation rel;
+};
+
+extern "C" int dann_pg_relation_open(const char *path, dann_pg_relation **out) try {
+    if (!path || !out) return fail(DANN_ERR_INVALID_ARG, "dann_pg_relation_open: NULL argument");
+    *out = nullptr;
+    dann_pg_relation *r = new dann_pg_relation();
+    const int rc = dannpg::open_relation(path, &r->rel);
+    if (rc != DANN_OK) {
+        const std::string msg = r->rel.err;
+        delete r;
+        return fail(rc, "dann_pg_relation_open: %s", msg.c_str());
+    }
+    *out = r;
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" void dann_pg_relation_close(dann_pg_relation *rel) { delete rel; }
+
+extern "C" int dann_pg_relation_stat(const dann_pg_relation *rel, dann_pg_relation_info *out) try {
+    if (!rel || !out) return fail(DANN_ERR_INVALID_ARG, "dann_pg_relation_stat: NULL argument");
+    dannpg::stat_relation(rel->rel, out);
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" int dann_pg_read_chain(const dann_pg_relation *rel, uint32_t block, uint16_t offset, int page_type, void *buf,
+                                  size_t cap, size_t *len) try {
+    if (!rel || !len || (cap && !buf)) return fail(DANN_ERR_INVALID_ARG, "dann_pg_read_chain: NULL argument");
+    std::vector<unsigned char> bytes;
+    std::string err;
+    const int rc = dannpg::read_chain(rel->rel, block, offset, page_type, bytes, err);
+    if (rc != DANN_OK) return fail(rc, "dann_pg_read_chain (%u,%u): %s", block, (unsigned)offset, err.c_str());
+    *len = bytes.size();
+    if (cap) memcpy(buf, bytes.data(), std::min(cap, bytes.size()));
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_sbq **out) try {
+    if (!rel || !meta || !out) return fail(DANN_ERR_INVALID_ARG, "dann_pg_extract_sbq: NULL argument");
+    *out = nullptr;
+    dannpg::SbqOut *o = new dannpg::SbqOut();
+    memset(&o->pub, 0, sizeof o->pub);
+    std::string err;
+    int rc;
+    try {
+        rc = dannpg::extract_sbq(rel->rel, meta, o, err);
+    } catch (...) {
+        delete o;
+        throw;
+    }
+    if (rc != DANN_OK) {
+        delete o;
+        return fail(rc, "dann_pg_extract_sbq: %s", err.c_str());
+    }
+    *out = &o->pub; /* first member: dann_pg_sbq_free casts back */
+    return DANN_OK;
+} DANN_CATCH
+
+extern "C" void dann_pg_sbq_free(dann_pg_sbq *s) {
+    if (s) delete reinterpret_cast<dannpg::SbqOut *>(s);
+}

@@ -79,6 +79,9 @@ EXPORTS = [
     "dann_build_graph", "dann_index_download_nbrs", "dann_index_set_vectors", "dann_index_set_vectors_device",
     "dann_last_search_plan",
     "dann_group_create", "dann_group_size", "dann_group_replica", "dann_group_search_batch", "dann_group_free",
+    # relation-file reader (host only; mirror in pgreader.py)
+    "dann_pg_relation_open", "dann_pg_relation_close", "dann_pg_relation_stat", "dann_pg_read_chain",
+    "dann_pg_extract_sbq", "dann_pg_sbq_free",
 ]
 
 _LIB = None

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <sys/un.h>
 #include <unistd.h>
@@ -96,7 +97,14 @@ static void *serve(void *arg) {
     for (;;) {
         int32_t h[5];
         if (read_full(fd, h, sizeof h) != 0) break;
-        if ((uint32_t)h[0] != 0x514E4144u /* 'DANQ' */ || h[1] < 1 || h[1] > 65536 || h[4] < -1 || h[4] > 32767) break;
+        if ((uint32_t)h[0] != 0x514E4144u /* 'DANQ' */ || h[1] < 1 || h[1] > 65536 || h[4] < -1 || h[4] > 32767) {
+            /* the stream cannot be resynchronised after a bad header: say why, then drop the connection */
+            static const char msg[] = "dann_sidecar: malformed request header (magic, k in 1..65536, nlabels in -1..32767)";
+            const int32_t head[2] = {DANN_ERR_INVALID_ARG, 0};
+            const uint32_t len = (uint32_t)(sizeof msg - 1);
+            if (write_full(fd, head, sizeof head) == 0 && write_full(fd, &len, 4) == 0) write_full(fd, msg, len);
+            break;
+        }
         const int k = h[1], nlabels = h[4];
         int16_t labels[64];
         int16_t *lab = labels, *big = NULL;
@@ -180,7 +188,8 @@ int main(int argc, char **argv) {
     addr.sun_family = AF_UNIX;
     strncpy(addr.sun_path, argv[2], sizeof addr.sun_path - 1);
     unlink(argv[2]);
-    if (ls < 0 || bind(ls, (struct sockaddr *)&addr, sizeof addr) != 0 || listen(ls, 512) != 0) {
+    umask(0077); /* the socket belongs to the account the sidecar runs under (postgres): no other local user may connect */
+    if (ls < 0 || bind(ls, (struct sockaddr *)&addr, sizeof addr) != 0 || chmod(argv[2], 0600) != 0 || listen(ls, 512) != 0) {
         perror("dann_sidecar: socket");
         return 1;
     }
@@ -205,17 +214,25 @@ int main(int argc, char **argv) {
     }
     close(ls);
     unlink(argv[2]);
-    /* wake every connection thread (its read() returns 0) and give them a moment to leave the coalescer */
+    /* wake every connection thread (its read() returns 0) and wait until the last one has left the coalescer: a request
+     * already inside dann_coalescer_search completes (the dispatcher is still running), so this terminates.  The
+     * coalescer and the index are destroyed only when no thread can touch them; if threads are still around after a
+     * minute something is wedged and the process exits without tearing down under them. */
     pthread_mutex_lock(&g_conn_mu);
     for (int i = 0; i < g_conn_n; i++) shutdown(g_conn_fd[i], SHUT_RDWR);
     pthread_mutex_unlock(&g_conn_mu);
-    for (int spin = 0; spin < 400; spin++) {
+    int left = 0;
+    for (int spin = 0; spin < 12000; spin++) {
         pthread_mutex_lock(&g_conn_mu);
-        const int left = g_conn_n;
+        left = g_conn_n;
         pthread_mutex_unlock(&g_conn_mu);
         if (!left) break;
         struct timespec ts = {0, 5 * 1000 * 1000};
         nanosleep(&ts, NULL);
+    }
+    if (left) {
+        fprintf(stderr, "dann_sidecar: %d connection threads still busy after 60 s, exiting without teardown\n", left);
+        _exit(1);
     }
     uint64_t batches = 0, queries = 0, largest = 0;
     dann_coalescer_stats(g_co, &batches, &queries, &largest);

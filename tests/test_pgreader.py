@@ -1,0 +1,174 @@
+"""the relation-file reader (dann_pg_*, csrc/dann_pgreader.h) against relation images written by
+tests/pgpages.py with the reference's own write rules (util/page.rs, util/chain.rs, util/tape.rs, meta_page.rs:360-384,
+sbq/node.rs:26-42).  Host-only entry points of the C-ABI library: they run on the CPU box.  Parity here is
+self-consistent (writer and reader are both restatements; nothing in the sandbox can produce a file with the reference
+itself) - the reader's header says so."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import build_case
+from pgvectorscale_b200.snapshot import COSINE, L2
+import pgpages
+
+
+@pytest.fixture(scope="module")
+def pg(lib_built):
+    from pgvectorscale_b200 import pgreader
+    return pgreader
+
+
+def _same_snapshot(a, b):
+    for f in ("n", "dim", "dim_index", "bits", "words", "R", "distance_type", "count", "start_default"):
+        assert getattr(a, f) == getattr(b, f), f
+    assert bool(a.has_labels) == bool(b.has_labels)
+    for f in ("codes", "nbrs", "heap_tid", "mean", "m2", "start_labels", "start_label_nodes", "label_off", "labels"):
+        x, y = getattr(a, f), getattr(b, f)
+        if x is None or y is None:
+            assert (x is None or len(x) == 0) and (y is None or len(y) == 0), f
+        else:
+            assert np.array_equal(np.asarray(x), np.asarray(y)), f
+
+
+@pytest.mark.parametrize("labels", [False, True])
+@pytest.mark.parametrize("order", [(0, 1, 2, 3), (3, 0, 2, 1), (1, 2, 3, 0)])
+def test_extracted_snapshot_equals_the_one_written(pg, tmp_path, labels, order):
+    s = build_case(700, 96, COSINE, seed=5, R=24, L_build=48, labels=labels, deleted_every=9)
+    path = str(tmp_path / "16384")
+    meta, tids, w = pgpages.write_index(s, path, field_order=order, dead_every=7)
+    with pg.PgRelation(path) as rel:
+        info = rel.info()
+        assert info["meta_magic"] == pgpages.TSV_MAGIC and info["meta_version"] == pgpages.TSV_VERSION
+        assert info["node_items"] == s.n and info["foreign_pages"] == 0 and info["new_pages"] == 0
+        assert info["pages_by_type"]["Meta"] == 1 and info["pages_by_type"]["SbqNode"] > 10
+        assert info["nblocks"] == len(w.pages)
+        got, index_tid, fp, layout = rel.extract_sbq(pg.PgMeta(**meta))
+    assert layout == order and fp == info["fingerprint"]
+    assert np.array_equal(index_tid, tids)            # dense ids = (block, offset) order, dead line pointers skipped
+    _same_snapshot(got, s)
+    assert got.vectors is None                        # heap rows are not in the index relation
+
+
+def test_scan_of_the_extracted_snapshot_equals_scan_of_the_original(pg, tmp_path):
+    """End of the row: the oracle scans the original snapshot and the one that went through the page format."""
+    from oracle import fixtures, oracle
+    s = build_case(500, 64, L2, seed=8, R=16, L_build=32, labels=True)
+    path = str(tmp_path / "rel")
+    meta, _, _ = pgpages.write_index(s, path)
+    with pg.PgRelation(path) as rel:
+        got, _, _, _ = rel.extract_sbq(pg.PgMeta(**meta))
+    got.vectors = s.vectors                            # the host fetches heap_tid[i] from the table
+    q = fixtures.gen_vectors(6, 64, 3, "normal")
+    labs = [[1], [2, 5], [], [7], [3, 3], [9]]
+    lo = np.cumsum([0] + [len(x) for x in labs]).astype(np.int32)
+    lf = np.array([y for x in labs for y in x], dtype=np.int16)
+    a = oracle.scan_batch(s, q, lf, lo, 30, 20, 10)
+    b = oracle.scan_batch(got, q, lf, lo, 30, 20, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_chains_across_pages_and_segments(pg, tmp_path, monkeypatch):
+    """util/chain.rs tests: payload sizes around one, two and three pages come back byte for byte; a relation split
+    into several segment files reads like one."""
+    w = pgpages.RelationWriter()
+    b0 = w.new_page(pgpages.PT_SBQ_MEANS)
+    items = []
+    cur = b0
+    for size in [1, 14, 8100, 8140, 8192 - 100, 8192 + 100, 2 * 8192 - 100, 2 * 8192 + 100, 3 * 8192 + 7]:
+        data = bytes((i * 7 + size) % 256 for i in range(size))
+        ip, cur = w.chain_write(pgpages.PT_SBQ_MEANS, cur, data)
+        items.append((ip, data))
+    path = str(tmp_path / "chain")
+    w.save(path, segment_blocks=4)
+    monkeypatch.setenv("DANN_PG_RELSEG_BLOCKS", "4")       # RELSEG_SIZE of this "server" (1 GB = 131072 blocks by default)
+    assert os.path.exists(path + ".1") and os.path.exists(path + ".2")
+    with pg.PgRelation(path) as rel:
+        assert rel.info()["nblocks"] == len(w.pages)
+        for (blk, off), data in items:
+            assert rel.read_chain(blk, off, pgpages.PT_SBQ_MEANS) == data
+        with pytest.raises(Exception) as e:
+            rel.read_chain(items[0][0][0], items[0][0][1], pgpages.PT_META)     # assert!(page.get_type() == self.page_type)
+        assert "PageType" in str(e.value)
+        with pytest.raises(Exception):
+            rel.read_chain(len(w.pages) + 3, 1)
+
+
+def test_fingerprint_moves_with_any_page_change(pg, tmp_path):
+    s = build_case(300, 48, L2, seed=2, R=12, L_build=24)
+    path = str(tmp_path / "rel")
+    meta, _, w = pgpages.write_index(s, path)
+    with pg.PgRelation(path) as rel:
+        fp0 = rel.info()
+    # an insert rewrites a neighbour list in place: same bytes layout, the page's LSN moves (GenericXLogFinish)
+    blob = bytearray(open(path, "rb").read())
+    blk = 3
+    lsn_lo = struct.unpack_from("<I", blob, blk * 8192 + 4)[0]
+    struct.pack_into("<I", blob, blk * 8192 + 4, lsn_lo + 0x40)
+    open(path, "wb").write(blob)
+    with pg.PgRelation(path) as rel:
+        fp1 = rel.info()
+    assert fp1["fingerprint"] != fp0["fingerprint"] and fp1["max_lsn"] >= fp0["max_lsn"] and fp1["nblocks"] == fp0["nblocks"]
+    # relation extension (a new, still all-zero page at the end)
+    open(path, "ab").write(b"\0" * 8192)
+    with pg.PgRelation(path) as rel:
+        fp2 = rel.info()
+        assert fp2["fingerprint"] != fp1["fingerprint"] and fp2["new_pages"] == 1
+        got, _, fp, _ = rel.extract_sbq(pg.PgMeta(**meta))        # a new page holds no nodes and is not an error
+        assert got.n == s.n and fp == fp2["fingerprint"]
+
+
+def _corrupt(path, pos, data):
+    blob = bytearray(open(path, "rb").read())
+    blob[pos:pos + len(data)] = data
+    open(path, "wb").write(blob)
+
+
+def test_everything_unexpected_is_refused_not_guessed(pg, tmp_path):
+    from pgvectorscale_b200.diskann import DiskAnnError
+    s = build_case(200, 48, L2, seed=4, R=12, L_build=24)
+    path = str(tmp_path / "rel")
+    meta, tids, w = pgpages.write_index(s, path)
+    good = open(path, "rb").read()
+
+    def expect(*msgs, **meta_over):
+        with pg.PgRelation(path) as rel:
+            with pytest.raises(DiskAnnError) as e:
+                rel.extract_sbq(pg.PgMeta(**{**meta, **meta_over}))
+        assert e.value.code in (-7, -1) and any(m in str(e.value) for m in msgs), str(e.value)
+
+    expect("no order of the archived root's fields", num_neighbors=13)        # wrong R: no layout fits
+    expect("no order of the archived root's fields", bq_bits=1)               # wrong code width
+    expect("start_nodes.default_node", start=(1, 999))
+    # a page of another access method in the middle of the relation
+    _corrupt(path, 2 * 8192 + 8192 - 8 + 2, b"\x00\x00")
+    expect("page id 0xAE24")
+    open(path, "wb").write(good)
+    # a neighbour pointer to an item that does not exist
+    blk, off = int(tids[5]) >> 16, int(tids[5]) & 0xFFFF
+    pgv = w.pages[blk]
+    lp = struct.unpack_from("<I", pgv.b, 24 + 4 * (off - 1))[0]
+    _corrupt(path, blk * 8192 + (lp & 0x7FFF) + s.words * 8, struct.pack("<IHH", blk, 200, 0))
+    expect("not a live node item", "no order of the archived root's fields")     # caught by the layout sample or by the full pass
+    open(path, "wb").write(good)
+    # truncated file: not a whole number of pages
+    open(path, "wb").write(good[:-100])
+    with pytest.raises(DiskAnnError) as e:
+        pg.PgRelation(path)
+    assert e.value.code == -7
+    # pd_upper beyond pd_special
+    open(path, "wb").write(good)
+    _corrupt(path, 1 * 8192 + 14, struct.pack("<H", 8190))
+    expect("pd_lower / pd_upper / pd_special")
+
+
+def test_meta_header_is_recognised_in_either_field_order(pg, tmp_path):
+    w = pgpages.RelationWriter()
+    b = w.new_page(pgpages.PT_META)
+    w.chain_write(pgpages.PT_META, b, struct.pack("<II", pgpages.TSV_VERSION, pgpages.TSV_MAGIC))     # (version, magic)
+    path = str(tmp_path / "m")
+    w.save(path)
+    with pg.PgRelation(path) as rel:
+        i = rel.info()
+    assert (i["meta_magic"], i["meta_version"]) == (pgpages.TSV_MAGIC, pgpages.TSV_VERSION)
