@@ -230,6 +230,23 @@ def cpu_latency(oracle, snap, qs, L, rescore, k):
             "qps_1thread": round(1e3 * len(lat) / sum(lat), 1)}
 
 
+def native_arm(oracle, snap, qs, L, rescore, k, threads, seconds):
+    """Optional CPU arm: the same oracle source built with -march=native on this box (AVX-512 VPOPCNTDQ
+    where the CPU has it) - NOT the reference's build flags (.cargo/config.toml: +avx2,+fma), reported beside them."""
+    try:
+        oracle.scan_batch(snap, qs[:8], None, None, L, rescore, k, threads=threads, native=True)      # builds the library
+        t1, reps = time.perf_counter(), 0
+        while True:
+            oracle.scan_batch(snap, qs, None, None, L, rescore, k, threads=threads, native=True)
+            reps += 1
+            if time.perf_counter() - t1 > seconds or reps >= 20:
+                break
+        return {"value": reps * qs.shape[0] / (time.perf_counter() - t1), "unit": "queries/s", "cores": threads,
+                "flags": "-O2 -march=native (not the reference's build flags)"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for this path on the box's host cores.
     The Rust/pgrx extension cannot be built in this image (no rustc/cargo/Postgres), so this is the oracle port
@@ -307,6 +324,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     qps = args.steps * sample / dt
     lat = cpu_latency(oracle, snap, qs[:16], L, rescore, k)
+    native = native_arm(oracle, snap, qs[:sample], L, rescore, k, threads, 3.0)
     line = {
         "impl": "reference", "metric": metric_name(n, dim),
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -318,7 +336,7 @@ def run_reference(args):
                    "note": f"CPU arm: each step scans a bounded sample of {sample} queries of the workload; index fixture "
                            "built by a child process, libdiskann_b200.so is never mapped here"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "cores_detail": cores,
-                         "single_thread": lat,
+                         "single_thread": lat, "march_native": native,
                          "sample": f"{args.steps} steps x {sample} queries, {threads} host threads "
                                    "(oracle/oracle.cpp, -O2 -mavx2 -mfma -mpopcnt)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -586,7 +604,7 @@ def run_ours(args, n, B, steps, warmup, device, rank, world, full=True):
         cpu_qps = reps * sample / (time.perf_counter() - t1)
         lat = cpu_latency(oracle, snap, qs[:16 if full else 8], L, rescore, k)
         cpu = {"value": cpu_qps, "unit": "queries/s", "cores": threads, "kind": "port", "cores_detail": cores,
-               "single_thread": lat,
+               "single_thread": lat, "march_native": native_arm(oracle, snap, qs, L, rescore, k, threads, 4.0 if full else 2.0),
                "sample": f"{reps} x {sample} queries of the same workload, {threads} host threads "
                          f"(oracle/oracle.cpp, -O2 -mavx2 -mfma -mpopcnt)"}
 

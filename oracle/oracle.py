@@ -247,8 +247,29 @@ def scan(s, query, labels=None, search_list_size: int = 100, rescore: int = 50,
                 stats={k: int(getattr(stats, k)) for k, _ in _Stats._fields_})
 
 
+_NATIVE = None
+
+
+def native_lib():
+    """liboracle_native.so: the same oracle.cpp compiled with -march=native (optional CPU-baseline arm, BASELINE.md §3:
+    "not the reference's build flags").  Only scan_batch(native=True) uses it; parity always runs on the reference-flag build."""
+    global _NATIVE
+    if _NATIVE is None:
+        # -march=native code must never run on another machine: the file name carries this CPU's model and flags
+        import hashlib
+        ident = "".join(l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags")))[:20000]
+        tag = hashlib.sha1(ident.encode()).hexdigest()[:10]
+        so = os.path.join(_HERE, f"liboracle_native_{tag}.so")
+        src = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle.h", "Makefile")]
+        if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in src):
+            subprocess.run(["make", "-C", _HERE, "-s", "native", f"NATIVE_SO={os.path.basename(so)}"], check=True,
+                           stdout=subprocess.DEVNULL)
+        _NATIVE = C.CDLL(so)
+    return _NATIVE
+
+
 def scan_batch(s, queries, labels=None, label_off=None, search_list_size: int = 100,
-               rescore: int = 50, k: int = 10, threads: int = 0):
+               rescore: int = 50, k: int = 10, threads: int = 0, native: bool = False):
     """One independent scan per query row. Returns tid[B,k] (~0 = none), dist[B,k], count[B], stats[B]."""
     st, keep = _snapshot_struct(s)
     q = _f32(queries)
@@ -261,7 +282,7 @@ def scan_batch(s, queries, labels=None, label_off=None, search_list_size: int = 
     if label_off is not None:
         lab = np.ascontiguousarray(labels, dtype=np.int16)
         lo = np.ascontiguousarray(label_off, dtype=np.int32)
-    lib().orc_scan_batch(C.byref(st), _p(q), _p(lab), _p(lo), C.c_uint32(B),
+    (native_lib() if native else lib()).orc_scan_batch(C.byref(st), _p(q), _p(lab), _p(lo), C.c_uint32(B),
                          C.c_uint32(search_list_size), C.c_uint32(rescore), C.c_uint32(k),
                          _p(tid), _p(dist), _p(count), _p(stats), C.c_uint32(threads))
     return tid, dist, count, stats
