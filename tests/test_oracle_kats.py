@@ -351,3 +351,17 @@ def test_golden_vectors():
         got = run_case(name)
         for key, val in got.items():
             assert np.array_equal(z[f"{name}/{key}"], val), (name, key)
+
+
+def test_march_native_build_of_the_oracle_returns_the_same_rows():
+    """bench.py's optional CPU arm times oracle.cpp built with -march=native; it is never used for
+    parity, but it must still be the same algorithm: rows, distance bits and counters equal the reference-flag build."""
+    from conftest import build_case
+    from oracle import fixtures, oracle
+    from pgvectorscale_b200.snapshot import COSINE
+    s = build_case(1200, 96, COSINE, seed=14, R=24, L_build=48, labels=True, deleted_every=7)
+    q = fixtures.gen_vectors(12, 96, 4, "normal")
+    a = oracle.scan_batch(s, q, None, None, 40, 30, 10, threads=2)
+    b = oracle.scan_batch(s, q, None, None, 40, 30, 10, threads=2, native=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
