@@ -230,6 +230,7 @@ void dann_group_free(dann_group *g);
  *   ChainItemReader::read                                 util/chain.rs:125-183  dann_pg_read_chain
  *   MetaPage::fetch: magic + version of MetaPageHeader    meta_page.rs:386-419   dann_pg_relation_info.meta_*
  *   ArchivedSbqNode accessors + SbqMeans::load            sbq/node.rs:236-330, sbq/mod.rs:88-122   dann_pg_extract_sbq
+ *   ArchivedPlainNode accessors                           plain/node.rs:15-120   dann_pg_extract_plain
  * The MetaPage BODY is an rkyv archive of a repr(Rust) struct whose field order cannot be pinned offline: the caller
  * supplies its scalars (dann_pg_meta; a Rust host fills them from MetaPage's getters) and the reader cross-checks them
  * against the node items; the node items' own field order is inferred and verified, never assumed (see the header of
@@ -269,17 +270,23 @@ typedef struct { /* MetaPage scalars (meta_page.rs:212-282) and the pointers it 
     uint32_t means_block;  /* quantizer_metadata; DANN_INVALID_NODE = the quantizer uses no means */
     uint16_t means_offset;
 } dann_pg_meta;
-typedef struct { /* owned by the library until dann_pg_sbq_free */
-    dann_snapshot_desc snap;   /* ready for dann_index_load except vectors == NULL: heap rows live in the TABLE; fetch
-                                  heap_tid[i] in order and attach them with dann_index_set_vectors */
+typedef struct { /* owned by the library until dann_pg_snapshot_free */
+    dann_snapshot_desc snap;   /* ready for dann_index_load (dann_index_load_plain with index_vectors below) except
+                                  vectors == NULL: heap rows live in the TABLE; fetch heap_tid[i] in order and attach
+                                  them with dann_index_set_vectors */
+    const float *index_vectors; /* plain layout: [n * dim_index] the vector each node stores (plain/node.rs:17-22); else NULL */
     const uint64_t *index_tid; /* [n] (block<<16)|offset of node i inside the index relation, ascending: the
                                   IndexPointer -> dense node id map */
     uint64_t fingerprint;      /* of the relation as extracted */
-    uint32_t layout[4];        /* which 8-byte cell of the archived root held: heap pointer, code vector, neighbour
-                                  vector, fourth vector (declaration order = 0,1,2,3) */
-} dann_pg_sbq;
-int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_sbq **out);
-void dann_pg_sbq_free(dann_pg_sbq *s);
+    uint32_t layout[4];        /* which 8-byte cell of the archived root held: heap pointer, code (or f32 vector),
+                                  neighbour vector, fourth vector */
+    void *self;                /* the library's owner object (dann_pg_snapshot_free) */
+} dann_pg_snapshot;
+/* storage_layout = memory_optimized: SbqNode pages (sbq/node.rs:26-42) + the SbqMeans chain */
+int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_snapshot **out);
+/* storage_layout = plain: Node pages (plain/node.rs:15-22); bq_bits, has_labels and the means pointer of `meta` are ignored */
+int dann_pg_extract_plain(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_snapshot **out);
+void dann_pg_snapshot_free(dann_pg_snapshot *s);
 
 /* How the last batch search of this index was planned (diagnostics for benchmarks and profiles). */
 typedef struct {

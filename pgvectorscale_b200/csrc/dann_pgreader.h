@@ -36,7 +36,7 @@
 // moved or removed (vacuum rewrites heap pointers / neighbour lists in place, inserts append items and rewrite
 // neighbour lists), so   fingerprint = hash over every page of (block, pd_lsn, pd_lower, pd_upper, pd_checksum)
 // changes iff some page changed, and nblocks / max_lsn order two fingerprints in time.  A snapshot is valid for
-// exactly the fingerprint it was extracted under: the loader records it (dann_pg_sbq.fingerprint), the host compares
+// exactly the fingerprint it was extracted under: the loader records it (dann_pg_snapshot.fingerprint), the host compares
 // dann_pg_relation_info() again before reusing a cached index handle - in a backend additionally on relcache
 // invalidation and after its own aminsert / ambulkdelete - and reloads on any difference.
 // A relation FILE shows only what has been written back: an external reader (the sidecar) needs a CHECKPOINT or a
@@ -231,18 +231,28 @@ static inline bool vec_cell(const unsigned char *item, uint32_t len, uint32_t ce
     return true;
 }
 
-static inline bool parse_node(const unsigned char *item, uint32_t len, const NodeLayout &lay, uint32_t words, uint32_t R, bool labeled,
-                              NodeFields *f) {
+/* what the four 8-byte cells of a node root are, per storage layout:
+ *   SBQ   (sbq/node.rs:26-42):   heap pointer | bq_vector: Vec<u64> [words] | neighbours [R] | Vec<Vec<u64>> (empty) or labels: Vec<u16>
+ *   plain (plain/node.rs:15-22): heap pointer | vector: Vec<f32> [dim_index] | neighbours [R] | pq_vector: Vec<u8> (empty)
+ * (the struct's declaration order differs - plain declares vector, pq_vector, neighbours, heap pointer - see decl_order) */
+struct NodeShape {
+    uint32_t main_len, main_elem, main_align; /* the code / vector cell */
+    uint32_t R;
+    uint32_t fourth_elem, fourth_align;
+    bool fourth_must_be_empty;
+};
+
+static inline bool parse_node(const unsigned char *item, uint32_t len, const NodeLayout &lay, const NodeShape &sh, NodeFields *f) {
     if (len < 32 || (len & 3)) return false;
     const uint32_t root = len - 32; /* archived root = the last size_of::<ArchivedNode>() bytes */
     const unsigned char *hp = item + root + 8 * lay.cell_heap;
     f->heap_block = rd32(hp);
     f->heap_offset = rd16(hp + 4);
     uint32_t n;
-    if (!vec_cell(item, len, root + 8 * lay.cell_code, 8, 8, &f->code, &n) || n != words) return false;
-    if (!vec_cell(item, len, root + 8 * lay.cell_nbrs, 8, 4, &f->nbrs, &n) || n != R) return false;
-    if (!vec_cell(item, len, root + 8 * lay.cell_fourth, labeled ? 2 : 8, labeled ? 2 : 4, &f->fourth, &f->n_fourth)) return false;
-    if (!labeled && f->n_fourth != 0) return false; /* _neighbor_vectors: "no longer used", always empty (sbq/node.rs:33) */
+    if (!vec_cell(item, len, root + 8 * lay.cell_code, sh.main_elem, sh.main_align, &f->code, &n) || n != sh.main_len) return false;
+    if (!vec_cell(item, len, root + 8 * lay.cell_nbrs, 8, 4, &f->nbrs, &n) || n != sh.R) return false;
+    if (!vec_cell(item, len, root + 8 * lay.cell_fourth, sh.fourth_elem, sh.fourth_align, &f->fourth, &f->n_fourth)) return false;
+    if (sh.fourth_must_be_empty && f->n_fourth != 0) return false; /* _neighbor_vectors / pq_vector: "no longer used", always empty */
     return true;
 }
 
@@ -337,8 +347,9 @@ static inline void stat_relation(const Relation &r, dann_pg_relation_info *o) {
     }
 }
 
-struct SbqOut { /* owns everything dann_pg_sbq points into */
-    dann_pg_sbq pub;
+struct SbqOut { /* owns everything dann_pg_snapshot points into */
+    dann_pg_snapshot pub;
+    std::vector<float> index_vectors; /* plain layout */
     std::vector<uint64_t> codes, heap_tid, index_tid;
     std::vector<uint32_t> nbrs, label_off, start_label_nodes;
     std::vector<int16_t> labels, start_labels;
@@ -385,14 +396,30 @@ static inline int parse_means(const std::vector<unsigned char> &buf, uint32_t di
     return DANN_OK;
 }
 
-static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *o, std::string &err) {
-    const uint32_t R = m->num_neighbors, bits = m->bq_bits, dimx = m->num_dimensions_to_index;
+static inline int extract_nodes(const Relation &r, const dann_pg_meta *m, bool plain, SbqOut *o, std::string &err) {
+    const uint32_t R = m->num_neighbors, bits = plain ? 1u : m->bq_bits, dimx = m->num_dimensions_to_index;
     if (!R || !bits || !dimx || m->num_dimensions < dimx || (uint64_t)dimx * bits > (1u << 24)) {
         err = "meta scalars: num_neighbors, bq_bits and num_dimensions_to_index (<= num_dimensions) must be positive";
         return DANN_ERR_INVALID_ARG;
     }
     const uint32_t words = (uint32_t)(((uint64_t)dimx * bits + 63) / 64); /* sbq/quantize.rs:38-46 */
     const bool labeled = m->has_labels != 0;
+    if (plain && labeled) { /* build.rs:264-290: label filtering needs the memory_optimized layout */
+        err = "a plain-storage index has no labels";
+        return DANN_ERR_INVALID_ARG;
+    }
+    const int node_page = plain ? PT_NODE : PT_SBQ_NODE; /* plain/storage.rs:124-126, sbq/storage.rs page_type() */
+    NodeShape sh;
+    sh.main_len = plain ? dimx : words;
+    sh.main_elem = plain ? 4u : 8u;
+    sh.main_align = plain ? 4u : 8u;
+    sh.R = R;
+    sh.fourth_elem = plain ? 1u : (labeled ? 2u : 8u);
+    sh.fourth_align = plain ? 1u : (labeled ? 2u : 4u);
+    sh.fourth_must_be_empty = plain || !labeled;
+    /* the struct's declaration order, as cells (heap, main, neighbours, fourth): PlainNode declares vector, pq_vector,
+     * neighbor_index_pointers, heap_item_pointer */
+    const int decl[4] = {plain ? 3 : 0, plain ? 0 : 1, 2, plain ? 1 : 3};
     /* pass 1: every live item of every SbqNode page, in (block, offset) order = dense node ids */
     std::vector<std::pair<const unsigned char *, uint32_t>> items;
     for (uint32_t b = 0; b < r.nblocks; b++) {
@@ -402,7 +429,7 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
             err = "block " + std::to_string(b) + ": " + v.why;
             return DANN_ERR_FORMAT;
         }
-        if (v.page_type != PT_SBQ_NODE) continue;
+        if (v.page_type != node_page) continue;
         for (uint32_t off = 1; off <= v.nitems; off++) {
             const unsigned char *it;
             uint32_t len;
@@ -437,7 +464,7 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
             for (uint32_t s = 0; s < sample && fit; s++) {
                 const auto &it = items[(uint64_t)s * n / sample];
                 NodeFields f;
-                if (!parse_node(it.first, it.second, c, words, R, labeled, &f)) {
+                if (!parse_node(it.first, it.second, c, sh, &f)) {
                     fit = false;
                     break;
                 }
@@ -453,14 +480,15 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
                 if (rd16(it.first + it.second - 32 + 8 * c.cell_heap + 6) != 0) fit = false; /* the heap pointer's padding */
             }
             if (fit) {
-                const bool decl = perm[0] == 0 && perm[1] == 1 && perm[2] == 2 && perm[3] == 3;
-                if (nfit == 0 || decl) memcpy(best, perm, sizeof best);
+                const bool is_decl = perm[0] == decl[0] && perm[1] == decl[1] && perm[2] == decl[2] && perm[3] == decl[3];
+                if (nfit == 0 || is_decl) memcpy(best, perm, sizeof best);
                 nfit++;
-                if (decl) break;
+                if (is_decl) break;
             }
         } while (std::next_permutation(perm, perm + 4));
         if (nfit == 0) {
-            err = "node items: no order of the archived root's fields satisfies bq_vector.len == " + std::to_string(words) +
+            err = std::string("node items: no order of the archived root's fields satisfies ") + (plain ? "vector.len == " : "bq_vector.len == ") +
+                  std::to_string(sh.main_len) +
                   ", neighbor_index_pointers.len == " + std::to_string(R) + " with pointers to live node items (wrong meta scalars, "
                   "another storage layout, or an rkyv layout this reader does not know)";
             return DANN_ERR_FORMAT;
@@ -469,18 +497,20 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
     }
     o->pub.layout[0] = lay.cell_heap, o->pub.layout[1] = lay.cell_code, o->pub.layout[2] = lay.cell_nbrs, o->pub.layout[3] = lay.cell_fourth;
     /* pass 2: every item into the flat arrays */
-    o->codes.resize((size_t)n * words);
+    if (plain) o->index_vectors.resize((size_t)n * dimx);
+    else o->codes.resize((size_t)n * words);
     o->nbrs.assign((size_t)n * R, DANN_INVALID_NODE);
     o->heap_tid.resize(n);
     if (labeled) o->label_off.assign((size_t)n + 1, 0);
     for (uint32_t i = 0; i < n; i++) {
         NodeFields f;
-        if (!parse_node(items[i].first, items[i].second, lay, words, R, labeled, &f)) {
+        if (!parse_node(items[i].first, items[i].second, lay, sh, &f)) {
             err = "node item (" + std::to_string(o->index_tid[i] >> 16) + "," + std::to_string(o->index_tid[i] & 0xFFFF) +
                   ") does not parse under the layout the sample fixed";
             return DANN_ERR_FORMAT;
         }
-        memcpy(&o->codes[(size_t)i * words], f.code, (size_t)words * 8);
+        if (plain) memcpy(&o->index_vectors[(size_t)i * dimx], f.code, (size_t)dimx * 4);
+        else memcpy(&o->codes[(size_t)i * words], f.code, (size_t)words * 8);
         /* heap pointer: offset 0 (InvalidOffsetNumber) = deleted tuple, kept as such (scan.rs:231-234) */
         o->heap_tid[i] = ip_key(f.heap_block, f.heap_offset);
         for (uint32_t j = 0; j < R; j++) { /* iter_neighbors: up to the first InvalidBlockNumber (sbq/node.rs:261-285) */
@@ -534,7 +564,9 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
         }
     }
     /* quantizer (SbqQuantizer::new: use_mean unless 1 bit with the default options - then there is no SbqMeans item) */
-    if (m->means_block != INVALID_BLOCK) {
+    if (plain) {
+        /* no quantizer */
+    } else if (m->means_block != INVALID_BLOCK) {
         std::vector<unsigned char> buf;
         int rc = read_chain(r, m->means_block, m->means_offset, PT_SBQ_MEANS, buf, err);
         if (rc != DANN_OK) return rc;
@@ -546,14 +578,15 @@ static inline int extract_sbq(const Relation &r, const dann_pg_meta *m, SbqOut *
     sn.n = n;
     sn.dim = m->num_dimensions;
     sn.dim_index = dimx;
-    sn.bits = bits;
-    sn.words = words;
+    sn.bits = plain ? 0u : bits;
+    sn.words = plain ? 0u : words;
     sn.R = R;
     sn.distance_type = m->distance_type;
     sn.has_labels = labeled ? 1 : 0;
-    sn.mean = o->mean.data();
+    sn.mean = o->mean.empty() ? nullptr : o->mean.data();
     sn.m2 = o->m2.empty() ? nullptr : o->m2.data();
-    sn.codes = o->codes.data();
+    sn.codes = plain ? nullptr : o->codes.data();
+    o->pub.index_vectors = plain ? o->index_vectors.data() : nullptr;
     sn.nbrs = o->nbrs.data();
     sn.heap_tid = o->heap_tid.data();
     sn.vectors = nullptr; /* heap rows live in the TABLE, not in the index: the caller fetches heap_tid[i] in order */

@@ -1565,27 +1565,36 @@ extern "C" int dann_pg_read_chain(const dann_pg_relation *rel, uint32_t block, u
     return DANN_OK;
 } DANN_CATCH
 
-extern "C" int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_sbq **out) try {
-    if (!rel || !meta || !out) return fail(DANN_ERR_INVALID_ARG, "dann_pg_extract_sbq: NULL argument");
+static int pg_extract(const dann_pg_relation *rel, const dann_pg_meta *meta, bool plain, dann_pg_snapshot **out, const char *who) {
+    if (!rel || !meta || !out) return fail(DANN_ERR_INVALID_ARG, "%s: NULL argument", who);
     *out = nullptr;
     dannpg::SbqOut *o = new dannpg::SbqOut();
     memset(&o->pub, 0, sizeof o->pub);
     std::string err;
     int rc;
     try {
-        rc = dannpg::extract_sbq(rel->rel, meta, o, err);
+        rc = dannpg::extract_nodes(rel->rel, meta, plain, o, err);
     } catch (...) {
         delete o;
         throw;
     }
     if (rc != DANN_OK) {
         delete o;
-        return fail(rc, "dann_pg_extract_sbq: %s", err.c_str());
+        return fail(rc, "%s: %s", who, err.c_str());
     }
-    *out = &o->pub; /* first member: dann_pg_sbq_free casts back */
+    o->pub.self = o;
+    *out = &o->pub;
     return DANN_OK;
+}
+
+extern "C" int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_snapshot **out) try {
+    return pg_extract(rel, meta, false, out, "dann_pg_extract_sbq");
 } DANN_CATCH
 
-extern "C" void dann_pg_sbq_free(dann_pg_sbq *s) {
-    if (s) delete reinterpret_cast<dannpg::SbqOut *>(s);
+extern "C" int dann_pg_extract_plain(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_snapshot **out) try {
+    return pg_extract(rel, meta, true, out, "dann_pg_extract_plain");
+} DANN_CATCH
+
+extern "C" void dann_pg_snapshot_free(dann_pg_snapshot *s) {
+    if (s) delete static_cast<dannpg::SbqOut *>(s->self);
 }

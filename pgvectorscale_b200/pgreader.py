@@ -35,8 +35,9 @@ class _PgMeta(C.Structure):
                 ("means_block", C.c_uint32), ("means_offset", C.c_uint16)]
 
 
-class _PgSbq(C.Structure):
-    _fields_ = [("snap", _SnapshotDesc), ("index_tid", C.c_void_p), ("fingerprint", C.c_uint64), ("layout", C.c_uint32 * 4)]
+class _PgSnapshot(C.Structure):
+    _fields_ = [("snap", _SnapshotDesc), ("index_vectors", C.c_void_p), ("index_tid", C.c_void_p), ("fingerprint", C.c_uint64),
+                ("layout", C.c_uint32 * 4), ("self", C.c_void_p)]
 
 
 @dataclass
@@ -62,9 +63,10 @@ def _bind(lib):
     lib.dann_pg_relation_close.restype = None
     lib.dann_pg_relation_stat.argtypes = [vp, C.POINTER(_RelationInfo)]
     lib.dann_pg_read_chain.argtypes = [vp, C.c_uint32, C.c_uint16, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
-    lib.dann_pg_extract_sbq.argtypes = [vp, C.POINTER(_PgMeta), C.POINTER(C.POINTER(_PgSbq))]
-    lib.dann_pg_sbq_free.argtypes = [C.POINTER(_PgSbq)]
-    lib.dann_pg_sbq_free.restype = None
+    lib.dann_pg_extract_sbq.argtypes = [vp, C.POINTER(_PgMeta), C.POINTER(C.POINTER(_PgSnapshot))]
+    lib.dann_pg_extract_plain.argtypes = [vp, C.POINTER(_PgMeta), C.POINTER(C.POINTER(_PgSnapshot))]
+    lib.dann_pg_snapshot_free.argtypes = [C.POINTER(_PgSnapshot)]
+    lib.dann_pg_snapshot_free.restype = None
     lib._pg_bound = True
     return lib
 
@@ -108,7 +110,14 @@ class PgRelation:
         return buf.raw[:n.value]
 
     def extract_sbq(self, meta: PgMeta):
-        """-> (Snapshot with vectors=None, index_tid [n] uint64, fingerprint, layout tuple)"""
+        """memory_optimized layout -> (Snapshot with vectors=None, index_tid [n] uint64, fingerprint, layout tuple)"""
+        return self._extract(meta, plain=False)
+
+    def extract_plain(self, meta: PgMeta):
+        """plain layout -> the same tuple; the Snapshot has storage_type=1 and index_vectors [n, dim_index]"""
+        return self._extract(meta, plain=True)
+
+    def _extract(self, meta: PgMeta, plain: bool):
         labs = sorted(meta.start_labels.items())
         sl = np.array([l for l, _ in labs], dtype=np.int16)
         sb = np.array([p[0] for _, p in labs], dtype=np.uint32)
@@ -118,15 +127,17 @@ class PgRelation:
                     len(labs), sl.ctypes.data if len(labs) else None, sb.ctypes.data if len(labs) else None,
                     so.ctypes.data if len(labs) else None, meta.means[0] if meta.means else INVALID_NODE,
                     meta.means[1] if meta.means else 0)
-        out = C.POINTER(_PgSbq)()
-        _check(self.lib, self.lib.dann_pg_extract_sbq(self.h, C.byref(m), C.byref(out)))
+        out = C.POINTER(_PgSnapshot)()
+        fn = self.lib.dann_pg_extract_plain if plain else self.lib.dann_pg_extract_sbq
+        _check(self.lib, fn(self.h, C.byref(m), C.byref(out)))
         try:
             d = out.contents.snap
             n, R, words = d.n, d.R, d.words
             nl = _copy(d.label_off, np.uint32, n + 1) if d.has_labels else None
             snap = Snapshot(
                 n=n, dim=d.dim, dim_index=d.dim_index, bits=d.bits, words=words, R=R, distance_type=d.distance_type,
-                has_labels=bool(d.has_labels), count=int(d.count), mean=_copy(d.mean, np.float32, d.dim_index),
+                has_labels=bool(d.has_labels), count=int(d.count),
+                mean=_copy(d.mean, np.float32, d.dim_index) if d.mean else np.zeros(d.dim_index, np.float32),
                 m2=_copy(d.m2, np.float32, d.dim_index) if d.m2 else None,
                 codes=_copy(d.codes, np.uint64, n * words).reshape(n, words),
                 nbrs=_copy(d.nbrs, np.uint32, n * R).reshape(n, R), heap_tid=_copy(d.heap_tid, np.uint64, n), vectors=None,
@@ -134,7 +145,10 @@ class PgRelation:
                 start_labels=_copy(d.start_labels, np.int16, d.n_start_labels) if d.n_start_labels else None,
                 start_label_nodes=_copy(d.start_label_nodes, np.uint32, d.n_start_labels) if d.n_start_labels else None,
                 label_off=nl, labels=_copy(d.labels, np.int16, int(nl[-1])) if nl is not None else None)
+            if plain:
+                snap.storage_type = 1
+                snap.index_vectors = _copy(out.contents.index_vectors, np.float32, n * d.dim_index).reshape(n, d.dim_index)
             index_tid = _copy(out.contents.index_tid, np.uint64, n)
             return snap, index_tid, int(out.contents.fingerprint), tuple(out.contents.layout)
         finally:
-            self.lib.dann_pg_sbq_free(out)
+            self.lib.dann_pg_snapshot_free(out)

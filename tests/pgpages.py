@@ -26,7 +26,7 @@ TSV_PAGE_ID = 0xAE24
 TSV_MAGIC = 768756476
 TSV_VERSION = 3
 INVALID_BLOCK = 0xFFFFFFFF
-PT_SBQ_NODE, PT_SBQ_MEANS, PT_META = 5, 7, 8
+PT_NODE, PT_SBQ_NODE, PT_SBQ_MEANS, PT_META = 1, 5, 7, 8
 
 
 def _align8(x):
@@ -138,6 +138,30 @@ def archive_node(heap_tid: int, code: np.ndarray, nbr_ptrs, fourth: bytes, n_fou
     return bytes(body) + b"".join(cells)
 
 
+def archive_plain_node(heap_tid: int, vector: np.ndarray, nbr_ptrs, field_order=(0, 1, 2, 3)) -> bytes:
+    """rkyv archive of PlainNode { vector: Vec<f32>, pq_vector: Vec<u8> (empty), neighbor_index_pointers, heap_item_pointer }
+    (plain/node.rs:15-22): [f32s][neighbour ItemPointers][32-byte root].  field_order[i] = the root cell of declared field i."""
+    body = bytearray()
+    body += np.ascontiguousarray(vector, dtype=np.float32).tobytes()
+    nbr_pos = len(body)
+    for b, o in nbr_ptrs:
+        body += item_pointer(b, o)
+    pq_pos = len(body)
+    while len(body) % 4:
+        body += b"\0"
+    root = len(body)
+    cells = [None] * 4
+
+    def vec(pos, n, cell):
+        return struct.pack("<iI", pos - (root + 8 * cell), n)
+
+    cells[field_order[0]] = vec(0, len(vector), field_order[0])
+    cells[field_order[1]] = vec(pq_pos, 0, field_order[1])
+    cells[field_order[2]] = vec(nbr_pos, len(nbr_ptrs), field_order[2])
+    cells[field_order[3]] = item_pointer(heap_tid >> 16, heap_tid & 0xFFFF)
+    return bytes(body) + b"".join(cells)
+
+
 def archive_means(count: int, mean: np.ndarray, m2) -> bytes:
     body = bytearray()
     mpos = 0
@@ -166,7 +190,9 @@ def write_index(snap, path: str, field_order=(0, 1, 2, 3), meta_body: bytes = b"
     # node items are written with invalid neighbours first, their IndexPointers collected, then the neighbour pointers are
     # patched in place - the order a build does it in (Tape::write, then the neighbour lists are rewritten)
     n, R = snap.n, snap.R
-    cur = w.new_page(PT_SBQ_NODE)
+    plain = getattr(snap, "storage_type", 0) == 1
+    node_pt = PT_NODE if plain else PT_SBQ_NODE
+    cur = w.new_page(node_pt)
     tids, where = [], []
     slot = 0
     for i in range(n):
@@ -178,10 +204,15 @@ def write_index(snap, path: str, field_order=(0, 1, 2, 3), meta_body: bytes = b"
             fourth, nf = np.ascontiguousarray(ls, dtype=np.int16).tobytes(), len(ls)
         else:
             fourth, nf = b"", 0
-        data = archive_node(int(snap.heap_tid[i]), snap.codes[i], [(INVALID_BLOCK, 0)] * R, fourth, nf, field_order)
-        ip, cur = w.tape_write(PT_SBQ_NODE, cur, data)
+        if plain:
+            data = archive_plain_node(int(snap.heap_tid[i]), snap.index_vectors[i], [(INVALID_BLOCK, 0)] * R, field_order)
+            nbr_at = snap.dim_index * 4
+        else:
+            data = archive_node(int(snap.heap_tid[i]), snap.codes[i], [(INVALID_BLOCK, 0)] * R, fourth, nf, field_order)
+            nbr_at = snap.words * 8
+        ip, cur = w.tape_write(node_pt, cur, data)
         tids.append(ip)
-        where.append((cur, w.pages[cur].upper + snap.words * 8))
+        where.append((cur, w.pages[cur].upper + nbr_at))
     for i in range(n):
         blk, pos = where[i]
         for j in range(R):
@@ -189,7 +220,7 @@ def write_index(snap, path: str, field_order=(0, 1, 2, 3), meta_body: bytes = b"
             if v != 0xFFFFFFFF:
                 w.pages[blk].b[pos + 8 * j:pos + 8 * j + 8] = item_pointer(*tids[v])
     means = None
-    if snap.mean is not None:
+    if snap.mean is not None and not plain:
         mb = w.new_page(PT_SBQ_MEANS)
         means, _ = w.chain_write(PT_SBQ_MEANS, mb, archive_means(int(snap.count), snap.mean, snap.m2))
     w.save(path, segment_blocks)

@@ -172,3 +172,30 @@ def test_meta_header_is_recognised_in_either_field_order(pg, tmp_path):
     with pg.PgRelation(path) as rel:
         i = rel.info()
     assert (i["meta_magic"], i["meta_version"]) == (pgpages.TSV_MAGIC, pgpages.TSV_VERSION)
+
+
+@pytest.mark.parametrize("order", [(0, 1, 2, 3), (2, 3, 0, 1)])
+def test_plain_storage_relation_round_trips(pg, tmp_path, order):
+    """storage_layout = plain: Node pages of PlainNode items (plain/node.rs:15-22) -> index_vectors + graph; the oracle's
+    plain scan of the extracted snapshot equals its scan of the original."""
+    from oracle import fixtures, oracle
+    s = fixtures.to_plain(build_case(400, 48, L2, seed=6, R=12, L_build=24, deleted_every=8))
+    path = str(tmp_path / "plain")
+    meta, tids, _ = pgpages.write_index(s, path, field_order=order, dead_every=5)
+    with pg.PgRelation(path) as rel:
+        info = rel.info()
+        assert info["pages_by_type"]["Node"] > 3 and "SbqNode" not in info["pages_by_type"]
+        got, index_tid, _, layout = rel.extract_plain(pg.PgMeta(**meta))
+        with pytest.raises(Exception) as e:
+            rel.extract_sbq(pg.PgMeta(**meta))          # no SbqNode pages: nothing to extract is not an error, a bad start node is
+        assert "start_nodes.default_node" in str(e.value)
+    # the reader reports cells as (heap, main, neighbours, fourth); the writer's order is per DECLARED field
+    assert layout == (order[3], order[0], order[2], order[1])
+    assert np.array_equal(index_tid, tids) and got.storage_type == 1
+    assert np.array_equal(got.index_vectors, s.index_vectors) and np.array_equal(got.nbrs, s.nbrs)
+    assert np.array_equal(got.heap_tid, s.heap_tid) and got.start_default == s.start_default
+    got.vectors = s.vectors
+    q = fixtures.gen_vectors(5, 48, 2, "normal")
+    a = oracle.scan_batch(s, q, None, None, 20, 0, 10)
+    b = oracle.scan_batch(got, q, None, None, 20, 0, 10)
+    assert np.array_equal(a[0], b[0])

@@ -159,6 +159,22 @@ def test_sidecar_process_serves_concurrent_backends(lib, lib_built, tmp_path):
             assert out[i]["count"] == n and out[i]["tid"][:n].tolist() == r["tid"].tolist()
             assert out[i]["dist"][:n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
             assert out[i]["stats"]["visits"] == r["stats"]["visits"]
+        # the socket belongs to the sidecar's account alone, and a malformed header is answered before the connection drops
+        import socket
+        import stat
+        import struct
+        assert stat.S_IMODE(os.stat(sock).st_mode) & 0o077 == 0
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.settimeout(20)
+        c.connect(sock)
+        assert len(c.recv(12, socket.MSG_WAITALL)) == 12                       # hello
+        c.sendall(struct.pack("<Iiiii", 0x12345678, 10, 40, 15, -1))            # wrong magic
+        status, count = struct.unpack("<iI", c.recv(8, socket.MSG_WAITALL))
+        (ln,) = struct.unpack("<I", c.recv(4, socket.MSG_WAITALL))
+        msg = c.recv(ln, socket.MSG_WAITALL).decode()
+        assert status == -1 and count == 0 and "malformed request header" in msg
+        assert c.recv(1) == b""                                                 # then the server closes
+        c.close()
     finally:
         proc.send_signal(signal.SIGTERM)
         try:
