@@ -54,7 +54,6 @@
 
 #include <algorithm>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/diskann_b200.h"
@@ -444,10 +443,18 @@ static inline int extract_nodes(const Relation &r, const dann_pg_meta *m, bool p
         return DANN_ERR_CAPACITY;
     }
     const uint32_t n = (uint32_t)n64;
+    /* IndexPointer -> dense id: the items of one block are consecutive in index_tid (at most a few hundred), so a
+     * per-block start index turns every lookup into a search inside one page's worth of entries */
+    std::vector<uint32_t> block_start((size_t)r.nblocks + 1, n);
+    for (uint32_t i = n; i-- > 0;) block_start[(size_t)(o->index_tid[i] >> 16)] = i;
+    for (uint32_t b = r.nblocks; b-- > 0;)
+        if (block_start[b] > block_start[b + 1]) block_start[b] = block_start[b + 1]; /* blocks without node items */
     auto dense_of = [&](uint32_t block, uint16_t off, uint32_t *id) {
+        if (block >= r.nblocks) return false;
         const uint64_t k = ip_key(block, off);
-        auto it = std::lower_bound(o->index_tid.begin(), o->index_tid.end(), k);
-        if (it == o->index_tid.end() || *it != k) return false;
+        auto lo = o->index_tid.begin() + block_start[block], hi = o->index_tid.begin() + block_start[block + 1];
+        auto it = std::lower_bound(lo, hi, k);
+        if (it == hi || *it != k) return false;
         *id = (uint32_t)(it - o->index_tid.begin());
         return true;
     };
