@@ -199,3 +199,53 @@ def test_plain_storage_relation_round_trips(pg, tmp_path, order):
     a = oracle.scan_batch(s, q, None, None, 20, 0, 10)
     b = oracle.scan_batch(got, q, None, None, 20, 0, 10)
     assert np.array_equal(a[0], b[0])
+
+
+def test_random_corruptions_never_crash_the_reader(pg, tmp_path):
+    """300 random byte / word corruptions of page headers, line pointers and item bodies: every call returns a snapshot
+    that passes its own invariants or a DANN_ERR_*; nothing reads outside the mapping (run under the ASan build of the
+    emulated ABI as well: DANN_EMULATE=1 DANN_EMULATE_ASAN=1 LD_PRELOAD=libasan.so)."""
+    from pgvectorscale_b200.diskann import DiskAnnError
+    s = build_case(150, 48, L2, seed=9, R=12, L_build=24, labels=True)
+    path = str(tmp_path / "rel")
+    meta, _, w = pgpages.write_index(s, path)
+    good = bytearray(open(path, "rb").read())
+    rng = np.random.default_rng(123)
+    nblocks = len(good) // 8192
+    outcomes = {"ok": 0, "refused": 0}
+    for it in range(300):
+        blob = bytearray(good)
+        for _ in range(int(rng.integers(1, 4))):
+            blk = int(rng.integers(0, nblocks))
+            kind = int(rng.integers(0, 4))
+            if kind == 0:                                   # page header field
+                pos = blk * 8192 + int(rng.integers(0, 24))
+            elif kind == 1:                                 # a line pointer
+                pos = blk * 8192 + 24 + int(rng.integers(0, 64))
+            elif kind == 2:                                 # the special area
+                pos = blk * 8192 + 8184 + int(rng.integers(0, 8))
+            else:                                           # anywhere in the item space (roots, relative pointers, lengths)
+                pos = blk * 8192 + int(rng.integers(24, 8184))
+            if rng.integers(0, 2):
+                blob[pos] ^= 1 << int(rng.integers(0, 8))
+            else:
+                v = [0, 0xFF, 0x7F, 0x80][int(rng.integers(0, 4))]
+                for j in range(int(rng.integers(1, 5))):
+                    if pos + j < len(blob):
+                        blob[pos + j] = v
+        open(path, "wb").write(blob)
+        try:
+            with pg.PgRelation(path) as rel:
+                rel.info()
+                try:
+                    rel.read_chain(0, 2)
+                except DiskAnnError:
+                    pass
+                got, tids, _, _ = rel.extract_sbq(pg.PgMeta(**meta))
+            valid = got.nbrs[got.nbrs != 0xFFFFFFFF]
+            assert got.codes.shape == (got.n, s.words) and (valid < got.n).all() and len(tids) == got.n
+            outcomes["ok"] += 1
+        except DiskAnnError as e:
+            assert e.code in (-7, -1, -5), e
+            outcomes["refused"] += 1
+    assert outcomes["refused"] > 50 and outcomes["ok"] > 20, outcomes
