@@ -231,6 +231,7 @@ void dann_group_free(dann_group *g);
  *   MetaPage::fetch: magic + version of MetaPageHeader    meta_page.rs:386-419   dann_pg_relation_info.meta_*
  *   ArchivedSbqNode accessors + SbqMeans::load            sbq/node.rs:236-330, sbq/mod.rs:88-122   dann_pg_extract_sbq
  *   ArchivedPlainNode accessors                           plain/node.rs:15-120   dann_pg_extract_plain
+ *   TableSlot::from_index_heap_pointer + PgVector::from_datum  util/table_slot.rs:13-53, pg_vector.rs:125-199   dann_pg_heap_fetch_vectors
  * The MetaPage BODY is an rkyv archive of a repr(Rust) struct whose field order cannot be pinned offline: the caller
  * supplies its scalars (dann_pg_meta; a Rust host fills them from MetaPage's getters) and the reader cross-checks them
  * against the node items; the node items' own field order is inferred and verified, never assumed (see the header of
@@ -287,6 +288,24 @@ int dann_pg_extract_sbq(const dann_pg_relation *rel, const dann_pg_meta *meta, d
 /* storage_layout = plain: Node pages (plain/node.rs:15-22); bq_bits, has_labels and the means pointer of `meta` are ignored */
 int dann_pg_extract_plain(const dann_pg_relation *rel, const dann_pg_meta *meta, dann_pg_snapshot **out);
 void dann_pg_snapshot_free(dann_pg_snapshot *s);
+
+/* The heap rows of a snapshot: the vector column of the TABLE's relation file(s), read the way the rerank reads it
+ * (sbq/storage.rs:304-328 -> util/table_slot.rs:13-53 -> pg_vector.rs:125-199: tuple by TID, detoast, f32[dim]).
+ * Postgres' documented heap / varlena / TOAST formats and pgvector's value layout only (no rkyv).  `heap` and `toast`
+ * are opened with dann_pg_relation_open on the table's and its TOAST table's files (toast may be NULL when every value
+ * is inline).  The caller describes the attributes IN FRONT of the vector column (pg_attribute.attlen: > 0 fixed, -1
+ * varlena; attalign 'c' 's' 'i' 'd').  Rows that are gone - heap_tid offset 0, dead or unused line pointer, NULL value -
+ * come back as zeros and are counted in *n_missing; HOT redirects are followed; there is no visibility test (the
+ * index names the tuples, the executor re-checks each row).  Compressed values are refused (the type is STORAGE external). */
+typedef struct {
+    uint32_t natts_before;  /* attributes in front of the vector column */
+    const int16_t *attlen;  /* [natts_before] */
+    const char *attalign;   /* [natts_before] */
+    uint32_t dim;           /* vector(dim) */
+    char vector_align;      /* 0 = 'i' (what CREATE TYPE vector declares) */
+} dann_pg_heap_layout;
+int dann_pg_heap_fetch_vectors(const dann_pg_relation *heap, const dann_pg_relation *toast, const dann_pg_heap_layout *layout,
+                               const uint64_t *heap_tid, uint32_t n, float *out, uint32_t *n_missing);
 
 /* How the last batch search of this index was planned (diagnostics for benchmarks and profiles). */
 typedef struct {

@@ -1598,3 +1598,15 @@ extern "C" int dann_pg_extract_plain(const dann_pg_relation *rel, const dann_pg_
 extern "C" void dann_pg_snapshot_free(dann_pg_snapshot *s) {
     if (s) delete static_cast<dannpg::SbqOut *>(s->self);
 }
+
+extern "C" int dann_pg_heap_fetch_vectors(const dann_pg_relation *heap, const dann_pg_relation *toast, const dann_pg_heap_layout *layout,
+                                          const uint64_t *heap_tid, uint32_t n, float *out, uint32_t *n_missing) try {
+    if (!heap || !layout || (n && (!heap_tid || !out)) || !layout->dim || (layout->natts_before && (!layout->attlen || !layout->attalign)))
+        return fail(DANN_ERR_INVALID_ARG, "dann_pg_heap_fetch_vectors: bad argument");
+    uint32_t missing = 0;
+    std::string err;
+    const int rc = dannpg::fetch_vectors(heap->rel, toast ? &toast->rel : nullptr, layout, heap_tid, n, out, &missing, err);
+    if (rc != DANN_OK) return fail(rc, "dann_pg_heap_fetch_vectors: %s", err.c_str());
+    if (n_missing) *n_missing = missing;
+    return DANN_OK;
+} DANN_CATCH

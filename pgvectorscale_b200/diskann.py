@@ -81,7 +81,7 @@ EXPORTS = [
     "dann_group_create", "dann_group_size", "dann_group_replica", "dann_group_search_batch", "dann_group_free",
     # relation-file reader (host only; mirror in pgreader.py)
     "dann_pg_relation_open", "dann_pg_relation_close", "dann_pg_relation_stat", "dann_pg_read_chain",
-    "dann_pg_extract_sbq", "dann_pg_extract_plain", "dann_pg_snapshot_free",
+    "dann_pg_extract_sbq", "dann_pg_extract_plain", "dann_pg_snapshot_free", "dann_pg_heap_fetch_vectors",
 ]
 
 _LIB = None

@@ -35,6 +35,11 @@ class _PgMeta(C.Structure):
                 ("means_block", C.c_uint32), ("means_offset", C.c_uint16)]
 
 
+class _HeapLayout(C.Structure):
+    _fields_ = [("natts_before", C.c_uint32), ("attlen", C.c_void_p), ("attalign", C.c_char_p), ("dim", C.c_uint32),
+                ("vector_align", C.c_char)]
+
+
 class _PgSnapshot(C.Structure):
     _fields_ = [("snap", _SnapshotDesc), ("index_vectors", C.c_void_p), ("index_tid", C.c_void_p), ("fingerprint", C.c_uint64),
                 ("layout", C.c_uint32 * 4), ("self", C.c_void_p)]
@@ -67,6 +72,7 @@ def _bind(lib):
     lib.dann_pg_extract_plain.argtypes = [vp, C.POINTER(_PgMeta), C.POINTER(C.POINTER(_PgSnapshot))]
     lib.dann_pg_snapshot_free.argtypes = [C.POINTER(_PgSnapshot)]
     lib.dann_pg_snapshot_free.restype = None
+    lib.dann_pg_heap_fetch_vectors.argtypes = [vp, vp, C.POINTER(_HeapLayout), vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
     lib._pg_bound = True
     return lib
 
@@ -152,3 +158,18 @@ class PgRelation:
             return snap, index_tid, int(out.contents.fingerprint), tuple(out.contents.layout)
         finally:
             self.lib.dann_pg_snapshot_free(out)
+
+
+def fetch_heap_vectors(heap: PgRelation, toast: Optional[PgRelation], heap_tid: np.ndarray, dim: int,
+                       atts_before: Sequence[tuple] = ()):
+    """Vector column of the table's relation file(s) for the rows heap_tid[i] -> (vectors [n, dim] f32, rows missing).
+    atts_before: (attlen, attalign) of every column in front of the vector column, e.g. [(8, 'd')] for a bigint id."""
+    tids = np.ascontiguousarray(heap_tid, dtype=np.uint64)
+    al = np.array([a for a, _ in atts_before], dtype=np.int16)
+    aa = "".join(c for _, c in atts_before).encode()
+    lay = _HeapLayout(len(atts_before), al.ctypes.data if len(al) else None, aa if aa else None, dim, b"\0")
+    out = np.zeros((len(tids), dim), np.float32)
+    miss = C.c_uint32()
+    _check(heap.lib, heap.lib.dann_pg_heap_fetch_vectors(heap.h, toast.h if toast else None, C.byref(lay), tids.ctypes.data,
+                                                         len(tids), out.ctypes.data, C.byref(miss)))
+    return out, int(miss.value)

@@ -231,3 +231,141 @@ def write_index(snap, path: str, field_order=(0, 1, 2, 3), meta_body: bytes = b"
                 {int(l): tids[int(v)] for l, v in zip(snap.start_labels, snap.start_label_nodes)},
                 means=means)
     return meta, np.array([(b << 16) | o for b, o in tids], dtype=np.uint64), w
+
+
+# ---- heap and TOAST relations (Postgres' own formats: htup_details.h, postgres.h varlena, detoast.h, heaptoast.h) ----------
+TOAST_MAX_CHUNK_SIZE = 1996
+
+
+class HeapPage(Page):
+    """PageInit(page, BLCKSZ, 0): no special space."""
+
+    def __init__(self, lsn: int = 0):
+        self.b = bytearray(BLCKSZ)
+        self.lower, self.upper = HDR, BLCKSZ
+        self.lsn = lsn
+        self.nitems = 0
+
+    def bytes(self) -> bytes:
+        struct.pack_into("<IIHHHHHHI", self.b, 0, self.lsn >> 32, self.lsn & 0xFFFFFFFF, 0, 0, self.lower, self.upper, BLCKSZ,
+                         BLCKSZ | 4, 0)
+        return bytes(self.b)
+
+    def add_redirect(self, to_offset: int) -> int:
+        struct.pack_into("<I", self.b, self.lower, to_offset | (2 << 15))      # LP_REDIRECT: lp_off = target offset number
+        self.lower += 4
+        self.nitems += 1
+        return self.nitems
+
+
+def _align(off, a):
+    n = {"c": 1, "s": 2, "i": 4, "d": 8}[a]
+    return (off + n - 1) & ~(n - 1)
+
+
+def varlena(payload: bytes, allow_short=True) -> bytes:
+    """what heap_fill_tuple stores for an inline value: 1-byte header when the whole thing fits 127 bytes, else 4-byte"""
+    if allow_short and len(payload) + 1 <= 0x7F:
+        return bytes([((len(payload) + 1) << 1) | 1]) + payload
+    return struct.pack("<I", (len(payload) + 4) << 2) + payload
+
+
+def toast_pointer(rawsize: int, extsize: int, valueid: int, toastrelid: int) -> bytes:
+    return bytes([0x01, 18]) + struct.pack("<iIII", rawsize, extsize, valueid, toastrelid)
+
+
+def heap_tuple(values, atts, block: int, offset: int) -> bytes:
+    """values[i]: None (NULL), bytes for a fixed-width attribute, or ("varlena", stored bytes incl. header) / ("pointer", bytes).
+    atts[i] = (attlen, attalign).  heap_fill_tuple's layout rules."""
+    natts = len(values)
+    hasnull = any(v is None for v in values)
+    hoff = 23 + ((natts + 7) // 8 if hasnull else 0)
+    hoff = (hoff + 7) & ~7
+    body = bytearray()
+    infomask = 0x0100 | 0x0800                                 # XMIN_COMMITTED | XMAX_INVALID
+    for v, (attlen, attalign) in zip(values, atts):
+        if v is None:
+            continue
+        off = hoff + len(body)
+        if attlen > 0:
+            body += b"\0" * (_align(off, attalign) - off) + v
+        else:
+            kind, data = v
+            infomask |= 0x0002                                  # HASVARWIDTH
+            if kind == "pointer":
+                infomask |= 0x0004                              # HASEXTERNAL
+            short = kind == "pointer" or (data[0] & 1)
+            if not short:
+                body += b"\0" * (_align(off, attalign) - off)   # 4-byte headers are aligned, 1-byte ones are not
+            body += data
+    if hasnull:
+        infomask |= 0x0001
+    hdr = bytearray(hoff)
+    struct.pack_into("<IIIHHHHHB", hdr, 0, 700, 0, 0, block >> 16, block & 0xFFFF, offset, natts, infomask, hoff)
+    if hasnull:
+        for i, v in enumerate(values):
+            if v is not None:
+                hdr[23 + (i >> 3)] |= 1 << (i & 7)
+    return bytes(hdr) + bytes(body)
+
+
+class HeapWriter:
+    def __init__(self):
+        self.pages = [HeapPage(0x2000)]
+
+    def add(self, make_tuple) -> tuple:
+        """make_tuple(block, offset) -> bytes; returns the TID"""
+        pg = self.pages[-1]
+        probe = make_tuple(len(self.pages) - 1, pg.nitems + 1)
+        if pg.upper - pg.lower - 4 < _align8(len(probe)):
+            self.pages.append(HeapPage(0x2000 + 0x30 * len(self.pages)))
+            pg = self.pages[-1]
+        blk = len(self.pages) - 1
+        return (blk, pg.add_item(make_tuple(blk, pg.nitems + 1)))
+
+    def save(self, path):
+        with open(path, "wb") as f:
+            for p in self.pages:
+                f.write(p.bytes())
+
+
+def write_table(vectors, path_heap, path_toast, prefix_values=None, prefix_atts=(), toastrelid=16999, null_rows=(), redirect_rows=(),
+                force_external_above=2000):
+    """vectors [n, dim] -> heap (+ TOAST) relation files of a table (prefix columns..., embedding vector(dim)).
+    Values above force_external_above bytes go out of line (TOAST_TUPLE_THRESHOLD); returns heap_tid [n] uint64.
+    redirect_rows: rows whose TID is an LP_REDIRECT to the real tuple (a HOT chain's root after pruning)."""
+    heap, toast = HeapWriter(), HeapWriter()
+    toast_atts = [(4, "i"), (4, "i"), (-1, "i")]
+    tids = []
+    next_value = 24000
+    for i, x in enumerate(vectors):
+        payload = struct.pack("<hh", len(x), 0) + np.ascontiguousarray(x, dtype=np.float32).tobytes()
+        pre = list(prefix_values[i]) if prefix_values is not None else []
+        if i in null_rows:
+            val = None
+        elif len(payload) + 4 > force_external_above:
+            vid = next_value
+            next_value += 1
+            for seq, s in enumerate(range(0, len(payload), TOAST_MAX_CHUNK_SIZE)):
+                chunk = payload[s:s + TOAST_MAX_CHUNK_SIZE]
+                toast.add(lambda b, o, seq=seq, chunk=chunk: heap_tuple(
+                    [struct.pack("<I", vid), struct.pack("<i", seq), ("varlena", varlena(chunk))], toast_atts, b, o))
+            val = ("pointer", toast_pointer(len(payload) + 4, len(payload), vid, toastrelid))
+        else:
+            val = ("varlena", varlena(payload))
+        atts = list(prefix_atts) + [(-1, "i")]
+        if i in redirect_rows:
+            pg = heap.pages[-1]
+            if pg.upper - pg.lower < 600 + len(payload):
+                heap.pages.append(HeapPage(0x2000 + 0x30 * len(heap.pages)))
+                pg = heap.pages[-1]
+            blk = len(heap.pages) - 1
+            root = pg.add_redirect(pg.nitems + 2)
+            real = pg.add_item(heap_tuple(pre + [val], atts, blk, root + 1))
+            assert real == root + 1
+            tids.append((blk, root))
+        else:
+            tids.append(heap.add(lambda b, o: heap_tuple(pre + [val], atts, b, o)))
+    heap.save(path_heap)
+    toast.save(path_toast)
+    return np.array([(b << 16) | o for b, o in tids], dtype=np.uint64)

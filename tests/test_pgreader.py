@@ -249,3 +249,57 @@ def test_random_corruptions_never_crash_the_reader(pg, tmp_path):
             assert e.code in (-7, -1, -5), e
             outcomes["refused"] += 1
     assert outcomes["refused"] > 50 and outcomes["ok"] > 20, outcomes
+
+
+@pytest.mark.parametrize("dim", [16, 48, 500, 768])
+def test_heap_vectors_inline_short_header_aligned_and_toasted(pg, tmp_path, dim):
+    """The vector column of the table's relation files, by TID: 1-byte-header inline values (dim 16), 4-byte-header inline
+    (48), out-of-line with a short last chunk (500: 1996 + 8 bytes) and the benchmark's 768 (two chunks); a bigint and a
+    nullable text column in front; NULL vectors, vacuumed TIDs, a dead line pointer and a HOT redirect on the way."""
+    import struct
+    rng = np.random.default_rng(dim)
+    n = 60
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    pre = []
+    for i in range(n):
+        tag = None if i % 5 == 0 else ("varlena", pgpages.varlena(b"t" * (i % 40)))
+        pre.append([struct.pack("<q", 1000 + i), tag])
+    heap_path, toast_path = str(tmp_path / "heap"), str(tmp_path / "toast")
+    tids = pgpages.write_table(x, heap_path, toast_path, prefix_values=pre, prefix_atts=[(8, "d"), (-1, "i")],
+                               null_rows={7, 31}, redirect_rows={11, 40})
+    want = x.copy()
+    want[[7, 31]] = 0
+    ask = tids.copy()
+    ask[3] &= np.uint64(0xFFFFFFFFFFFF0000)                 # vacuumed: offset 0
+    want[3] = 0
+    ask[20] = (ask[20] & np.uint64(0xFFFFFFFFFFFF0000)) | np.uint64(999)      # a line pointer that does not exist
+    want[20] = 0
+    with pg.PgRelation(heap_path) as heap, pg.PgRelation(toast_path) as toast:
+        got, missing = pg.fetch_heap_vectors(heap, toast, ask, dim, [(8, "d"), (-1, "i")])
+        assert missing == 4 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        if dim >= 500:
+            with pytest.raises(Exception) as e:
+                pg.fetch_heap_vectors(heap, None, ask, dim, [(8, "d"), (-1, "i")])
+            assert "no TOAST relation" in str(e.value)
+        with pytest.raises(Exception) as e:                  # the wrong dimension is refused, not reinterpreted
+            pg.fetch_heap_vectors(heap, toast, ask, dim + 1, [(8, "d"), (-1, "i")])
+        assert "not a vector(" in str(e.value)
+
+
+def test_whole_loader_index_heap_toast_to_snapshot(pg, tmp_path):
+    """index relation + table + TOAST files -> the complete snapshot a load takes; the oracle scans it like the original."""
+    from oracle import fixtures, oracle
+    s = build_case(300, 768, COSINE, seed=21, R=16, L_build=32)
+    ipath, hpath, tpath = str(tmp_path / "idx"), str(tmp_path / "heap"), str(tmp_path / "toast")
+    meta, _, _ = pgpages.write_index(s, ipath)
+    htids = pgpages.write_table(s.vectors, hpath, tpath)
+    s.heap_tid = htids                                       # the index points at where the rows really are
+    meta, _, _ = pgpages.write_index(s, ipath)
+    with pg.PgRelation(ipath) as rel, pg.PgRelation(hpath) as heap, pg.PgRelation(tpath) as toast:
+        got, _, _, _ = rel.extract_sbq(pg.PgMeta(**meta))
+        got.vectors, missing = pg.fetch_heap_vectors(heap, toast, got.heap_tid, 768)
+    assert missing == 0 and np.array_equal(got.vectors, s.vectors)
+    q = fixtures.gen_vectors(4, 768, 6, "normal")
+    a = oracle.scan_batch(s, q, None, None, 30, 20, 10)
+    b = oracle.scan_batch(got, q, None, None, 30, 20, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
