@@ -7,6 +7,12 @@
  * one batch on the GPU.  Plain C99 + pthreads over include/diskann_b200.h.
  *
  *   dann_sidecar <snapshot.raw> <socket path> [max_batch=1024] [max_wait_us=200]
+ *   dann_sidecar --relation <index file> <heap file> <toast file | -> <socket path> key=value...
+ *       cold start from a checkpointed data directory (dann_pg_*): the index relation's pages, the
+ *       table's vector column.  Keys = what MetaPage's getters and pg_attribute say: dim= dim_index= bits= R= distance=
+ *       (0 cosine, 1 l2, 2 ip) start=<block>:<offset> means=<block>:<offset> [atts=8d,-1i (attlen+attalign of the columns
+ *       in front of the vector column)] [max_batch=] [max_wait_us=].  SIGHUP re-reads the index relation's page headers
+ *       and exits with status 5 when its fingerprint has moved (the supervisor restarts it: that is the reload).
  *
  * Wire protocol (little-endian, one request -> one reply, any number per connection):
  *   request : u32 magic 'DANQ', i32 k, i32 search_list_size, i32 rescore, i32 nlabels (-1 = no scan key),
@@ -151,28 +157,124 @@ static void on_term(int sig) {
     g_stop = 1;
 }
 
+static volatile sig_atomic_t g_hup;
+static void on_hup(int sig) {
+    (void)sig;
+    g_hup = 1;
+}
+
+static const char *kv(int argc, char **argv, int from, const char *key) {
+    const size_t n = strlen(key);
+    for (int i = from; i < argc; i++)
+        if (strncmp(argv[i], key, n) == 0 && argv[i][n] == '=') return argv[i] + n + 1;
+    return NULL;
+}
+
+/* --relation: index pages + the table's vector column -> a loaded index; *fingerprint = the relation state it is valid for */
+static int load_from_relation(int argc, char **argv, dann_index **ix, dann_pg_relation **index_rel, uint64_t *fingerprint) {
+    const char *need[] = {"dim", "R", "start"};
+    for (int i = 0; i < 3; i++)
+        if (!kv(argc, argv, 6, need[i])) {
+            fprintf(stderr, "dann_sidecar: --relation needs %s=\n", need[i]);
+            return 2;
+        }
+    dann_pg_meta m;
+    memset(&m, 0, sizeof m);
+    m.num_dimensions = (uint32_t)atoi(kv(argc, argv, 6, "dim"));
+    m.num_dimensions_to_index = kv(argc, argv, 6, "dim_index") ? (uint32_t)atoi(kv(argc, argv, 6, "dim_index")) : m.num_dimensions;
+    m.bq_bits = kv(argc, argv, 6, "bits") ? (uint32_t)atoi(kv(argc, argv, 6, "bits")) : (m.num_dimensions_to_index < 900 ? 2u : 1u);
+    m.num_neighbors = (uint32_t)atoi(kv(argc, argv, 6, "R"));
+    m.distance_type = kv(argc, argv, 6, "distance") ? atoi(kv(argc, argv, 6, "distance")) : DANN_COSINE;
+    unsigned sb = 0, so = 0, mb = DANN_INVALID_NODE, mo = 0;
+    if (sscanf(kv(argc, argv, 6, "start"), "%u:%u", &sb, &so) != 2) return 2;
+    if (kv(argc, argv, 6, "means") && sscanf(kv(argc, argv, 6, "means"), "%u:%u", &mb, &mo) != 2) return 2;
+    m.start_block = sb;
+    m.start_offset = (uint16_t)so;
+    m.means_block = mb;
+    m.means_offset = (uint16_t)mo;
+    int16_t attlen[32];
+    char attalign[32];
+    uint32_t natts = 0;
+    const char *atts = kv(argc, argv, 6, "atts");
+    while (atts && *atts && natts < 32) { /* "8d,-1i" */
+        char *end;
+        const long l = strtol(atts, &end, 10);
+        if (end == atts || !*end) return 2;
+        attlen[natts] = (int16_t)l;
+        attalign[natts++] = *end;
+        atts = end + 1;
+        if (*atts == ',') atts++;
+    }
+    dann_pg_relation *heap = NULL, *toast = NULL;
+    dann_pg_snapshot *snap = NULL;
+    float *vectors = NULL;
+    int rc = dann_pg_relation_open(argv[2], index_rel);
+    if (rc == DANN_OK) rc = dann_pg_relation_open(argv[3], &heap);
+    if (rc == DANN_OK && strcmp(argv[4], "-") != 0) rc = dann_pg_relation_open(argv[4], &toast);
+    if (rc == DANN_OK) rc = dann_pg_extract_sbq(*index_rel, &m, &snap);
+    if (rc == DANN_OK) {
+        const dann_pg_heap_layout lay = {natts, attlen, attalign, m.num_dimensions, 0};
+        uint32_t missing = 0;
+        vectors = (float *)malloc((size_t)snap->snap.n * m.num_dimensions * sizeof(float) + 4);
+        rc = vectors ? dann_pg_heap_fetch_vectors(heap, toast, &lay, snap->snap.heap_tid, snap->snap.n, vectors, &missing) : DANN_ERR_OOM;
+        if (rc == DANN_OK) {
+            dann_snapshot_desc d = snap->snap;
+            d.vectors = vectors;
+            rc = dann_index_load(&d, 0, ix);
+            g_dim = d.dim;
+            g_n = d.n;
+            *fingerprint = snap->fingerprint;
+            fprintf(stderr, "dann_sidecar: %u nodes from %s (%u heap rows gone), relation fingerprint %016llx\n", d.n, argv[2], missing,
+                    (unsigned long long)snap->fingerprint);
+        }
+    }
+    if (rc != DANN_OK) fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
+    free(vectors);
+    dann_pg_snapshot_free(snap);
+    dann_pg_relation_close(heap);
+    dann_pg_relation_close(toast);
+    return rc == DANN_OK ? 0 : (rc == DANN_ERR_NO_DEVICE ? 3 : 1);
+}
+
 int main(int argc, char **argv) {
-    if (argc < 3) {
-        fprintf(stderr, "usage: %s snapshot.raw socket_path [max_batch] [max_wait_us]\n", argv[0]);
+    const int from_relation = argc > 1 && strcmp(argv[1], "--relation") == 0;
+    if (argc < 3 || (from_relation && argc < 6)) {
+        fprintf(stderr, "usage: %s snapshot.raw socket_path [max_batch] [max_wait_us]\n"
+                        "       %s --relation index_file heap_file toast_file|- socket_path dim= R= start=B:O [means=B:O bits= distance= atts=]\n",
+                argv[0], argv[0]);
         return 2;
     }
-    dann_snapshot_desc s;
-    const float *iv = NULL;
-    void *buf = dann_snapshot_raw_read(argv[1], &s, &iv);
-    if (!buf) {
-        fprintf(stderr, "dann_sidecar: cannot read %s\n", argv[1]);
-        return 1;
-    }
     dann_index *ix = NULL;
-    int rc = iv ? dann_index_load_plain(&s, iv, 0, &ix) : dann_index_load(&s, 0, &ix);
-    g_dim = s.dim;
-    g_n = s.n;
-    free(buf);
-    if (rc != DANN_OK) {
-        fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
-        return rc == DANN_ERR_NO_DEVICE ? 3 : 1;
+    dann_pg_relation *index_rel = NULL;
+    uint64_t fingerprint = 0;
+    int max_batch = 1024, max_wait = 200;
+    const char *index_path = from_relation ? argv[2] : NULL;
+    if (from_relation) {
+        const int lrc = load_from_relation(argc, argv, &ix, &index_rel, &fingerprint);
+        if (lrc) return lrc;
+        if (kv(argc, argv, 6, "max_batch")) max_batch = atoi(kv(argc, argv, 6, "max_batch"));
+        if (kv(argc, argv, 6, "max_wait_us")) max_wait = atoi(kv(argc, argv, 6, "max_wait_us"));
+        argv[2] = argv[5]; /* the socket path, where the code below expects it */
+    } else {
+        dann_snapshot_desc s;
+        const float *iv = NULL;
+        void *buf = dann_snapshot_raw_read(argv[1], &s, &iv);
+        if (!buf) {
+            fprintf(stderr, "dann_sidecar: cannot read %s\n", argv[1]);
+            return 1;
+        }
+        int rc = iv ? dann_index_load_plain(&s, iv, 0, &ix) : dann_index_load(&s, 0, &ix);
+        g_dim = s.dim;
+        g_n = s.n;
+        free(buf);
+        if (rc != DANN_OK) {
+            fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
+            return rc == DANN_ERR_NO_DEVICE ? 3 : 1;
+        }
+        if (argc > 3) max_batch = atoi(argv[3]);
+        if (argc > 4) max_wait = atoi(argv[4]);
     }
-    if (dann_coalescer_create(ix, argc > 3 ? atoi(argv[3]) : 1024, argc > 4 ? atoi(argv[4]) : 200, &g_co) != DANN_OK) {
+    if (dann_coalescer_create(ix, max_batch, max_wait, &g_co) != DANN_OK) {
         fprintf(stderr, "dann_sidecar: %s\n", dann_last_error());
         return 1;
     }
@@ -181,6 +283,8 @@ int main(int argc, char **argv) {
     sa.sa_handler = on_term;
     sigaction(SIGTERM, &sa, NULL);
     sigaction(SIGINT, &sa, NULL);
+    sa.sa_handler = on_hup;
+    sigaction(SIGHUP, &sa, NULL);
     signal(SIGPIPE, SIG_IGN);
     int ls = socket(AF_UNIX, SOCK_STREAM, 0);
     struct sockaddr_un addr;
@@ -195,10 +299,26 @@ int main(int argc, char **argv) {
     }
     fprintf(stderr, "dann_sidecar: %u nodes x %u dims in HBM (%.2f GB), listening on %s\n", g_n, g_dim,
             (double)dann_index_hbm_bytes(ix) / 1e9, argv[2]);
+    int stale = 0;
     while (!g_stop) {
         int fd = accept(ls, NULL, NULL);
         if (fd < 0) {
-            if (errno == EINTR) continue;
+            if (errno == EINTR) {
+                if (g_hup && index_rel) { /* invalidation rule: is the snapshot still the relation's state? */
+                    g_hup = 0;
+                    dann_pg_relation *now = NULL;
+                    dann_pg_relation_info info;
+                    if (dann_pg_relation_open(index_path, &now) == DANN_OK &&
+                        dann_pg_relation_stat(now, &info) == DANN_OK && info.fingerprint != fingerprint) {
+                        fprintf(stderr, "dann_sidecar: the index relation changed (fingerprint %016llx -> %016llx): reload needed\n",
+                                (unsigned long long)fingerprint, (unsigned long long)info.fingerprint);
+                        stale = 1;
+                        g_stop = 1;
+                    }
+                    dann_pg_relation_close(now);
+                }
+                continue;
+            }
             break;
         }
         pthread_t th;
@@ -240,5 +360,6 @@ int main(int argc, char **argv) {
             (unsigned long long)batches, (unsigned long long)largest);
     dann_coalescer_destroy(g_co);
     dann_index_free(ix);
-    return 0;
+    dann_pg_relation_close(index_rel);
+    return stale ? 5 : 0;
 }

@@ -182,3 +182,72 @@ def test_sidecar_process_serves_concurrent_backends(lib, lib_built, tmp_path):
         except subprocess.TimeoutExpired:
             proc.kill()
     assert "queries in" in proc.stderr.read()
+
+
+def test_sidecar_cold_start_from_relation_files_and_staleness_signal(lib, lib_built, tmp_path):
+    """dann_sidecar --relation: index pages (dann_pg_extract_sbq) + the table's vector column from its heap and TOAST
+    files (dann_pg_heap_fetch_vectors) -> the served index; scans equal the oracle's on the snapshot the files were
+    written from.  SIGHUP re-reads the page headers: unchanged -> keeps serving; a page LSN moved -> exits with status 5."""
+    import os
+    import shutil
+    import signal
+    import struct
+    import subprocess
+    import time
+    import pgpages
+    from oracle import fixtures, oracle
+    from pgvectorscale_b200.sidecar_client import SidecarClient
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dann_sidecar")
+    libdir = os.path.dirname(lib_built)
+    subprocess.run([gcc, "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "sidecar", "dann_sidecar.c"), "-L" + libdir, "-l:" + os.path.basename(lib_built),
+                    "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    s = build_case(500, 768, COSINE, seed=17, kind="normal", R=16, L_build=32, deleted_every=9)
+    ipath, hpath, tpath = str(tmp_path / "idx"), str(tmp_path / "heap"), str(tmp_path / "toast")
+    pre = [[struct.pack("<q", i)] for i in range(s.n)]
+    htids = pgpages.write_table(s.vectors, hpath, tpath, prefix_values=pre, prefix_atts=[(8, "d")])
+    dead = (s.heap_tid & np.uint64(0xFFFF)) == 0               # vacuumed nodes keep their invalid heap pointer
+    s.heap_tid = np.where(dead, htids & np.uint64(0xFFFFFFFFFFFF0000), htids)
+    meta, _, _ = pgpages.write_index(s, ipath)
+    sock = str(tmp_path / "pg.sock")
+    args = [exe, "--relation", ipath, hpath, tpath, sock, "dim=768", f"R={s.R}", "bits=%d" % s.bits, "distance=0",
+            "start=%d:%d" % meta["start"], "means=%d:%d" % meta["means"], "atts=8d", "max_batch=16", "max_wait_us=2000"]
+    proc = subprocess.Popen(args, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock) or proc.poll() is not None:
+                break
+            time.sleep(0.05)
+        if proc.poll() is not None:
+            err = proc.stderr.read()
+            if "unavailable" in err or "exclusive" in err.lower():
+                pytest.skip("a second process cannot open the GPU on this box: " + err.strip()[-120:])
+            pytest.fail("sidecar exited: " + err)
+        q = fixtures.gen_vectors(6, 768, 23, "normal")
+        with SidecarClient(sock) as c:
+            assert (c.dim, c.n) == (768, s.n)
+            for i in range(6):
+                got = c.scan(q[i], k=10, search_list_size=40, rescore=20)
+                r = oracle.scan(s, q[i], None, 40, 20, 10)
+                n = len(r["tid"])
+                assert got["count"] == n and got["tid"][:n].tolist() == r["tid"].tolist()
+                assert got["dist"][:n].view(np.uint32).tolist() == r["dist"].view(np.uint32).tolist()
+        proc.send_signal(signal.SIGHUP)                          # nothing changed: keeps serving
+        time.sleep(0.5)
+        assert proc.poll() is None
+        with SidecarClient(sock) as c:
+            assert c.scan(q[0], k=5, search_list_size=20, rescore=10)["count"] == 5
+        blob = bytearray(open(ipath, "rb").read())               # an insert rewrote a neighbour list: the page's LSN moved
+        lo = struct.unpack_from("<I", blob, 2 * 8192 + 4)[0]
+        struct.pack_into("<I", blob, 2 * 8192 + 4, lo + 0x58)
+        open(ipath, "wb").write(blob)
+        proc.send_signal(signal.SIGHUP)
+        assert proc.wait(timeout=30) == 5
+        assert "reload needed" in proc.stderr.read()
+    finally:
+        if proc.poll() is None:
+            proc.kill()
