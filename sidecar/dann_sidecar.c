@@ -25,11 +25,13 @@
  * first k rows repeat). */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
+#include <fcntl.h>
 #include <pthread.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/select.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <time.h>
@@ -95,8 +97,21 @@ static int write_full(int fd, const void *buf, size_t n) {
     return 0;
 }
 
+/* SIGTERM / SIGINT / SIGHUP are for the main thread alone (it sits in accept() and acts on them): every other thread -
+ * the library's dispatcher and CUDA's own, created while main() still has them blocked, and the connection threads -
+ * keeps them blocked, so the kernel cannot hand one to a thread that would swallow it. */
+static void block_control_signals(int how) {
+    sigset_t set;
+    sigemptyset(&set);
+    sigaddset(&set, SIGTERM);
+    sigaddset(&set, SIGINT);
+    sigaddset(&set, SIGHUP);
+    pthread_sigmask(how, &set, NULL);
+}
+
 static void *serve(void *arg) {
     const int fd = (int)(intptr_t)arg;
+    block_control_signals(SIG_BLOCK);
     const uint32_t hello[3] = {0x484E4144u /* 'DANH' */, g_dim, g_n};
     float *query = (float *)malloc((size_t)g_dim * sizeof(float));
     if (!query || write_full(fd, hello, sizeof hello) != 0) goto out;
@@ -244,6 +259,7 @@ int main(int argc, char **argv) {
                 argv[0], argv[0]);
         return 2;
     }
+    block_control_signals(SIG_BLOCK); /* until the accept loop: threads created by the load inherit the mask */
     dann_index *ix = NULL;
     dann_pg_relation *index_rel = NULL;
     uint64_t fingerprint = 0;
@@ -300,8 +316,24 @@ int main(int argc, char **argv) {
     fprintf(stderr, "dann_sidecar: %u nodes x %u dims in HBM (%.2f GB), listening on %s\n", g_n, g_dim,
             (double)dann_index_hbm_bytes(ix) / 1e9, argv[2]);
     int stale = 0;
+    /* the control signals stay blocked except inside pselect(): none can slip in between the flag test and the wait */
+    sigset_t wait_mask;
+    pthread_sigmask(SIG_BLOCK, NULL, &wait_mask);
+    sigdelset(&wait_mask, SIGTERM);
+    sigdelset(&wait_mask, SIGINT);
+    sigdelset(&wait_mask, SIGHUP);
+    fcntl(ls, F_SETFL, fcntl(ls, F_GETFL, 0) | O_NONBLOCK);
     while (!g_stop) {
-        int fd = accept(ls, NULL, NULL);
+        fd_set rf;
+        FD_ZERO(&rf);
+        FD_SET(ls, &rf);
+        int fd = -1;
+        if (pselect(ls + 1, &rf, NULL, NULL, NULL, &wait_mask) > 0) {
+            fd = accept(ls, NULL, NULL);
+            if (fd < 0 && (errno == EAGAIN || errno == EWOULDBLOCK || errno == ECONNABORTED)) errno = EINTR;
+        } else {
+            errno = EINTR; /* a signal (or a spurious wake-up): look at the flags */
+        }
         if (fd < 0) {
             if (errno == EINTR) {
                 if (g_hup && index_rel) { /* invalidation rule: is the snapshot still the relation's state? */
