@@ -1,5 +1,5 @@
-// dann_pgreader.h — host-side reader of a pgvectorscale `diskann` index RELATION FILE: Postgres
-// pages -> the flat arrays of dann_snapshot_desc.  Pure host C++ (no CUDA); compiled into the C-ABI library and
+// dann_pgreader.h — host-side reader of a pgvectorscale `diskann` index RELATION FILE and of the table's heap / TOAST
+// files: Postgres pages -> the flat arrays of dann_snapshot_desc.  Pure host C++ (no CUDA); compiled into the C-ABI library and
 // exported as dann_pg_* (include/diskann_b200.h).  Reference paths are relative to /root/reference/pgvectorscale/src/.
 //
 // What is read, and what pins its layout:
@@ -37,11 +37,14 @@
 // neighbour lists), so   fingerprint = hash over every page of (block, pd_lsn, pd_lower, pd_upper, pd_checksum)
 // changes iff some page changed, and nblocks / max_lsn order two fingerprints in time.  A snapshot is valid for
 // exactly the fingerprint it was extracted under: the loader records it (dann_pg_snapshot.fingerprint), the host compares
-// dann_pg_relation_info() again before reusing a cached index handle - in a backend additionally on relcache
+// dann_pg_relation_stat() again before reusing a cached index handle - in a backend additionally on relcache
 // invalidation and after its own aminsert / ambulkdelete - and reloads on any difference.
 // A relation FILE shows only what has been written back: an external reader (the sidecar) needs a CHECKPOINT or a
-// clean shutdown first; inside a backend the exporter walks the buffer manager instead and uses this file format
-// knowledge only through the same item parser (dann_pg_parse_node_item).
+// clean shutdown first; inside a backend the exporter of INTEGRATION.md §4b(ii) walks the buffer manager with the
+// reference's own accessors instead.
+//
+// The table side (the vector column a rerank reads) is at the end of this file: heap tuples by TID, varlena headers,
+// TOAST chunks - Postgres' own documented formats and pgvector's value layout, nothing from rkyv.
 #pragma once
 #include <errno.h>
 #include <fcntl.h>
