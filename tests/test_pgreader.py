@@ -303,3 +303,23 @@ def test_whole_loader_index_heap_toast_to_snapshot(pg, tmp_path):
     a = oracle.scan_batch(s, q, None, None, 30, 20, 10)
     b = oracle.scan_batch(got, q, None, None, 30, 20, 10)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_relation_files_to_raw_snapshot_tool(pg, tmp_path, capsys):
+    """tools/pg_to_snapshot.py: index + heap + TOAST files -> the DANNSNP1 file the sidecar and the C harnesses read."""
+    import struct
+    from pgvectorscale_b200.snapshot import Snapshot
+    from tools import pg_to_snapshot
+    s = build_case(250, 768, COSINE, seed=31, R=12, L_build=24)
+    ipath, hpath, tpath, out = (str(tmp_path / x) for x in ("idx", "heap", "toast", "snap.raw"))
+    pre = [[struct.pack("<q", i)] for i in range(s.n)]
+    s.heap_tid = pgpages.write_table(s.vectors, hpath, tpath, prefix_values=pre, prefix_atts=[(8, "d")])
+    meta, _, _ = pgpages.write_index(s, ipath)
+    rc = pg_to_snapshot.main(["--index", ipath, "--heap", hpath, "--toast", tpath, "--out", out, "--dim", "768", "--R", str(s.R),
+                              "--bits", str(s.bits), "--start", "%d:%d" % meta["start"], "--means", "%d:%d" % meta["means"], "--atts", "8d"])
+    assert rc == 0 and "250 nodes, 0 heap rows gone" in capsys.readouterr().out
+    blob = open(out, "rb").read()
+    assert blob[:8] == Snapshot.RAW_MAGIC
+    hdr = np.frombuffer(blob, dtype=np.uint64, count=16, offset=8)
+    assert (int(hdr[0]), int(hdr[1]), int(hdr[5])) == (s.n, 768, s.R)
+    assert s.vectors.tobytes() in blob and s.codes.tobytes() in blob
